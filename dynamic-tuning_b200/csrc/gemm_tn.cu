@@ -1,0 +1,97 @@
+// Host launcher + C-ABI entry for the tcgen05 GEMM (see gemm_tn.cuh).
+#include <stdarg.h>
+
+#include "../../include/dyt_b200.h"
+#include "gemm_tn.cuh"
+#include "host_utils.h"
+
+namespace dyt {
+
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_tn_kernel<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    DYT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int m_tiles = (p.M + Cfg::BM - 1) / Cfg::BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  int grid = m_tiles * n_tiles;
+  const int sms = sm_count();
+  if (grid > sms) grid = sms;
+  if (grid < 1) grid = 1;
+  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  return cuda_status(cudaGetLastError(), "gemm_tn_kernel launch");
+}
+
+template <int BN>
+static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb,
+                        const GemmParams& p, cudaStream_t s) {
+  switch (epi) {
+    case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(ta, tb, p, s);
+    case EPI_BIAS_GELU: return launch_gemm<BN, EPI_BIAS_GELU>(ta, tb, p, s);
+    case EPI_BIAS_RELU: return launch_gemm<BN, EPI_BIAS_RELU>(ta, tb, p, s);
+    case EPI_BIAS_RESID: return launch_gemm<BN, EPI_BIAS_RESID>(ta, tb, p, s);
+    default: return fail(DYT_EINVAL, "unknown epilogue %d", epi);
+  }
+}
+
+// Internal entry used by the composite block forward as well.
+int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, int K,
+            const int* m_dev, int epi, const __half* bias, __half* out_h, int ldo_h, float* out_f,
+            int ldo_f, const float* resid, int ld_res, float scale, cudaStream_t stream) {
+  DYT_CHECK_ARG(a != nullptr && w != nullptr, "gemm: null operand");
+  DYT_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  DYT_CHECK_ARG(N % 8 == 0 && K % 8 == 0, "gemm: N and K must be multiples of 8 (N=%d K=%d)", N, K);
+  DYT_CHECK_ARG(lda >= K && ldw >= K, "gemm: leading dimension smaller than K");
+  if (epi == EPI_BIAS_RESID) {
+    DYT_CHECK_ARG(out_f != nullptr && resid != nullptr, "gemm: residual epilogue needs out_f/resid");
+    DYT_CHECK_ARG(ldo_f % 4 == 0 && ld_res % 4 == 0, "gemm: fp32 strides must be multiples of 4");
+    DYT_CHECK_ARG(out_h == nullptr || ldo_h % 4 == 0, "gemm: fp16 stride must be a multiple of 4");
+  } else {
+    DYT_CHECK_ARG(out_h != nullptr && ldo_h % 4 == 0, "gemm: fp16 output missing / misaligned");
+  }
+  if (M == 0) return DYT_OK;
+
+  // BN: widest tile that divides the work without a mostly-empty last column tile.
+  int bn = 256;
+  if (N <= 64) bn = 64;
+  else if (N <= 128 || (N % 256 != 0 && N % 128 == 0)) bn = 128;
+
+  CUtensorMap ta, tb;
+  int s = make_tmap_f16_sw128(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(K),
+                              static_cast<uint64_t>(lda), 128);
+  if (s != DYT_OK) return s;
+  s = make_tmap_f16_sw128(&tb, w, static_cast<uint64_t>(N), static_cast<uint64_t>(K),
+                          static_cast<uint64_t>(ldw), static_cast<uint32_t>(bn));
+  if (s != DYT_OK) return s;
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.m_dev = m_dev;
+  p.bias = bias;
+  p.out_h = out_h; p.out_f = out_f; p.resid = resid;
+  p.ldo_h = ldo_h; p.ldo_f = ldo_f; p.ld_res = ld_res;
+  p.scale = scale;
+  switch (bn) {
+    case 64: return dispatch_epi<64>(epi, ta, tb, p, stream);
+    case 128: return dispatch_epi<128>(epi, ta, tb, p, stream);
+    default: return dispatch_epi<256>(epi, ta, tb, p, stream);
+  }
+}
+
+}  // namespace dyt
+
+extern "C" int dyt_linear_f16(const void* x, int ldx, const void* w, int ldw, int M, int N, int K,
+                              const int* m_dev, int epilogue, const void* bias, void* out_f16,
+                              int ldo_f16, float* out_f32, int ldo_f32, const float* resid,
+                              int ld_resid, float scale, void* stream) {
+  return dyt::gemm_tn(static_cast<const __half*>(x), ldx, static_cast<const __half*>(w), ldw, M, N,
+                      K, m_dev, epilogue, static_cast<const __half*>(bias),
+                      static_cast<__half*>(out_f16), ldo_f16, out_f32, ldo_f32, resid, ld_resid,
+                      scale, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,96 @@
+// Host-side plumbing shared by the C-ABI entry points: status codes, last-error text,
+// TMA tensor-map encoding through the driver entry point (no link-time libcuda dependency).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace dyt {
+
+// Status convention of include/dyt_b200.h: 0 ok, <0 argument error, >0 cudaError_t.
+constexpr int DYT_OK = 0;
+constexpr int DYT_EINVAL = -1;
+constexpr int DYT_EUNSUPPORTED = -2;
+constexpr int DYT_EDRIVER = -3;
+
+inline char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+inline int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+inline int cuda_status(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return DYT_OK;
+  snprintf(last_error_buf(), 512, "%s: %s", what, cudaGetErrorString(e));
+  return static_cast<int>(e);
+}
+
+#define DYT_CHECK_ARG(cond, ...)                               \
+  do {                                                         \
+    if (!(cond)) return ::dyt::fail(::dyt::DYT_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+#define DYT_CUDA(call)                                      \
+  do {                                                      \
+    int _s = ::dyt::cuda_status((call), #call);             \
+    if (_s != 0) return _s;                                 \
+  } while (0)
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+  }
+  return fn;
+}
+
+// 2-D fp16 row-major tensor [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols]
+// (64 halves = 128 B = the swizzle span), SWIZZLE_128B, OOB elements read as zero.
+inline int make_tmap_f16_sw128(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols,
+                               uint64_t ld, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return fail(DYT_EDRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0)
+    return fail(DYT_EINVAL, "TMA operand must be 16-byte aligned with a 16-byte multiple row stride");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DYT_EDRIVER, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
+  return DYT_OK;
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace dyt

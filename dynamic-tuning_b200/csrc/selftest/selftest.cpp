@@ -1,0 +1,237 @@
+// Standalone GPU self-test of the C-ABI (no Python, no torch): each hand-written kernel is
+// checked against a naive CUDA-core reference computed in this file, then timed with CUDA events.
+// Build: make -C dynamic-tuning_b200/csrc build/selftest ; run on a B200: build/selftest [filter]
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "dyt_b200.h"
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      printf("CUDA error %s at %s:%d: %s\n", #call, __FILE__, __LINE__,               \
+             cudaGetErrorString(e_));                                                 \
+      exit(2);                                                                        \
+    }                                                                                 \
+  } while (0)
+
+#define DYT(call)                                                                     \
+  do {                                                                                \
+    int s_ = (call);                                                                  \
+    if (s_ != 0) {                                                                    \
+      printf("dyt error %d at %s:%d: %s\n", s_, __FILE__, __LINE__, dyt_last_error()); \
+      exit(3);                                                                        \
+    }                                                                                 \
+  } while (0)
+
+static int g_fail = 0;
+
+// ------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------
+__global__ void fill_half(__half* p, size_t n, uint32_t seed, float scale) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x = (uint32_t)(i * 2654435761u) ^ seed;
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  float u = (float)(x & 0xFFFFFF) / 16777216.0f * 2.0f - 1.0f;
+  p[i] = __float2half_rn(u * scale);
+}
+__global__ void fill_float(float* p, size_t n, uint32_t seed, float scale) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x = (uint32_t)(i * 2654435761u) ^ seed;
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  float u = (float)(x & 0xFFFFFF) / 16777216.0f * 2.0f - 1.0f;
+  p[i] = u * scale;
+}
+static void fillh(__half* p, size_t n, uint32_t seed, float scale) {
+  fill_half<<<(unsigned)((n + 255) / 256), 256>>>(p, n, seed, scale);
+}
+static void fillf(float* p, size_t n, uint32_t seed, float scale) {
+  fill_float<<<(unsigned)((n + 255) / 256), 256>>>(p, n, seed, scale);
+}
+
+__device__ inline float ref_round16(float x) { return __half2float(__float2half_rn(x)); }
+
+// naive reference: rows listed in `rows` (nr of them); one thread per output element
+__global__ void ref_linear(const __half* a, int lda, const __half* w, int ldw, const __half* bias,
+                           const int* rows, int nr, int N, int K, int epi, const float* resid,
+                           int ldres, float scale, float* out /* [nr, N] */) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int ri = blockIdx.y;
+  if (j >= N || ri >= nr) return;
+  int r = rows[ri];
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k)
+    acc += __half2float(a[(size_t)r * lda + k]) * __half2float(w[(size_t)j * ldw + k]);
+  float v = ref_round16(acc + (bias ? __half2float(bias[j]) : 0.f));
+  if (epi == DYT_EPI_BIAS_GELU) v = ref_round16(0.5f * v * (1.0f + erff(v * 0.70710678118654752f)));
+  if (epi == DYT_EPI_BIAS_RELU) v = fmaxf(v, 0.f);
+  if (epi == DYT_EPI_BIAS_RESID) {
+    if (scale != 1.0f) v = ref_round16(v * scale);
+    v = resid[(size_t)r * ldres + j] + v;
+  }
+  out[(size_t)ri * N + j] = v;
+}
+
+struct Timer {
+  cudaEvent_t a, b;
+  Timer() { CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); }
+  void start() { CK(cudaEventRecord(a)); }
+  float stop() { CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b)); float ms; CK(cudaEventElapsedTime(&ms, a, b)); return ms; }
+};
+
+static void report(const char* name, double max_abs, double max_rel_viol, bool ok, const char* extra) {
+  printf("[%s] %-52s max_abs_err=%.3e worst_tol_ratio=%.3f %s\n", ok ? "PASS" : "FAIL", name,
+         max_abs, max_rel_viol, extra);
+  fflush(stdout);
+  if (!ok) g_fail++;
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMM tests
+// ------------------------------------------------------------------------------------------
+static void test_linear(int M, int N, int K, int epi, bool use_mdev, int m_valid, bool with_copy,
+                        bool timeit) {
+  char name[256];
+  snprintf(name, sizeof name, "linear M=%d N=%d K=%d epi=%d mdev=%d(%d) copy=%d", M, N, K, epi,
+           (int)use_mdev, m_valid, (int)with_copy);
+  __half *a, *w, *bias, *outh;
+  float *outf = nullptr, *resid = nullptr;
+  CK(cudaMalloc(&a, (size_t)M * K * 2));
+  CK(cudaMalloc(&w, (size_t)N * K * 2));
+  CK(cudaMalloc(&bias, (size_t)N * 2));
+  CK(cudaMalloc(&outh, (size_t)M * N * 2));
+  CK(cudaMemset(outh, 0xFF, (size_t)M * N * 2));  // NaN pattern: unwritten outputs are detected
+  fillh(a, (size_t)M * K, 0x1234u + M, 1.0f);
+  fillh(w, (size_t)N * K, 0x9876u + N, 1.0f / sqrtf((float)K));
+  fillh(bias, (size_t)N, 0x5555u, 0.5f);
+  if (epi == DYT_EPI_BIAS_RESID) {
+    CK(cudaMalloc(&outf, (size_t)M * N * 4));
+    CK(cudaMalloc(&resid, (size_t)M * N * 4));
+    CK(cudaMemset(outf, 0xFF, (size_t)M * N * 4));
+    fillf(resid, (size_t)M * N, 0x4242u, 2.0f);
+  }
+  int* mdev = nullptr;
+  if (use_mdev) {
+    CK(cudaMalloc(&mdev, 4));
+    CK(cudaMemcpy(mdev, &m_valid, 4, cudaMemcpyHostToDevice));
+  }
+  const int m_eff = use_mdev ? m_valid : M;
+  const float scale = (epi == DYT_EPI_BIAS_RESID) ? 0.1f : 1.0f;
+  __half* oh = (epi == DYT_EPI_BIAS_RESID && !with_copy) ? nullptr : outh;
+  DYT(dyt_linear_f16(a, K, w, K, M, N, K, mdev, epi, bias, oh, N, outf, N, resid, N, scale, 0));
+  CK(cudaDeviceSynchronize());
+
+  // rows to verify: first 160, last 160 valid, 64 pseudo-random
+  std::vector<int> rows;
+  for (int i = 0; i < std::min(160, m_eff); ++i) rows.push_back(i);
+  for (int i = std::max(0, m_eff - 160); i < m_eff; ++i) rows.push_back(i);
+  uint32_t s = 12345;
+  for (int i = 0; i < 64 && m_eff > 0; ++i) { s = s * 1664525u + 1013904223u; rows.push_back((int)(s % (uint32_t)m_eff)); }
+  int nr = (int)rows.size();
+  int* drows; float* dref;
+  CK(cudaMalloc(&drows, nr * 4 + 4));
+  CK(cudaMalloc(&dref, (size_t)nr * N * 4 + 4));
+  CK(cudaMemcpy(drows, rows.data(), nr * 4, cudaMemcpyHostToDevice));
+  if (nr > 0) {
+    dim3 g((N + 127) / 128, nr);
+    ref_linear<<<g, 128>>>(a, K, w, K, bias, drows, nr, N, K, epi, resid, N, scale, dref);
+    CK(cudaDeviceSynchronize());
+  }
+  std::vector<float> ref((size_t)nr * N);
+  CK(cudaMemcpy(ref.data(), dref, (size_t)nr * N * 4, cudaMemcpyDeviceToHost));
+  std::vector<__half> hh((size_t)M * N);
+  CK(cudaMemcpy(hh.data(), outh, (size_t)M * N * 2, cudaMemcpyDeviceToHost));
+  std::vector<float> hf;
+  if (outf) { hf.resize((size_t)M * N); CK(cudaMemcpy(hf.data(), outf, (size_t)M * N * 4, cudaMemcpyDeviceToHost)); }
+
+  double max_abs = 0, worst = 0;
+  bool ok = true;
+  for (int ri = 0; ri < nr; ++ri) {
+    int r = rows[ri];
+    for (int j = 0; j < N; ++j) {
+      float e = ref[(size_t)ri * N + j];
+      float g = outf ? hf[(size_t)r * N + j] : __half2float(hh[(size_t)r * N + j]);
+      double d = fabs((double)g - (double)e);
+      double tol = 2e-3 + 2e-3 * fabs(e);
+      if (!(d <= tol)) ok = false;  // also catches NaN
+      if (d > max_abs || d != d) max_abs = d;
+      if (d / tol > worst) worst = d / tol;
+      if (outf && oh) {
+        float gh = __half2float(hh[(size_t)r * N + j]);
+        float eh = __half2float(__float2half_rn(g));
+        if (gh != eh) ok = false;
+      }
+    }
+  }
+  // rows >= m_eff must be untouched (still the 0xFFFF NaN pattern)
+  if (use_mdev && m_eff < M && !outf) {
+    for (int r = m_eff; r < std::min(M, m_eff + 130); ++r)
+      for (int j = 0; j < N; j += 7) {
+        uint16_t bits; memcpy(&bits, &hh[(size_t)r * N + j], 2);
+        if (bits != 0xFFFF) { ok = false; worst = 1e9; }
+      }
+  }
+  char extra[128] = "";
+  if (timeit) {
+    Timer t;
+    for (int i = 0; i < 3; ++i)
+      DYT(dyt_linear_f16(a, K, w, K, M, N, K, mdev, epi, bias, oh, N, outf, N, resid, N, scale, 0));
+    t.start();
+    const int iters = 20;
+    for (int i = 0; i < iters; ++i)
+      DYT(dyt_linear_f16(a, K, w, K, M, N, K, mdev, epi, bias, oh, N, outf, N, resid, N, scale, 0));
+    float ms = t.stop() / iters;
+    double tf = 2.0 * m_eff * (double)N * K / (ms * 1e-3) / 1e12;
+    snprintf(extra, sizeof extra, "time=%.1f us  %.1f TFLOP/s", ms * 1e3, tf);
+  }
+  report(name, max_abs, worst, ok, extra);
+  cudaFree(a); cudaFree(w); cudaFree(bias); cudaFree(outh); cudaFree(drows); cudaFree(dref);
+  if (outf) cudaFree(outf);
+  if (resid) cudaFree(resid);
+  if (mdev) cudaFree(mdev);
+}
+
+static void run_gemm_tests() {
+  // small / ragged shapes first (cheap to fail)
+  test_linear(128, 256, 64, DYT_EPI_BIAS, false, 0, false, false);
+  test_linear(128, 256, 128, DYT_EPI_BIAS, false, 0, false, false);
+  test_linear(300, 256, 768, DYT_EPI_BIAS, false, 0, false, false);
+  test_linear(197, 64, 768, DYT_EPI_BIAS_RELU, false, 0, false, false);   // BN=64 path
+  test_linear(394, 384, 64, DYT_EPI_BIAS, false, 0, false, false);        // BN=128 path
+  test_linear(1000, 2304, 768, DYT_EPI_BIAS, false, 0, false, false);
+  test_linear(1000, 3072, 768, DYT_EPI_BIAS_GELU, true, 777, false, false);
+  test_linear(1000, 768, 3072, DYT_EPI_BIAS, true, 1, false, false);
+  test_linear(1000, 768, 768, DYT_EPI_BIAS_RESID, false, 0, true, false);
+  test_linear(1000, 768, 64, DYT_EPI_BIAS_RESID, false, 0, false, false);
+  test_linear(1000, 1000, 200, DYT_EPI_BIAS, false, 0, false, false);     // ragged N and K
+  // config-2 shapes (B=256): timing
+  test_linear(50432, 2304, 768, DYT_EPI_BIAS, false, 0, false, true);
+  test_linear(50432, 768, 768, DYT_EPI_BIAS_RESID, false, 0, true, true);
+  test_linear(50432, 3072, 768, DYT_EPI_BIAS_GELU, true, 25344, false, true);
+  test_linear(50432, 768, 3072, DYT_EPI_BIAS, true, 25344, false, true);
+  test_linear(50432, 64, 768, DYT_EPI_BIAS_RELU, false, 0, false, true);
+  test_linear(50432, 768, 64, DYT_EPI_BIAS_RESID, false, 0, false, true);
+}
+
+int main(int argc, char** argv) {
+  std::string filter = argc > 1 ? argv[1] : "all";
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device: %s, %d SMs, cc %d.%d, dyt abi %d\n", prop.name, prop.multiProcessorCount,
+         prop.major, prop.minor, dyt_version());
+  if (filter == "all" || filter == "gemm") run_gemm_tests();
+  printf("selftest: %d failure(s)\n", g_fail);
+  return g_fail ? 1 : 0;
+}
