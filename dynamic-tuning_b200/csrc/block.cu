@@ -1,0 +1,159 @@
+// One DyT block forward = the launch sequence of the sm_100a kernels, all on the caller's stream,
+// no host synchronisation and no allocation (the caller provides the workspace).
+// Mirrors Block.batch_forward of the reference (models/model_speed_test.py:274-310):
+//   x1  = x + proj(attn(qkv(LN1(x))))                    :278
+//   mask, logits = TokenSelect(x1)                        :284     (fused dispatcher)
+//   adapt = up(relu(down(x1))) * scale                    :291     (all tokens)
+//   mlp_packed = fc2(gelu(fc1(LN2(x1[kept]))))            :297-304 (kept tokens only)
+//   x   = adapt + (x1 + scatter(mlp_packed))              :305-308
+#include <stdarg.h>
+
+#include "../../include/dyt_b200.h"
+#include "gemm_tn.cuh"
+#include "host_utils.h"
+#include "internal.h"
+
+namespace dyt {
+
+static inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+struct BlockWorkspace {
+  __half* xn;       // [T, C]   LN1(x)
+  __half* attn_o;   // [T, C]   attention output
+  __half* qkv;      // [T, 3C]
+  float* x1;        // [T, C]   fp32 residual stream after attention
+  __half* x1h;      // [T, C]   fp16 copy of x1 (adapter A operand)
+  __half* packed;   // [T, C]   LN2 of kept rows (capacity T)
+  __half* hidden;   // [T, hidden]
+  __half* mlp;      // [T, C]   packed MLP output
+  __half* down;     // [T, bottleneck_padded]
+  __half* adapt;    // [T, C]
+  int* packed_idx;  // [T]
+  int* token_pos;   // [T]
+  int* cu_seqlens;  // [B+1]
+  int* n_kept;      // [1]
+  void* dispatch_ws;
+  size_t total;
+};
+
+static BlockWorkspace carve(const dyt_block_shape* s, void* base) {
+  const size_t T = static_cast<size_t>(s->B) * s->N;
+  const size_t C = s->C;
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  BlockWorkspace w;
+  auto take = [&](size_t bytes) {
+    void* r = p ? p + off : nullptr;
+    off += align256(bytes);
+    return r;
+  };
+  w.xn = static_cast<__half*>(take(T * C * 2));
+  w.attn_o = static_cast<__half*>(take(T * C * 2));
+  w.qkv = static_cast<__half*>(take(T * 3 * C * 2));
+  w.x1 = static_cast<float*>(take(T * C * 4));
+  w.x1h = static_cast<__half*>(take(T * C * 2));
+  w.packed = static_cast<__half*>(take(T * C * 2));
+  w.hidden = static_cast<__half*>(take(T * static_cast<size_t>(s->hidden) * 2));
+  w.mlp = static_cast<__half*>(take(T * C * 2));
+  w.down = static_cast<__half*>(take(T * static_cast<size_t>(s->bottleneck) * 2));
+  w.adapt = static_cast<__half*>(take(T * C * 2));
+  w.packed_idx = static_cast<int*>(take(T * 4));
+  w.token_pos = static_cast<int*>(take(T * 4));
+  w.cu_seqlens = static_cast<int*>(take((static_cast<size_t>(s->B) + 1) * 4));
+  w.n_kept = static_cast<int*>(take(256));
+  w.dispatch_ws = take(dyt_dispatch_workspace_bytes(s->B));
+  w.total = off;
+  return w;
+}
+
+static int check_shape(const dyt_block_shape* s) {
+  DYT_CHECK_ARG(s != nullptr, "block: null shape");
+  DYT_CHECK_ARG(s->B >= 1 && s->N >= 2, "block: bad B=%d N=%d", s->B, s->N);
+  DYT_CHECK_ARG(s->H >= 1 && s->C == s->H * 64, "block: C must be 64*H (C=%d H=%d)", s->C, s->H);
+  DYT_CHECK_ARG(s->hidden % 8 == 0 && s->bottleneck % 8 == 0 && s->bottleneck >= 8,
+                "block: hidden/bottleneck must be multiples of 8");
+  return DYT_OK;
+}
+
+}  // namespace dyt
+
+extern "C" size_t dyt_block_workspace_bytes(const dyt_block_shape* shape) {
+  if (dyt::check_shape(shape) != 0) return 0;
+  return dyt::carve(shape, nullptr).total;
+}
+
+extern "C" int dyt_block_workspace_layout(const dyt_block_shape* shape, void* workspace,
+                                          dyt_block_buffers* out) {
+  using namespace dyt;
+  int st = check_shape(shape);
+  if (st != 0) return st;
+  DYT_CHECK_ARG(out != nullptr, "block: null layout output");
+  BlockWorkspace w = carve(shape, workspace);
+  out->xn = w.xn; out->attn_o = w.attn_o; out->qkv = w.qkv; out->x1 = w.x1; out->x1h = w.x1h;
+  out->packed = w.packed; out->hidden = w.hidden; out->mlp = w.mlp; out->down = w.down;
+  out->adapt = w.adapt; out->packed_idx = w.packed_idx; out->token_pos = w.token_pos;
+  out->cu_seqlens = w.cu_seqlens; out->n_kept = w.n_kept;
+  return DYT_OK;
+}
+
+extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weights* wt,
+                             const dyt_block_opts* opt, float* x, float* mask_out,
+                             float* logits_out, void* workspace, size_t workspace_bytes,
+                             void* stream_) {
+  using namespace dyt;
+  int st = check_shape(shape);
+  if (st != 0) return st;
+  DYT_CHECK_ARG(wt && opt && x && mask_out && logits_out && workspace, "block: null argument");
+  DYT_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+                "block: workspace must be 256-byte aligned");
+  BlockWorkspace w = carve(shape, workspace);
+  DYT_CHECK_ARG(workspace_bytes >= w.total, "block: workspace too small (%zu < %zu)",
+                workspace_bytes, w.total);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int B = shape->B, N = shape->N, C = shape->C, H = shape->H;
+  const int T = B * N;
+  const __half* h = nullptr;
+  (void)h;
+#define DYT_TRY(call)        \
+  do {                       \
+    int s_ = (call);         \
+    if (s_ != 0) return s_;  \
+  } while (0)
+#define HP(p) static_cast<const __half*>(p)
+
+  // 1. LN1 (skipped when the previous block's merge already produced it)
+  if (!opt->xn_ready)
+    DYT_TRY(layernorm_f16(x, C, nullptr, nullptr, T, C, wt->ln1_w, wt->ln1_b, opt->eps, w.xn, C,
+                          stream));
+  // 2. qkv
+  DYT_TRY(gemm_tn(w.xn, C, HP(wt->qkv_w), C, T, 3 * C, C, nullptr, EPI_BIAS, HP(wt->qkv_b), w.qkv,
+                  3 * C, nullptr, 0, nullptr, 0, 1.0f, stream));
+  // 3. attention (uniform sequences of N tokens)
+  DYT_TRY(attn_varlen_fwd(w.qkv, 3 * C, nullptr, B, N, N, T, H, 64, w.attn_o, C, stream));
+  // 4. proj + residual -> x1 (fp32) and its fp16 copy
+  DYT_TRY(gemm_tn(w.attn_o, C, HP(wt->proj_w), C, T, C, C, nullptr, EPI_BIAS_RESID,
+                  HP(wt->proj_b), w.x1h, C, w.x1, C, x, C, 1.0f, stream));
+  // 5. dispatcher: score, gate, compaction, LN2 of kept rows
+  DYT_TRY(dyt_dispatch_fwd(w.x1, C, wt->sel_w, wt->sel_b, opt->logit_fp16, opt->min_kept,
+                           opt->noise1, opt->noise2, opt->tau, B, N, C, wt->ln2_w, wt->ln2_b,
+                           opt->eps, opt->forced_mask, mask_out, opt->gate_out, logits_out, w.packed_idx,
+                           w.token_pos, w.cu_seqlens, w.n_kept, w.packed, C, w.dispatch_ws,
+                           stream_));
+  // 6./7. MLP on the kept rows only (row count read from device memory)
+  DYT_TRY(gemm_tn(w.packed, C, HP(wt->fc1_w), C, T, shape->hidden, C, w.n_kept, EPI_BIAS_GELU,
+                  HP(wt->fc1_b), w.hidden, shape->hidden, nullptr, 0, nullptr, 0, 1.0f, stream));
+  DYT_TRY(gemm_tn(w.hidden, shape->hidden, HP(wt->fc2_w), shape->hidden, T, C, shape->hidden,
+                  w.n_kept, EPI_BIAS, HP(wt->fc2_b), w.mlp, C, nullptr, 0, nullptr, 0, 1.0f, stream));
+  // 8./9. adapter on every token
+  DYT_TRY(gemm_tn(w.x1h, C, HP(wt->down_w), C, T, shape->bottleneck, C, nullptr, EPI_BIAS_RELU,
+                  HP(wt->down_b), w.down, shape->bottleneck, nullptr, 0, nullptr, 0, 1.0f, stream));
+  DYT_TRY(gemm_tn(w.down, shape->bottleneck, HP(wt->up_w), shape->bottleneck, T, C,
+                  shape->bottleneck, nullptr, EPI_BIAS, HP(wt->up_b), w.adapt, C, nullptr, 0,
+                  nullptr, 0, wt->adapter_scale, stream));
+  // 10. scatter-merge back to [B, N, C] (in place into x), optionally with the next LayerNorm
+  DYT_TRY(scatter_merge(w.x1, C, w.adapt, C, w.mlp, C, w.token_pos, T, C, x, C, opt->next_ln_w,
+                        opt->next_ln_b, opt->eps, opt->next_ln_w ? w.xn : nullptr, C, stream));
+#undef DYT_TRY
+#undef HP
+  return DYT_OK;
+}

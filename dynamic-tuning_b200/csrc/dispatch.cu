@@ -1,0 +1,300 @@
+// Fused token dispatcher (sm_100a, HBM-bound): one persistent kernel, no host sync.
+//   phase 1  score  : logit[b,n] = <x1[b,n,:], w> + bias for the N-1 patch tokens (warp per token,
+//                     128-bit coalesced row loads, fp16-rounded operands / fp32 accumulate / one
+//                     rounding of the logit when the activation dtype is fp16)
+//            gate   : keep = sigmoid(logit) > threshold evaluated in the logit dtype, implemented as
+//                     the equivalent monotone test `logit >= min_kept` (the host derives min_kept
+//                     from torch's own sigmoid, see dyt_b200/gate.py); train mode adds the two
+//                     caller-drawn Gumbel terms and the temperature first.  cls token always kept.
+//   grid barrier    : all CTAs are co-resident (grid <= occupancy * #SMs)
+//   phase 2  compact: per-image exclusive base from the per-image counts, ballot/popc warp scan of
+//                     the keep flags -> packed_idx (ascending flat index == nonzero() order),
+//                     token_pos (inverse map), cu_seqlens, n_kept
+//            pack   : for every kept token LayerNorm2(x1 row) -> fp16 row of the packed buffer
+//                     (the A operand of the MLP fc1 GEMM)
+//
+// Replaces TokenSelect.forward + _gumbel_sigmoid (reference models/dynamic_adapter.py:25-77,
+// models/model_speed_test.py:27-60), the nonzero()/gather glue (models/model_speed_test.py:297-301)
+// and norm2 on the gathered rows (:303).
+#include <stdarg.h>
+
+#include "../../include/dyt_b200.h"
+#include "host_utils.h"
+#include "rowwise.cuh"
+
+namespace dyt {
+
+struct DispatchParams {
+  const float* x1;      // [B*N, ldx] fp32 residual stream after attention
+  int ldx;
+  const float* sel_w;   // [C] selector weight (fp32 master copy)
+  const float* sel_b;   // [1] selector bias
+  int logit_fp16;       // 1: emulate fp16 autocast rounding points; 0: pure fp32
+  float min_kept;       // keep iff gate input >= min_kept
+  const float* noise1;  // optional [B, N-1] Gumbel draws (train mode); nullptr in eval
+  const float* noise2;
+  float tau;
+  int B, N;
+  const float* ln_w;    // norm2 weight / bias
+  const float* ln_b;
+  float eps;
+  const float* forced_mask;  // optional [B, N]: imposed keep mask (BASELINE config 1), cls forced
+  float* mask;          // [B, N]   out: 1.0 kept / 0.0 dropped, cls = 1 (after forcing)
+  float* gate_out;      // optional [B, N]: the selector's own decision, ignoring forced_mask
+  float* logits;        // [B, N-1] out
+  int* packed_idx;      // [B*N]    out (first n_kept entries valid)
+  int* token_pos;       // [B*N]    out: packed position or -1
+  int* cu_seqlens;      // [B+1]    out
+  int* n_kept;          // [1]      out
+  __half* packed;       // [B*N, ldp] out: LayerNorm2 of the kept rows, fp16
+  int ldp;
+  int* counts;          // [B] workspace
+  unsigned int* sync;   // [2] workspace, zero before the first launch; the kernel leaves it zeroed
+};
+
+constexpr int DISPATCH_MAX_N = 2048;
+
+__device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+dispatch_kernel(const DispatchParams p) {
+  __shared__ int s_list[DISPATCH_MAX_N];
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  __shared__ int s_count;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int N = p.N;
+
+  // selector weight in registers, laid out like a row
+  float4 w[NV];
+  load_row_f32<NV>(p.sel_w, lane, w);
+  float bias = p.sel_b[0];
+  if (p.logit_fp16) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      w[i].x = r16(w[i].x); w[i].y = r16(w[i].y); w[i].z = r16(w[i].z); w[i].w = r16(w[i].w);
+    }
+    bias = r16(bias);
+  }
+
+  // ------------------------------- phase 1: score + gate -------------------------------
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    int my_count = 0;
+    for (int n = warp; n < N; n += 8) {
+      const size_t t = static_cast<size_t>(b) * N + n;
+      if (n == 0) {
+        if (lane == 0) {
+          p.mask[t] = 1.0f;
+          if (p.gate_out != nullptr) p.gate_out[t] = 1.0f;
+        }
+        my_count += 1;
+        continue;
+      }
+      float4 v[NV];
+      load_row_f32<NV>(p.x1 + t * p.ldx, lane, v);
+      float acc = 0.f;
+      if (p.logit_fp16) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          acc = fmaf(r16(v[i].x), w[i].x, acc);
+          acc = fmaf(r16(v[i].y), w[i].y, acc);
+          acc = fmaf(r16(v[i].z), w[i].z, acc);
+          acc = fmaf(r16(v[i].w), w[i].w, acc);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          acc = fmaf(v[i].x, w[i].x, acc);
+          acc = fmaf(v[i].y, w[i].y, acc);
+          acc = fmaf(v[i].z, w[i].z, acc);
+          acc = fmaf(v[i].w, w[i].w, acc);
+        }
+      }
+      acc = warp_sum(acc);
+      float logit = acc + bias;
+      if (p.logit_fp16) logit = r16(logit);
+      float g = logit;
+      const size_t li = static_cast<size_t>(b) * (N - 1) + (n - 1);
+      if (p.noise1 != nullptr) {
+        // (logits + g1 - g2) / tau, every op rounded in the logit dtype (dynamic_adapter.py:41)
+        if (p.logit_fp16) {
+          g = r16(g + r16(p.noise1[li]));
+          g = r16(g - r16(p.noise2[li]));
+          g = r16(g / r16(p.tau));
+        } else {
+          g = ((g + p.noise1[li]) - p.noise2[li]) / p.tau;
+        }
+      }
+      bool keep = g >= p.min_kept;  // NaN -> dropped, +inf -> kept
+      if (lane == 0 && p.gate_out != nullptr) p.gate_out[t] = keep ? 1.0f : 0.0f;
+      if (p.forced_mask != nullptr) keep = p.forced_mask[t] != 0.0f;
+      if (lane == 0) {
+        p.logits[li] = logit;
+        p.mask[t] = keep ? 1.0f : 0.0f;
+      }
+      my_count += keep ? 1 : 0;
+    }
+    if (lane == 0) atomicAdd(&s_count, my_count);
+    __syncthreads();
+    if (threadIdx.x == 0) p.counts[b] = s_count;
+    __syncthreads();
+  }
+
+  // ------------------------------- grid barrier -------------------------------
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&p.sync[0], 1u);
+    const long long t0 = clock64();
+    while (atomicAdd(&p.sync[0], 0u) < gridDim.x) {
+      __nanosleep(100);
+      if (clock64() - t0 > 4000000000ll) {
+        printf("dyt: dispatcher grid barrier timeout (block %d)\n", (int)blockIdx.x);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+
+  // ------------------------------- phase 2: compact + pack -------------------------------
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    // exclusive base = sum of counts[0..b)
+    int part = 0;
+    for (int i = threadIdx.x; i < b; i += blockDim.x) part += __ldcg(p.counts + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_warp[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int s = 0;
+      for (int i = 0; i < 8; ++i) s += s_warp[i];
+      s_base = s;
+    }
+    __syncthreads();
+    const int base = s_base;
+    int running = 0;  // kept tokens of this image before the current 256-token chunk
+    for (int c0 = 0; c0 < N; c0 += 256) {
+      const int n = c0 + threadIdx.x;
+      const size_t t = static_cast<size_t>(b) * N + n;
+      const bool keep = (n < N) && (p.mask[t] != 0.0f);
+      const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+      const int rank = __popc(ballot & ((1u << lane) - 1u));
+      __syncthreads();  // previous use of s_warp is complete
+      if (lane == 0) s_warp[warp] = __popc(ballot);
+      __syncthreads();
+      int before = 0, total = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = s_warp[i];
+        before += (i < warp) ? c : 0;
+        total += c;
+      }
+      if (n < N) {
+        if (keep) {
+          const int j = running + before + rank;
+          s_list[j] = n;
+          p.packed_idx[base + j] = static_cast<int>(t);
+          p.token_pos[t] = base + j;
+        } else {
+          p.token_pos[t] = -1;
+        }
+      }
+      running += total;
+    }
+    __syncthreads();
+    const int count = running;
+    if (threadIdx.x == 0) {
+      p.cu_seqlens[b] = base;
+      if (b == p.B - 1) {
+        p.cu_seqlens[p.B] = base + count;
+        p.n_kept[0] = base + count;
+      }
+    }
+    if (p.packed != nullptr) {
+      for (int j = warp; j < count; j += 8) {
+        const int n = s_list[j];
+        float4 v[NV];
+        load_row_f32<NV>(p.x1 + (static_cast<size_t>(b) * N + n) * p.ldx, lane, v);
+        row_layernorm<NV>(v, p.ln_w, p.ln_b, p.eps, lane);
+        store_row_f16<NV>(p.packed + static_cast<size_t>(base + j) * p.ldp, lane, v);
+      }
+    }
+    __syncthreads();
+  }
+
+  // leave the barrier words zeroed for the next launch
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(&p.sync[1], 1u);
+    if (prev == gridDim.x - 1) {
+      p.sync[0] = 0u;
+      p.sync[1] = 0u;
+      __threadfence();
+    }
+  }
+}
+
+template <int NV>
+static int launch_dispatch(const DispatchParams& p, cudaStream_t stream) {
+  static int max_blocks = 0;
+  if (max_blocks == 0) {
+    int per_sm = 0;
+    DYT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dispatch_kernel<NV>, 256, 0));
+    if (per_sm < 1) return fail(DYT_EDRIVER, "dispatch kernel does not fit on an SM");
+    if (per_sm > 4) per_sm = 4;
+    max_blocks = per_sm * sm_count();
+  }
+  int grid = p.B < max_blocks ? p.B : max_blocks;
+  dispatch_kernel<NV><<<grid, 256, 0, stream>>>(p);
+  return cuda_status(cudaGetLastError(), "dispatch_kernel launch");
+}
+
+}  // namespace dyt
+
+extern "C" size_t dyt_dispatch_workspace_bytes(int B) {
+  return static_cast<size_t>(B) * sizeof(int) + 64;
+}
+
+extern "C" int dyt_dispatch_fwd(const float* x1, int ldx, const float* sel_w, const float* sel_b,
+                                int logit_fp16, float min_kept, const float* noise1,
+                                const float* noise2, float tau, int B, int N, int C,
+                                const float* ln_w, const float* ln_b, float eps,
+                                const float* forced_mask, float* mask, float* gate_out,
+                                float* logits, int* packed_idx, int* token_pos, int* cu_seqlens, int* n_kept,
+                                void* packed_f16, int ldp, void* workspace, void* stream) {
+  using namespace dyt;
+  DYT_CHECK_ARG(x1 && sel_w && sel_b && mask && logits && packed_idx && token_pos && cu_seqlens &&
+                    n_kept && workspace,
+                "dispatch: null buffer");
+  DYT_CHECK_ARG(B >= 1 && N >= 1 && N <= DISPATCH_MAX_N, "dispatch: bad B=%d N=%d", B, N);
+  DYT_CHECK_ARG(ldx >= C && ldx % 4 == 0, "dispatch: bad ldx");
+  DYT_CHECK_ARG((noise1 == nullptr) == (noise2 == nullptr), "dispatch: need both noise tensors");
+  DYT_CHECK_ARG(packed_f16 == nullptr || (ln_w && ln_b && ldp >= C && ldp % 4 == 0),
+                "dispatch: packed output needs norm2 parameters");
+  DYT_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "dispatch: workspace alignment");
+  DispatchParams p;
+  p.x1 = x1; p.ldx = ldx; p.sel_w = sel_w; p.sel_b = sel_b;
+  p.logit_fp16 = logit_fp16; p.min_kept = min_kept;
+  p.noise1 = noise1; p.noise2 = noise2; p.tau = tau;
+  p.B = B; p.N = N;
+  p.ln_w = ln_w; p.ln_b = ln_b; p.eps = eps;
+  p.forced_mask = forced_mask;
+  p.mask = mask; p.gate_out = gate_out; p.logits = logits; p.packed_idx = packed_idx; p.token_pos = token_pos;
+  p.cu_seqlens = cu_seqlens; p.n_kept = n_kept;
+  p.packed = static_cast<__half*>(packed_f16); p.ldp = ldp;
+  p.sync = static_cast<unsigned int*>(workspace);
+  p.counts = reinterpret_cast<int*>(static_cast<char*>(workspace) + 64);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (C) {
+    case 768: return launch_dispatch<6>(p, s);
+    case 1024: return launch_dispatch<8>(p, s);
+    case 384: return launch_dispatch<3>(p, s);
+    case 128: return launch_dispatch<1>(p, s);
+    default:
+      return fail(DYT_EUNSUPPORTED, "dispatch: embed dim %d not instantiated (128/384/768/1024)", C);
+  }
+}

@@ -15,7 +15,7 @@
 namespace dyt {
 
 enum GemmEpilogue : int {
-  EPI_BIAS = 0,        // out_h = f16(acc + bias)
+  EPI_BIAS = 0,        // out_h = f16(acc + bias); if scale != 1: out_h = f16(out_h * scale)
   EPI_BIAS_GELU = 1,   // out_h = f16(gelu_erf(f16(acc + bias)))
   EPI_BIAS_RELU = 2,   // out_h = f16(relu(f16(acc + bias)))
   EPI_BIAS_RESID = 3,  // v = f16(acc + bias); if scale != 1: v = f16(v * scale);
@@ -224,6 +224,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (grow < m_eff && col_ok) {
             float v0 = round_f16(a.x + b0), v1 = round_f16(a.y + b1);
             float v2 = round_f16(a.z + b2), v3 = round_f16(a.w + b3);
+            if constexpr (EPI == EPI_BIAS) {
+              if (p.scale != 1.0f) {
+                v0 = round_f16(v0 * p.scale); v1 = round_f16(v1 * p.scale);
+                v2 = round_f16(v2 * p.scale); v3 = round_f16(v3 * p.scale);
+              }
+            }
             if constexpr (EPI == EPI_BIAS_GELU) {
               v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
             } else if constexpr (EPI == EPI_BIAS_RELU) {

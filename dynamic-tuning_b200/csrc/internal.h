@@ -1,0 +1,25 @@
+// Internal (non-ABI) entry points shared between translation units of libdyt_b200.so.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace dyt {
+
+int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, int K,
+            const int* m_dev, int epi, const __half* bias, __half* out_h, int ldo_h, float* out_f,
+            int ldo_f, const float* resid, int ld_res, float scale, cudaStream_t stream);
+
+int attn_varlen_fwd(const __half* qkv, int ld_qkv, const int* cu_seqlens, int num_seqs,
+                    int uniform_len, int max_seqlen, int total_tokens, int num_heads, int head_dim,
+                    __half* out, int ldo, cudaStream_t stream);
+
+int layernorm_f16(const float* x, int ldx, const int* row_idx, const int* n_rows_dev, int n_rows,
+                  int C, const float* gamma, const float* beta, float eps, __half* out, int ldo,
+                  cudaStream_t stream);
+
+int scatter_merge(const float* x1, int ldx, const __half* adapt, int lda, const __half* mlp_packed,
+                  int ldm, const int* token_pos, int n_rows, int C, float* out, int ldo,
+                  const float* nln_w, const float* nln_b, float eps, __half* nln_out, int ldn,
+                  cudaStream_t stream);
+
+}  // namespace dyt

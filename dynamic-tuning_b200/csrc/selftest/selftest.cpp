@@ -225,6 +225,99 @@ static void run_gemm_tests() {
   test_linear(50432, 768, 64, DYT_EPI_BIAS_RESID, false, 0, false, true);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// attention test
+// ------------------------------------------------------------------------------------------
+// one thread per (sequence, head, query row): fp32 math, P rounded to fp16, fp32 row sum
+__global__ void ref_attn(const __half* qkv, int ld, const int* cu, int nseq, int uniform_len, int H,
+                         float scale, float* out /* [T, H*64] */) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int b = blockIdx.z, h = blockIdx.y;
+  int start = cu ? cu[b] : b * uniform_len;
+  int len = cu ? cu[b + 1] - start : uniform_len;
+  if (idx >= len) return;
+  const int C = H * 64;
+  const __half* q = qkv + (size_t)(start + idx) * ld + h * 64;
+  float mx = -INFINITY;
+  for (int j = 0; j < len; ++j) {
+    const __half* k = qkv + (size_t)(start + j) * ld + C + h * 64;
+    float s = 0.f;
+    for (int d = 0; d < 64; ++d) s += __half2float(q[d]) * __half2float(k[d]);
+    mx = fmaxf(mx, s * scale);
+  }
+  float acc[64];
+  for (int d = 0; d < 64; ++d) acc[d] = 0.f;
+  float sum = 0.f;
+  for (int j = 0; j < len; ++j) {
+    const __half* k = qkv + (size_t)(start + j) * ld + C + h * 64;
+    const __half* v = qkv + (size_t)(start + j) * ld + 2 * C + h * 64;
+    float s = 0.f;
+    for (int d = 0; d < 64; ++d) s += __half2float(q[d]) * __half2float(k[d]);
+    float e = expf(s * scale - mx);
+    sum += e;
+    float e16 = ref_round16(e);
+    for (int d = 0; d < 64; ++d) acc[d] += e16 * __half2float(v[d]);
+  }
+  for (int d = 0; d < 64; ++d) out[(size_t)(start + idx) * C + h * 64 + d] = acc[d] / sum;
+}
+
+static void test_attn(int nseq, int H, const std::vector<int>& lens, bool uniform, bool timeit) {
+  int T = 0, maxlen = 0;
+  std::vector<int> cu(nseq + 1, 0);
+  for (int i = 0; i < nseq; ++i) { cu[i + 1] = cu[i] + lens[i % lens.size()]; maxlen = std::max(maxlen, lens[i % lens.size()]); }
+  T = cu[nseq];
+  const int C = H * 64;
+  char name[256];
+  snprintf(name, sizeof name, "attn nseq=%d H=%d T=%d maxlen=%d uniform=%d", nseq, H, T, maxlen, (int)uniform);
+  __half *qkv, *out; float* ref; int* dcu = nullptr;
+  CK(cudaMalloc(&qkv, (size_t)T * 3 * C * 2));
+  CK(cudaMalloc(&out, (size_t)T * C * 2));
+  CK(cudaMalloc(&ref, (size_t)T * C * 4));
+  CK(cudaMemset(out, 0xFF, (size_t)T * C * 2));
+  fillh(qkv, (size_t)T * 3 * C, 0xABCDu + nseq, 2.0f);
+  if (!uniform) { CK(cudaMalloc(&dcu, (nseq + 1) * 4)); CK(cudaMemcpy(dcu, cu.data(), (nseq + 1) * 4, cudaMemcpyHostToDevice)); }
+  DYT(dyt_attn_varlen_fwd(qkv, 3 * C, dcu, nseq, uniform ? maxlen : 0, maxlen, T, H, 64, out, C, 0));
+  CK(cudaDeviceSynchronize());
+  dim3 g((maxlen + 63) / 64, H, nseq);
+  ref_attn<<<g, 64>>>(qkv, 3 * C, dcu, nseq, maxlen, H, 0.125f, ref);
+  CK(cudaDeviceSynchronize());
+  std::vector<__half> ho((size_t)T * C); std::vector<float> hr((size_t)T * C);
+  CK(cudaMemcpy(ho.data(), out, (size_t)T * C * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hr.data(), ref, (size_t)T * C * 4, cudaMemcpyDeviceToHost));
+  double max_abs = 0, worst = 0; bool ok = true;
+  for (size_t i = 0; i < ho.size(); ++i) {
+    double g_ = __half2float(ho[i]), e = hr[i];
+    double d = fabs(g_ - e), tol = 2e-3 + 3e-3 * fabs(e);
+    if (!(d <= tol)) ok = false;
+    if (d > max_abs || d != d) max_abs = d;
+    if (d / tol > worst) worst = d / tol;
+  }
+  char extra[128] = "";
+  if (timeit) {
+    Timer t;
+    for (int i = 0; i < 3; ++i) DYT(dyt_attn_varlen_fwd(qkv, 3 * C, dcu, nseq, uniform ? maxlen : 0, maxlen, T, H, 64, out, C, 0));
+    t.start();
+    const int iters = 20;
+    for (int i = 0; i < iters; ++i) DYT(dyt_attn_varlen_fwd(qkv, 3 * C, dcu, nseq, uniform ? maxlen : 0, maxlen, T, H, 64, out, C, 0));
+    float ms = t.stop() / iters;
+    double fl = 0; for (int i = 0; i < nseq; ++i) { double l = cu[i + 1] - cu[i]; fl += 4.0 * l * l * 64 * H; }
+    snprintf(extra, sizeof extra, "time=%.1f us  %.1f TFLOP/s (useful)", ms * 1e3, fl / (ms * 1e-3) / 1e12);
+  }
+  report(name, max_abs, worst, ok, extra);
+  cudaFree(qkv); cudaFree(out); cudaFree(ref); if (dcu) cudaFree(dcu);
+}
+
+static void run_attn_tests() {
+  test_attn(1, 1, {16}, true, false);
+  test_attn(1, 1, {128}, true, false);
+  test_attn(2, 2, {197}, true, false);
+  test_attn(3, 12, {197}, true, false);
+  test_attn(5, 4, {1, 17, 128, 129, 256}, false, false);
+  test_attn(7, 12, {197, 33, 250, 64}, false, false);
+  test_attn(256, 12, {197}, true, true);
+}
+
 int main(int argc, char** argv) {
   std::string filter = argc > 1 ? argv[1] : "all";
   cudaDeviceProp prop;
@@ -232,6 +325,7 @@ int main(int argc, char** argv) {
   printf("device: %s, %d SMs, cc %d.%d, dyt abi %d\n", prop.name, prop.multiProcessorCount,
          prop.major, prop.minor, dyt_version());
   if (filter == "all" || filter == "gemm") run_gemm_tests();
+  if (filter == "all" || filter == "attn") run_attn_tests();
   printf("selftest: %d failure(s)\n", g_fail);
   return g_fail ? 1 : 0;
 }

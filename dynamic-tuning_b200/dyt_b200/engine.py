@@ -1,0 +1,187 @@
+"""Host-side driver of the block forward: fp16 weight cache, workspace, one C-ABI call per block.
+
+`run_blocks` is what the drop-in `models.*.VisionTransformer.forward_features` loop calls instead
+of `for blk in self.blocks: x = blk(x)` (reference models/model_speed_test.py:478-479,
+models/vision_transformer_IN21K.py:357-365).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BlockBuffers, BlockOpts, BlockShape, BlockWeights, DytError, check
+from .gate import min_kept_logit
+
+_WEIGHT_FIELDS_F16 = {
+    "qkv_w": "attn.qkv.weight", "qkv_b": "attn.qkv.bias",
+    "proj_w": "attn.proj.weight", "proj_b": "attn.proj.bias",
+    "fc1_w": "mlp.fc1.weight", "fc1_b": "mlp.fc1.bias",
+    "fc2_w": "mlp.fc2.weight", "fc2_b": "mlp.fc2.bias",
+    "down_w": "adaptmlp.down_proj.weight", "down_b": "adaptmlp.down_proj.bias",
+    "up_w": "adaptmlp.up_proj.weight", "up_b": "adaptmlp.up_proj.bias",
+}
+_WEIGHT_FIELDS_F32 = {
+    "ln1_w": "norm1.weight", "ln1_b": "norm1.bias", "ln2_w": "norm2.weight", "ln2_b": "norm2.bias",
+    "sel_w": "mlp_token_select.mlp_head.weight", "sel_b": "mlp_token_select.mlp_head.bias",
+}
+
+
+def _get(module: torch.nn.Module, dotted: str) -> torch.Tensor:
+    obj = module
+    for part in dotted.split("."):
+        obj = getattr(obj, part)
+    return obj
+
+
+class PreparedBlock:
+    """Device-resident fp16 copies of a Block's Linear parameters + the ctypes weight struct.
+    Rebuilt automatically when a parameter is modified in place or replaced (fine-tuning)."""
+
+    def __init__(self, block: torch.nn.Module):
+        self.block = block
+        self.key = None
+        self.tensors: Dict[str, torch.Tensor] = {}
+        self.struct = BlockWeights()
+
+    def _signature(self):
+        sig = []
+        for dotted in list(_WEIGHT_FIELDS_F16.values()) + list(_WEIGHT_FIELDS_F32.values()):
+            p = _get(self.block, dotted)
+            sig.append((p.data_ptr(), p._version, p.device))
+        return tuple(sig)
+
+    def get(self) -> BlockWeights:
+        sig = self._signature()
+        if sig != self.key:
+            with torch.no_grad():
+                for field, dotted in _WEIGHT_FIELDS_F16.items():
+                    p = _get(self.block, dotted)
+                    if not p.is_cuda:
+                        raise DytError("dyt_b200: block parameters must live on a CUDA device")
+                    t = p.detach().to(torch.float16).contiguous()
+                    self.tensors[field] = t
+                    setattr(self.struct, field, t.data_ptr())
+                for field, dotted in _WEIGHT_FIELDS_F32.items():
+                    p = _get(self.block, dotted)
+                    t = p.detach().to(torch.float32).contiguous().reshape(-1)
+                    self.tensors[field] = t
+                    setattr(self.struct, field, t.data_ptr())
+            scale = self.block.adaptmlp.scale
+            self.struct.adapter_scale = float(scale.item() if torch.is_tensor(scale) else scale)
+            self.key = sig
+        return self.struct
+
+
+_workspaces: Dict[Tuple, torch.Tensor] = {}
+
+
+def block_shape_of(block: torch.nn.Module, B: int, N: int) -> BlockShape:
+    C_ = block.attn.qkv.in_features
+    H = block.attn.num_heads
+    if C_ != 64 * H:
+        raise DytError(f"dyt_b200 attention kernel needs head_dim 64 (C={C_}, heads={H})")
+    return BlockShape(B, N, C_, H, block.mlp.fc1.out_features, block.adaptmlp.down_proj.out_features)
+
+
+def _workspace(shape: BlockShape, device: torch.device) -> torch.Tensor:
+    need = int(_lib.lib().dyt_block_workspace_bytes(C.byref(shape)))
+    if need == 0:
+        raise DytError("dyt_block_workspace_bytes rejected the shape: " +
+                       _lib.lib().dyt_last_error().decode())
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = None
+        _workspaces.pop(key, None)
+        ws = torch.zeros(need, dtype=torch.uint8, device=device)   # zero-filled once (ABI contract)
+        _workspaces[key] = ws
+    return ws
+
+
+def workspace_buffers(shape: BlockShape, ws: torch.Tensor) -> BlockBuffers:
+    bufs = BlockBuffers()
+    check(_lib.lib().dyt_block_workspace_layout(C.byref(shape), ws.data_ptr(), C.byref(bufs)),
+          "dyt_block_workspace_layout")
+    return bufs
+
+
+def _prepared(block: torch.nn.Module) -> PreparedBlock:
+    prep = block.__dict__.get("_dyt_prepared")
+    if prep is None:
+        prep = PreparedBlock(block)
+        block.__dict__["_dyt_prepared"] = prep
+    return prep
+
+
+def run_blocks(x: torch.Tensor, blocks: Sequence[torch.nn.Module], *, eps: float = 1e-6,
+               logit_dtype: torch.dtype = torch.float16, forced_masks=None,
+               noises=None, final_ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+               fuse_next_ln: bool = True, report_gate: bool = False):
+    """x [B, N, C] fp32 CUDA -> (x_out fp32 [B,N,C], masks [L,B,N] f32, logits [L,B,N-1] f32,
+    final_ln_out f16 [B,N,C] or None).  report_gate=True returns the selectors' own decisions as
+    `masks` even where a mask is forced (teacher pass, complete_model=True).  forced_masks[i] ([B,N] or [B,N,1]) imposes layer i's mask;
+    noises[i] = (g1, g2) switches layer i's gate to the train-mode Gumbel form."""
+    if not x.is_cuda:
+        raise DytError("dyt_b200.run_blocks needs a CUDA tensor: the sm_100a kernels are the only "
+                       "implementation (no CPU fallback)")
+    if x.dim() != 3:
+        raise DytError("run_blocks expects x [B, N, C]")
+    x = x.to(torch.float32).contiguous().clone()
+    B, N, _ = x.shape
+    L = len(blocks)
+    dev = x.device
+    masks = torch.empty((L, B, N), dtype=torch.float32, device=dev)
+    logits = torch.empty((L, B, max(N - 1, 1)), dtype=torch.float32, device=dev)
+    gates = torch.empty((L, B, N), dtype=torch.float32, device=dev) if report_gate else None
+    lib = _lib.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    keep_alive = []
+    xn_ready = 0
+    shape = ws = None
+    for i, blk in enumerate(blocks):
+        shape = block_shape_of(blk, B, N)
+        ws = _workspace(shape, dev)
+        wt = _prepared(blk).get()
+        opts = BlockOpts()
+        opts.eps = eps
+        opts.logit_fp16 = 1 if logit_dtype == torch.float16 else 0
+        thr = float(getattr(blk.mlp_token_select, "threshold", 0.5))
+        opts.min_kept = float(min_kept_logit(logit_dtype, thr))
+        opts.tau = float(getattr(blk.mlp_token_select, "tau", 5.0))
+        if noises is not None and noises[i] is not None:
+            g1 = noises[i][0].to(torch.float32).contiguous()
+            g2 = noises[i][1].to(torch.float32).contiguous()
+            keep_alive += [g1, g2]
+            opts.noise1, opts.noise2 = g1.data_ptr(), g2.data_ptr()
+        if forced_masks is not None and forced_masks[i] is not None:
+            fm = forced_masks[i].to(device=dev, dtype=torch.float32).reshape(B, N).contiguous()
+            keep_alive.append(fm)
+            opts.forced_mask = fm.data_ptr()
+        if gates is not None:
+            opts.gate_out = gates[i].data_ptr()
+        opts.xn_ready = xn_ready
+        nxt = None
+        if fuse_next_ln:
+            if i + 1 < L:
+                nprep = _prepared(blocks[i + 1])
+                nprep.get()
+                nxt = (nprep.tensors["ln1_w"], nprep.tensors["ln1_b"])
+            elif final_ln is not None:
+                nxt = (final_ln[0].detach().float().contiguous(), final_ln[1].detach().float().contiguous())
+                keep_alive += list(nxt)
+        if nxt is not None:
+            opts.next_ln_w, opts.next_ln_b = nxt[0].data_ptr(), nxt[1].data_ptr()
+        check(lib.dyt_block_fwd(C.byref(shape), C.byref(wt), C.byref(opts), x.data_ptr(),
+                                masks[i].data_ptr(), logits[i].data_ptr(), ws.data_ptr(),
+                                ws.numel(), stream), f"dyt_block_fwd(layer {i})")
+        xn_ready = 1 if (nxt is not None and i + 1 < L) else 0
+    final_out = None
+    if fuse_next_ln and final_ln is not None and L > 0:
+        bufs = workspace_buffers(shape, ws)
+        C_ = shape.C
+        off = bufs.xn - ws.data_ptr()
+        final_out = ws[off:off + B * N * C_ * 2].view(torch.float16).reshape(B, N, C_)
+    return x, (gates if gates is not None else masks), logits, final_out

@@ -1,0 +1,195 @@
+"""torch-tensor front-ends of the C-ABI kernels (PyTorch here = device memory + streams only)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import DytError, check
+from .gate import min_kept_logit
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors: Optional[torch.Tensor]) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise DytError("dyt_b200 kernels run on CUDA tensors only (sm_100a); "
+                           "there is no CPU fallback")
+
+
+def _rows2d(t: torch.Tensor) -> torch.Tensor:
+    t2 = t.reshape(-1, t.shape[-1])
+    if t2.stride(-1) != 1:
+        t2 = t2.contiguous()
+    return t2
+
+
+def linear_f16(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+               epilogue: int = _lib.EPI_BIAS, resid: Optional[torch.Tensor] = None,
+               scale: float = 1.0, m_dev: Optional[torch.Tensor] = None,
+               want_f16_copy: bool = False,
+               out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """y = epilogue(x @ w.T + bias).  x [..., K] fp16, w [N, K] fp16, bias [N] fp16.
+    Returns (out, f16_copy): out is fp16 [..., N], or fp32 for EPI_BIAS_RESID (resid fp32)."""
+    _need_cuda(x, w, bias, resid, m_dev)
+    if x.dtype != torch.float16 or w.dtype != torch.float16:
+        raise DytError("linear_f16 expects fp16 operands")
+    x2 = _rows2d(x)
+    M, K = x2.shape
+    N = w.shape[0]
+    lead = x.shape[:-1]
+    out_h = out_f = None
+    r2 = None
+    if epilogue == _lib.EPI_BIAS_RESID:
+        if resid is None or resid.dtype != torch.float32:
+            raise DytError("EPI_BIAS_RESID needs an fp32 residual")
+        r2 = _rows2d(resid)
+        out_f = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=x.device)
+        if want_f16_copy:
+            out_h = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    else:
+        out_h = out if out is not None else torch.empty((M, N), dtype=torch.float16, device=x.device)
+    check(_lib.lib().dyt_linear_f16(
+        x2.data_ptr(), x2.stride(0), w.data_ptr(), w.stride(0), M, N, K, _ptr(m_dev), epilogue,
+        _ptr(bias), _ptr(out_h), N, _ptr(out_f), N, _ptr(r2), 0 if r2 is None else r2.stride(0),
+        float(scale), _stream()), "dyt_linear_f16")
+    if epilogue == _lib.EPI_BIAS_RESID:
+        return out_f.reshape(*lead, N), (None if out_h is None else out_h.reshape(*lead, N))
+    return out_h.reshape(*lead, N), None
+
+
+def attn_varlen(qkv: torch.Tensor, num_heads: int, cu_seqlens: Optional[torch.Tensor] = None,
+                num_seqs: Optional[int] = None, max_seqlen: Optional[int] = None) -> torch.Tensor:
+    """qkv: fp16 [B, N, 3*C] (uniform) or [T, 3*C] with int32 cu_seqlens [num_seqs+1].
+    Returns fp16 [.., C]."""
+    _need_cuda(qkv, cu_seqlens)
+    if qkv.dtype != torch.float16:
+        raise DytError("attn_varlen expects fp16 qkv")
+    C3 = qkv.shape[-1]
+    Cdim = C3 // 3
+    q2 = _rows2d(qkv)
+    T = q2.shape[0]
+    if cu_seqlens is None:
+        if qkv.dim() != 3:
+            raise DytError("uniform attention expects qkv [B, N, 3C]")
+        nseq, uni = qkv.shape[0], qkv.shape[1]
+        mx = uni
+    else:
+        nseq = int(num_seqs if num_seqs is not None else cu_seqlens.numel() - 1)
+        if max_seqlen is None:
+            raise DytError("varlen attention needs max_seqlen (no host sync is done here)")
+        uni, mx = 0, int(max_seqlen)
+    out = torch.empty((T, Cdim), dtype=torch.float16, device=qkv.device)
+    check(_lib.lib().dyt_attn_varlen_fwd(
+        q2.data_ptr(), q2.stride(0), _ptr(cu_seqlens), nseq, uni, mx, T, num_heads,
+        Cdim // num_heads, out.data_ptr(), Cdim, _stream()), "dyt_attn_varlen_fwd")
+    return out.reshape(*qkv.shape[:-1], Cdim)
+
+
+def layernorm_f16(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6,
+                  row_idx: Optional[torch.Tensor] = None,
+                  n_rows_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, weight, bias, row_idx, n_rows_dev)
+    if x.dtype != torch.float32:
+        raise DytError("layernorm_f16 expects an fp32 input (the residual stream)")
+    x2 = _rows2d(x)
+    Cdim = x2.shape[1]
+    n_rows = x2.shape[0] if row_idx is None else row_idx.numel()
+    out = torch.empty((n_rows, Cdim), dtype=torch.float16, device=x.device)
+    check(_lib.lib().dyt_layernorm_f16(
+        x2.data_ptr(), x2.stride(0), _ptr(row_idx), _ptr(n_rows_dev), n_rows, Cdim,
+        weight.data_ptr(), bias.data_ptr(), float(eps), out.data_ptr(), Cdim, _stream()),
+        "dyt_layernorm_f16")
+    return out if row_idx is not None else out.reshape(*x.shape[:-1], Cdim)
+
+
+_dispatch_ws = {}
+
+
+def _dispatch_workspace(device: torch.device, B: int) -> torch.Tensor:
+    need = int(_lib.lib().dyt_dispatch_workspace_bytes(B))
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _dispatch_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 4096), dtype=torch.uint8, device=device)
+        _dispatch_ws[key] = ws
+    return ws
+
+
+def dispatch(x1: torch.Tensor, sel_w: torch.Tensor, sel_b: torch.Tensor, *,
+             logit_dtype: torch.dtype = torch.float16, threshold: float = 0.5,
+             noise: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, tau: float = 5.0,
+             ln_w: Optional[torch.Tensor] = None, ln_b: Optional[torch.Tensor] = None,
+             eps: float = 1e-6, forced_mask: Optional[torch.Tensor] = None, pack: bool = True):
+    """Fused dispatcher on x1 [B, N, C] fp32.  Returns dict(mask [B,N,1] f32, logits [B,N-1,1] f32,
+    packed_idx i32 [B*N], token_pos i32 [B*N], cu_seqlens i32 [B+1], n_kept i32 [1],
+    packed f16 [B*N, C] or None).  Counts stay on the device (no sync)."""
+    _need_cuda(x1, sel_w, sel_b, ln_w, ln_b, forced_mask)
+    if x1.dtype != torch.float32 or x1.dim() != 3:
+        raise DytError("dispatch expects x1 [B, N, C] fp32")
+    if logit_dtype not in (torch.float16, torch.float32):
+        raise DytError("dispatch implements fp16 and fp32 logits")
+    x1 = x1.contiguous()
+    B, N, Cdim = x1.shape
+    dev = x1.device
+    mask = torch.empty((B, N, 1), dtype=torch.float32, device=dev)
+    logits = torch.empty((B, N - 1, 1), dtype=torch.float32, device=dev)
+    packed_idx = torch.empty(B * N, dtype=torch.int32, device=dev)
+    token_pos = torch.empty(B * N, dtype=torch.int32, device=dev)
+    cu = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    n_kept = torch.empty(1, dtype=torch.int32, device=dev)
+    packed = None
+    if pack:
+        if ln_w is None or ln_b is None:
+            raise DytError("dispatch(pack=True) needs the norm2 parameters")
+        packed = torch.empty((B * N, Cdim), dtype=torch.float16, device=dev)
+    n1 = n2 = None
+    if noise is not None:
+        n1 = noise[0].to(torch.float32).contiguous()
+        n2 = noise[1].to(torch.float32).contiguous()
+    fm = None if forced_mask is None else forced_mask.to(torch.float32).contiguous()
+    sw = sel_w.reshape(-1).to(torch.float32).contiguous()
+    sb = sel_b.reshape(-1).to(torch.float32).contiguous()
+    gate = torch.empty((B, N, 1), dtype=torch.float32, device=dev) if fm is not None else None
+    ws = _dispatch_workspace(dev, B)
+    check(_lib.lib().dyt_dispatch_fwd(
+        x1.data_ptr(), Cdim, sw.data_ptr(), sb.data_ptr(),
+        1 if logit_dtype == torch.float16 else 0, float(min_kept_logit(logit_dtype, threshold)),
+        _ptr(n1), _ptr(n2), float(tau), B, N, Cdim, _ptr(ln_w), _ptr(ln_b), float(eps), _ptr(fm),
+        mask.data_ptr(), _ptr(gate), logits.data_ptr(), packed_idx.data_ptr(), token_pos.data_ptr(),
+        cu.data_ptr(), n_kept.data_ptr(), _ptr(packed), Cdim, ws.data_ptr(), _stream()),
+        "dyt_dispatch_fwd")
+    return dict(mask=mask, gate=gate if gate is not None else mask, logits=logits, packed_idx=packed_idx, token_pos=token_pos,
+                cu_seqlens=cu, n_kept=n_kept, packed=packed)
+
+
+def scatter_merge(x1: torch.Tensor, adapt: torch.Tensor, mlp_packed: torch.Tensor,
+                  token_pos: torch.Tensor, next_ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                  eps: float = 1e-6):
+    """out = adapt + (x1 + scatter(mlp_packed)); optionally also LayerNorm(out) in fp16."""
+    _need_cuda(x1, adapt, mlp_packed, token_pos)
+    x2 = _rows2d(x1)
+    a2 = _rows2d(adapt)
+    m2 = _rows2d(mlp_packed)
+    T, Cdim = x2.shape
+    out = torch.empty((T, Cdim), dtype=torch.float32, device=x1.device)
+    nln_out = None
+    nw = nb = None
+    if next_ln is not None:
+        nw, nb = next_ln
+        nln_out = torch.empty((T, Cdim), dtype=torch.float16, device=x1.device)
+    check(_lib.lib().dyt_scatter_merge_fwd(
+        x2.data_ptr(), x2.stride(0), a2.data_ptr(), a2.stride(0), m2.data_ptr(), m2.stride(0),
+        token_pos.data_ptr(), T, Cdim, out.data_ptr(), Cdim, _ptr(nw), _ptr(nb), float(eps),
+        _ptr(nln_out), Cdim, _stream()), "dyt_scatter_merge_fwd")
+    out = out.reshape(x1.shape)
+    return (out, None if nln_out is None else nln_out.reshape(x1.shape))

@@ -18,6 +18,7 @@
 #ifndef DYT_B200_H_
 #define DYT_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -48,6 +49,113 @@ int dyt_linear_f16(const void* x, int ldx, const void* w, int ldw, int M, int N,
                    const int* m_dev, int epilogue, const void* bias, void* out_f16, int ldo_f16,
                    float* out_f32, int ldo_f32, const float* resid, int ld_resid, float scale,
                    void* stream);
+
+/* Multi-head attention over packed variable-length sequences.
+ * Replaces F.scaled_dot_product_attention(q, k, v) in Attention.forward (reference
+ * models/model_speed_test.py:145-166 == models/vision_transformer_IN21K.py:54-75): non-causal,
+ * scale = head_dim^-0.5, no dropout, q_norm/k_norm = Identity.
+ * qkv: fp16 [total_tokens, 3, num_heads, head_dim] (the qkv Linear output, row stride ld_qkv);
+ * sequence b covers rows [cu_seqlens[b], cu_seqlens[b+1]); cu_seqlens == NULL means num_seqs
+ * sequences of uniform_len (== max_seqlen) tokens each.  out: fp16 [total_tokens, num_heads*head_dim]
+ * (the layout of x.transpose(1, 2).reshape(B, N, C)).  head_dim must be 64, max_seqlen <= 256. */
+int dyt_attn_varlen_fwd(const void* qkv, int ld_qkv, const int* cu_seqlens, int num_seqs,
+                        int uniform_len, int max_seqlen, int total_tokens, int num_heads,
+                        int head_dim, void* out, int ldo, void* stream);
+
+/* LayerNorm(eps) over the last dim of fp32 rows, result rounded once to fp16 (the rounding the
+ * consumer Linear applies under autocast).  Output row r reads input row row_idx[r] (or r when
+ * row_idx is NULL); n_rows_dev optionally bounds the row count from device memory.
+ * Replaces nn.LayerNorm norm1 / norm2 (reference models/vision_transformer_IN21K.py:110, :123). */
+int dyt_layernorm_f16(const float* x, int ldx, const int* row_idx, const int* n_rows_dev,
+                      int n_rows, int C, const float* gamma, const float* beta, float eps,
+                      void* out_f16, int ldo, void* stream);
+
+/* Fused token dispatcher: selector score + gate + stable compaction (+ LayerNorm2 of the kept rows
+ * into the packed fp16 buffer).  No host synchronisation: counts stay on the device.
+ * Replaces TokenSelect.forward / _gumbel_sigmoid (reference models/dynamic_adapter.py:25-77,
+ * models/model_speed_test.py:27-60), `nonzero()` + row gather (models/model_speed_test.py:297-301)
+ * and norm2 of the gathered rows (:303).
+ *   x1 [B*N, ldx] fp32; sel_w [C], sel_b [1] fp32 (mlp_token_select.mlp_head).
+ *   logit_fp16 = 1: fp16 autocast arithmetic (operands rounded to fp16, fp32 accumulate, logit
+ *   rounded once to fp16); 0: plain fp32.
+ *   keep(b,n) = gate_input >= min_kept, where min_kept is the smallest logit for which
+ *   sigmoid(l) > threshold holds in the logit dtype (computed on the host from torch's sigmoid);
+ *   gate_input = logit in eval, ((logit + noise1) - noise2) / tau in train mode (noise* = the two
+ *   Gumbel draws of _gumbel_sigmoid, [B, N-1], NULL in eval).  Token 0 (cls) is always kept.
+ *   forced_mask (optional, [B, N]) overrides the gate (BASELINE.json config 1).
+ * Outputs: mask [B, N] (1/0, cls = 1; equals forced_mask when one is given), gate_out (optional,
+ * [B, N]: the selector's own decision even when a mask is forced), logits [B, N-1], packed_idx [B*N] (first n_kept valid,
+ * ascending flat token index == nonzero() order), token_pos [B*N] (packed position or -1),
+ * cu_seqlens [B+1], n_kept [1], packed_f16 [B*N, ldp] (optional; needs ln_w/ln_b = norm2).
+ * workspace: dyt_dispatch_workspace_bytes(B) bytes, 16-byte aligned, zero-filled once by the
+ * caller before first use (the kernel restores the zeros it needs). */
+size_t dyt_dispatch_workspace_bytes(int B);
+int dyt_dispatch_fwd(const float* x1, int ldx, const float* sel_w, const float* sel_b,
+                     int logit_fp16, float min_kept, const float* noise1, const float* noise2,
+                     float tau, int B, int N, int C, const float* ln_w, const float* ln_b,
+                     float eps, const float* forced_mask, float* mask, float* gate_out,
+                     float* logits, int* packed_idx, int* token_pos, int* cu_seqlens, int* n_kept,
+                     void* packed_f16, int ldp, void* workspace, void* stream);
+
+/* Vectorised scatter-merge: out[t] = adapt[t] + (x1[t] + (token_pos[t] >= 0 ? mlp[token_pos[t]] : 0)).
+ * Replaces torch.zeros + index_put + the two adds (reference models/model_speed_test.py:302-308).
+ * Optionally also writes next_ln_out = f16(LayerNorm(out)) with the following norm's parameters. */
+int dyt_scatter_merge_fwd(const float* x1, int ldx, const void* adapt_f16, int lda,
+                          const void* mlp_packed_f16, int ldm, const int* token_pos, int n_rows,
+                          int C, float* out, int ldo, const float* next_ln_w,
+                          const float* next_ln_b, float eps, void* next_ln_out_f16, int ldn,
+                          void* stream);
+
+/* ---- whole block: Block.batch_forward (reference models/model_speed_test.py:274-310) ---------- */
+typedef struct dyt_block_shape {
+  int B;          /* images (sequences) */
+  int N;          /* tokens per image incl. cls (197) */
+  int C;          /* embed dim = 64 * H */
+  int H;          /* heads */
+  int hidden;     /* MLP hidden (4C) */
+  int bottleneck; /* adapter width (tuning_config.ffn_num) */
+} dyt_block_shape;
+
+typedef struct dyt_block_weights { /* device pointers; *_w of Linears are fp16 [out,in], their
+                                      biases fp16; LayerNorm and selector parameters fp32 */
+  const float* ln1_w; const float* ln1_b;
+  const void* qkv_w;  const void* qkv_b;
+  const void* proj_w; const void* proj_b;
+  const float* ln2_w; const float* ln2_b;
+  const void* fc1_w;  const void* fc1_b;
+  const void* fc2_w;  const void* fc2_b;
+  const void* down_w; const void* down_b;
+  const void* up_w;   const void* up_b;
+  const float* sel_w; const float* sel_b;
+  float adapter_scale;
+} dyt_block_weights;
+
+typedef struct dyt_block_opts {
+  float eps;               /* LayerNorm eps (1e-6) */
+  int logit_fp16;          /* see dyt_dispatch_fwd */
+  float min_kept;
+  const float* noise1;     /* train-mode Gumbel draws or NULL */
+  const float* noise2;
+  float tau;
+  const float* forced_mask;/* optional imposed mask [B, N] */
+  float* gate_out;         /* optional [B, N]: selector decision ignoring forced_mask */
+  int xn_ready;            /* 1: workspace already holds LN1(x) (written by the previous call) */
+  const float* next_ln_w;  /* optional: also emit LayerNorm(out) for the next block / final norm */
+  const float* next_ln_b;
+} dyt_block_opts;
+
+typedef struct dyt_block_buffers { /* where dyt_block_fwd keeps its intermediates (for tests) */
+  void* xn; void* attn_o; void* qkv; float* x1; void* x1h; void* packed; void* hidden; void* mlp;
+  void* down; void* adapt; int* packed_idx; int* token_pos; int* cu_seqlens; int* n_kept;
+} dyt_block_buffers;
+
+size_t dyt_block_workspace_bytes(const dyt_block_shape* shape);
+int dyt_block_workspace_layout(const dyt_block_shape* shape, void* workspace, dyt_block_buffers* out);
+/* x [B, N, C] fp32 is updated in place; mask_out [B, N]; logits_out [B, N-1].  The workspace
+ * (256-byte aligned, dyt_block_workspace_bytes) must be zero-filled once before first use. */
+int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weights* weights,
+                  const dyt_block_opts* opts, float* x, float* mask_out, float* logits_out,
+                  void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

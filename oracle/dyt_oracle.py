@@ -1,0 +1,358 @@
+"""CPU oracle for the DyT token-dispatched ViT block forward.   *** TEST INFRASTRUCTURE ONLY ***
+
+A plain-PyTorch (CPU) restatement of the reference algorithm, function by function, each citing
+the reference file:line it follows (paths relative to NUS-HPC-AI-Lab/Dynamic-Tuning @ d1744f0).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product package (dynamic-tuning_b200/) never does.
+
+Parity pin: PINNED.  tests/golden/*.pt hold outputs of the *unmodified reference modules*
+(imported from /root/reference through oracle/ref_shim, script: oracle/gen_golden.py) and
+tests/test_oracle_golden.py checks every function below against them.
+
+Two arithmetic policies:
+  "fp32"  - what the reference computes on CPU (torch.cuda.amp.autocast is a no-op there).
+  "amp16" - emulation of what torch.cuda.amp.autocast() does to the reference on a GPU
+            (speed.py:254): Linear / attention operands rounded to fp16, products accumulated in
+            fp32, results rounded once to fp16; LayerNorm and the residual stream in fp32.
+            This is the arithmetic the CUDA kernels implement, so kernel-vs-oracle tolerances are
+            tight (accumulation-order noise only).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+# ----------------------------------------------------------------------------------------------
+# arithmetic helpers
+# ----------------------------------------------------------------------------------------------
+def _r16(x: Tensor) -> Tensor:
+    """value held by an fp16 tensor, returned as fp32"""
+    return x.to(torch.float16).to(torch.float32)
+
+
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor], policy: str = "fp32") -> Tensor:
+    """nn.Linear forward.  amp16: fp16 operands, fp32 accumulate, bias added before the single
+    rounding to fp16 (cuBLASLt bias epilogue).  Returns fp32 tensors holding fp16 values."""
+    if policy == "fp32":
+        return F.linear(x, w, b)
+    y = F.linear(_r16(x), _r16(w), None if b is None else _r16(b))
+    return _r16(y)
+
+
+def layer_norm(x: Tensor, w: Tensor, b: Tensor, eps: float = 1e-6) -> Tensor:
+    """nn.LayerNorm(eps=1e-6) (reference models/vision_transformer_IN21K.py:262); autocast keeps
+    layer_norm in fp32, so both policies agree."""
+    return F.layer_norm(x.float(), (x.shape[-1],), w.float(), b.float(), eps)
+
+
+def gelu(x: Tensor, policy: str = "fp32") -> Tensor:
+    """nn.GELU() exact-erf form (timm Mlp act_layer, models/vision_transformer_IN21K.py:261)."""
+    y = F.gelu(x)
+    return y if policy == "fp32" else _r16(y)
+
+
+# ----------------------------------------------------------------------------------------------
+# a4: _gumbel_sigmoid (reference models/dynamic_adapter.py:25-54; eval copy
+#     models/model_speed_test.py:27-37)
+# ----------------------------------------------------------------------------------------------
+def gumbel_sigmoid_hard(logits: Tensor, tau: float = 5.0, threshold: float = 0.5,
+                        training: bool = False,
+                        noise: Optional[Tuple[Tensor, Tensor]] = None) -> Tensor:
+    """Forward value of the hard straight-through gate, computed in logits.dtype exactly as the
+    reference does: y_soft = sigmoid(l) (eval) or sigmoid((l + g1 - g2) / tau) (train, g = Gumbel
+    noise drawn by the caller so the test can share it with the kernel);
+    y_hard = zeros.masked_fill(y_soft > threshold, 1).  `ret = y_hard - y_soft.detach() + y_soft`
+    has the forward value y_hard (up to the rounding of that expression, which the eval-only copy
+    model_speed_test.py:27-37 drops)."""
+    if training:
+        assert noise is not None, "training-mode oracle needs the Gumbel draws"
+        g1, g2 = noise
+        y_soft = ((logits + g1 - g2) / tau).sigmoid()
+    else:
+        y_soft = logits.sigmoid()
+    return torch.zeros_like(logits).masked_fill(y_soft > threshold, 1.0)
+
+
+def min_kept_logit(dtype: torch.dtype, threshold: float = 0.5) -> float:
+    """Smallest logit (as a python float) that the gate keeps in `dtype`: the gate is monotone, so
+    `sigmoid(l) > threshold` evaluated in `dtype` is equivalent to `l >= min_kept_logit`.
+    SURVEY.md section 0.4: fp16 -> 2^-10 * (1 + 2^-10), bf16 -> just above 2^-7."""
+    if dtype in (torch.float16, torch.bfloat16):
+        bits = torch.arange(0, 1 << 16, dtype=torch.int32).to(torch.int16)
+        vals = bits.view(dtype)
+        keep = gumbel_sigmoid_hard(vals) > 0
+        finite = torch.isfinite(vals)
+        return float(vals[keep & finite].float().min())
+    # fp32: bisection on the monotone gate
+    lo, hi = -1.0, 1.0
+    lo_t = torch.tensor(lo, dtype=torch.float32)
+    hi_t = torch.tensor(hi, dtype=torch.float32)
+    for _ in range(80):
+        mid = ((lo_t.double() + hi_t.double()) / 2).float()
+        if mid == lo_t or mid == hi_t:
+            break
+        if gumbel_sigmoid_hard(mid.view(1), threshold=threshold).item() > 0:
+            hi_t = mid
+        else:
+            lo_t = mid
+    return float(hi_t)
+
+
+# ----------------------------------------------------------------------------------------------
+# a3: TokenSelect.forward (reference models/dynamic_adapter.py:70-77 == model_speed_test.py:53-60)
+# ----------------------------------------------------------------------------------------------
+def token_select(x: Tensor, w: Tensor, b: Tensor, policy: str = "fp32", tau: float = 5.0,
+                 threshold: float = 0.5, training: bool = False,
+                 noise: Optional[Tuple[Tensor, Tensor]] = None) -> Tuple[Tensor, Tensor]:
+    """x [B,N,C] -> (token_select [B,N,1] in {0,1} with the cls slot forced to 1, logits [B,N-1,1]).
+    amp16: logits are an fp16 tensor (fp32-accumulated, rounded once) and the gate runs in fp16."""
+    bsz = x.shape[0]
+    if policy == "fp32":
+        logits = F.linear(x[:, 1:, :], w, b)
+    else:
+        logits = linear(x[:, 1:, :], w, b, "amp16").to(torch.float16)
+        if noise is not None:
+            noise = (noise[0].to(torch.float16), noise[1].to(torch.float16))
+    sel = gumbel_sigmoid_hard(logits, tau, threshold, training, noise)
+    sel = torch.cat([sel.new_ones(bsz, 1, 1), sel], dim=1)
+    return sel.float(), logits.float()
+
+
+# ----------------------------------------------------------------------------------------------
+# a9: gather / scatter glue (reference models/model_speed_test.py:297-305)
+# ----------------------------------------------------------------------------------------------
+def compact(mask: Tensor) -> Tuple[Tensor, Tensor]:
+    """mask [B,N,1] -> (packed_idx int64 [T_kept] = flat (b*N+n) indices in ascending order, the
+    order nonzero() returns (model_speed_test.py:300); cu_seqlens int32 [B+1])."""
+    bsz, n = mask.shape[:2]
+    flat = mask.reshape(bsz * n)
+    packed_idx = flat.nonzero()[:, 0]
+    counts = mask.reshape(bsz, n).sum(dim=1).to(torch.int32)
+    cu = torch.zeros(bsz + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(counts, 0)
+    return packed_idx, cu
+
+
+# ----------------------------------------------------------------------------------------------
+# a5: Adapter.forward (reference models/dynamic_adapter.py:120-140; speed copy
+#     models/model_speed_test.py:103-114).  LN option "none", add_residual=False, eval (no dropout)
+# ----------------------------------------------------------------------------------------------
+def adapter(x: Tensor, p: Dict[str, Tensor], prefix: str, scale: float,
+            policy: str = "fp32") -> Tensor:
+    down = linear(x, p[prefix + "down_proj.weight"], p[prefix + "down_proj.bias"], policy)
+    down = F.relu(down)
+    up = linear(down, p[prefix + "up_proj.weight"], p[prefix + "up_proj.bias"], policy)
+    up = up * scale
+    return up if policy == "fp32" else _r16(up)
+
+
+# ----------------------------------------------------------------------------------------------
+# a6: Attention.forward (reference models/vision_transformer_IN21K.py:54-75 ==
+#     models/model_speed_test.py:145-166); q_norm/k_norm Identity, dropout 0
+# ----------------------------------------------------------------------------------------------
+def attention_core(qkv: Tensor, num_heads: int, policy: str = "fp32") -> Tensor:
+    """softmax(q k^T / sqrt(d)) v for qkv [B, N, 3*C] laid out [3, H, d] along the last dim
+    (models/model_speed_test.py:147-161); returns [B, N, C]."""
+    bsz, n, c3 = qkv.shape
+    c = c3 // 3
+    d = c // num_heads
+    qkv = qkv.reshape(bsz, n, 3, num_heads, d).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv.unbind(0)
+    s = (q @ k.transpose(-2, -1)) * (d ** -0.5)
+    if policy == "fp32":
+        o = s.softmax(dim=-1) @ v
+    else:
+        # fused fp16 attention: fp32 scores and statistics, P rounded to fp16 for the PV product,
+        # fp32 accumulation, normalisation by the fp32 row sum, one rounding of O to fp16
+        m = s.max(dim=-1, keepdim=True).values
+        e = torch.exp(s - m)
+        o = (_r16(e) @ v) / e.sum(dim=-1, keepdim=True)
+        o = _r16(o)
+    return o.transpose(1, 2).reshape(bsz, n, c)
+
+
+def attention(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int,
+              policy: str = "fp32") -> Tensor:
+    qkv = linear(x, p[prefix + "qkv.weight"], p[prefix + "qkv.bias"], policy)
+    o = attention_core(qkv, num_heads, policy)
+    return linear(o, p[prefix + "proj.weight"], p[prefix + "proj.bias"], policy)
+
+
+# ----------------------------------------------------------------------------------------------
+# a7: timm.layers.Mlp (timm==0.9.12, not vendored in the reference; call site
+#     models/vision_transformer_IN21K.py:124-129): fc2(GELU(fc1(x))), dropouts p=0
+# ----------------------------------------------------------------------------------------------
+def mlp(x: Tensor, p: Dict[str, Tensor], prefix: str, policy: str = "fp32") -> Tensor:
+    h = gelu(linear(x, p[prefix + "fc1.weight"], p[prefix + "fc1.bias"], policy), policy)
+    return linear(h, p[prefix + "fc2.weight"], p[prefix + "fc2.bias"], policy)
+
+
+# ----------------------------------------------------------------------------------------------
+# a1: Block.batch_forward, the sparse inference block (reference models/model_speed_test.py:274-310)
+# ----------------------------------------------------------------------------------------------
+def block_sparse(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int, scale: float,
+                 policy: str = "fp32", forced_mask: Optional[Tensor] = None,
+                 threshold: float = 0.5) -> Dict[str, Tensor]:
+    """Returns dict(out, x1, mask [B,N,1], logits [B,N-1,1], packed_idx, cu_seqlens).
+    forced_mask (config 1 of BASELINE.json) overrides the selector's decision."""
+    bsz, n, c = x.shape
+    x1 = x + attention(layer_norm(x, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"]), p,
+                       prefix + "attn.", num_heads, policy)                       # :278
+    mask, logits = token_select(x1, p[prefix + "mlp_token_select.mlp_head.weight"],
+                                p[prefix + "mlp_token_select.mlp_head.bias"], policy,
+                                threshold=threshold)                             # :284
+    if forced_mask is not None:
+        mask = forced_mask.float()
+    adapt_x = adapter(x1, p, prefix + "adaptmlp.", scale, policy)                 # :291
+    packed_idx, cu = compact(mask)                                                # :297-300
+    flat = x1.reshape(bsz * n, c)
+    gather_x = flat[packed_idx, :]                                                # :301
+    mlp_x = torch.zeros_like(flat)                                                # :302
+    mlp_x[packed_idx, :] = mlp(layer_norm(gather_x, p[prefix + "norm2.weight"],
+                                          p[prefix + "norm2.bias"]), p, prefix + "mlp.",
+                               policy)                                            # :303-304
+    out = adapt_x + (x1 + mlp_x.reshape(bsz, n, c))                               # :305-308
+    return dict(out=out, x1=x1, mask=mask, logits=logits, packed_idx=packed_idx, cu_seqlens=cu)
+
+
+# ----------------------------------------------------------------------------------------------
+# a2: Block.forward, the dense masked block in eval mode
+#     (reference models/vision_transformer_IN21K.py:144-165)
+# ----------------------------------------------------------------------------------------------
+def block_dense(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int, scale: float,
+                policy: str = "fp32", complete_model: bool = False,
+                forced_mask: Optional[Tensor] = None) -> Dict[str, Tensor]:
+    x1 = x + attention(layer_norm(x, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"]), p,
+                       prefix + "attn.", num_heads, policy)                       # :148
+    mask, logits = token_select(x1, p[prefix + "mlp_token_select.mlp_head.weight"],
+                                p[prefix + "mlp_token_select.mlp_head.bias"], policy)  # :150-152
+    if forced_mask is not None:
+        mask = forced_mask.float()
+    adapt_x = adapter(x1, p, prefix + "adaptmlp.", scale, policy)                 # :157
+    mlp_x = mlp(layer_norm(x1, p[prefix + "norm2.weight"], p[prefix + "norm2.bias"]), p,
+                prefix + "mlp.", policy)                                          # :159
+    if not complete_model:
+        mlp_x = mask * mlp_x                                                      # :161-162
+    out = x1 + mlp_x + adapt_x                                                    # :163
+    return dict(out=out, x1=x1, mask=mask, logits=logits)
+
+
+# ----------------------------------------------------------------------------------------------
+# a10: VisionTransformer.forward (reference models/model_speed_test.py:467-496 and
+#      models/vision_transformer_IN21K.py:343-385)
+# ----------------------------------------------------------------------------------------------
+def patch_embed(img: Tensor, p: Dict[str, Tensor], patch: int, policy: str = "fp32") -> Tensor:
+    """timm PatchEmbed: Conv2d(3, C, k=patch, s=patch) -> flatten(2).transpose(1,2); as a GEMM over
+    unfolded patches so the amp16 rounding points are those of a Linear."""
+    w = p["patch_embed.proj.weight"]
+    b = p["patch_embed.proj.bias"]
+    cols = F.unfold(img, kernel_size=patch, stride=patch).transpose(1, 2)  # [B, L, 3*patch*patch]
+    return linear(cols, w.reshape(w.shape[0], -1), b, policy)
+
+
+def vit_forward(img: Tensor, p: Dict[str, Tensor], depth: int, num_heads: int, scale: float,
+                patch: int = 16, policy: str = "fp32", sparse: bool = True,
+                complete_model: bool = False, forced_masks=None) -> Dict[str, Tensor]:
+    """Whole model.  Returns dict(logits [B,classes], token_select [B,depth,N-1,1],
+    token_logits [B,depth,N-1,1], x_final)."""
+    x = patch_embed(img, p, patch, policy)
+    bsz = x.shape[0]
+    x = torch.cat((p["cls_token"].expand(bsz, -1, -1), x), dim=1)   # model_speed_test.py:470-471
+    x = x + p["pos_embed"]                                          # :472
+    sels, logs = [], []
+    for i in range(depth):
+        fm = None if forced_masks is None else forced_masks[i]
+        if sparse:
+            r = block_sparse(x, p, f"blocks.{i}.", num_heads, scale, policy, forced_mask=fm)
+        else:
+            r = block_dense(x, p, f"blocks.{i}.", num_heads, scale, policy,
+                            complete_model=complete_model, forced_mask=fm)
+        x = r["out"]
+        sels.append(r["mask"])
+        logs.append(r["logits"])
+    xn = layer_norm(x, p["norm.weight"], p["norm.bias"])            # :483
+    logits = linear(xn[:, 0], p["head.weight"], p["head.bias"], policy)  # :486-491
+    return dict(logits=logits, token_select=torch.stack(sels, dim=1)[:, :, 1:, :],
+                token_logits=torch.stack(logs, dim=1), x_final=x)
+
+
+# ----------------------------------------------------------------------------------------------
+# deterministic synthetic parameters (shared by the golden generator, the tests and bench.py)
+# ----------------------------------------------------------------------------------------------
+def synthetic_state_dict(embed_dim: int = 768, depth: int = 12, num_heads: int = 12,
+                         mlp_ratio: float = 4.0, bottleneck: int = 64, num_classes: int = 100,
+                         img_size: int = 224, patch: int = 16, seed: int = 0) -> Dict[str, Tensor]:
+    """Random-init weights with the reference's state_dict keys drawn key by key from
+    a generator seeded with (seed, key), so the result does not depend on module construction
+    order.  Scales follow SURVEY.md section 8d: trunc-normal(0.02)-like Linear weights, non-degenerate
+    adapters (up_proj ~ N(0, 0.02^2)) and selectors (mlp_head ~ N(0, 0.5^2)); selector biases are
+    left at zero here and calibrated to the target keep-rate by `calibrate_selector_bias`."""
+    c, hid = embed_dim, int(embed_dim * mlp_ratio)
+    n_tok = (img_size // patch) ** 2 + 1
+    shapes = {
+        "cls_token": ((1, 1, c), 0.02), "pos_embed": ((1, n_tok, c), 0.02),
+        "patch_embed.proj.weight": ((c, 3, patch, patch), 0.02), "patch_embed.proj.bias": ((c,), 0.02),
+        "norm.weight": ((c,), None), "norm.bias": ((c,), 0.02),
+        "head.weight": ((num_classes, c), 0.02), "head.bias": ((num_classes,), 0.02),
+    }
+    for i in range(depth):
+        b = f"blocks.{i}."
+        shapes.update({
+            b + "norm1.weight": ((c,), None), b + "norm1.bias": ((c,), 0.02),
+            b + "attn.qkv.weight": ((3 * c, c), 0.02), b + "attn.qkv.bias": ((3 * c,), 0.02),
+            b + "attn.proj.weight": ((c, c), 0.02), b + "attn.proj.bias": ((c,), 0.02),
+            b + "norm2.weight": ((c,), None), b + "norm2.bias": ((c,), 0.02),
+            b + "mlp.fc1.weight": ((hid, c), 0.02), b + "mlp.fc1.bias": ((hid,), 0.02),
+            b + "mlp.fc2.weight": ((c, hid), 0.02), b + "mlp.fc2.bias": ((c,), 0.02),
+            b + "adaptmlp.down_proj.weight": ((bottleneck, c), 0.02),
+            b + "adaptmlp.down_proj.bias": ((bottleneck,), 0.02),
+            b + "adaptmlp.up_proj.weight": ((c, bottleneck), 0.02),
+            b + "adaptmlp.up_proj.bias": ((c,), 0.02),
+            b + "mlp_token_select.mlp_head.weight": ((1, c), 0.5),
+            b + "mlp_token_select.mlp_head.bias": ((1,), 0.0),
+        })
+    sd = {}
+    for idx, key in enumerate(sorted(shapes)):
+        shape, std = shapes[key]
+        g = torch.Generator().manual_seed(seed * 1000003 + idx)
+        if std is None:      # LayerNorm weight: around one
+            sd[key] = 1.0 + 0.05 * torch.randn(shape, generator=g)
+        elif std == 0.0:
+            sd[key] = torch.zeros(shape)
+        else:
+            sd[key] = std * torch.randn(shape, generator=g)
+    return sd
+
+
+def calibrate_selector_bias(sd: Dict[str, Tensor], img: Tensor, depth: int, num_heads: int,
+                            scale: float, rate: float, patch: int = 16,
+                            policy: str = "fp32") -> Dict[str, Tensor]:
+    """Set each layer's selector bias to minus the (1-rate)-quantile of that layer's logits on `img`
+    so the realised keep-rate is ~rate.  Layer by layer, since layer i's mask changes
+    the input of layer i+1."""
+    sd = dict(sd)
+    x = patch_embed(img, sd, patch, policy)
+    x = torch.cat((sd["cls_token"].expand(x.shape[0], -1, -1), x), dim=1) + sd["pos_embed"]
+    for i in range(depth):
+        key = f"blocks.{i}.mlp_token_select.mlp_head.bias"
+        sd[key] = torch.zeros(1)
+        r = block_sparse(x, sd, f"blocks.{i}.", num_heads, scale, policy)
+        q = torch.quantile(r["logits"].flatten().float(), 1.0 - rate)
+        sd[key] = (-q).reshape(1).clone()
+        r = block_sparse(x, sd, f"blocks.{i}.", num_heads, scale, policy)
+        x = r["out"]
+    return sd
+
+
+def checkerboard_mask(bsz: int, n_tok: int) -> Tensor:
+    """BASELINE.json config 1: keep cls + even-indexed patches (exactly half of the patches)."""
+    m = torch.zeros(bsz, n_tok, 1)
+    m[:, 0] = 1.0
+    m[:, 1::2] = 1.0   # token index 1 is patch 0 (even-indexed patches)
+    return m

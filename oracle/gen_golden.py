@@ -1,0 +1,155 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference modules (imported from
+/root/reference through oracle/ref_shim.py).   *** TEST INFRASTRUCTURE ONLY ***
+
+Run here (the container that has /root/reference):   python oracle/gen_golden.py
+The fixtures travel with the repo; nothing at test/bench time reads /root/reference.
+
+The reference ships no tests or golden vectors, so these outputs of the reference
+itself are the pins of the oracle (oracle/dyt_oracle.py):
+  gate_tables.pt    exhaustive fp16 / bf16 truth tables of the eval gate (both reference copies)
+  gumbel_train.pt   train-mode hard Gumbel gate given the RNG draws (fp32 and fp16 logits)
+  tiny_vit.pt       a 2-layer dim-128 ViT (reference generic ctor): full state_dict, inputs, every
+                    model-level output of both reference models + per-block activations
+  vitb_b2.pt        ViT-B/16, synthetic seed-0 weights (regenerated from the seed, not stored),
+                    calibrated selector biases, B=2: logits / masks / token logits of the speed model
+                    and the train model (eval, complete_model on/off), config-1 imposed-mask logits
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import dyt_oracle as O  # noqa: E402
+import ref_shim  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def gate_tables(ref_speed, ref_dyn):
+    out = {}
+    for name, dt in (("fp16", torch.float16), ("bf16", torch.bfloat16)):
+        bits = torch.arange(0, 1 << 16, dtype=torch.int32).to(torch.int16)
+        vals = bits.view(dt)
+        a = ref_speed._gumbel_sigmoid(vals, 5, True, threshold=0.5, training=False)
+        b = ref_dyn._gumbel_sigmoid(vals, 5, True, threshold=0.5, training=False)
+        # the train-capable copy returns y_hard - y_soft.detach() + y_soft: equal to y_hard up to
+        # one rounding, so compare it through > 0.5
+        assert torch.equal(a > 0.5, b.float() > 0.5), "reference copies of the gate disagree"
+        out[name] = (a > 0.5).to(torch.uint8)
+    return out
+
+
+def gumbel_train(ref_dyn):
+    out = {}
+    for name, dt in (("fp32", torch.float32), ("fp16", torch.float16)):
+        g = torch.Generator().manual_seed(7)
+        logits = (torch.randn(4, 196, 1, generator=g) * 2).to(dt)
+        torch.manual_seed(1234)
+        ret = ref_dyn._gumbel_sigmoid(logits, 5, True, threshold=0.5, training=True)
+        torch.manual_seed(1234)   # replay the two draws (models/dynamic_adapter.py:30-39)
+        g1 = -torch.empty_like(logits).exponential_().log()
+        g2 = -torch.empty_like(logits).exponential_().log()
+        out[name] = dict(logits=logits, g1=g1, g2=g2, hard=(ret.float() > 0.5).to(torch.uint8))
+    return out
+
+
+def _build(ref_mod, sd, num_classes, embed_dim, depth, heads, img, ffn_num, scalar, generic):
+    tuning, select = ref_shim.reference_configs(ffn_num=ffn_num, scalar=scalar, d_model=embed_dim)
+    if generic:
+        m = ref_mod.VisionTransformer(img_size=img, patch_size=16, embed_dim=embed_dim, depth=depth,
+                                      num_heads=heads, mlp_ratio=4.0, qkv_bias=True,
+                                      num_classes=num_classes, tuning_config=tuning,
+                                      select_config=select)
+    else:
+        m = ref_mod.vit_base_patch16_224_in21k(num_classes=num_classes, drop_path_rate=0.0,
+                                               tuning_config=tuning, select_config=select)
+    missing = m.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m.eval()
+
+
+def tiny_vit(ref_speed, ref_train):
+    dims = dict(embed_dim=128, depth=2, num_heads=2, bottleneck=16, num_classes=10, img_size=32)
+    sd = O.synthetic_state_dict(seed=3, **dims)
+    g = torch.Generator().manual_seed(11)
+    img = torch.randn(3, 3, 32, 32, generator=g)
+    sd = O.calibrate_selector_bias(sd, img, 2, 2, 0.1, 0.5)
+    ms = _build(ref_speed, sd, 10, 128, 2, 2, 32, 16, "0.1", True)
+    mt = _build(ref_train, sd, 10, 128, 2, 2, 32, 16, "0.1", True)
+    out = dict(dims=dims, scale=0.1, state_dict=sd, img=img)
+    with torch.no_grad():
+        out["speed_logits"] = ms(img)
+        lg, d = mt(img)
+        out["train_logits"], out["token_select"], out["token_logits"] = lg, d["token_select"], d["token_logits"]
+        lg, d = mt(img, complete_model=True)
+        out["teacher_logits"], out["teacher_token_select"] = lg, d["token_select"]
+        # per-block activations of the speed model
+        x = ms.patch_embed(img)
+        x = torch.cat((ms.cls_token.expand(x.shape[0], -1, -1), x), dim=1) + ms.pos_embed
+        out["x0"] = x.clone()
+        blk = ms.blocks[0]
+        out["blk0_attn"] = blk.attn(blk.norm1(x))
+        x1 = x + out["blk0_attn"]
+        sel, logit = blk.mlp_token_select(x1)
+        out["blk0_sel"], out["blk0_logit"] = sel, logit
+        out["blk0_adapter"] = blk.adaptmlp(x1, add_residual=False)
+        out["blk0_mlp_dense"] = blk.mlp(blk.norm2(x1))
+        out["blk0_out"] = blk(x)
+        out["blk0_out_b1"] = blk(x[:1])          # single_forward path (B == 1)
+        out["blk0_train_out"] = mt.blocks[0](x)[0]
+    return out
+
+
+def vitb_b2(ref_speed, ref_train):
+    sd = O.synthetic_state_dict(seed=0)
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(2, 3, 224, 224, generator=g)
+    sd = O.calibrate_selector_bias(sd, img, 12, 12, 0.1, 0.5)
+    biases = torch.stack([sd[f"blocks.{i}.mlp_token_select.mlp_head.bias"] for i in range(12)])
+    ms = _build(ref_speed, sd, 100, 768, 12, 12, 224, 64, "0.1", False)
+    mt = _build(ref_train, sd, 100, 768, 12, 12, 224, 64, "0.1", False)
+    out = dict(seed=0, img_seed=0, scale=0.1, selector_bias=biases)
+    with torch.no_grad():
+        out["speed_logits"] = ms(img)
+        lg, d = mt(img)
+        out["train_logits"] = lg
+        out["token_select"] = d["token_select"].to(torch.uint8)
+        out["token_logits"] = d["token_logits"]
+        out["teacher_logits"] = mt(img, complete_model=True)[0]
+        # BASELINE.json config 1: imposed 50% mask (cls + even-indexed patches)
+        forced = O.checkerboard_mask(2, 197)
+        def imposed(self, x):
+            logits = self.mlp_head(x[:, 1:, :])
+            return forced.to(x.dtype), logits
+        for mod, key in ((ref_speed, "config1_speed_logits"), (ref_train, "config1_train_logits")):
+            orig = mod.TokenSelect.forward
+            mod.TokenSelect.forward = imposed
+            try:
+                r = (ms if mod is ref_speed else mt)(img)
+                out[key] = r if mod is ref_speed else r[0]
+            finally:
+                mod.TokenSelect.forward = orig
+    return out
+
+
+def main():
+    assert ref_shim.reference_available(), "needs the reference checkout at " + ref_shim.REFERENCE_ROOT
+    torch.set_num_threads(os.cpu_count())
+    ref_dyn = ref_shim.import_reference("models.dynamic_adapter")
+    ref_speed = ref_shim.import_reference("models.model_speed_test")
+    ref_train = ref_shim.import_reference("models.vision_transformer_IN21K")
+    os.makedirs(OUT, exist_ok=True)
+    torch.save(gate_tables(ref_speed, ref_dyn), os.path.join(OUT, "gate_tables.pt"))
+    torch.save(gumbel_train(ref_dyn), os.path.join(OUT, "gumbel_train.pt"))
+    torch.save(tiny_vit(ref_speed, ref_train), os.path.join(OUT, "tiny_vit.pt"))
+    torch.save(vitb_b2(ref_speed, ref_train), os.path.join(OUT, "vitb_b2.pt"))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,284 @@
+"""GPU parity tests, kernel by kernel: every hand-written sm_100a kernel is called through the
+C ABI (dyt_b200.ops -> libdyt_b200.so) and compared with the CPU oracle (oracle/dyt_oracle.py,
+"amp16" policy = the fp16-autocast arithmetic) on the same seeded inputs.
+Bar: masks / indices bit-exact; floating point within the tolerance stated in each test."""
+import pytest
+import torch
+
+import dyt_oracle as O
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from dyt_b200 import lib
+    lib()
+    return torch.device("cuda:0")
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _close(got, ref, atol, rtol):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    assert not bool(bad.any()), f"max err {err.max().item():.3e}, {int(bad.sum())} elements out of tolerance"
+
+
+# ---------------------------------------------------------------------------------------------
+# GEMM + epilogues (nn.Linear under fp16 autocast)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(1, 8, 8), (197, 64, 768), (394, 2304, 768), (300, 768, 3072),
+                                   (130, 1000, 200), (257, 768, 64), (64, 16, 768)])
+@pytest.mark.parametrize("epi", ["bias", "gelu", "relu"])
+def test_linear_epilogues(dev, M, N, K, epi):
+    from dyt_b200 import ops, _lib
+    g = _gen(M * 7 + N)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) * 0.5
+    ref = O.linear(x, w, b, "amp16")
+    if epi == "gelu":
+        ref = O.gelu(ref, "amp16")
+    elif epi == "relu":
+        ref = torch.relu(ref)
+    code = dict(bias=_lib.EPI_BIAS, gelu=_lib.EPI_BIAS_GELU, relu=_lib.EPI_BIAS_RELU)[epi]
+    out, _ = ops.linear_f16(x.half().to(dev), w.half().to(dev), b.half().to(dev), epilogue=code)
+    assert out.dtype == torch.float16 and out.shape == (M, N)
+    # fp32 accumulation order differs from the CPU GEMM: allow one fp16 ulp
+    _close(out, ref, atol=1e-3, rtol=2e-3)
+
+
+def test_linear_residual_and_device_row_count(dev):
+    from dyt_b200 import ops, _lib
+    g = _gen(5)
+    M, N, K = 500, 768, 768
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g) * 3
+    v = O.linear(x, w, b, "amp16")
+    for scale in (1.0, 0.1):
+        vv = v if scale == 1.0 else O._r16(v * scale)
+        out, out_h = ops.linear_f16(x.half().to(dev), w.half().to(dev), b.half().to(dev),
+                                    epilogue=_lib.EPI_BIAS_RESID, resid=res.to(dev), scale=scale,
+                                    want_f16_copy=True)
+        assert out.dtype == torch.float32
+        _close(out, res + vv, atol=1.5e-3, rtol=2e-3)
+        assert torch.equal(out_h, out.half())
+    # device-resident row count: rows >= m_dev are left untouched
+    m_dev = torch.tensor([123], dtype=torch.int32, device=dev)
+    buf = torch.full((M, N), -7.0, dtype=torch.float16, device=dev)
+    ops.linear_f16(x.half().to(dev), w.half().to(dev), b.half().to(dev), m_dev=m_dev, out=buf)
+    _close(buf[:123], v[:123], atol=1e-3, rtol=2e-3)
+    assert bool((buf[123:] == -7.0).all())
+
+
+def test_linear_rejects_bad_arguments(dev):
+    from dyt_b200 import ops, DytError
+    with pytest.raises(DytError):
+        ops.linear_f16(torch.zeros(4, 12, dtype=torch.float16, device=dev),
+                       torch.zeros(8, 12, dtype=torch.float16, device=dev))       # K % 8 != 0
+    with pytest.raises(DytError):
+        ops.linear_f16(torch.zeros(4, 16), torch.zeros(8, 16))                      # CPU tensors
+
+
+# ---------------------------------------------------------------------------------------------
+# LayerNorm
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C", [128, 768, 1024])
+def test_layernorm(dev, C):
+    from dyt_b200 import ops
+    g = _gen(C)
+    x = torch.randn(3, 197, C, generator=g) * 2 + 0.3
+    w = 1 + 0.1 * torch.randn(C, generator=g)
+    b = 0.1 * torch.randn(C, generator=g)
+    ref = O._r16(O.layer_norm(x, w, b, 1e-6))
+    out = ops.layernorm_f16(x.to(dev), w.to(dev), b.to(dev), 1e-6)
+    _close(out, ref, atol=1e-3, rtol=1e-3)      # one fp16 ulp
+    idx = torch.tensor([5, 0, 590, 17, 17], dtype=torch.int32)
+    out = ops.layernorm_f16(x.to(dev), w.to(dev), b.to(dev), 1e-6, row_idx=idx.to(dev))
+    _close(out, ref.reshape(-1, C)[idx.long()], atol=1e-3, rtol=1e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# attention (TMA + tcgen05, P in TMEM)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,N", [(1, 1, 16), (2, 12, 197), (3, 2, 128), (2, 16, 256), (4, 3, 1)])
+def test_attention_uniform(dev, B, H, N):
+    from dyt_b200 import ops
+    g = _gen(B * 100 + N)
+    qkv = torch.randn(B, N, 3 * H * 64, generator=g) * 1.5
+    ref = O.attention_core(O._r16(qkv), H, "amp16")
+    out = ops.attn_varlen(qkv.half().to(dev), H)
+    assert out.shape == (B, N, H * 64)
+    _close(out, ref, atol=2e-3, rtol=3e-3)
+
+
+def test_attention_varlen(dev):
+    from dyt_b200 import ops
+    H = 4
+    lens = [1, 17, 128, 129, 197, 256, 64]
+    cu = torch.tensor([0] + lens).cumsum(0).to(torch.int32)
+    T = int(cu[-1])
+    qkv = torch.randn(T, 3 * H * 64, generator=_gen(9))
+    out = ops.attn_varlen(qkv.half().to(dev), H, cu_seqlens=cu.to(dev), max_seqlen=max(lens))
+    for i, n in enumerate(lens):
+        s = int(cu[i])
+        ref = O.attention_core(O._r16(qkv[s:s + n]).unsqueeze(0), H, "amp16")[0]
+        _close(out[s:s + n], ref, atol=2e-3, rtol=3e-3)
+
+
+def test_attention_unsupported_is_loud(dev):
+    from dyt_b200 import ops, DytError
+    with pytest.raises(DytError):
+        ops.attn_varlen(torch.zeros(1, 300, 3 * 64, dtype=torch.float16, device=dev), 1)   # > 256 keys
+    with pytest.raises(DytError):
+        ops.attn_varlen(torch.zeros(1, 16, 3 * 32, dtype=torch.float16, device=dev), 1)    # head_dim 32
+
+
+# ---------------------------------------------------------------------------------------------
+# fused dispatcher: score + gate + compaction + LN2 pack
+# ---------------------------------------------------------------------------------------------
+def _dispatch_case(dev, B, N, C, seed, forced=None, policy="amp16"):
+    from dyt_b200 import ops
+    g = _gen(seed)
+    x1 = torch.randn(B, N, C, generator=g)
+    w = torch.randn(1, C, generator=g) * 0.5
+    b = torch.randn(1, generator=g) * 0.1
+    lw = 1 + 0.1 * torch.randn(C, generator=g)
+    lb = 0.1 * torch.randn(C, generator=g)
+    r = ops.dispatch(x1.to(dev), w.to(dev), b.to(dev), ln_w=lw.to(dev), ln_b=lb.to(dev),
+                     logit_dtype=torch.float16 if policy == "amp16" else torch.float32,
+                     forced_mask=None if forced is None else forced.to(dev))
+    torch.cuda.synchronize()
+    mask_ref, logit_ref = O.token_select(x1, w, b, policy)
+    return x1, (lw, lb), r, mask_ref, logit_ref
+
+
+@pytest.mark.parametrize("B,N,C", [(2, 197, 768), (5, 197, 1024), (3, 5, 128), (1, 2, 128),
+                                   (300, 50, 128), (2, 600, 384), (700, 5, 128)])
+@pytest.mark.parametrize("policy", ["amp16", "fp32"])
+def test_dispatch_matches_oracle(dev, B, N, C, policy):
+    x1, (lw, lb), r, mask_ref, logit_ref = _dispatch_case(dev, B, N, C, B * N + C, policy=policy)
+    logits = r["logits"].cpu()
+    mask = r["mask"].cpu()
+    if policy == "amp16":
+        # the logit is rounded once to fp16: kernel and oracle may differ by accumulation order
+        # only for values within half an ulp of a rounding boundary -> allow one fp16 ulp
+        _close(logits, logit_ref, atol=2e-5, rtol=1.1e-3)
+    else:
+        _close(logits, logit_ref, atol=1e-4, rtol=1e-5)
+    # the gate itself is exact given the logits the kernel produced ...
+    dt = torch.float16 if policy == "amp16" else torch.float32
+    gate_of_kernel_logits = O.gumbel_sigmoid_hard(logits.to(dt)).float()
+    assert torch.equal(mask[:, 1:], gate_of_kernel_logits)
+    assert bool((mask[:, 0] == 1).all())
+    # ... and bit-equal to the oracle's mask except where the oracle's logit sits on the threshold
+    mism = mask != mask_ref
+    if bool(mism.any()):
+        thr = O.min_kept_logit(dt)
+        slack = 1.2e-5 if policy == "amp16" else 2e-4
+        near = (logit_ref[mism[:, 1:]] - thr).abs() <= slack
+        assert bool(near.all()), "mask mismatch away from the gate threshold"
+        assert int(mism.sum()) <= 2
+    # compaction: nonzero() order, inverse map, cu_seqlens, count
+    n_kept = int(r["n_kept"].item())
+    idx_ref, cu_ref = O.compact(mask)
+    assert n_kept == idx_ref.numel()
+    assert torch.equal(r["packed_idx"][:n_kept].cpu().long(), idx_ref)
+    assert torch.equal(r["cu_seqlens"].cpu(), cu_ref)
+    pos = r["token_pos"].cpu().long()
+    flat = mask.reshape(-1) != 0
+    assert bool((pos[~flat] == -1).all())
+    assert torch.equal(pos[flat], torch.arange(n_kept))
+    # packed buffer = LayerNorm2 of the kept rows, fp16
+    ref_rows = O._r16(O.layer_norm(x1.reshape(B * N, C)[idx_ref], lw, lb))
+    _close(r["packed"][:n_kept], ref_rows, atol=1e-3, rtol=1e-3)
+
+
+def test_dispatch_gate_exhaustive_fp16(dev):
+    """Every fp16 bit pattern as a logit: x1 rows are one-hot * value, w = e_0, bias 0, so the
+    kernel's logit IS the pattern; the mask must equal the reference gate's truth table (golden,
+    from the reference's own _gumbel_sigmoid) and torch's CUDA sigmoid."""
+    from dyt_b200 import ops
+    gold = load_golden("gate_tables.pt")["fp16"].bool()
+    C, N = 128, 129
+    B = 65536 // (N - 1)
+    vals = torch.arange(0, 1 << 16, dtype=torch.int32).to(torch.int16).view(torch.float16)
+    x1 = torch.zeros(B, N, C)
+    x1[:, 1:, 0] = vals.float().reshape(B, N - 1)
+    w = torch.zeros(1, C)
+    w[0, 0] = 1.0
+    r = ops.dispatch(x1.to(dev), w.to(dev), torch.zeros(1, device=dev), pack=False)
+    mask = r["mask"][:, 1:, 0].reshape(-1).cpu() != 0
+    finite = torch.isfinite(vals)
+    nan = torch.isnan(vals)
+    assert torch.equal(mask[~nan], gold[~nan])
+    assert not bool(mask[nan].any())              # NaN -> dropped
+    cuda_gate = (vals.to(dev).sigmoid() > 0.5).cpu()
+    assert torch.equal(mask[finite], cuda_gate[finite])
+    lg = r["logits"].reshape(-1).cpu()
+    assert torch.equal(lg[~nan], vals.float()[~nan])
+
+
+@pytest.mark.parametrize("name", ["fp16", "fp32"])
+def test_dispatch_train_mode_gumbel(dev, name):
+    """Train-mode gate with the reference's own RNG draws (golden fixture)."""
+    from dyt_b200 import ops
+    gfix = load_golden("gumbel_train.pt")[name]
+    logits = gfix["logits"].float()            # [4, 196, 1]
+    B, N, C = 4, 197, 128
+    x1 = torch.zeros(B, N, C)
+    x1[:, 1:, 0] = logits[..., 0]
+    w = torch.zeros(1, C)
+    w[0, 0] = 1.0
+    r = ops.dispatch(x1.to(dev), w.to(dev), torch.zeros(1, device=dev), pack=False,
+                     logit_dtype=torch.float16 if name == "fp16" else torch.float32,
+                     noise=(gfix["g1"].float().to(dev), gfix["g2"].float().to(dev)), tau=5.0)
+    assert torch.equal(r["mask"][:, 1:].cpu() != 0, gfix["hard"].bool())
+
+
+def test_dispatch_forced_mask_and_gate_report(dev):
+    forced = O.checkerboard_mask(3, 197)
+    x1, _, r, mask_ref, _ = _dispatch_case(dev, 3, 197, 768, 77, forced=forced)
+    assert torch.equal(r["mask"].cpu(), forced)
+    assert int(r["n_kept"].item()) == 3 * 99
+    assert torch.equal(r["gate"].cpu(), mask_ref)      # selector's own decision still reported
+
+
+def test_dispatch_workspace_is_reusable(dev):
+    """The grid-barrier words must be left zeroed: run twice back to back with different B."""
+    for B in (7, 300, 7):
+        x1, _, r, mask_ref, _ = _dispatch_case(dev, B, 50, 128, 1000 + B)
+        assert int(r["n_kept"].item()) == int(r["mask"].sum().item())
+
+
+# ---------------------------------------------------------------------------------------------
+# scatter-merge
+# ---------------------------------------------------------------------------------------------
+def test_scatter_merge(dev):
+    from dyt_b200 import ops
+    g = _gen(3)
+    B, N, C = 3, 197, 768
+    x1 = torch.randn(B, N, C, generator=g)
+    adapt = (torch.randn(B, N, C, generator=g) * 0.1).half()
+    mask = (torch.rand(B, N, 1, generator=g) > 0.5).float()
+    idx, _ = O.compact(mask)
+    mlp = torch.randn(idx.numel(), C, generator=g).half()
+    pos = torch.full((B * N,), -1, dtype=torch.int32)
+    pos[idx] = torch.arange(idx.numel(), dtype=torch.int32)
+    full = torch.zeros(B * N, C)
+    full[idx] = mlp.float()
+    ref = adapt.float() + (x1 + full.reshape(B, N, C))          # model_speed_test.py:305-308
+    lw, lb = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    out, ln = ops.scatter_merge(x1.to(dev), adapt.to(dev), mlp.to(dev), pos.to(dev),
+                                next_ln=(lw.to(dev), lb.to(dev)))
+    assert torch.equal(out.cpu(), ref)                          # same fp32 additions: bit-exact
+    _close(ln, O._r16(O.layer_norm(ref, lw, lb)), atol=1e-3, rtol=1e-3)
