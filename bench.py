@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""Benchmark of the DyT token-dispatched ViT forward (BASELINE.json metric: images/s, ViT-B/16 DyT,
+r = 0.5, batch 256 per GPU, 224x224 synthetic images; reference protocol speed.py:247-275).
+
+  python bench.py --gpus N --steps K --warmup W            # our sm_100a path (one rank per GPU)
+  python bench.py --impl reference --gpus N ...            # reference algorithm on the host CPU
+
+A step = one forward of the whole model over one batch.  `value` is device-timed (CUDA events,
+inputs resident in HBM); `e2e` goes through the public drop-in API (model(images) under autocast)
+with pinned host images copied H2D and the logits read back D2H inside the timed region.
+Multi-GPU: images shard over ranks with no data-path collective (weak scaling, 256 images / GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "dynamic-tuning_b200"))
+
+import torch  # noqa: E402
+
+METRIC = "images/sec ViT-B/16 DyT r=0.5 bs256"
+BATCH = 256
+RATE = 0.5
+N_TOK, C_DIM, DEPTH, HEADS, HIDDEN, BOTTLENECK, NUM_CLASSES = 197, 768, 12, 12, 3072, 64, 100
+
+
+def flops_per_image(kept_tokens: float) -> float:
+    """Algorithmic FLOPs (2 x MAC) of one ViT-B/16 DyT forward, SURVEY.md section 8d."""
+    n, c = N_TOK, C_DIM
+    per_block = (2 * n * c * 3 * c + 4 * n * n * c + 2 * n * c * c + 2 * (n - 1) * c +
+                 4 * n * c * BOTTLENECK + 4 * kept_tokens * c * HIDDEN)
+    return DEPTH * per_block + 2 * 196 * c * 768 + 2 * c * NUM_CLASSES
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.idx)], stdout=open(self.path, "w"),
+                stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                sm.append(float(f[1]))
+                mx = float(f[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        dist.init_process_group(backend=backend)
+    return world, rank, local
+
+
+def shard_images(total: int, world: int, rank: int):
+    """Contiguous image shard of rank `rank`: images are independent (no cross-image state), the
+    reference shards the same way (strided Subset, speed.py:188).  Returns (start, count)."""
+    base, rem = divmod(total, world)
+    start = rank * base + min(rank, rem)
+    return start, base + (1 if rank < rem else 0)
+
+
+def max_over_ranks(seconds: float, world: int, device) -> float:
+    if world == 1:
+        return seconds
+    import torch.distributed as dist
+    t = torch.tensor([seconds], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world: int):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU oracle (restatement of the reference forward, pinned to the
+# reference's own outputs by tests/test_oracle_golden.py) on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(state_dict, steps: int, warmup: int, sample_batch: int, seed: int = 0):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dyt_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    img = torch.randn(sample_batch, 3, 224, 224, generator=torch.Generator().manual_seed(seed))
+    sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.vit_forward(img, sd, DEPTH, HEADS, 0.1, policy="fp32", sparse=True)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r = O.vit_forward(img, sd, DEPTH, HEADS, 0.1, policy="fp32", sparse=True)
+        dt = time.perf_counter() - t0
+    keep = r["token_select"].float().mean().item()
+    return dict(value=sample_batch * steps / dt, ms_per_step=dt / steps * 1e3, cores=cores,
+                keep_rate=keep,
+                sample=f"{steps} forward(s) of {sample_batch} seed-{seed} images, fp32, "
+                       f"torch {torch.__version__} CPU, {cores} threads")
+
+
+def synthetic_cpu_state_dict(seed: int = 0):
+    """Same construction as dyt_b200.synthetic.build_vit_b16 but on the CPU, with the selector bias
+    calibrated by the oracle (used when no GPU is present, i.e. the pure reference arm)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dyt_oracle as O
+    sd = O.synthetic_state_dict(seed=seed)
+    img = torch.randn(8, 3, 224, 224, generator=torch.Generator().manual_seed(seed))
+    return O.calibrate_selector_bias(sd, img, DEPTH, HEADS, 0.1, RATE)
+
+
+def run_reference(args, world, rank):
+    if rank != 0:
+        return
+    sample = 16
+    sd = synthetic_cpu_state_dict(0)
+    r = cpu_reference_run(sd, max(1, args.steps), max(1, min(args.warmup, 2)), sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ViT-B/16 DyT inference 224x224 r~0.5 (speed.py path), CPU sample "
+                               f"of {sample} images per step", "keep_rate": r["keep_rate"]},
+        "cpu_baseline": {"value": r["value"], "unit": "images/s", "cores": r["cores"],
+                         "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def time_kernel(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters * 1e-3
+
+
+def kernel_table(model, x_blocks, kept_total, peaks, device):
+    """Each hot-path kernel timed alone (CUDA events on the launching stream) at the bench shapes:
+    algorithmic bytes / FLOPs per launch over the measured duration."""
+    from dyt_b200 import _lib, ops
+    blk = model.blocks[0]
+    T = x_blocks.shape[0] * N_TOK
+    h16 = torch.float16
+    f = lambda t: t.detach().to(h16).contiguous()
+    xn = torch.randn(T, C_DIM, device=device, dtype=h16)
+    qkv_w, qkv_b = f(blk.attn.qkv.weight), f(blk.attn.qkv.bias)
+    proj_w, proj_b = f(blk.attn.proj.weight), f(blk.attn.proj.bias)
+    fc1_w, fc1_b = f(blk.mlp.fc1.weight), f(blk.mlp.fc1.bias)
+    fc2_w, fc2_b = f(blk.mlp.fc2.weight), f(blk.mlp.fc2.bias)
+    dn_w, dn_b = f(blk.adaptmlp.down_proj.weight), f(blk.adaptmlp.down_proj.bias)
+    up_w, up_b = f(blk.adaptmlp.up_proj.weight), f(blk.adaptmlp.up_proj.bias)
+    x32 = x_blocks.reshape(T, C_DIM).contiguous()
+    qkv = torch.randn(x_blocks.shape[0], N_TOK, 3 * C_DIM, device=device, dtype=h16)
+    K = int(kept_total)
+    m_dev = torch.tensor([K], dtype=torch.int32, device=device)
+    hid = torch.randn(T, HIDDEN, device=device, dtype=h16)
+    dn = torch.randn(T, BOTTLENECK, device=device, dtype=h16)
+    out_qkv = torch.empty(T, 3 * C_DIM, device=device, dtype=h16)
+    out_c = torch.empty(T, C_DIM, device=device, dtype=h16)
+    out_f = torch.empty(T, C_DIM, device=device, dtype=torch.float32)
+    out_h = torch.empty(T, HIDDEN, device=device, dtype=h16)
+    out_d = torch.empty(T, BOTTLENECK, device=device, dtype=h16)
+    ln_w, ln_b = blk.norm2.weight.detach().float(), blk.norm2.bias.detach().float()
+    sel_w, sel_b = blk.mlp_token_select.mlp_head.weight.detach(), blk.mlp_token_select.mlp_head.bias.detach()
+    d = ops.dispatch(x_blocks, sel_w, sel_b, ln_w=ln_w, ln_b=ln_b)
+    rows = []
+
+    def add(name, fn, flops, bytes_, bound):
+        t = time_kernel(fn)
+        ach = (flops / t / 1e12) if bound == "tensor" else (bytes_ / t / 1e9)
+        peak = peaks["tf_burst"] if bound == "tensor" else peaks["hbm"]
+        rows.append(dict(kernel=name, us=t * 1e6, bound=bound, achieved=ach,
+                         unit="TFLOP/s" if bound == "tensor" else "GB/s", frac=ach / peak,
+                         flops=flops, bytes=bytes_))
+
+    add("gemm qkv [T,768]x[2304,768]", lambda: ops.linear_f16(xn, qkv_w, qkv_b, out=out_qkv),
+        2.0 * T * 3 * C_DIM * C_DIM, T * C_DIM * 2 + T * 3 * C_DIM * 2, "tensor")
+    add("attention 12 heads x 197", lambda: ops.attn_varlen(qkv, HEADS),
+        4.0 * x_blocks.shape[0] * HEADS * N_TOK * N_TOK * 64, T * 4 * C_DIM * 2, "tensor")
+    add("gemm proj + residual", lambda: ops.linear_f16(xn, proj_w, proj_b, epilogue=_lib.EPI_BIAS_RESID,
+                                                       resid=x32, out=out_f, want_f16_copy=False),
+        2.0 * T * C_DIM * C_DIM, T * C_DIM * (2 + 4 + 4), "tensor")
+    add("dispatcher (score+gate+compact+LN2 pack)",
+        lambda: ops.dispatch(x_blocks, sel_w, sel_b, ln_w=ln_w, ln_b=ln_b),
+        2.0 * T * C_DIM, T * C_DIM * 4 + K * C_DIM * (4 + 2), "hbm")
+    add("gemm fc1 + GELU (kept rows)", lambda: ops.linear_f16(xn, fc1_w, fc1_b, epilogue=_lib.EPI_BIAS_GELU,
+                                                              m_dev=m_dev, out=out_h),
+        2.0 * K * HIDDEN * C_DIM, K * (C_DIM + HIDDEN) * 2, "tensor")
+    add("gemm fc2 (kept rows)", lambda: ops.linear_f16(hid, fc2_w, fc2_b, m_dev=m_dev, out=out_c),
+        2.0 * K * HIDDEN * C_DIM, K * (C_DIM + HIDDEN) * 2, "tensor")
+    add("gemm adapter down + ReLU", lambda: ops.linear_f16(xn, dn_w, dn_b, epilogue=_lib.EPI_BIAS_RELU, out=out_d),
+        2.0 * T * BOTTLENECK * C_DIM, T * (C_DIM + BOTTLENECK) * 2, "hbm")
+    add("gemm adapter up * scale", lambda: ops.linear_f16(dn, up_w, up_b, scale=0.1, out=out_c),
+        2.0 * T * BOTTLENECK * C_DIM, T * (C_DIM + BOTTLENECK) * 2, "hbm")
+    add("scatter-merge (+ next LN1)",
+        lambda: ops.scatter_merge(x_blocks, out_c.reshape(x_blocks.shape), out_c, d["token_pos"],
+                                  next_ln=(ln_w, ln_b)),
+        0.0, T * C_DIM * (4 + 2 + 4 + 2) + K * C_DIM * 2, "hbm")
+    return rows
+
+
+def run_ours(args, world, rank, local):
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the sm_100a kernels are the only implementation "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    from dyt_b200 import engine, lib, synthetic
+    lib()
+    peaks = load_peaks()
+    model = synthetic.build_vit_b16(device, num_classes=NUM_CLASSES, seed=0)
+    # every rank generates the same seed-0 global batch and keeps its shard
+    start, count = shard_images(BATCH * world, world, rank)
+    assert count == BATCH
+    gen = torch.Generator().manual_seed(rank)          # rank-specific images, same distribution
+    host_images = torch.randn(BATCH, 3, 224, 224, generator=gen).pin_memory()
+    images = host_images.to(device, non_blocking=True)
+    cal = torch.randn(64, 3, 224, 224, generator=torch.Generator().manual_seed(0)).to(device)
+    keep_cal = synthetic.calibrate_keep_rate(model, cal, RATE)
+
+    def forward(imgs):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            return model(imgs)
+
+    warm = max(3, args.warmup)
+    for _ in range(warm):
+        logits = forward(images)
+    torch.cuda.synchronize()
+    # realised keep rate on the bench batch
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        x0 = model._embed(images).float()
+    _, masks, _, _ = engine.run_blocks(x0, list(model.blocks))
+    keep_rate = masks[:, :, 1:].mean().item()
+    kept_tokens = masks.sum(dim=2).mean().item()       # mean kept tokens per image per layer
+
+    # ---- device-resident timing ----
+    sampler = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    ev0.record()
+    for _ in range(args.steps):
+        logits = forward(images)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    clocks = sampler.stop() if rank == 0 else None
+    sec = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, world, device)
+    value = BATCH * world * args.steps / sec
+
+    # ---- end to end: pinned host images -> H2D -> model(images) -> logits D2H, every step ----
+    host_logits = torch.empty(BATCH, NUM_CLASSES, dtype=torch.float16).pin_memory()
+    dev_in = torch.empty_like(images)
+    for _ in range(2):
+        dev_in.copy_(host_images, non_blocking=True)
+        host_logits.copy_(forward(dev_in), non_blocking=True)
+    barrier(world)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        dev_in.copy_(host_images, non_blocking=True)
+        host_logits.copy_(forward(dev_in), non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    sec_e2e = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, world, device)
+    e2e_value = BATCH * world * args.steps / sec_e2e
+
+    if rank != 0:
+        return
+    fl_img = flops_per_image(kept_tokens)
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warm, "ms_per_step": sec / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+        "data": "synthetic",
+        "config": {"workload": "ViT-B/16 DyT inference bs256 224x224 r~0.5 on 1xB200 (speed.py path)",
+                   "batch_per_gpu": BATCH, "keep_rate": round(keep_rate, 4),
+                   "kept_tokens_per_image_layer": round(kept_tokens, 2),
+                   "l2": "per-step working set ~1.1 GB of activations >> 126 MB L2 (no flush needed)",
+                   "weights": "random init seed 0, selector bias calibrated on the GPU path",
+                   "stem_head": "patch-embed conv / final LN / head via torch library ops (1% of FLOPs)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/s",
+                "h2d_bytes_per_step": host_images.numel() * 4,
+                "d2h_bytes_per_step": host_logits.numel() * 2},
+        "gpu_launches": args.steps * (DEPTH * 9 + 1),
+        "model_flops_per_image": fl_img,
+        "model_tflops": value / world * fl_img / 1e12,
+        "frac_of_r_scaled_compute_roofline": value / world * fl_img / 1e12 / peaks["tf_sust"],
+        "peaks": peaks,
+    }
+    if world == 1:
+        rows = kernel_table(model, x0, kept_tokens * BATCH, peaks, device)
+        top = max((r for r in rows if r["bound"] == "tensor"), key=lambda r: r["us"])
+        line["roofline"] = {"kernel": top["kernel"], "bound": "tensor", "achieved": top["achieved"],
+                            "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": top["frac"],
+                            "traffic": None, "us_per_launch": top["us"],
+                            "peak_source": peaks["source"] + " bf16 burst (kernel timed alone)"}
+        line["kernels"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()}
+                           for r in rows]
+        if not args.no_cpu_baseline:
+            sd = model.state_dict()
+            r = cpu_reference_run(sd, steps=10, warmup=1, sample_batch=16)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "images/s", "cores": r["cores"],
+                                    "kind": "port", "sample": r["sample"]}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=15)
+    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        # CPU arm: rank 0 alone works, nobody needs a process group
+        run_reference(args, int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")))
+        return
+    world, rank, local = dist_setup(args.gpus)
+    try:
+        run_ours(args, world, rank, local)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -242,7 +242,7 @@ def test_full_batch_properties(dev, vitb_sd):
     n_kept = int(view(bufs.n_kept, 1, torch.int32).item())
     cu = view(bufs.cu_seqlens, B + 1, torch.int32).cpu()
     idx = view(bufs.packed_idx, B * 197, torch.int32)[:n_kept].cpu().long()
-    last = masks[-1].cpu()
+    last = masks_p[-1].cpu()       # the workspace holds the most recent (permuted) run
     assert n_kept == int(last.sum().item()) == int(cu[-1])
     assert torch.equal(cu[1:] - cu[:-1], last.sum(dim=1).to(torch.int32))
     assert bool((idx[1:] > idx[:-1]).all())
