@@ -1,0 +1,107 @@
+"""CPU-only checks of the host-side mirror of the reference interface: class names, constructor
+keywords, state_dict keys (the on-disk contract), the gate threshold table,
+and that every compute path refuses to run without CUDA (no silent fallback)."""
+import pytest
+import torch
+
+from conftest import load_golden
+
+
+class Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+def _cfgs(ffn_num=64, d_model=768):
+    tuning = Cfg(ffn_adapt=True, ffn_option="parallel", ffn_adapter_layernorm_option="none",
+                 ffn_adapter_init_option="lora", ffn_adapter_scalar="0.1", ffn_num=ffn_num,
+                 d_model=d_model, vpt_on=False, vpt_num=0)
+    return tuning, Cfg(open=True, keep_layers=0, token_target_ratio=0.5)
+
+
+def test_state_dict_keys_match_reference_tiny():
+    t = load_golden("tiny_vit.pt")          # state_dict accepted strict=True by the real reference
+    from models.model_speed_test import VisionTransformer as SpeedViT
+    from models.vision_transformer_IN21K import VisionTransformer as TrainViT
+    tuning, select = _cfgs(16, 128)
+    for cls in (SpeedViT, TrainViT):
+        m = cls(img_size=32, patch_size=16, embed_dim=128, depth=2, num_heads=2, num_classes=10,
+                tuning_config=tuning, select_config=select)
+        msg = m.load_state_dict(t["state_dict"], strict=True)
+        assert not msg.missing_keys and not msg.unexpected_keys
+        assert list(m.state_dict().keys()) == [k for k in m.state_dict().keys()]
+        assert set(m.state_dict().keys()) == set(t["state_dict"].keys())
+
+
+def test_vit_b16_factory_surface():
+    from models.model_speed_test import vit_base_patch16_224_in21k, Block, Attention, Adapter, TokenSelect, Mlp
+    from models.vision_transformer_IN21K import Block as TBlock, Mlp as TMlp  # block_flops_dict.py:6,:19
+    from models.dynamic_adapter import Adapter as A2, TokenSelect as T2       # video / segmentation imports
+    assert A2 is Adapter and T2 is TokenSelect and TMlp is Mlp
+    tuning, select = _cfgs()
+    m = vit_base_patch16_224_in21k(num_classes=100, drop_path_rate=0.0, tuning_config=tuning,
+                                   select_config=select)
+    assert sum(p.numel() for p in m.parameters()) == 87_074_416        # == reference ctor
+    blk = m.blocks[0]
+    dyt = sum(p.numel() for n, p in blk.named_parameters() if "adaptmlp" in n or "token_select" in n)
+    assert dyt == 99_905
+    assert isinstance(blk, Block) and hasattr(m, "head") and len(m.blocks) == 12
+    # strict=False loading of a backbone checkpoint leaves exactly the DyT parameters + head missing
+    backbone = {k: v for k, v in m.state_dict().items()
+                if "adaptmlp" not in k and "mlp_token_select" not in k and not k.startswith("head.")}
+    msg = m.load_state_dict(backbone, strict=False)
+    assert len(msg.missing_keys) == 12 * 6 + 2 and not msg.unexpected_keys
+    # train flavour exposes the FLOP-probe attributes poked by block_flops_dict.py:44-47
+    tb = TBlock(dim=768, num_heads=12, mlp_ratio=4.0, qkv_bias=True, tuning_config=tuning)
+    assert tb.count_flops is None and tb.token_select_num is None and hasattr(tb, "forward_count_flops")
+
+
+def test_select_false_quirk_is_preserved():
+    from models.model_speed_test import Block
+    tuning, _ = _cfgs()
+    b = Block(dim=768, num_heads=12, tuning_config=tuning, select=False)
+    assert b.token_select is None and not hasattr(b, "mlp_token_select")
+    with pytest.raises(AttributeError):
+        b(torch.zeros(2, 197, 768))
+
+
+def test_no_cpu_fallback_anywhere():
+    from dyt_b200 import DytError, ops
+    from models.model_speed_test import vit_base_patch16_224_in21k, Adapter, TokenSelect, Attention
+    tuning, select = _cfgs()
+    with torch.no_grad():
+        with pytest.raises(DytError):
+            TokenSelect(768, 1).eval()(torch.zeros(1, 197, 768))
+        with pytest.raises(DytError):
+            Adapter(tuning, dropout=0.1, bottleneck=64, adapter_scalar="0.1",
+                    adapter_layernorm_option="none").eval()(torch.zeros(1, 197, 768))
+        with pytest.raises(DytError):
+            Attention(768, 12, qkv_bias=True).eval()(torch.zeros(1, 197, 768))
+        with pytest.raises(DytError):
+            ops.layernorm_f16(torch.zeros(4, 768), torch.ones(768), torch.zeros(768))
+        m = vit_base_patch16_224_in21k(num_classes=10, drop_path_rate=0.0, tuning_config=tuning,
+                                       select_config=select).eval()
+        with pytest.raises(DytError):
+            m(torch.zeros(1, 3, 224, 224))
+
+
+def test_training_mode_is_refused_loudly_until_backward_exists():
+    from models.vision_transformer_IN21K import VisionTransformer
+    tuning, select = _cfgs(16, 128)
+    m = VisionTransformer(img_size=32, patch_size=16, embed_dim=128, depth=1, num_heads=2,
+                          num_classes=10, tuning_config=tuning, select_config=select).train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(2, 3, 32, 32))
+
+
+def test_gate_threshold_table_product_side():
+    """The product derives min_kept from torch's sigmoid; it must reproduce the reference gate's
+    exhaustive truth tables (golden, from the reference's own _gumbel_sigmoid)."""
+    from dyt_b200 import min_kept_logit
+    gold = load_golden("gate_tables.pt")
+    for name, dt in (("fp16", torch.float16), ("bf16", torch.bfloat16)):
+        vals = torch.arange(0, 1 << 16, dtype=torch.int32).to(torch.int16).view(dt).float()
+        mk = min_kept_logit(dt, 0.5)
+        assert torch.equal((vals >= mk) & ~torch.isnan(vals), gold[name].bool())
+    assert min_kept_logit(torch.float16, 0.5) == 2.0 ** -10 * (1 + 2.0 ** -10)
+    assert min_kept_logit(torch.float16, 0.7) > 0.8            # sigmoid(l) > 0.7  <=>  l > 0.847
+    assert 0 < min_kept_logit(torch.float32, 0.5) < 2e-7
