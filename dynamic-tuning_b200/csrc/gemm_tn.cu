@@ -24,7 +24,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   const int sms = sm_count();
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
   return cuda_status(cudaGetLastError(), "gemm_tn_kernel launch");
 }
 

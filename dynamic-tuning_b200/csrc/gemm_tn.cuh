@@ -3,9 +3,11 @@
 //   B : fp16 row-major nn.Linear weight [out,in]=[N,K]    -> TMA, 128B-swizzled K-major smem tiles
 //   D : fp32 accumulators in TMEM, two stages of BN columns so the epilogue of tile i overlaps the
 //       MMA main loop of tile i+1.
-// Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer (one elected thread),
-// warp2 = TMEM allocator, warps4-7 = epilogue (TMEM -> regs -> swizzled smem transpose ->
-// coalesced 128-bit global stores, with bias / GELU / ReLU / fp32-residual fused).
+// Warp roles (384 threads): warp0 = TMA producer, warp1 = MMA issuer (one elected thread),
+// warp2 = TMEM allocator, warps4-11 = epilogue: two warps per TMEM lane quarter, each owning half
+// of the tile's columns (TMEM -> regs -> swizzled smem transpose -> coalesced 128-bit global
+// accesses, with bias / GELU / ReLU / scale / fp32-residual fused).  Bias and residual loads are
+// issued before the accumulator wait so their latency overlaps the main loop.
 //
 // Replaces the cuBLASLt calls behind nn.Linear in the reference block
 // (reference models/model_speed_test.py:147 qkv, :164 proj, :106-111 adapter, timm Mlp fc1/fc2).
@@ -45,19 +47,33 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SLAB_BYTES = 32 * 128;  // 32 rows x 32 fp32
-  static constexpr int EPI_BYTES = 4 * 2 * SLAB_BYTES;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int THREADS = 128 + EPI_WARPS * 32;
+  static constexpr int SLAB_BYTES = 32 * 128;  // 32 rows x 32 fp32, one per epilogue warp
+  static constexpr int EPI_BYTES = EPI_WARPS * SLAB_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: all powers of two
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
 };
 
+// exact-erf GELU, branch-free: erf via Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below
+// the fp16 rounding applied to the result), 2 MUFU (rcp, ex2) + ~12 FMA per element.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = ex2_approx(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-p, e, 1.0f);          // erf(|x|/sqrt2)
+  const float erf_s = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_s);
 }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -98,7 +114,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4);
+      mbar_init(&tmem_empty_bar[a], Cfg::EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -169,31 +185,66 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
-    const int q = warp_idx - 4;  // == warp_idx % 4: TMEM lane quarter this warp may access
-    uint8_t* slab_base = epi_smem + q * 2 * Cfg::SLAB_BYTES;
-    const int cl = lane & 7;    // 16-byte chunk (4 fp32 columns) within the 32-column slab row
-    const int rsub = lane >> 3; // row within a group of 4
+    constexpr int HALF = BN / 2;      // columns owned by this warp
+    constexpr int NCH = HALF / 32;    // 32-column chunks per warp per tile
+    const int e = warp_idx - 4;
+    const int q = e & 3;              // == warp_idx % 4: TMEM lane quarter this warp may access
+    const int half = e >> 2;
+    uint8_t* slab = epi_smem + e * Cfg::SLAB_BYTES;
+    const int cl = lane & 7;     // 16-byte chunk (4 fp32 columns) within the 32-column slab row
+    const int rsub = lane >> 3;  // row within a group of 4
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * BM;
-      const int n0 = (tile % n_tiles) * BN;
+      const int n0 = (tile % n_tiles) * BN + half * HALF;
+      const int row_base = m0 + q * 32 + rsub;
+
+      // bias for every chunk of this tile: issued before the accumulator is ready
+      float bias_r[NCH][4];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col = n0 + c * 32 + cl * 4;
+        bias_r[c][0] = bias_r[c][1] = bias_r[c][2] = bias_r[c][3] = 0.f;
+        if (p.bias != nullptr && col < p.N) {
+          const uint2 bb = *reinterpret_cast<const uint2*>(p.bias + col);
+          const __half2 h01 = *reinterpret_cast<const __half2*>(&bb.x);
+          const __half2 h23 = *reinterpret_cast<const __half2*>(&bb.y);
+          bias_r[c][0] = __low2float(h01);
+          bias_r[c][1] = __high2float(h01);
+          bias_r[c][2] = __low2float(h23);
+          bias_r[c][3] = __high2float(h23);
+        }
+      }
+      // residual of the first chunk: in flight while the main loop of this tile finishes
+      float4 res[8];
+      if constexpr (EPI == EPI_BIAS_RESID) {
+        const int col = n0 + cl * 4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int grow = row_base + it * 4;
+          res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (grow < m_eff && col < p.N)
+            res[it] = *reinterpret_cast<const float4*>(p.resid +
+                                                       static_cast<size_t>(grow) * p.ld_res + col);
+        }
+      }
+
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                             static_cast<uint32_t>(acc * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+                             static_cast<uint32_t>(acc * BN + half * HALF);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
         uint32_t r[32];
         tmem_ld32(t_row + c * 32, r);
         tmem_ld_wait();
-        if (c == BN / 32 - 1) {
+        if (c == NCH - 1) {
           // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
-        uint8_t* slab = slab_base + (c & 1) * Cfg::SLAB_BYTES;
         {
           uint8_t* rowp = slab + lane * 128;
 #pragma unroll
@@ -205,25 +256,34 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         __syncwarp();
         const int col = n0 + c * 32 + cl * 4;
         const bool col_ok = col < p.N;
-        float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-        if (p.bias != nullptr && col_ok) {
-          const uint2 bb = *reinterpret_cast<const uint2*>(p.bias + col);
-          const __half2 h01 = *reinterpret_cast<const __half2*>(&bb.x);
-          const __half2 h23 = *reinterpret_cast<const __half2*>(&bb.y);
-          b0 = __low2float(h01);
-          b1 = __high2float(h01);
-          b2 = __low2float(h23);
-          b3 = __high2float(h23);
-        }
+        float4 a[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = it * 4 + rsub;
-          const int grow = m0 + q * 32 + rr;
-          const float4 a =
-              *reinterpret_cast<const float4*>(slab + rr * 128 + ((cl ^ (rr & 7)) << 4));
+          a[it] = *reinterpret_cast<const float4*>(slab + rr * 128 + ((cl ^ (rr & 7)) << 4));
+        }
+        __syncwarp();  // slab may be overwritten by the next chunk
+        // prefetch the next chunk's residual while this chunk is processed
+        float4 res_next[8];
+        if constexpr (EPI == EPI_BIAS_RESID) {
+          if (c + 1 < NCH) {
+            const int ncol = col + 32;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int grow = row_base + it * 4;
+              res_next[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (grow < m_eff && ncol < p.N)
+                res_next[it] = *reinterpret_cast<const float4*>(
+                    p.resid + static_cast<size_t>(grow) * p.ld_res + ncol);
+            }
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int grow = row_base + it * 4;
           if (grow < m_eff && col_ok) {
-            float v0 = round_f16(a.x + b0), v1 = round_f16(a.y + b1);
-            float v2 = round_f16(a.z + b2), v3 = round_f16(a.w + b3);
+            float v0 = round_f16(a[it].x + bias_r[c][0]), v1 = round_f16(a[it].y + bias_r[c][1]);
+            float v2 = round_f16(a[it].z + bias_r[c][2]), v3 = round_f16(a[it].w + bias_r[c][3]);
             if constexpr (EPI == EPI_BIAS) {
               if (p.scale != 1.0f) {
                 v0 = round_f16(v0 * p.scale); v1 = round_f16(v1 * p.scale);
@@ -240,18 +300,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 v0 = round_f16(v0 * p.scale); v1 = round_f16(v1 * p.scale);
                 v2 = round_f16(v2 * p.scale); v3 = round_f16(v3 * p.scale);
               }
-              const float4 res = *reinterpret_cast<const float4*>(
-                  p.resid + static_cast<size_t>(grow) * p.ld_res + col);
-              float4 o = make_float4(res.x + v0, res.y + v1, res.z + v2, res.w + v3);
+              const float4 o = make_float4(res[it].x + v0, res[it].y + v1, res[it].z + v2,
+                                           res[it].w + v3);
               *reinterpret_cast<float4*>(p.out_f + static_cast<size_t>(grow) * p.ldo_f + col) = o;
               if (p.out_h != nullptr) {
-                uint2 oh = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+                const uint2 oh = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
                 *reinterpret_cast<uint2*>(p.out_h + static_cast<size_t>(grow) * p.ldo_h + col) = oh;
               }
             } else {
-              uint2 oh = make_uint2(pack_half2(v0, v1), pack_half2(v2, v3));
+              const uint2 oh = make_uint2(pack_half2(v0, v1), pack_half2(v2, v3));
               *reinterpret_cast<uint2*>(p.out_h + static_cast<size_t>(grow) * p.ldo_h + col) = oh;
             }
+          }
+        }
+        if constexpr (EPI == EPI_BIAS_RESID) {
+          if (c + 1 < NCH) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) res[it] = res_next[it];
           }
         }
       }

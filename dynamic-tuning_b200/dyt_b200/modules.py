@@ -339,12 +339,28 @@ class VisionTransformer(nn.Module):
     def no_weight_decay(self):
         return {"pos_embed", "cls_token", "dist_token"}
 
-    # -- stem: patch embedding + cls + position (library conv; SURVEY.md section 8f rank 2 is "next") --
+    # -- stem: patch embedding + cls + position through the sm_100a im2col / GEMM / assemble path --
     def _embed(self, x):
-        x = self.patch_embed(x)
-        x = torch.cat((self.cls_token.expand(x.shape[0], -1, -1), x), dim=1)
-        x = x + self.pos_embed
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("dyt_b200: train-mode forward/backward is the next scope row; "
+                                      "call model.eval() under torch.no_grad()")
+        if not x.is_cuda:
+            raise DytError("dyt_b200 VisionTransformer needs CUDA inputs (no CPU fallback)")
+        pe = self.patch_embed
+        if not isinstance(pe, PatchEmbed) or not isinstance(pe.norm, nn.Identity):
+            raise NotImplementedError("dyt_b200 stem implements the plain PatchEmbed (Conv2d k=s=P)")
+        if tuple(x.shape[-2:]) != tuple(pe.img_size):
+            raise ValueError(f"input size {tuple(x.shape[-2:])} != model size {pe.img_size}")
+        x = ops.patch_embed(x, pe.proj.weight, pe.proj.bias, self.cls_token, self.pos_embed,
+                            pe.patch_size[0])
         return self.norm_pre(self.patch_drop(self.pos_drop(x)))
+
+    def _pooled_norm(self, x):
+        """norm() then pooling == pooling then norm() for the 'token' pool (LayerNorm is per row):
+        normalise only the cls rows instead of all B*N tokens."""
+        if self.global_pool == "token" and isinstance(self.fc_norm, nn.Identity):
+            return self.head_drop(self.norm(x[:, 0]))
+        return None
 
     def _blocks(self, x, complete_model=False):
         if self.training and torch.is_grad_enabled():
@@ -381,7 +397,11 @@ class SpeedVisionTransformer(VisionTransformer):
         return self.norm(x)
 
     def forward(self, x):
-        return self.forward_head(self.forward_features(x))
+        tokens, _, _ = self._blocks(self._embed(x))
+        pooled = self._pooled_norm(tokens)
+        if pooled is not None:
+            return self.head(pooled)
+        return self.forward_head(self.norm(tokens))
 
 
 class TrainVisionTransformer(VisionTransformer):
@@ -397,5 +417,11 @@ class TrainVisionTransformer(VisionTransformer):
         return self.norm(x), dict(token_select=token_select, token_logits=token_logits)
 
     def forward(self, x, complete_model=False):
-        x, token_select = self.forward_features(x, complete_model)
-        return self.forward_head(x), token_select
+        tokens, masks, logits = self._blocks(self._embed(x), complete_model)
+        dt = _act_dtype()
+        token_select = dict(token_select=masks.permute(1, 0, 2)[:, :, 1:].unsqueeze(-1).to(dt),
+                            token_logits=logits.permute(1, 0, 2).unsqueeze(-1).to(dt))
+        pooled = self._pooled_norm(tokens)
+        if pooled is not None:
+            return self.head(pooled), token_select
+        return self.forward_head(self.norm(tokens)), token_select

@@ -193,3 +193,35 @@ def scatter_merge(x1: torch.Tensor, adapt: torch.Tensor, mlp_packed: torch.Tenso
         _ptr(nln_out), Cdim, _stream()), "dyt_scatter_merge_fwd")
     out = out.reshape(x1.shape)
     return (out, None if nln_out is None else nln_out.reshape(x1.shape))
+
+
+_stem_ws = {}
+
+
+def patch_embed(img: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torch.Tensor],
+                cls_token: torch.Tensor, pos_embed: torch.Tensor, patch: int) -> torch.Tensor:
+    """ViT stem: img [B, Cin, H, W] fp32 -> tokens [B, L+1, C] fp32 (patch GEMM + cls + pos).
+    conv_w [C, Cin, P, P] / conv_b [C] are the PatchEmbed.proj parameters (fp16 copies made here)."""
+    _need_cuda(img, conv_w, conv_b, cls_token, pos_embed)
+    img = img.to(torch.float32).contiguous()
+    B, Cin, H, W = img.shape
+    Cdim = conv_w.shape[0]
+    L = (H // patch) * (W // patch)
+    w16 = conv_w.detach().reshape(Cdim, -1).to(torch.float16).contiguous()
+    b16 = None if conv_b is None else conv_b.detach().to(torch.float16).contiguous()
+    cls = cls_token.detach().reshape(-1).to(torch.float32).contiguous()
+    pos = pos_embed.detach().reshape(L + 1, Cdim).to(torch.float32).contiguous()
+    need = int(_lib.lib().dyt_patch_embed_workspace_bytes(B, H, W, patch, Cin, Cdim))
+    if need == 0:
+        raise DytError(f"patch_embed: unsupported geometry H={H} W={W} P={patch}")
+    key = (img.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _stem_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=img.device)
+        _stem_ws[key] = ws
+    x = torch.empty((B, L + 1, Cdim), dtype=torch.float32, device=img.device)
+    check(_lib.lib().dyt_patch_embed_fwd(
+        img.data_ptr(), B, Cin, H, W, patch, w16.data_ptr(), _ptr(b16), cls.data_ptr(),
+        pos.data_ptr(), Cdim, x.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+        "dyt_patch_embed_fwd")
+    return x

@@ -106,6 +106,15 @@ int dyt_scatter_merge_fwd(const float* x1, int ldx, const void* adapt_f16, int l
                           const float* next_ln_b, float eps, void* next_ln_out_f16, int ldn,
                           void* stream);
 
+/* ViT stem: x[b,0] = cls + pos[0]; x[b,1+p] = f16(patch_p . W^T + bias) + pos[1+p]  (fp32 out).
+ * Replaces PatchEmbed.proj (Conv2d k = s = P) + cls concat + pos_embed add (reference
+ * models/model_speed_test.py:467-472).  img [B, Cin, H, W] fp32; w_f16 [C, Cin*P*P] (the conv
+ * weight flattened), bias_f16 [C]; cls [C], pos [(H/P)*(W/P)+1, C] fp32; x_out [B, L+1, C] fp32. */
+size_t dyt_patch_embed_workspace_bytes(int B, int H, int W, int P, int Cin, int C);
+int dyt_patch_embed_fwd(const float* img, int B, int Cin, int H, int W, int P, const void* w_f16,
+                        const void* bias_f16, const float* cls, const float* pos, int C,
+                        float* x_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- whole block: Block.batch_forward (reference models/model_speed_test.py:274-310) ---------- */
 typedef struct dyt_block_shape {
   int B;          /* images (sequences) */
