@@ -1,19 +1,31 @@
 // Variable-length multi-head attention over a packed [T, 3, H, 64] fp16 qkv buffer (sm_100a).
-//   S = Q K^T  : tcgen05.mma kind::f16, A = Q tile (TMA, 128B-swizzled K-major), B = K tile
-//                (TMA, K-major), fp32 accumulator in TMEM columns [0, nk)
-//   softmax    : one thread per query row (TMEM lane): two passes over the TMEM row (max; exp2 +
-//                fp32 row sum), P written back to TMEM as packed fp16 aliasing S columns [0, nk/2)
-//   O = P V    : tcgen05.mma with A = P from TMEM, B = V tile (TMA, 128B-swizzled MN-major),
-//                accumulator in TMEM columns [128, 192); normalised by the fp32 row sum, rounded
-//                once to fp16 and stored as [T, H*64].
-// One CTA per (sequence, head, 128-query tile); sequences of up to 256 keys (one KV tile), so no
-// online-softmax rescaling is needed.  256 TMEM columns and ~70 KB smem per CTA -> 2 CTAs / SM, so
-// one CTA's softmax overlaps the other's TMA/MMA.
+//
+// Persistent kernel, one CTA per SM, work unit = (sequence, head); sequences of up to 256 keys
+// (one KV tile, so no online-softmax rescaling), i.e. up to two 128-query tiles A and B per unit.
+//   warp 0      TMA producer: Q (two 128-row boxes), K, V of the next unit into a 2-stage smem ring
+//   warp 1      tcgen05.mma issuer (one thread):
+//                 S = Q K^T : A = Q tile, B = K tile (both 128B-swizzled K-major smem), fp32
+//                             accumulator in TMEM
+//                 O = P V   : A = P from TMEM (packed fp16 aliasing the first half of S),
+//                             B = V tile (128B-swizzled MN-major smem)
+//               The two tiles are independent streams S(u), PV(u), S(u'), ...; the issuer polls
+//               the barriers of both and issues whichever step is ready, so the two softmax
+//               warpgroups drift out of phase and the MUFU pipe (the real bound of d=64
+//               attention: 8 cycles per warp-wide ex2) stays busy.
+//   warp 2      TMEM allocator (512 columns)
+//   warps 4-7   softmax warpgroup of tile A, warps 8-11 of tile B: one thread per query row (TMEM
+//               lane); pass 1 row max, pass 2 exp2 + fp32 row sum, P written back to TMEM as fp16;
+//               then O read back, normalised by the row sum, rounded once to fp16 and stored as
+//               [T, H*64].  Warps whose 32 rows are all past the sequence end skip the math.
+// TMEM columns: S_A at 0, S_B at nk; O_A / O_B live outside the S regions when they fit
+// (2*nk + 128 <= 512), otherwise inside their own S region at +128 (free once P is complete), in
+// which case the next S of that tile has to wait for the O read-out.
 //
 // Replaces F.scaled_dot_product_attention in Attention.forward of the reference
 // (models/model_speed_test.py:145-166; models/vision_transformer_IN21K.py:54-75): non-causal,
 // scale = head_dim^-0.5, dropout 0, q_norm/k_norm = Identity.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/dyt_b200.h"
 #include "host_utils.h"
@@ -24,64 +36,115 @@ namespace dyt {
 struct AttnParams {
   const int* cu_seqlens;  // [B+1] device int32, or nullptr -> every sequence has uniform_len tokens
   int uniform_len;
-  int nk_box;  // rows of the K/V TMA box: round_up(max_seqlen, 16) <= 256
-  int C;       // H * 64
+  int nk_box;     // rows of the K/V TMA box: round_up(max_seqlen, 16) <= 256
+  int C;          // H * 64
+  int H;
+  int num_units;  // num_seqs * H
   __half* out;
   int ldo;
   float scale_log2e;  // head_dim^-0.5 * log2(e)
+  int s_col[2];       // TMEM column of S for tile A / B
+  int o_col[2];       // TMEM column of O for tile A / B
+  int o_alias[2];     // 1: O lives inside the tile's own S region
+  long long* trace;   // debug only (DYT_ATTN_TRACE=1): clock64 timeline of CTA 0, else nullptr
 };
 
 constexpr int ATT_BM = 128;
 constexpr int ATT_D = 64;
-constexpr int ATT_TMEM_COLS = 256;
-constexpr int ATT_O_COL = 128;
+constexpr int ATT_THREADS = 384;
+constexpr int ATT_TMEM_COLS = 512;
+constexpr int ATT_Q_BYTES = 2 * ATT_BM * 128;  // both query tiles of a unit
+constexpr int ATT_TRACE_ITERS = 24, ATT_TRACE_EVENTS = 8, ATT_TRACE_ROLES = 4;
 
-__global__ void __launch_bounds__(192, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
-                const __grid_constant__ CUtensorMap tmap_kv, const AttnParams p) {
-  const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  int seq_start, seq_len;
+__device__ __forceinline__ void trace_ev(const AttnParams& p, int role, uint32_t iter, int ev) {
+  if (p.trace != nullptr && blockIdx.x == 0 && iter < ATT_TRACE_ITERS)
+    p.trace[(role * ATT_TRACE_ITERS + iter) * ATT_TRACE_EVENTS + ev] = clock64();
+}
+
+__device__ __forceinline__ void unit_span(const AttnParams& p, int unit, int& b, int& h,
+                                          int& seq_start, int& seq_len) {
+  b = unit / p.H;
+  h = unit - b * p.H;
   if (p.cu_seqlens != nullptr) {
-    seq_start = p.cu_seqlens[b];
-    seq_len = p.cu_seqlens[b + 1] - seq_start;
+    seq_start = __ldg(p.cu_seqlens + b);
+    seq_len = __ldg(p.cu_seqlens + b + 1) - seq_start;
   } else {
     seq_start = b * p.uniform_len;
     seq_len = p.uniform_len;
   }
   if (seq_len > p.nk_box) seq_len = p.nk_box;
-  if (t * ATT_BM >= seq_len) return;  // uniform for the whole CTA, before any barrier / TMEM use
-  const int nk = (seq_len + 15) & ~15;
+  if (seq_len < 0) seq_len = 0;
+}
 
+// pass 2 of one 32-column chunk: exponentials, row sum, packed fp16 P back to TMEM
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&r)[32], int c, int seq_len, float sl2,
+                                              float mb, float& sum, uint32_t p_addr) {
+  uint32_t pk[16];
+  const int c0 = c * 32;
+  if (c0 + 32 <= seq_len) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), sl2, -mb));
+      const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), sl2, -mb));
+      sum += e0 + e1;
+      pk[j] = pack_half2(e0, e1);
+    }
+  } else {
+    // tail chunk: the column index is uniform across the warp, so masked columns cost no MUFU
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float e0 = 0.f, e1 = 0.f;
+      if (c0 + 2 * j < seq_len) e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), sl2, -mb));
+      if (c0 + 2 * j + 1 < seq_len) e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), sl2, -mb));
+      sum += e0 + e1;
+      pk[j] = pack_half2(e0, e1);
+    }
+  }
+  tmem_st16(p_addr + c * 16, pk);
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                const __grid_constant__ CUtensorMap tmap_kv, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + ATT_BM * 128;
-  uint8_t* sV = sK + p.nk_box * 128;  // nk_box is a multiple of 16 -> 2 KB granularity keeps 1 KB alignment
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.nk_box * 128);
-  uint64_t* bar_qk = bars + 0;
-  uint64_t* bar_v = bars + 1;
-  uint64_t* bar_s = bars + 2;
-  uint64_t* bar_p = bars + 3;
-  uint64_t* bar_o = bars + 4;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 5);
+  const uint32_t kv_bytes = static_cast<uint32_t>(p.nk_box) * 128u;
+  const uint32_t stage_bytes = ATT_Q_BYTES + 2 * kv_bytes;  // multiple of 2 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+  uint64_t* full_qk = bars + 0;     // [2] TMA -> MMA
+  uint64_t* full_v = bars + 2;      // [2] TMA -> MMA
+  uint64_t* smem_empty = bars + 4;  // [2] MMA -> TMA
+  uint64_t* s_full = bars + 6;      // [2: tile] MMA -> softmax
+  uint64_t* p_full = bars + 8;      // [2: tile] softmax -> MMA
+  uint64_t* o_full = bars + 10;     // [2: tile] MMA -> softmax
+  uint64_t* o_free = bars + 12;     // [2: tile] softmax -> MMA (O read out)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // kernel parameters are not indexed dynamically (would force a local-memory copy)
+  auto s_col = [&](int tile) { return static_cast<uint32_t>(tile ? p.s_col[1] : p.s_col[0]); };
+  auto o_col = [&](int tile) { return static_cast<uint32_t>(tile ? p.o_col[1] : p.o_col[0]); };
+  auto o_alias = [&](int tile) { return (tile ? p.o_alias[1] : p.o_alias[0]) != 0; };
 
-  if (warp_idx == 5 && lane == 0) {
-    mbar_init(bar_qk, 1);
-    mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
-    mbar_init(bar_o, 1);
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full_qk[i], 1);
+      mbar_init(&full_v[i], 1);
+      mbar_init(&smem_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], 4);
+    }
     fence_mbar_init();
   }
-  if (warp_idx == 4) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tmap_q);
-      tma_prefetch_desc(&tmap_kv);
-    }
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv);
+  }
+  if (warp_idx == 2) {
     tmem_alloc(tmem_ptr_smem, ATT_TMEM_COLS);
     tmem_relinquish();
   }
@@ -90,118 +153,240 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp_idx == 4) {
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
     if (lane == 0) {
-      const uint32_t kv_bytes = static_cast<uint32_t>(p.nk_box) * 128u;
-      mbar_arrive_expect_tx(bar_qk, ATT_BM * 128 + kv_bytes);
-      tma_load_2d(sQ, &tmap_q, bar_qk, h * ATT_D, seq_start + t * ATT_BM);
-      tma_load_2d(sK, &tmap_kv, bar_qk, p.C + h * ATT_D, seq_start);
-      mbar_arrive_expect_tx(bar_v, kv_bytes);
-      tma_load_2d(sV, &tmap_kv, bar_v, 2 * p.C + h * ATT_D, seq_start);
+      int it = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        int b, h, seq_start, seq_len;
+        unit_span(p, unit, b, h, seq_start, seq_len);
+        if (seq_len == 0) continue;
+        const int s = it & 1;
+        mbar_wait(&smem_empty[s], ((it >> 1) & 1) ^ 1);
+        trace_ev(p, 3, it, 0);
+        uint8_t* sQ = smem + s * stage_bytes;
+        uint8_t* sK = sQ + ATT_Q_BYTES;
+        uint8_t* sV = sK + kv_bytes;
+        const bool has_b = seq_len > ATT_BM;
+        mbar_arrive_expect_tx(&full_qk[s], (has_b ? 2u : 1u) * ATT_BM * 128u + kv_bytes);
+        tma_load_2d(sQ, &tmap_q, &full_qk[s], h * ATT_D, seq_start);
+        tma_load_2d(sK, &tmap_kv, &full_qk[s], p.C + h * ATT_D, seq_start);
+        if (has_b) tma_load_2d(sQ + ATT_BM * 128, &tmap_q, &full_qk[s], h * ATT_D, seq_start + ATT_BM);
+        mbar_arrive_expect_tx(&full_v[s], kv_bytes);
+        tma_load_2d(sV, &tmap_kv, &full_v[s], 2 * p.C + h * ATT_D, seq_start);
+        ++it;
+      }
     }
-  } else if (warp_idx == 5) {
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (event loop over the two tile streams) ==============
+    // Each stream alternates S(u), PV(u), S(u'), PV(u'), ... over its units; whichever step has
+    // all its inputs ready is issued next, so the two softmax warpgroups drift out of phase and
+    // one of them is (almost) always in its exponentials.
     if (lane == 0) {
-      // ---- S = Q K^T ----
-      mbar_wait(bar_qk, 0);
-      tc_fence_after();
-      const uint32_t idesc_s = umma_idesc_f16(ATT_BM, nk, 0, 0);
-      const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
-      const uint64_t k_desc = umma_desc_sw128(smem_u32(sK));
-#pragma unroll
-      for (int k = 0; k < ATT_D / 16; ++k)
-        umma_ss_f16(tmem_base, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-      umma_commit(bar_s);
-      // ---- O = P V ----
-      mbar_wait(bar_v, 0);
-      mbar_wait(bar_p, 0);
-      tc_fence_after();
       const uint32_t idesc_o = umma_idesc_f16(ATT_BM, ATT_D, 0, 1);  // B = V is MN-major
-      const uint64_t v_desc = umma_desc_sw128(smem_u32(sV));
-      for (int kk = 0; kk < nk / 16; ++kk) {
-        // 16 keys per MMA: 8 TMEM columns of packed fp16 P; 16 V rows = 2048 B = +128 (16 B units)
-        umma_ts_f16(tmem_base + ATT_O_COL, tmem_base + kk * 8, v_desc + kk * 128, idesc_o,
-                    kk != 0 ? 1u : 0u);
-      }
-      umma_commit(bar_o);
-    }
-  } else {
-    // ===================== softmax + output (warps 0..3, TMEM lane quarter = warp_idx) ==========
-    const int q = warp_idx;
-    const int row = q * 32 + lane;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const int nchunks = (nk + 31) >> 5;
-    mbar_wait(bar_s, 0);
-    tc_fence_after();
-    float mx = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t r[32];
-      tmem_ld32(taddr + c * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float v = (c * 32 + j < seq_len) ? __uint_as_float(r[j]) : -INFINITY;
-        mx = fmaxf(mx, v);
-      }
-    }
-    const float sl2 = p.scale_log2e;
-    const float mb = mx * sl2;
-    float sum = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t r[32];
-      tmem_ld32(taddr + c * 32, r);
-      tmem_ld_wait();
-      uint32_t pk[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = c * 32 + 2 * j;
-        float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), sl2, -mb));
-        float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), sl2, -mb));
-        e0 = (col < seq_len) ? e0 : 0.f;
-        e1 = (col + 1 < seq_len) ? e1 : 0.f;
-        sum += e0 + e1;
-        pk[j] = pack_half2(e0, e1);
-      }
-      tmem_st16(taddr + c * 16, pk);
-    }
-    tmem_st_wait();
-    tc_fence_before();
-    mbar_arrive(bar_p);
+      struct Stream {
+        int unit;       // current unit (>= num_units: finished)
+        int it;         // index of `unit` among the CTA's non-empty units (-> smem stage, parity)
+        int seq_len;
+        uint32_t k;     // S/PV pairs completed so far (-> parities of p_full / o_free)
+        int pv_phase;   // 0: S of `unit` not issued yet; 1: S issued, PV pending
+      } st[2];
+      int pv_issued[2] = {0, 0};  // per smem stage: PVs issued for the unit occupying it
 
-    mbar_wait(bar_o, 0);
-    tc_fence_after();
-    uint32_t o0[32], o1[32];
-    tmem_ld32(taddr + ATT_O_COL, o0);
-    tmem_ld32(taddr + ATT_O_COL + 32, o1);
-    tmem_ld_wait();
-    const int qrow = t * ATT_BM + row;
-    if (qrow < seq_len) {
-      const float inv = 1.0f / sum;
-      uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(seq_start + qrow) * p.ldo +
-                                            h * ATT_D);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 v;
-        v.x = pack_half2(__uint_as_float(o0[8 * j + 0]) * inv, __uint_as_float(o0[8 * j + 1]) * inv);
-        v.y = pack_half2(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv);
-        v.z = pack_half2(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv);
-        v.w = pack_half2(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv);
-        dst[j] = v;
+      // advance a stream to its next unit that has this tile (it counts every non-empty unit)
+      auto advance = [&](int tile, Stream& sm, int from_unit, int from_it) {
+        int unit = from_unit, it = from_it, len = 0;
+        while (unit < p.num_units) {
+          int b, h, start;
+          unit_span(p, unit, b, h, start, len);
+          if (len > tile * ATT_BM) break;
+          if (len > 0) ++it;
+          unit += gridDim.x;
+        }
+        sm.unit = unit; sm.it = it; sm.seq_len = len; sm.pv_phase = 0;
+      };
+      for (int tile = 0; tile < 2; ++tile) {
+        st[tile].k = 0;
+        advance(tile, st[tile], blockIdx.x, 0);
       }
+      long long t_last = clock64();
+      while (st[0].unit < p.num_units || st[1].unit < p.num_units) {
+        bool progress = false;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 v;
-        v.x = pack_half2(__uint_as_float(o1[8 * j + 0]) * inv, __uint_as_float(o1[8 * j + 1]) * inv);
-        v.y = pack_half2(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv);
-        v.z = pack_half2(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv);
-        v.w = pack_half2(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv);
-        dst[4 + j] = v;
+        for (int tile = 0; tile < 2; ++tile) {
+          Stream& sm = st[tile];
+          if (sm.unit >= p.num_units) continue;
+          const int s = sm.it & 1;
+          const uint32_t ring_par = (sm.it >> 1) & 1;
+          const int nk = (sm.seq_len + 15) & ~15;
+          const uint32_t stage_addr = smem_u32(smem + s * stage_bytes);
+          if (sm.pv_phase == 0) {
+            // ---- S = Q K^T: needs Q/K in smem and the tile's S (and aliased O) region free ----
+            if (!mbar_test(&full_qk[s], ring_par)) continue;
+            if (o_alias(tile) && !mbar_test(&o_free[tile], (sm.k & 1) ^ 1)) continue;
+            tc_fence_after();
+            const uint32_t idesc_s = umma_idesc_f16(ATT_BM, nk, 0, 0);
+            const uint64_t q_desc = umma_desc_sw128(stage_addr + tile * ATT_BM * 128);
+            const uint64_t k_desc = umma_desc_sw128(stage_addr + ATT_Q_BYTES);
+#pragma unroll
+            for (int k = 0; k < ATT_D / 16; ++k)
+              umma_ss_f16(tmem_base + s_col(tile), q_desc + 2 * k, k_desc + 2 * k, idesc_s,
+                          k != 0 ? 1u : 0u);
+            umma_commit(&s_full[tile]);
+            trace_ev(p, 2, sm.k, tile * 2);
+            sm.pv_phase = 1;
+            progress = true;
+          } else {
+            // ---- O = P V: needs P from the softmax warps, V in smem, the O region read out ----
+            if (!mbar_test(&p_full[tile], sm.k & 1)) continue;
+            if (!mbar_test(&full_v[s], ring_par)) continue;
+            if (!o_alias(tile) && !mbar_test(&o_free[tile], (sm.k & 1) ^ 1)) continue;
+            tc_fence_after();
+            const uint64_t v_desc = umma_desc_sw128(stage_addr + ATT_Q_BYTES + kv_bytes);
+            for (int kk = 0; kk < nk / 16; ++kk) {
+              // 16 keys per MMA: 8 TMEM columns of packed fp16 P; 16 V rows = 2048 B = +128
+              umma_ts_f16(tmem_base + o_col(tile), tmem_base + s_col(tile) + kk * 8,
+                          v_desc + kk * 128, idesc_o, kk != 0 ? 1u : 0u);
+            }
+            umma_commit(&o_full[tile]);
+            trace_ev(p, 2, sm.k, tile * 2 + 1);
+            // the smem stage is free once every tile of the unit has had its PV issued
+            const int need = sm.seq_len > ATT_BM ? 2 : 1;
+            if (++pv_issued[s] == need) {
+              pv_issued[s] = 0;
+              umma_commit(&smem_empty[s]);
+            }
+            ++sm.k;
+            advance(tile, sm, sm.unit + gridDim.x, sm.it + 1);
+            progress = true;
+          }
+        }
+        if (progress) {
+          t_last = clock64();
+        } else if (clock64() - t_last > DYT_WAIT_TIMEOUT_CYCLES) {
+          printf("dyt: attention MMA event loop stalled (block %d)\n", (int)blockIdx.x);
+          __trap();
+        }
       }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================== softmax + output =====================
+    const int tile = (warp_idx - 4) >> 2;
+    const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_off + s_col(tile);
+    const uint32_t o_addr = tmem_base + lane_off + o_col(tile);
+    const float sl2 = p.scale_log2e;
+    uint32_t cnt = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int b, h, seq_start, seq_len;
+      unit_span(p, unit, b, h, seq_start, seq_len);
+      if (seq_len <= tile * ATT_BM) continue;  // this tile does not exist for the unit
+      const int qrow = tile * ATT_BM + row;
+      const bool active = tile * ATT_BM + q * 32 < seq_len;  // warp-uniform
+      const int nchunks = (seq_len + 31) >> 5;
+
+      mbar_wait(&s_full[tile], cnt & 1);
+      tc_fence_after();
+      if (q == 0 && lane == 0) trace_ev(p, tile, cnt, 0);
+      float sum = 0.f;
+      if (active) {
+        uint32_t ra[32], rb[32];
+        // ---- pass 1: row max ----
+        float mx = -INFINITY;
+        tmem_ld32(s_addr, ra);
+        tmem_ld_wait();
+        for (int c = 0; c < nchunks; c += 2) {
+          if (c + 1 < nchunks) tmem_ld32(s_addr + (c + 1) * 32, rb);
+          if (c * 32 + 32 <= seq_len) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(ra[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j < seq_len) mx = fmaxf(mx, __uint_as_float(ra[j]));
+          }
+          tmem_ld_wait();
+          if (c + 1 < nchunks) {
+            if (c + 2 < nchunks) tmem_ld32(s_addr + (c + 2) * 32, ra);
+            if (c * 32 + 64 <= seq_len) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(rb[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c * 32 + 32 + j < seq_len) mx = fmaxf(mx, __uint_as_float(rb[j]));
+            }
+            tmem_ld_wait();
+          }
+        }
+        if (q == 0 && lane == 0) trace_ev(p, tile, cnt, 1);
+        // ---- pass 2: exponentials, row sum, P -> TMEM ----
+        const float mb = mx * sl2;
+        tmem_ld32(s_addr, ra);
+        tmem_ld_wait();
+        for (int c = 0; c < nchunks; c += 2) {
+          if (c + 1 < nchunks) tmem_ld32(s_addr + (c + 1) * 32, rb);
+          softmax_chunk(ra, c, seq_len, sl2, mb, sum, s_addr);
+          tmem_ld_wait();
+          if (c + 1 < nchunks) {
+            if (c + 2 < nchunks) tmem_ld32(s_addr + (c + 2) * 32, ra);
+            softmax_chunk(rb, c + 1, seq_len, sl2, mb, sum, s_addr);
+            tmem_ld_wait();
+          }
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[tile]);
+      if (q == 0 && lane == 0) trace_ev(p, tile, cnt, 2);
+
+      mbar_wait(&o_full[tile], cnt & 1);
+      tc_fence_after();
+      if (q == 0 && lane == 0) trace_ev(p, tile, cnt, 3);
+      uint32_t o0[32], o1[32];
+      if (active) {
+        tmem_ld32(o_addr, o0);
+        tmem_ld32(o_addr + 32, o1);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[tile]);
+      if (q == 0 && lane == 0) trace_ev(p, tile, cnt, 4);
+      if (active && qrow < seq_len) {
+        const float inv = 1.0f / sum;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(seq_start + qrow) * p.ldo +
+                                              h * ATT_D);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 v;
+          v.x = pack_half2(__uint_as_float(o0[8 * j + 0]) * inv, __uint_as_float(o0[8 * j + 1]) * inv);
+          v.y = pack_half2(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv);
+          v.z = pack_half2(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv);
+          v.w = pack_half2(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv);
+          dst[j] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 v;
+          v.x = pack_half2(__uint_as_float(o1[8 * j + 0]) * inv, __uint_as_float(o1[8 * j + 1]) * inv);
+          v.y = pack_half2(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv);
+          v.z = pack_half2(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv);
+          v.w = pack_half2(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv);
+          dst[4 + j] = v;
+        }
+      }
+      if (q == 0 && lane == 0) trace_ev(p, tile, cnt, 5);
+      ++cnt;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp_idx == 4) {
+  if (warp_idx == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);
   }
@@ -238,18 +423,62 @@ int attn_varlen_fwd(const __half* qkv, int ld_qkv, const int* cu_seqlens, int nu
   p.uniform_len = uniform_len;
   p.nk_box = nk_box;
   p.C = C;
+  p.H = num_heads;
+  p.num_units = num_seqs * num_heads;
   p.out = out;
   p.ldo = ldo;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
-  const int smem_bytes = 1024 + ATT_BM * 128 + 2 * nk_box * 128 + 64;
+  // TMEM plan (512 columns).  The softmax reads S in 32-column chunks, so an S region is read up
+  // to round_up(nk, 32) columns: reads past nk only touch other live regions, never write them.
+  if (2 * nk_box + 2 * ATT_D <= ATT_TMEM_COLS) {
+    p.s_col[0] = 0; p.s_col[1] = nk_box;
+    p.o_col[0] = 2 * nk_box; p.o_col[1] = 2 * nk_box + ATT_D;
+    p.o_alias[0] = 0; p.o_alias[1] = 0;
+  } else if (2 * nk_box + ATT_D <= ATT_TMEM_COLS) {  // 192 < nk <= 224, e.g. 197 tokens
+    p.s_col[0] = 0; p.s_col[1] = nk_box;
+    p.o_col[0] = 2 * nk_box; p.o_col[1] = nk_box + 128;
+    p.o_alias[0] = 0; p.o_alias[1] = 1;
+  } else {
+    p.s_col[0] = 0; p.s_col[1] = 256;
+    p.o_col[0] = 128; p.o_col[1] = 256 + 128;
+    p.o_alias[0] = 1; p.o_alias[1] = 1;
+  }
+  const int smem_bytes = 1024 + 2 * (ATT_Q_BYTES + 2 * nk_box * 128) + 256;
   static int configured_smem = 0;
   if (smem_bytes > configured_smem) {
     DYT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   smem_bytes));
     configured_smem = smem_bytes;
   }
-  dim3 grid((max_seqlen + ATT_BM - 1) / ATT_BM, num_heads, num_seqs);
-  attn_fwd_kernel<<<grid, 192, smem_bytes, stream>>>(tq, tkv, p);
+  const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
+  p.trace = nullptr;
+  static const bool want_trace = getenv("DYT_ATTN_TRACE") != nullptr;
+  if (want_trace && p.num_units >= 8 * sm_count()) {
+    // debug: per-event clock64 timeline of CTA 0 (synchronises; never enabled in production)
+    const size_t n = ATT_TRACE_ROLES * ATT_TRACE_ITERS * ATT_TRACE_EVENTS;
+    long long* d = nullptr;
+    cudaMalloc(&d, n * sizeof(long long));
+    cudaMemsetAsync(d, 0, n * sizeof(long long), stream);
+    p.trace = d;
+    attn_fwd_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tq, tkv, p);
+    cudaStreamSynchronize(stream);
+    static long long h[ATT_TRACE_ROLES * ATT_TRACE_ITERS * ATT_TRACE_EVENTS];
+    cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    long long t0 = h[(2 * ATT_TRACE_ITERS) * ATT_TRACE_EVENTS];  // first S issue
+    const char* names[4] = {"wgA", "wgB", "mma", "tma"};
+    for (int r = 0; r < ATT_TRACE_ROLES; ++r)
+      for (int i = 0; i < ATT_TRACE_ITERS; ++i) {
+        fprintf(stderr, "trace %s it=%2d:", names[r], i);
+        for (int e = 0; e < ATT_TRACE_EVENTS; ++e) {
+          long long v = h[(r * ATT_TRACE_ITERS + i) * ATT_TRACE_EVENTS + e];
+          fprintf(stderr, " %8lld", v ? v - t0 : -1);
+        }
+        fprintf(stderr, "\n");
+      }
+    return cuda_status(cudaGetLastError(), "attn_fwd_kernel launch");
+  }
+  attn_fwd_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tq, tkv, p);
   return cuda_status(cudaGetLastError(), "attn_fwd_kernel launch");
 }
 

@@ -16,6 +16,7 @@
 namespace dyt {
 
 static inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+constexpr int kMaxBatch = 16384;  // fixes the size of the dispatcher's (always-zero) workspace slot
 
 struct BlockWorkspace {
   __half* xn;       // [T, C]   LN1(x)
@@ -47,6 +48,8 @@ static BlockWorkspace carve(const dyt_block_shape* s, void* base) {
     off += align256(bytes);
     return r;
   };
+  // first, so its address is the same for every shape sharing one workspace (it must stay zeroed)
+  w.dispatch_ws = take(dyt_dispatch_workspace_bytes(kMaxBatch));
   w.xn = static_cast<__half*>(take(T * C * 2));
   w.attn_o = static_cast<__half*>(take(T * C * 2));
   w.qkv = static_cast<__half*>(take(T * 3 * C * 2));
@@ -61,14 +64,13 @@ static BlockWorkspace carve(const dyt_block_shape* s, void* base) {
   w.token_pos = static_cast<int*>(take(T * 4));
   w.cu_seqlens = static_cast<int*>(take((static_cast<size_t>(s->B) + 1) * 4));
   w.n_kept = static_cast<int*>(take(256));
-  w.dispatch_ws = take(dyt_dispatch_workspace_bytes(s->B));
   w.total = off;
   return w;
 }
 
 static int check_shape(const dyt_block_shape* s) {
   DYT_CHECK_ARG(s != nullptr, "block: null shape");
-  DYT_CHECK_ARG(s->B >= 1 && s->N >= 2, "block: bad B=%d N=%d", s->B, s->N);
+  DYT_CHECK_ARG(s->B >= 1 && s->B <= kMaxBatch && s->N >= 2, "block: bad B=%d N=%d", s->B, s->N);
   DYT_CHECK_ARG(s->H >= 1 && s->C == s->H * 64, "block: C must be 64*H (C=%d H=%d)", s->C, s->H);
   DYT_CHECK_ARG(s->hidden % 8 == 0 && s->bottleneck % 8 == 0 && s->bottleneck >= 8,
                 "block: hidden/bottleneck must be multiples of 8");

@@ -48,24 +48,39 @@ struct DispatchParams {
   int* n_kept;          // [1]      out
   __half* packed;       // [B*N, ldp] out: LayerNorm2 of the kept rows, fp16
   int ldp;
-  int* counts;          // [B] workspace
-  unsigned int* sync;   // [2] workspace, zero before the first launch; the kernel leaves it zeroed
+  int* counts;          // [B] workspace (see dispatch_kernel)
+  unsigned int* sync;   // [2] workspace; zero before the first launch, left zeroed by the kernel
 };
 
 constexpr int DISPATCH_MAX_N = 2048;
+constexpr int DISPATCH_CHUNK = 16;  // rows per phase-2 work item
 
 __device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
 
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Work distribution: phase 1 strides warps over all B*N rows (consecutive warps read consecutive
+// rows); phase 2 strides warps over (image, 16-row chunk) items, each warp deriving the packed
+// base of its image from the per-image counts and its rank inside the image from the mask.
+// Workspace: sync[0] barrier arrivals, sync[1] finished CTAs, counts[B] kept tokens per image.
+// All of it must be zero at launch; the last CTA to finish zeroes it again, so a workspace that was
+// zero-filled once stays valid for every later launch, whatever its B.
 template <int NV>
 __global__ void __launch_bounds__(256)
 dispatch_kernel(const DispatchParams p) {
-  __shared__ int s_list[DISPATCH_MAX_N];
-  __shared__ int s_warp[8];
-  __shared__ int s_base;
-  __shared__ int s_count;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int N = p.N;
+  const int gw = blockIdx.x * 8 + warp;
+  const int nw = gridDim.x * 8;
+  const int T = p.B * N;
+
+  __shared__ int s_last;
+  int* cur = p.counts;
 
   // selector weight in registers, laid out like a row
   float4 w[NV];
@@ -80,68 +95,60 @@ dispatch_kernel(const DispatchParams p) {
   }
 
   // ------------------------------- phase 1: score + gate -------------------------------
-  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-    int my_count = 0;
-    for (int n = warp; n < N; n += 8) {
-      const size_t t = static_cast<size_t>(b) * N + n;
-      if (n == 0) {
-        if (lane == 0) {
-          p.mask[t] = 1.0f;
-          if (p.gate_out != nullptr) p.gate_out[t] = 1.0f;
-        }
-        my_count += 1;
-        continue;
-      }
-      float4 v[NV];
-      load_row_f32<NV>(p.x1 + t * p.ldx, lane, v);
-      float acc = 0.f;
-      if (p.logit_fp16) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          acc = fmaf(r16(v[i].x), w[i].x, acc);
-          acc = fmaf(r16(v[i].y), w[i].y, acc);
-          acc = fmaf(r16(v[i].z), w[i].z, acc);
-          acc = fmaf(r16(v[i].w), w[i].w, acc);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          acc = fmaf(v[i].x, w[i].x, acc);
-          acc = fmaf(v[i].y, w[i].y, acc);
-          acc = fmaf(v[i].z, w[i].z, acc);
-          acc = fmaf(v[i].w, w[i].w, acc);
-        }
-      }
-      acc = warp_sum(acc);
-      float logit = acc + bias;
-      if (p.logit_fp16) logit = r16(logit);
-      float g = logit;
-      const size_t li = static_cast<size_t>(b) * (N - 1) + (n - 1);
-      if (p.noise1 != nullptr) {
-        // (logits + g1 - g2) / tau, every op rounded in the logit dtype (dynamic_adapter.py:41)
-        if (p.logit_fp16) {
-          g = r16(g + r16(p.noise1[li]));
-          g = r16(g - r16(p.noise2[li]));
-          g = r16(g / r16(p.tau));
-        } else {
-          g = ((g + p.noise1[li]) - p.noise2[li]) / p.tau;
-        }
-      }
-      bool keep = g >= p.min_kept;  // NaN -> dropped, +inf -> kept
-      if (lane == 0 && p.gate_out != nullptr) p.gate_out[t] = keep ? 1.0f : 0.0f;
-      if (p.forced_mask != nullptr) keep = p.forced_mask[t] != 0.0f;
+  for (int t = gw; t < T; t += nw) {
+    const int b = t / N;
+    const int n = t - b * N;
+    if (n == 0) {
       if (lane == 0) {
-        p.logits[li] = logit;
-        p.mask[t] = keep ? 1.0f : 0.0f;
+        p.mask[t] = 1.0f;
+        if (p.gate_out != nullptr) p.gate_out[t] = 1.0f;
+        atomicAdd(cur + b, 1);
       }
-      my_count += keep ? 1 : 0;
+      continue;
     }
-    if (lane == 0) atomicAdd(&s_count, my_count);
-    __syncthreads();
-    if (threadIdx.x == 0) p.counts[b] = s_count;
-    __syncthreads();
+    float4 v[NV];
+    load_row_f32<NV>(p.x1 + static_cast<size_t>(t) * p.ldx, lane, v);
+    float acc = 0.f;
+    if (p.logit_fp16) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        acc = fmaf(r16(v[i].x), w[i].x, acc);
+        acc = fmaf(r16(v[i].y), w[i].y, acc);
+        acc = fmaf(r16(v[i].z), w[i].z, acc);
+        acc = fmaf(r16(v[i].w), w[i].w, acc);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        acc = fmaf(v[i].x, w[i].x, acc);
+        acc = fmaf(v[i].y, w[i].y, acc);
+        acc = fmaf(v[i].z, w[i].z, acc);
+        acc = fmaf(v[i].w, w[i].w, acc);
+      }
+    }
+    acc = warp_sum(acc);
+    float logit = acc + bias;
+    if (p.logit_fp16) logit = r16(logit);
+    float g = logit;
+    const size_t li = static_cast<size_t>(b) * (N - 1) + (n - 1);
+    if (p.noise1 != nullptr) {
+      // (logits + g1 - g2) / tau, every op rounded in the logit dtype (dynamic_adapter.py:41)
+      if (p.logit_fp16) {
+        g = r16(g + r16(p.noise1[li]));
+        g = r16(g - r16(p.noise2[li]));
+        g = r16(g / r16(p.tau));
+      } else {
+        g = ((g + p.noise1[li]) - p.noise2[li]) / p.tau;
+      }
+    }
+    bool keep = g >= p.min_kept;  // NaN -> dropped, +inf -> kept
+    if (lane == 0 && p.gate_out != nullptr) p.gate_out[t] = keep ? 1.0f : 0.0f;
+    if (p.forced_mask != nullptr) keep = p.forced_mask[t] != 0.0f;
+    if (lane == 0) {
+      p.logits[li] = logit;
+      p.mask[t] = keep ? 1.0f : 0.0f;
+      if (keep) atomicAdd(cur + b, 1);
+    }
   }
 
   // ------------------------------- grid barrier -------------------------------
@@ -162,79 +169,75 @@ dispatch_kernel(const DispatchParams p) {
   __syncthreads();
 
   // ------------------------------- phase 2: compact + pack -------------------------------
-  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-    // exclusive base = sum of counts[0..b)
+  const int cpi = (N + DISPATCH_CHUNK - 1) / DISPATCH_CHUNK;  // chunks per image
+  const int items = p.B * cpi;
+  for (int item = gw; item < items; item += nw) {
+    const int b = item / cpi;
+    const int n0 = (item - b * cpi) * DISPATCH_CHUNK;
+    // packed base of the image = kept tokens of all previous images
     int part = 0;
-    for (int i = threadIdx.x; i < b; i += blockDim.x) part += __ldcg(p.counts + i);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) s_warp[warp] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int s = 0;
-      for (int i = 0; i < 8; ++i) s += s_warp[i];
-      s_base = s;
+    for (int i = lane; i < b; i += 32) part += __ldcg(cur + i);
+    const int base = warp_sum_int(part);
+    // kept tokens of this image before the chunk
+    const float* mrow = p.mask + static_cast<size_t>(b) * N;
+    int before = 0;
+    for (int i0 = 0; i0 < n0; i0 += 32) {
+      const int n = i0 + lane;
+      const bool k = (n < n0) && (__ldcg(mrow + n) != 0.0f);
+      before += __popc(__ballot_sync(0xffffffffu, k));
     }
-    __syncthreads();
-    const int base = s_base;
-    int running = 0;  // kept tokens of this image before the current 256-token chunk
-    for (int c0 = 0; c0 < N; c0 += 256) {
-      const int n = c0 + threadIdx.x;
+    const int n = n0 + lane;
+    const bool valid = lane < DISPATCH_CHUNK && n < N;
+    const bool keep = valid && (__ldcg(mrow + n) != 0.0f);
+    unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    const int rank = __popc(ballot & ((1u << lane) - 1u));
+    const int first = base + before;
+    if (valid) {
       const size_t t = static_cast<size_t>(b) * N + n;
-      const bool keep = (n < N) && (p.mask[t] != 0.0f);
-      const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-      const int rank = __popc(ballot & ((1u << lane) - 1u));
-      __syncthreads();  // previous use of s_warp is complete
-      if (lane == 0) s_warp[warp] = __popc(ballot);
-      __syncthreads();
-      int before = 0, total = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = s_warp[i];
-        before += (i < warp) ? c : 0;
-        total += c;
+      if (keep) {
+        p.packed_idx[first + rank] = static_cast<int>(t);
+        p.token_pos[t] = first + rank;
+      } else {
+        p.token_pos[t] = -1;
       }
-      if (n < N) {
-        if (keep) {
-          const int j = running + before + rank;
-          s_list[j] = n;
-          p.packed_idx[base + j] = static_cast<int>(t);
-          p.token_pos[t] = base + j;
-        } else {
-          p.token_pos[t] = -1;
-        }
-      }
-      running += total;
     }
-    __syncthreads();
-    const int count = running;
-    if (threadIdx.x == 0) {
+    if (n0 == 0 && lane == 0) {
       p.cu_seqlens[b] = base;
       if (b == p.B - 1) {
-        p.cu_seqlens[p.B] = base + count;
-        p.n_kept[0] = base + count;
+        const int total = base + __ldcg(cur + b);
+        p.cu_seqlens[p.B] = total;
+        p.n_kept[0] = total;
       }
     }
     if (p.packed != nullptr) {
-      for (int j = warp; j < count; j += 8) {
-        const int n = s_list[j];
+      int j = first;
+      while (ballot != 0u) {
+        const int l = __ffs(ballot) - 1;
+        ballot &= ballot - 1u;
         float4 v[NV];
-        load_row_f32<NV>(p.x1 + (static_cast<size_t>(b) * N + n) * p.ldx, lane, v);
+        load_row_f32<NV>(p.x1 + (static_cast<size_t>(b) * N + n0 + l) * p.ldx, lane, v);
         row_layernorm<NV>(v, p.ln_w, p.ln_b, p.eps, lane);
-        store_row_f16<NV>(p.packed + static_cast<size_t>(base + j) * p.ldp, lane, v);
+        store_row_f16<NV>(p.packed + static_cast<size_t>(j) * p.ldp, lane, v);
+        ++j;
       }
     }
-    __syncthreads();
   }
 
-  // leave the barrier words zeroed for the next launch
+  // last CTA out: leave the workspace zeroed for the next launch
+  __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     const unsigned prev = atomicAdd(&p.sync[1], 1u);
-    if (prev == gridDim.x - 1) {
+    s_last = (prev == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    for (int i = threadIdx.x; i < p.B; i += blockDim.x) cur[i] = 0;
+    if (threadIdx.x == 0) {
       p.sync[0] = 0u;
       p.sync[1] = 0u;
-      __threadfence();
     }
+    __threadfence();
   }
 }
 
@@ -246,9 +249,10 @@ static int launch_dispatch(const DispatchParams& p, cudaStream_t stream) {
     DYT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dispatch_kernel<NV>, 256, 0));
     if (per_sm < 1) return fail(DYT_EDRIVER, "dispatch kernel does not fit on an SM");
     if (per_sm > 4) per_sm = 4;
-    max_blocks = per_sm * sm_count();
+    max_blocks = per_sm * sm_count();  // all CTAs co-resident: required by the grid barrier
   }
-  int grid = p.B < max_blocks ? p.B : max_blocks;
+  const int want = (p.B * p.N + 7) / 8;
+  const int grid = want < max_blocks ? want : max_blocks;
   dispatch_kernel<NV><<<grid, 256, 0, stream>>>(p);
   return cuda_status(cudaGetLastError(), "dispatch_kernel launch");
 }
