@@ -2,21 +2,24 @@
 //
 // Persistent kernel, one CTA per SM, work unit = (sequence, head); sequences of up to 256 keys
 // (one KV tile, so no online-softmax rescaling), i.e. up to two 128-query tiles A and B per unit.
-//   warp 0      TMA producer: Q (two 128-row boxes), K, V of the next unit into a 2-stage smem ring
-//   warp 1      tcgen05.mma issuer (one thread):
-//                 S = Q K^T : A = Q tile, B = K tile (both 128B-swizzled K-major smem), fp32
-//                             accumulator in TMEM
-//                 O = P V   : A = P from TMEM (packed fp16 aliasing the first half of S),
-//                             B = V tile (128B-swizzled MN-major smem)
-//               The two tiles are independent streams S(u), PV(u), S(u'), ...; the issuer polls
-//               the barriers of both and issues whichever step is ready, so the two softmax
-//               warpgroups drift out of phase and the MUFU pipe (the real bound of d=64
-//               attention: 8 cycles per warp-wide ex2) stays busy.
-//   warp 2      TMEM allocator (512 columns)
-//   warps 4-7   softmax warpgroup of tile A, warps 8-11 of tile B: one thread per query row (TMEM
-//               lane); pass 1 row max, pass 2 exp2 + fp32 row sum, P written back to TMEM as fp16;
-//               then O read back, normalised by the row sum, rounded once to fp16 and stored as
-//               [T, H*64].  Warps whose 32 rows are all past the sequence end skip the math.
+//   warp 0       TMA producer: Q (two 128-row boxes), K, V of the next unit into a 2-stage smem ring
+//   warp 1       tcgen05.mma issuer (one thread), fixed order with blocking barrier waits:
+//                  S = Q K^T : A = Q tile, B = K tile (both 128B-swizzled K-major smem), fp32
+//                              accumulator in TMEM
+//                  O = P V   : A = P from TMEM (packed fp16 aliasing the first half of S),
+//                              B = V tile (128B-swizzled MN-major smem); issued in two parts, the
+//                              first 128 keys as soon as the softmax has produced them
+//                S_A(u0) S_B(u0) | PV_A(u) S_A(u+1) PV_B(u) S_B(u+1) | ...
+//   warp 2       TMEM allocator (512 columns)
+//   warps 4-7    softmax warpgroup of tile A, warps 8-11 of tile B: one thread per query row (TMEM
+//                lane); pass 1 row max (three TMEM loads in flight), pass 2 exp2 + fp32 row sum, P
+//                written back to TMEM as fp16, 1/rowsum handed to the output warps through smem.
+//                The softmax warps never wait for the PV product: they go straight to the next S.
+//   warps 12-15  output warpgroup: O read back from TMEM, normalised, rounded once to fp16,
+//                transposed through smem and stored as full 128-byte rows of [T, H*64].
+// Measured on B200 (scripts/ubench/tmem_mufu.cu): MUFU.EX2 8 clk per warp instruction per SM
+// sub-partition, tcgen05.ld x32 ~180 clk latency, a TMEM-sourced 128x64x16 MMA ~85 clk: the kernel
+// is bound by the ex2 pipe (~3300 clk per unit per sub-partition at N = 197) and by the PV MMAs.
 // TMEM columns: S_A at 0, S_B at nk; O_A / O_B live outside the S regions when they fit
 // (2*nk + 128 <= 512), otherwise inside their own S region at +128 (free once P is complete), in
 // which case the next S of that tile has to wait for the O read-out.
@@ -51,10 +54,13 @@ struct AttnParams {
 
 constexpr int ATT_BM = 128;
 constexpr int ATT_D = 64;
-constexpr int ATT_THREADS = 384;
+constexpr int ATT_THREADS = 512;
 constexpr int ATT_TMEM_COLS = 512;
 constexpr int ATT_Q_BYTES = 2 * ATT_BM * 128;  // both query tiles of a unit
-constexpr int ATT_TRACE_ITERS = 24, ATT_TRACE_EVENTS = 8, ATT_TRACE_ROLES = 4;
+constexpr int ATT_OSTAGE_BYTES = 4 * 32 * 128;  // per-output-warp transpose slabs
+constexpr int ATT_INV_BYTES = 2 * 2 * ATT_BM * 4;  // 1/rowsum: [unit parity][tile][row]
+constexpr int ATT_SPLIT_KEYS = 128;  // keys covered by the early first part of the PV product
+constexpr int ATT_TRACE_ITERS = 24, ATT_TRACE_EVENTS = 8, ATT_TRACE_ROLES = 6;
 
 __device__ __forceinline__ void trace_ev(const AttnParams& p, int role, uint32_t iter, int ev) {
   if (p.trace != nullptr && blockIdx.x == 0 && iter < ATT_TRACE_ITERS)
@@ -76,31 +82,46 @@ __device__ __forceinline__ void unit_span(const AttnParams& p, int unit, int& b,
   if (seq_len < 0) seq_len = 0;
 }
 
-// pass 2 of one 32-column chunk: exponentials, row sum, packed fp16 P back to TMEM
-__device__ __forceinline__ void softmax_chunk(const uint32_t (&r)[32], int c, int seq_len, float sl2,
-                                              float mb, float& sum, uint32_t p_addr) {
+// ---- softmax building blocks.  A row (one thread) walks its keys in full 32-key chunks (no
+// masking at all) and then in at most two 16-key tail pieces whose out-of-sequence keys are set to
+// -inf first, so there is one copy of the arithmetic and the loops stay inside the instruction cache.
+__device__ __forceinline__ void max32(const uint32_t (&r)[32], float (&mx)[4]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(r[j]));
+}
+__device__ __forceinline__ void mask16(uint32_t (&r)[16], int k0, int seq_len) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (k0 + j >= seq_len) r[j] = 0xff800000u;  // -inf: ignored by max, exp2 -> +0
+}
+// exponentials of one chunk (back-to-back MUFU), row-sum partials (four chains), fp16 P -> TMEM
+__device__ __forceinline__ void exp32(uint32_t (&r)[32], float sl2, float mb, float (&sum)[4],
+                                      uint32_t p_addr) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    r[j] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(r[j]), sl2, -mb)));
   uint32_t pk[16];
-  const int c0 = c * 32;
-  if (c0 + 32 <= seq_len) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), sl2, -mb));
-      const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), sl2, -mb));
-      sum += e0 + e1;
-      pk[j] = pack_half2(e0, e1);
-    }
-  } else {
-    // tail chunk: the column index is uniform across the warp, so masked columns cost no MUFU
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float e0 = 0.f, e1 = 0.f;
-      if (c0 + 2 * j < seq_len) e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), sl2, -mb));
-      if (c0 + 2 * j + 1 < seq_len) e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), sl2, -mb));
-      sum += e0 + e1;
-      pk[j] = pack_half2(e0, e1);
-    }
+  for (int j = 0; j < 16; ++j) {
+    const float e0 = __uint_as_float(r[2 * j]), e1 = __uint_as_float(r[2 * j + 1]);
+    sum[j & 3] += e0 + e1;
+    pk[j] = pack_half2(e0, e1);
   }
-  tmem_st16(p_addr + c * 16, pk);
+  tmem_st16(p_addr, pk);
+}
+__device__ __forceinline__ void exp16(uint32_t (&r)[16], float sl2, float mb, float (&sum)[4],
+                                      uint32_t p_addr) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    r[j] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(r[j]), sl2, -mb)));
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float e0 = __uint_as_float(r[2 * j]), e1 = __uint_as_float(r[2 * j + 1]);
+    sum[j & 3] += e0 + e1;
+    pk[j] = pack_half2(e0, e1);
+  }
+  tmem_st8(p_addr, pk);
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -111,15 +132,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                              ~static_cast<uintptr_t>(1023));
   const uint32_t kv_bytes = static_cast<uint32_t>(p.nk_box) * 128u;
   const uint32_t stage_bytes = ATT_Q_BYTES + 2 * kv_bytes;  // multiple of 2 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+  uint8_t* o_stage = smem + 2 * stage_bytes;                // 4 warps x 32 rows x 128 B
+  const uint32_t inv_addr = smem_u32(o_stage + ATT_OSTAGE_BYTES);  // float [2][2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(o_stage + ATT_OSTAGE_BYTES + ATT_INV_BYTES);
   uint64_t* full_qk = bars + 0;     // [2] TMA -> MMA
   uint64_t* full_v = bars + 2;      // [2] TMA -> MMA
-  uint64_t* smem_empty = bars + 4;  // [2] MMA -> TMA
+  uint64_t* qk_empty = bars + 4;    // [2] MMA -> TMA: both tiles' S MMAs have read Q / K
   uint64_t* s_full = bars + 6;      // [2: tile] MMA -> softmax
-  uint64_t* p_full = bars + 8;      // [2: tile] softmax -> MMA
-  uint64_t* o_full = bars + 10;     // [2: tile] MMA -> softmax
-  uint64_t* o_free = bars + 12;     // [2: tile] softmax -> MMA (O read out)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* p_half = bars + 8;      // [2: tile] softmax -> MMA (first ATT_SPLIT_KEYS keys of P)
+  uint64_t* p_full = bars + 10;     // [2: tile] softmax -> MMA (all of P)
+  uint64_t* o_full = bars + 12;     // [2: tile] MMA -> output warps
+  uint64_t* o_free = bars + 14;     // [2: tile] output warps -> MMA (O read out)
+  uint64_t* v_empty = bars + 16;    // [2] MMA -> TMA: both tiles' PV MMAs have read V
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -132,8 +157,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int i = 0; i < 2; ++i) {
       mbar_init(&full_qk[i], 1);
       mbar_init(&full_v[i], 1);
-      mbar_init(&smem_empty[i], 1);
+      mbar_init(&qk_empty[i], 2);  // one arrival per tile stream
+      mbar_init(&v_empty[i], 2);
       mbar_init(&s_full[i], 1);
+      mbar_init(&p_half[i], 4);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
       mbar_init(&o_free[i], 4);
@@ -153,8 +180,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // register budget per warpgroup (512 threads start at 128 each): control 56, softmax 168,
+  // output 96 -> 128 * (56 + 2 * 168 + 96) = 62464 <= 65536
+
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
+    reg_dealloc<56>();
     if (lane == 0) {
       int it = 0;
       for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
@@ -162,8 +193,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
         unit_span(p, unit, b, h, seq_start, seq_len);
         if (seq_len == 0) continue;
         const int s = it & 1;
-        mbar_wait(&smem_empty[s], ((it >> 1) & 1) ^ 1);
-        trace_ev(p, 3, it, 0);
+        mbar_wait(&qk_empty[s], ((it >> 1) & 1) ^ 1);
+        trace_ev(p, 4, it, 0);
         uint8_t* sQ = smem + s * stage_bytes;
         uint8_t* sK = sQ + ATT_Q_BYTES;
         uint8_t* sV = sK + kv_bytes;
@@ -172,215 +203,282 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tma_load_2d(sQ, &tmap_q, &full_qk[s], h * ATT_D, seq_start);
         tma_load_2d(sK, &tmap_kv, &full_qk[s], p.C + h * ATT_D, seq_start);
         if (has_b) tma_load_2d(sQ + ATT_BM * 128, &tmap_q, &full_qk[s], h * ATT_D, seq_start + ATT_BM);
+        mbar_wait(&v_empty[s], ((it >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&full_v[s], kv_bytes);
         tma_load_2d(sV, &tmap_kv, &full_v[s], 2 * p.C + h * ATT_D, seq_start);
         ++it;
       }
     }
-  } else if (warp_idx == 1) {
-    // ===================== MMA issuer (event loop over the two tile streams) ==============
-    // Each stream alternates S(u), PV(u), S(u'), PV(u'), ... over its units; whichever step has
-    // all its inputs ready is issued next, so the two softmax warpgroups drift out of phase and
-    // one of them is (almost) always in its exponentials.
-    if (lane == 0) {
+  } else if (warp_idx == 1 || warp_idx == 3) {
+    // ===================== MMA issuers: warp 1 drives tile A, warp 3 tile B =====================
+    // Each tile is an independent stream S(u) -> [softmax] -> PV(u) -> S(u') ... with its own TMEM
+    // regions; tcgen05.commit tracks the issuing thread's MMAs only, so the two streams never wait
+    // for each other and the two softmax warpgroups drift out of phase: one is in its exponentials
+    // (MUFU) while the other waits for its PV / next S.  Q/K and V of a smem stage are released
+    // separately, each once both streams are done with it (two arrivals per barrier).
+    reg_dealloc<56>();
+    {
+      // The whole warp runs this loop with warp-uniform values (descriptors and addresses live in
+      // uniform registers); one elected lane issues the MMAs.  Issuing from inside an
+      // `if (lane == 0)` region instead costs ~100 clk of scalar code per MMA -- more than a
+      // 128x64x16 MMA itself takes.
+      const int tile = warp_idx == 3 ? 1 : 0;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc_o = umma_idesc_f16(ATT_BM, ATT_D, 0, 1);  // B = V is MN-major
-      struct Stream {
-        int unit;       // current unit (>= num_units: finished)
-        int it;         // index of `unit` among the CTA's non-empty units (-> smem stage, parity)
-        int seq_len;
-        uint32_t k;     // S/PV pairs completed so far (-> parities of p_full / o_free)
-        int pv_phase;   // 0: S of `unit` not issued yet; 1: S issued, PV pending
-      } st[2];
-      int pv_issued[2] = {0, 0};  // per smem stage: PVs issued for the unit occupying it
-
-      // advance a stream to its next unit that has this tile (it counts every non-empty unit)
-      auto advance = [&](int tile, Stream& sm, int from_unit, int from_it) {
-        int unit = from_unit, it = from_it, len = 0;
-        while (unit < p.num_units) {
-          int b, h, start;
-          unit_span(p, unit, b, h, start, len);
-          if (len > tile * ATT_BM) break;
-          if (len > 0) ++it;
-          unit += gridDim.x;
-        }
-        sm.unit = unit; sm.it = it; sm.seq_len = len; sm.pv_phase = 0;
-      };
-      for (int tile = 0; tile < 2; ++tile) {
-        st[tile].k = 0;
-        advance(tile, st[tile], blockIdx.x, 0);
-      }
-      long long t_last = clock64();
-      while (st[0].unit < p.num_units || st[1].unit < p.num_units) {
-        bool progress = false;
-#pragma unroll
-        for (int tile = 0; tile < 2; ++tile) {
-          Stream& sm = st[tile];
-          if (sm.unit >= p.num_units) continue;
-          const int s = sm.it & 1;
-          const uint32_t ring_par = (sm.it >> 1) & 1;
-          const int nk = (sm.seq_len + 15) & ~15;
-          const uint32_t stage_addr = smem_u32(smem + s * stage_bytes);
-          if (sm.pv_phase == 0) {
-            // ---- S = Q K^T: needs Q/K in smem and the tile's S (and aliased O) region free ----
-            if (!mbar_test(&full_qk[s], ring_par)) continue;
-            if (o_alias(tile) && !mbar_test(&o_free[tile], (sm.k & 1) ^ 1)) continue;
-            tc_fence_after();
-            const uint32_t idesc_s = umma_idesc_f16(ATT_BM, nk, 0, 0);
-            const uint64_t q_desc = umma_desc_sw128(stage_addr + tile * ATT_BM * 128);
-            const uint64_t k_desc = umma_desc_sw128(stage_addr + ATT_Q_BYTES);
-#pragma unroll
-            for (int k = 0; k < ATT_D / 16; ++k)
-              umma_ss_f16(tmem_base + s_col(tile), q_desc + 2 * k, k_desc + 2 * k, idesc_s,
-                          k != 0 ? 1u : 0u);
-            umma_commit(&s_full[tile]);
-            trace_ev(p, 2, sm.k, tile * 2);
-            sm.pv_phase = 1;
-            progress = true;
-          } else {
-            // ---- O = P V: needs P from the softmax warps, V in smem, the O region read out ----
-            if (!mbar_test(&p_full[tile], sm.k & 1)) continue;
-            if (!mbar_test(&full_v[s], ring_par)) continue;
-            if (!o_alias(tile) && !mbar_test(&o_free[tile], (sm.k & 1) ^ 1)) continue;
-            tc_fence_after();
-            const uint64_t v_desc = umma_desc_sw128(stage_addr + ATT_Q_BYTES + kv_bytes);
-            for (int kk = 0; kk < nk / 16; ++kk) {
-              // 16 keys per MMA: 8 TMEM columns of packed fp16 P; 16 V rows = 2048 B = +128
-              umma_ts_f16(tmem_base + o_col(tile), tmem_base + s_col(tile) + kk * 8,
-                          v_desc + kk * 128, idesc_o, kk != 0 ? 1u : 0u);
-            }
-            umma_commit(&o_full[tile]);
-            trace_ev(p, 2, sm.k, tile * 2 + 1);
-            // the smem stage is free once every tile of the unit has had its PV issued
-            const int need = sm.seq_len > ATT_BM ? 2 : 1;
-            if (++pv_issued[s] == need) {
-              pv_issued[s] = 0;
-              umma_commit(&smem_empty[s]);
-            }
-            ++sm.k;
-            advance(tile, sm, sm.unit + gridDim.x, sm.it + 1);
-            progress = true;
+      const uint32_t d_tmem = tmem_u + o_col(tile);
+      const uint32_t a_tmem = tmem_u + s_col(tile);
+      const bool alias = o_alias(tile);
+      const uint32_t smem_base_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      uint32_t k = 0;  // tile-units completed so far (-> barrier parities)
+      int it = 0;      // index among the CTA's non-empty units (-> smem stage, ring parity)
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        int b, h, seq_start, seq_len;
+        unit_span(p, unit, b, h, seq_start, seq_len);
+        seq_len = __shfl_sync(0xffffffffu, seq_len, 0);
+        if (seq_len == 0) continue;
+        const int s = it & 1;
+        const uint32_t ring_par = (it >> 1) & 1;
+        ++it;
+        mbar_wait(&full_qk[s], ring_par);
+        if (seq_len <= tile * ATT_BM) {  // no such tile in this unit: only the stage accounting
+          if (elect_one()) {
+            mbar_arrive(&qk_empty[s]);
+            mbar_arrive(&v_empty[s]);
           }
+          __syncwarp();
+          continue;
         }
-        if (progress) {
-          t_last = clock64();
-        } else if (clock64() - t_last > DYT_WAIT_TIMEOUT_CYCLES) {
-          printf("dyt: attention MMA event loop stalled (block %d)\n", (int)blockIdx.x);
-          __trap();
+        const int nk = (seq_len + 15) & ~15;
+        const int steps = nk / 16;  // PV: 16 keys per MMA
+        // first part of PV as soon as the first ATT_SPLIT_KEYS keys of P exist -- not when O lives
+        // inside this tile's S region, which is still being read as S until P is complete
+        const int early = (!alias && (seq_len >> 5) >= ATT_SPLIT_KEYS / 32) ? ATT_SPLIT_KEYS / 16 : 0;
+        const uint32_t stage_addr = smem_base_u + s * stage_bytes;
+        // ---- S = Q K^T ----
+        if (alias) mbar_wait(&o_free[tile], (k & 1) ^ 1);  // O(k-1) sits inside this S region
+        tc_fence_after();
+        {
+          const uint32_t idesc_s = umma_idesc_f16(ATT_BM, nk, 0, 0);
+          const uint64_t q_desc = umma_desc_sw128(stage_addr + tile * ATT_BM * 128);
+          const uint64_t k_desc = umma_desc_sw128(stage_addr + ATT_Q_BYTES);
+          if (elect_one()) {
+#pragma unroll
+            for (int k16 = 0; k16 < ATT_D / 16; ++k16)
+              umma_ss_f16(a_tmem, q_desc + 2 * k16, k_desc + 2 * k16, idesc_s, k16 != 0 ? 1u : 0u);
+            umma_commit(&s_full[tile]);
+            umma_commit(&qk_empty[s]);  // Q / K of this stage are free once both tiles' S retire
+          }
+          __syncwarp();
         }
+        if (lane == 0) trace_ev(p, 2 + tile, k, 0);
+        // ---- O = P V ----  (16 keys per MMA: 8 TMEM columns of packed fp16 P; 16 V rows = +128)
+        const uint64_t v_desc = umma_desc_sw128(stage_addr + ATT_Q_BYTES + kv_bytes);
+        mbar_wait(&p_half[tile], k & 1);
+        if (lane == 0) trace_ev(p, 2 + tile, k, 1);
+        mbar_wait(&full_v[s], ring_par);
+        if (!alias) mbar_wait(&o_free[tile], (k & 1) ^ 1);  // O(k-1) read out
+        tc_fence_after();
+        if (elect_one()) {
+          for (int kk = 0; kk < early; ++kk)
+            umma_ts_f16(d_tmem, a_tmem + kk * 8, v_desc + kk * 128, idesc_o, kk != 0 ? 1u : 0u);
+        }
+        __syncwarp();
+        if (lane == 0) trace_ev(p, 2 + tile, k, 2);
+        mbar_wait(&p_full[tile], k & 1);
+        tc_fence_after();
+        if (lane == 0) trace_ev(p, 2 + tile, k, 3);
+        if (elect_one()) {
+          for (int kk = early; kk < steps; ++kk)
+            umma_ts_f16(d_tmem, a_tmem + kk * 8, v_desc + kk * 128, idesc_o, kk != 0 ? 1u : 0u);
+          umma_commit(&o_full[tile]);
+          umma_commit(&v_empty[s]);  // V of this stage is free once both tiles' PV retire
+        }
+        __syncwarp();
+        if (lane == 0) trace_ev(p, 2 + tile, k, 4);
+        ++k;
       }
     }
-  } else if (warp_idx >= 4) {
-    // ===================== softmax + output =====================
+  } else if (warp_idx == 2) {
+    reg_dealloc<56>();
+  } else if (warp_idx < 12) {
+    // ===================== softmax =====================
+    reg_alloc<168>();
     const int tile = (warp_idx - 4) >> 2;
     const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_off + s_col(tile);
-    const uint32_t o_addr = tmem_base + lane_off + o_col(tile);
     const float sl2 = p.scale_log2e;
     uint32_t cnt = 0;
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
       int b, h, seq_start, seq_len;
       unit_span(p, unit, b, h, seq_start, seq_len);
       if (seq_len <= tile * ATT_BM) continue;  // this tile does not exist for the unit
-      const int qrow = tile * ATT_BM + row;
       const bool active = tile * ATT_BM + q * 32 < seq_len;  // warp-uniform
-      const int nchunks = (seq_len + 31) >> 5;
+      const int nfull = seq_len >> 5;                         // full 32-key chunks
+      const int ntail = (((seq_len + 15) & ~15) - nfull * 32) >> 4;  // 16-key tail pieces (0..2)
+      const bool split = nfull >= ATT_SPLIT_KEYS / 32;        // the issuer derives the same flag
 
       mbar_wait(&s_full[tile], cnt & 1);
       tc_fence_after();
       if (q == 0 && lane == 0) trace_ev(p, tile, cnt, 0);
-      float sum = 0.f;
+      bool half_sent = false;
       if (active) {
-        uint32_t ra[32], rb[32];
-        // ---- pass 1: row max ----
-        float mx = -INFINITY;
-        tmem_ld32(s_addr, ra);
-        tmem_ld_wait();
-        for (int c = 0; c < nchunks; c += 2) {
-          if (c + 1 < nchunks) tmem_ld32(s_addr + (c + 1) * 32, rb);
-          if (c * 32 + 32 <= seq_len) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(ra[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c * 32 + j < seq_len) mx = fmaxf(mx, __uint_as_float(ra[j]));
-          }
+        float mx;
+        {
+          // ---- pass 1: row max; three chunk loads in flight (a tcgen05.ld takes ~180 clk) ----
+          uint32_t ra[32], rb[32], rc[32];
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          const int n1 = nfull;
+          // (loads past the row's keys stay inside the 512 allocated columns and are ignored)
+          tmem_ld32(s_addr, ra);
+          tmem_ld32(s_addr + 32, rb);
+          tmem_ld32(s_addr + 64, rc);
           tmem_ld_wait();
-          if (c + 1 < nchunks) {
-            if (c + 2 < nchunks) tmem_ld32(s_addr + (c + 2) * 32, ra);
-            if (c * 32 + 64 <= seq_len) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(rb[j]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c * 32 + 32 + j < seq_len) mx = fmaxf(mx, __uint_as_float(rb[j]));
+#pragma unroll 1
+          for (int c = 0; c < n1; c += 3) {
+            max32(ra, mx4);
+            if (c + 3 < n1) tmem_ld32(s_addr + (c + 3) * 32, ra);
+            if (c + 1 < n1) {
+              max32(rb, mx4);
+              if (c + 4 < n1) tmem_ld32(s_addr + (c + 4) * 32, rb);
+            }
+            if (c + 2 < n1) {
+              max32(rc, mx4);
+              if (c + 5 < n1) tmem_ld32(s_addr + (c + 5) * 32, rc);
             }
             tmem_ld_wait();
           }
+#pragma unroll 1
+          for (int t = 0; t < ntail; ++t) {
+            uint32_t rt[16];
+            const int k0 = nfull * 32 + t * 16;
+            tmem_ld16(s_addr + k0, rt);
+            tmem_ld_wait();
+            mask16(rt, k0, seq_len);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(rt[j]));
+          }
+          mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         }
         if (q == 0 && lane == 0) trace_ev(p, tile, cnt, 1);
-        // ---- pass 2: exponentials, row sum, P -> TMEM ----
+        // ---- pass 2: exponentials, row sum, P -> TMEM (aliasing the consumed part of S) ----
+        uint32_t ra[32], rb[32];
         const float mb = mx * sl2;
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
         tmem_ld32(s_addr, ra);
         tmem_ld_wait();
-        for (int c = 0; c < nchunks; c += 2) {
-          if (c + 1 < nchunks) tmem_ld32(s_addr + (c + 1) * 32, rb);
-          softmax_chunk(ra, c, seq_len, sl2, mb, sum, s_addr);
+#pragma unroll 1
+        for (int c = 0; c < nfull; c += 2) {
+          if (c + 1 < nfull) tmem_ld32(s_addr + (c + 1) * 32, rb);
+          exp32(ra, sl2, mb, sum4, s_addr + c * 16);
           tmem_ld_wait();
-          if (c + 1 < nchunks) {
-            if (c + 2 < nchunks) tmem_ld32(s_addr + (c + 2) * 32, ra);
-            softmax_chunk(rb, c + 1, seq_len, sl2, mb, sum, s_addr);
+          if (c + 1 < nfull) {
+            if (c + 2 < nfull) tmem_ld32(s_addr + (c + 2) * 32, ra);
+            exp32(rb, sl2, mb, sum4, s_addr + (c + 1) * 16);
             tmem_ld_wait();
           }
+          if (split && c + 2 == ATT_SPLIT_KEYS / 32) {
+            // the first ATT_SPLIT_KEYS keys of P are in TMEM: let their PV MMAs start
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_half[tile]);
+            half_sent = true;
+          }
+        }
+#pragma unroll 1
+        for (int t = 0; t < ntail; ++t) {
+          uint32_t rt[16];
+          const int k0 = nfull * 32 + t * 16;
+          tmem_ld16(s_addr + k0, rt);
+          tmem_ld_wait();
+          mask16(rt, k0, seq_len);
+          exp16(rt, sl2, mb, sum4, s_addr + (k0 >> 1));
         }
         tmem_st_wait();
+        sts32(inv_addr + (((cnt & 1) * 2 + tile) * ATT_BM + q * 32 + lane) * 4,
+              __float_as_uint(1.0f / ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]))));
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[tile]);
+      if (lane == 0) {
+        if (!half_sent) mbar_arrive(&p_half[tile]);
+        mbar_arrive(&p_full[tile]);
+      }
       if (q == 0 && lane == 0) trace_ev(p, tile, cnt, 2);
-
-      mbar_wait(&o_full[tile], cnt & 1);
-      tc_fence_after();
-      if (q == 0 && lane == 0) trace_ev(p, tile, cnt, 3);
-      uint32_t o0[32], o1[32];
-      if (active) {
-        tmem_ld32(o_addr, o0);
-        tmem_ld32(o_addr + 32, o1);
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_free[tile]);
-      if (q == 0 && lane == 0) trace_ev(p, tile, cnt, 4);
-      if (active && qrow < seq_len) {
-        const float inv = 1.0f / sum;
-        uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(seq_start + qrow) * p.ldo +
-                                              h * ATT_D);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 v;
-          v.x = pack_half2(__uint_as_float(o0[8 * j + 0]) * inv, __uint_as_float(o0[8 * j + 1]) * inv);
-          v.y = pack_half2(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv);
-          v.z = pack_half2(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv);
-          v.w = pack_half2(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv);
-          dst[j] = v;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 v;
-          v.x = pack_half2(__uint_as_float(o1[8 * j + 0]) * inv, __uint_as_float(o1[8 * j + 1]) * inv);
-          v.y = pack_half2(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv);
-          v.z = pack_half2(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv);
-          v.w = pack_half2(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv);
-          dst[4 + j] = v;
-        }
-      }
-      if (q == 0 && lane == 0) trace_ev(p, tile, cnt, 5);
       ++cnt;
+    }
+  } else {
+    // ===================== output =====================
+    reg_dealloc<96>();
+    const int q = warp_idx & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t stg = smem_u32(o_stage) + q * (32 * 128);  // this warp's 32 x 128 B transpose slab
+    uint32_t cnt_a = 0, cnt_b = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int b, h, seq_start, seq_len;
+      unit_span(p, unit, b, h, seq_start, seq_len);
+#pragma unroll 1
+      for (int tile = 0; tile < 2; ++tile) {
+        if (seq_len <= tile * ATT_BM) continue;
+        const uint32_t cnt = tile ? cnt_b : cnt_a;
+        const bool active = tile * ATT_BM + q * 32 < seq_len;  // warp-uniform
+        mbar_wait(&o_full[tile], cnt & 1);
+        tc_fence_after();
+        if (q == 0 && lane == 0) trace_ev(p, 5, cnt, tile * 4 + 0);
+        uint32_t o0[32], o1[32];
+        if (active) {
+          const uint32_t o_addr = tmem_base + lane_off + o_col(tile);
+          tmem_ld32(o_addr, o0);
+          tmem_ld32(o_addr + 32, o1);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_free[tile]);
+        if (q == 0 && lane == 0) trace_ev(p, 5, cnt, tile * 4 + 1);
+        if (active) {
+          // normalise, round once to fp16, transpose through the warp's smem slab (16-byte chunks
+          // XOR-swizzled by row: conflict-free both ways) so that every global store instruction
+          // writes four full 128-byte rows instead of 32 scattered 16-byte pieces.
+          const float inv = __uint_as_float(
+              lds32(inv_addr + (((cnt & 1) * 2 + tile) * ATT_BM + q * 32 + lane) * 4));
+          const uint32_t my = stg + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 v;
+            v.x = pack_half2(__uint_as_float(o0[8 * j + 0]) * inv, __uint_as_float(o0[8 * j + 1]) * inv);
+            v.y = pack_half2(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv);
+            v.z = pack_half2(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv);
+            v.w = pack_half2(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv);
+            sts128(my + ((j ^ (lane & 7)) << 4), v);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 v;
+            v.x = pack_half2(__uint_as_float(o1[8 * j + 0]) * inv, __uint_as_float(o1[8 * j + 1]) * inv);
+            v.y = pack_half2(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv);
+            v.z = pack_half2(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv);
+            v.w = pack_half2(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv);
+            sts128(my + (((4 + j) ^ (lane & 7)) << 4), v);
+          }
+          __syncwarp();
+          const int ch = lane & 7;    // 16-byte chunk of the 128-byte row
+          const int rs = lane >> 3;   // row within a group of four
+          const int row0 = tile * ATT_BM + q * 32;
+          __half* gbase = p.out + static_cast<size_t>(seq_start) * p.ldo + h * ATT_D + ch * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rs;
+            const uint4 v = lds128(stg + r * 128 + ((ch ^ (r & 7)) << 4));
+            if (row0 + r < seq_len)
+              *reinterpret_cast<uint4*>(gbase + static_cast<size_t>(row0 + r) * p.ldo) = v;
+          }
+          __syncwarp();  // the slab is rewritten by the next tile
+        }
+        if (q == 0 && lane == 0) trace_ev(p, 5, cnt, tile * 4 + 2);
+        if (tile) ++cnt_b; else ++cnt_a;
+      }
     }
   }
 
@@ -443,7 +541,7 @@ int attn_varlen_fwd(const __half* qkv, int ld_qkv, const int* cu_seqlens, int nu
     p.o_col[0] = 128; p.o_col[1] = 256 + 128;
     p.o_alias[0] = 1; p.o_alias[1] = 1;
   }
-  const int smem_bytes = 1024 + 2 * (ATT_Q_BYTES + 2 * nk_box * 128) + 256;
+  const int smem_bytes = 1024 + 2 * (ATT_Q_BYTES + 2 * nk_box * 128) + ATT_OSTAGE_BYTES + ATT_INV_BYTES + 256;
   static int configured_smem = 0;
   if (smem_bytes > configured_smem) {
     DYT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -465,8 +563,8 @@ int attn_varlen_fwd(const __half* qkv, int ld_qkv, const int* cu_seqlens, int nu
     static long long h[ATT_TRACE_ROLES * ATT_TRACE_ITERS * ATT_TRACE_EVENTS];
     cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
     cudaFree(d);
-    long long t0 = h[(2 * ATT_TRACE_ITERS) * ATT_TRACE_EVENTS];  // first S issue
-    const char* names[4] = {"wgA", "wgB", "mma", "tma"};
+    long long t0 = h[(2 * ATT_TRACE_ITERS) * ATT_TRACE_EVENTS];  // first S issue of tile A
+    const char* names[6] = {"wgA", "wgB", "mmA", "mmB", "tma", "out"};
     for (int r = 0; r < ATT_TRACE_ROLES; ++r)
       for (int i = 0; i < ATT_TRACE_ITERS; ++i) {
         fprintf(stderr, "trace %s it=%2d:", names[r], i);

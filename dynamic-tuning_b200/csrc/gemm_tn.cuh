@@ -151,37 +151,45 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+    // The whole warp walks the pipeline with warp-uniform state (descriptors in uniform registers)
+    // and one elected lane issues; issuing from inside an `if (lane == 0)` region makes the
+    // compiler wrap every tcgen05.mma in a lane-serialising loop (~100 clk of scalar code each).
+    constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+    const int tiles_u = __shfl_sync(0xffffffffu, total_tiles, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < tiles_u; tile += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(acc * BN);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t a_desc = umma_desc_sw128(sa);
-          const uint64_t b_desc = umma_desc_sw128(sa + Cfg::A_BYTES);
+        const uint32_t sa = smem_u + stage * Cfg::STAGE_BYTES;
+        const uint64_t a_desc = umma_desc_sw128(sa);
+        const uint64_t b_desc = umma_desc_sw128(sa + Cfg::A_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 halves = 32 B along K inside the swizzle row: +2 in 16-byte units
             umma_ss_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator ready for the epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (elect_one()) umma_commit(&tmem_full_bar[acc]);  // accumulator ready for the epilogue
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
@@ -190,7 +198,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int e = warp_idx - 4;
     const int q = e & 3;              // == warp_idx % 4: TMEM lane quarter this warp may access
     const int half = e >> 2;
-    uint8_t* slab = epi_smem + e * Cfg::SLAB_BYTES;
+    const uint32_t slab = smem_u32(epi_smem) + e * Cfg::SLAB_BYTES;
     const int cl = lane & 7;     // 16-byte chunk (4 fp32 columns) within the 32-column slab row
     const int rsub = lane >> 3;  // row within a group of 4
     int acc = 0;
@@ -246,12 +254,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
         {
-          uint8_t* rowp = slab + lane * 128;
+          const uint32_t rowp = slab + lane * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 v = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-            *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = v;
-          }
+          for (int j = 0; j < 8; ++j)
+            sts128(rowp + ((j ^ (lane & 7)) << 4),
+                   make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
         }
         __syncwarp();
         const int col = n0 + c * 32 + cl * 4;
@@ -260,7 +267,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = it * 4 + rsub;
-          a[it] = *reinterpret_cast<const float4*>(slab + rr * 128 + ((cl ^ (rr & 7)) << 4));
+          const uint4 u = lds128(slab + rr * 128 + ((cl ^ (rr & 7)) << 4));
+          a[it] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z),
+                              __uint_as_float(u.w));
         }
         __syncwarp();  // slab may be overwritten by the next chunk
         // prefetch the next chunk's residual while this chunk is processed

@@ -29,6 +29,41 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Explicit shared-space accesses.  The dynamic-smem base pointer goes through an integer round-up
+// to 1024 B, after which the compiler no longer knows the address space and would emit generic
+// LD/ST (slower issue, tracked on the long scoreboard) instead of LDS/STS.
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// Warpgroup register re-allocation (all four warps of an aligned warpgroup must execute it).
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
@@ -85,12 +120,19 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > DYT_WAIT_TIMEOUT_CYCLES) {
-      printf("dyt: mbarrier wait timeout block=%d thread=%d bar=%u parity=%u\n", (int)blockIdx.x,
-             (int)threadIdx.x, smem_u32(bar), parity);
-      __trap();
+  // try_wait suspends the thread only briefly, so this loop does spin: keep it to two instructions
+  // and look at the clock (dead-lock guard) once every 4096 polls.
+  long long t0 = 0;
+  for (uint32_t n = 1;; ++n) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((n & 4095u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > DYT_WAIT_TIMEOUT_CYCLES) {
+        printf("dyt: mbarrier wait timeout block=%d thread=%d bar=%u parity=%u\n", (int)blockIdx.x,
+               (int)threadIdx.x, smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }

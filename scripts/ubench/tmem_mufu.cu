@@ -1,0 +1,151 @@
+// Micro-benchmarks (debug aid, not product): LDTM / STTM bandwidth and MUFU.EX2 throughput on one SM,
+// for 1, 2 and 4 warps per SM sub-partition.  nvcc -gencode arch=compute_100a,code=sm_100a
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../dynamic-tuning_b200/csrc/ptx.cuh"
+using namespace dyt;
+
+__global__ void k_ldtm(long long* out, int iters, int mode) {
+  __shared__ uint32_t tptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) { tmem_alloc(&tptr, 512); tmem_relinquish(); }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t base = tptr + (uint32_t((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  if (mode == 0) {          // back-to-back x32 loads, wait after each pair
+    for (int i = 0; i < iters; ++i) {
+      uint32_t a[32], b[32];
+      tmem_ld32(base + ((i * 64) & 255), a);
+      tmem_ld32(base + ((i * 64 + 32) & 255), b);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc ^= a[j] ^ b[j];
+    }
+  } else if (mode == 1) {   // x16 stores
+    uint32_t v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = lane + j;
+    for (int i = 0; i < iters; ++i) {
+      tmem_st16(base + ((i * 32) & 255), v);
+      tmem_st16(base + ((i * 32 + 16) & 255), v);
+      tmem_st_wait();
+    }
+  } else if (mode == 2) {   // one x32 load, wait (latency)
+    for (int i = 0; i < iters; ++i) {
+      uint32_t a[32];
+      tmem_ld32(base + ((i * 32) & 255), a);
+      tmem_ld_wait();
+      acc ^= a[i & 31];
+    }
+  }
+  else if (mode == 3) {   // ld x32 (prefetch) + st x16 mixed, wait::ld only
+    uint32_t a[32], b[32];
+    tmem_ld32(base, a); tmem_ld_wait();
+    for (int i = 0; i < iters; ++i) {
+      tmem_ld32(base + 32 + ((i * 32) & 127), b);
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = a[2*j] + a[2*j+1];
+      tmem_st16(base + 256 + ((i * 16) & 127), pk);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = b[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc ^= a[j];
+  } else if (mode == 4 || mode == 5) {   // softmax-like chunk loop: ld prefetch, ffma+ex2 x32, pack, st
+    uint32_t a[32], b[32];
+    float sum = 0.f;
+    tmem_ld32(base, a); tmem_ld_wait();
+    for (int i = 0; i < iters; ++i) {
+      tmem_ld32(base + 32 + ((i * 32) & 127), b);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(a[j]), 0.18f, -1.f)));
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { sum += __uint_as_float(a[2*j]) + __uint_as_float(a[2*j+1]); pk[j] = pack_half2(__uint_as_float(a[2*j]), __uint_as_float(a[2*j+1])); }
+      if (mode == 4) tmem_st16(base + 256 + ((i * 16) & 127), pk);
+      else { 
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc ^= pk[j]; }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = b[j];
+    }
+    acc ^= __float_as_uint(sum);
+  }
+  long long t1 = clock64();
+  if (lane == 0) out[warp] = t1 - t0;
+  if (acc == 0x12345) out[63] = acc;
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tptr, 512); }
+}
+
+__global__ void k_mufu(long long* out, float* sink, int iters, int mode) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float x[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) x[j] = -0.01f * (lane + j);
+  __syncthreads();
+  long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    if (mode == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = ex2_approx(x[j]);
+    } else if (mode == 1) {   // softmax-like: ffma + ex2 + pack + sum
+      float s = 0.f;
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = ex2_approx(fmaf(x[j], 0.18f, -1.0f));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { s += x[2*j] + x[2*j+1]; pk[j] = pack_half2(x[2*j], x[2*j+1]); }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[2*j] += __uint_as_float(pk[j] & 0x7fff) * 1e-30f;
+      x[1] += s * 1e-30f;
+    } else {                  // fmnmx3
+      float m0 = x[0], m1 = x[1];
+#pragma unroll
+      for (int j = 2; j < 32; j += 2) { m0 = fmaxf(fmaxf(m0, x[j]), x[(j + 7) & 31]); m1 = fmaxf(fmaxf(m1, x[j + 1]), x[(j+9)&31]); }
+      x[i & 31] = m0 + m1;
+    }
+  }
+  long long t1 = clock64();
+  float s = 0; 
+#pragma unroll
+  for (int j = 0; j < 32; ++j) s += x[j];
+  if (lane == 0) out[warp] = t1 - t0;
+  if (s == 123.f) sink[0] = s;
+}
+
+int main() {
+  long long* d; float* sink; cudaMalloc(&d, 64 * 8); cudaMalloc(&sink, 4);
+  long long h[64];
+  const int iters = 200;
+  for (int mode = 0; mode < 6; ++mode)
+    for (int nw : {1, 4, 8, 16}) {
+      if (mode == 2) continue;
+      k_ldtm<<<1, nw * 32>>>(d, iters, mode); cudaDeviceSynchronize();
+      k_ldtm<<<1, nw * 32>>>(d, iters, mode); cudaDeviceSynchronize();
+      cudaMemcpy(h, d, 64 * 8, cudaMemcpyDeviceToHost);
+      long long mx = 0; for (int i = 0; i < nw; ++i) mx = h[i] > mx ? h[i] : mx;
+      double bytes = (mode == 2 ? 4096.0 : (mode == 0 ? 8192.0 : 4096.0)) * iters * nw;
+      printf("tmem mode %d (%s) warps %2d: %lld clk, %.1f B/clk/SM, %.1f clk per op per warp\n", mode,
+             mode == 0 ? "ld x32 pairs" : mode == 1 ? "st x16 pairs" : mode == 3 ? "ld32+st16 mixed" : mode == 4 ? "softmax chunk ld+ex2+st" : "softmax chunk ld+ex2 (no st)", nw, mx, bytes / mx,
+             (double)mx / iters / (mode >= 2 ? 1 : 2));
+      printf("  err: %s\n", cudaGetErrorString(cudaGetLastError()));
+    }
+  for (int mode = 0; mode < 3; ++mode)
+    for (int nw : {1, 4, 8, 16}) {
+      k_mufu<<<1, nw * 32>>>(d, sink, iters, mode); cudaDeviceSynchronize();
+      k_mufu<<<1, nw * 32>>>(d, sink, iters, mode); cudaDeviceSynchronize();
+      cudaMemcpy(h, d, 64 * 8, cudaMemcpyDeviceToHost);
+      long long mx = 0; for (int i = 0; i < nw; ++i) mx = h[i] > mx ? h[i] : mx;
+      printf("alu mode %d (%s) warps %2d: %lld clk, %.2f clk per warp-element (per SMSP: %.2f)\n", mode,
+             mode == 0 ? "ex2 only" : mode == 1 ? "ffma+ex2+sum+pack" : "fmnmx3", nw, mx,
+             (double)mx / iters / 32, (double)mx / iters / 32 / ((nw + 3) / 4));
+    }
+  return 0;
+}
