@@ -20,12 +20,23 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }
   const int m_tiles = (p.M + Cfg::BM - 1) / Cfg::BM;
   const int n_tiles = (p.N + BN - 1) / BN;
-  int grid = m_tiles * n_tiles;
-  const int sms = sm_count();
-  if (grid > sms) grid = sms;
-  if (grid < 1) grid = 1;
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
-  return cuda_status(cudaGetLastError(), "gemm_tn_kernel launch");
+  int clusters = ((m_tiles + 1) / 2) * n_tiles;  // one pair of tiles per cluster of two CTAs
+  const int max_clusters = sm_count() / 2;
+  if (clusters > max_clusters) clusters = max_clusters;
+  if (clusters < 1) clusters = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cuda_status(cudaLaunchKernelEx(&cfg, kern, ta, tb, p), "gemm_tn_kernel launch");
 }
 
 template <int BN>
@@ -66,8 +77,9 @@ int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, in
   int s = make_tmap_f16_sw128(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(K),
                               static_cast<uint64_t>(lda), 128);
   if (s != DYT_OK) return s;
+  // B box = half a tile: each CTA of a cluster fetches one half and multicasts it to both
   s = make_tmap_f16_sw128(&tb, w, static_cast<uint64_t>(N), static_cast<uint64_t>(K),
-                          static_cast<uint64_t>(ldw), static_cast<uint32_t>(bn));
+                          static_cast<uint64_t>(ldw), static_cast<uint32_t>(bn / 2));
   if (s != DYT_OK) return s;
 
   GemmParams p;
@@ -77,6 +89,8 @@ int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, in
   p.out_h = out_h; p.out_f = out_f; p.resid = resid;
   p.ldo_h = ldo_h; p.ldo_f = ldo_f; p.ld_res = ld_res;
   p.scale = scale;
+  p.vec8 = (out_h != nullptr && ldo_h % 8 == 0 && N % 8 == 0 &&
+            (reinterpret_cast<uintptr_t>(out_h) & 15) == 0) ? 1 : 0;
   switch (bn) {
     case 64: return dispatch_epi<64>(epi, ta, tb, p, stream);
     case 128: return dispatch_epi<128>(epi, ta, tb, p, stream);

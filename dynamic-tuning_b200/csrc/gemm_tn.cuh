@@ -3,11 +3,19 @@
 //   B : fp16 row-major nn.Linear weight [out,in]=[N,K]    -> TMA, 128B-swizzled K-major smem tiles
 //   D : fp32 accumulators in TMEM, two stages of BN columns so the epilogue of tile i overlaps the
 //       MMA main loop of tile i+1.
+// CTAs run as clusters of two that work on vertically adjacent tiles (m, n) / (m+1, n): each CTA
+// fetches its own A tile and one half of the shared B tile, multicast into both CTAs' shared
+// memory, which cuts the L2 -> SM operand traffic by a third (the kernel is bound by that traffic,
+// not by HBM or the tensor pipe: 48 KB per 128x256x64 MMA block per SM otherwise).  A smem stage is
+// recycled once the MMAs of both CTAs have read it (tcgen05.commit multicast to both producers).
 // Warp roles (384 threads): warp0 = TMA producer, warp1 = MMA issuer (one elected thread),
 // warp2 = TMEM allocator, warps4-11 = epilogue: two warps per TMEM lane quarter, each owning half
-// of the tile's columns (TMEM -> regs -> swizzled smem transpose -> coalesced 128-bit global
-// accesses, with bias / GELU / ReLU / scale / fp32-residual fused).  Bias and residual loads are
-// issued before the accumulator wait so their latency overlaps the main loop.
+// of the tile's columns.  The epilogue arithmetic (bias / GELU / ReLU / scale, one rounding to
+// fp16 per Linear output) runs in the TMEM register layout (thread = row, 32 columns); only the
+// fp16 result goes through a bank-conflict-free smem transpose (64-byte rows, 16-byte chunks XORed
+// with (row>>1)&3) to reach coalesced 128-bit global accesses.  The main loop's operand reads
+// already use about half of the shared-memory pipe, so the epilogue must stay light on it: the
+// earlier fp32 transpose cost 3x the wavefronts and made the kernel shared-memory bound.
 //
 // Replaces the cuBLASLt calls behind nn.Linear in the reference block
 // (reference models/model_speed_test.py:147 qkv, :164 proj, :106-111 adapter, timm Mlp fc1/fc2).
@@ -37,6 +45,7 @@ struct GemmParams {
   int ldo_f;   // row stride of out_f
   int ld_res;  // row stride of resid
   float scale;
+  int vec8;    // 1: out_h rows are 16-byte aligned and N % 8 == 0 -> 128-bit fp16 stores
 };
 
 template <int BN>
@@ -49,8 +58,9 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_WARPS = 8;
   static constexpr int THREADS = 128 + EPI_WARPS * 32;
-  static constexpr int SLAB_BYTES = 32 * 128;  // 32 rows x 32 fp32, one per epilogue warp
-  static constexpr int EPI_BYTES = EPI_WARPS * SLAB_BYTES;
+  static constexpr int SLAB_BYTES = 32 * 64;   // 32 rows x 32 fp16 (one 32-column chunk), per warp
+  static constexpr int BIAS_BYTES = (BN / 2) * 4;  // fp32 bias of the warp's half of the tile
+  static constexpr int EPI_BYTES = EPI_WARPS * (SLAB_BYTES + BIAS_BYTES);
   static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: all powers of two
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
@@ -100,7 +110,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
   const int m_tiles = (m_eff + BM - 1) / BM;
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int total_tiles = m_tiles * n_tiles;
+  // work item = a pair of vertically adjacent tiles, one per CTA of the cluster (the odd last tile
+  // row pairs with an all-masked dummy: its TMA boxes are out of bounds and read as zeros)
+  const int total_tiles = ((m_tiles + 1) / 2) * n_tiles;
   const int k_blocks = (p.K + BK - 1) / BK;
 
   if (warp_idx == 0 && lane == 0) {
@@ -110,7 +122,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], 2);  // the MMA warps of both CTAs of the cluster
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
@@ -124,24 +136,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const int cta_rank = static_cast<int>(cluster_ctarank());
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * BM;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int m0 = ((tile / n_tiles) * 2 + cta_rank) * BM;
         const int n0 = (tile % n_tiles) * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sb = sa + Cfg::A_BYTES + cta_rank * (Cfg::B_BYTES / 2);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);  // A + both halves of B
           tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+          tma_load_2d_mc(sb, &tmap_b, &full_bar[stage], kb * BK, n0 + cta_rank * (BN / 2), 0x3);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -162,7 +178,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < tiles_u; tile += gridDim.x) {
+    for (int tile = cluster_id; tile < tiles_u; tile += num_clusters) {
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(acc * BN);
@@ -178,7 +194,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // advance 16 halves = 32 B along K inside the swizzle row: +2 in 16-byte units
             umma_ss_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          umma_commit_mc(&empty_bar[stage], 0x3);  // to both producers, once these MMAs retire
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -198,54 +214,53 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int e = warp_idx - 4;
     const int q = e & 3;              // == warp_idx % 4: TMEM lane quarter this warp may access
     const int half = e >> 2;
-    const uint32_t slab = smem_u32(epi_smem) + e * Cfg::SLAB_BYTES;
-    const int cl = lane & 7;     // 16-byte chunk (4 fp32 columns) within the 32-column slab row
-    const int rsub = lane >> 3;  // row within a group of 4
+    const uint32_t slab = smem_u32(epi_smem) + e * (Cfg::SLAB_BYTES + Cfg::BIAS_BYTES);
+    const uint32_t bias_s = slab + Cfg::SLAB_BYTES;
+    const uint32_t my_row = slab + lane * 64;
+    const int swz_w = (lane >> 1) & 3;  // chunk swizzle of the row this lane writes
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * BM;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int m0 = ((tile / n_tiles) * 2 + cta_rank) * BM;
       const int n0 = (tile % n_tiles) * BN + half * HALF;
-      const int row_base = m0 + q * 32 + rsub;
 
-      // bias for every chunk of this tile: issued before the accumulator is ready
-      float bias_r[NCH][4];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int col = n0 + c * 32 + cl * 4;
-        bias_r[c][0] = bias_r[c][1] = bias_r[c][2] = bias_r[c][3] = 0.f;
+      // fp32 bias of this warp's columns -> smem (read back as warp-wide broadcasts); in flight
+      // while the main loop of this tile finishes
+      for (int i = lane; i < HALF / 4; i += 32) {
+        const int col = n0 + i * 4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias != nullptr && col < p.N) {
           const uint2 bb = *reinterpret_cast<const uint2*>(p.bias + col);
-          const __half2 h01 = *reinterpret_cast<const __half2*>(&bb.x);
-          const __half2 h23 = *reinterpret_cast<const __half2*>(&bb.y);
-          bias_r[c][0] = __low2float(h01);
-          bias_r[c][1] = __high2float(h01);
-          bias_r[c][2] = __low2float(h23);
-          bias_r[c][3] = __high2float(h23);
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&bb.x));
+          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&bb.y));
+          bv = make_float4(lo.x, lo.y, hi.x, hi.y);
         }
+        sts128(bias_s + i * 16, make_uint4(__float_as_uint(bv.x), __float_as_uint(bv.y),
+                                           __float_as_uint(bv.z), __float_as_uint(bv.w)));
       }
-      // residual of the first chunk: in flight while the main loop of this tile finishes
-      float4 res[8];
-      if constexpr (EPI == EPI_BIAS_RESID) {
-        const int col = n0 + cl * 4;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int grow = row_base + it * 4;
-          res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (grow < m_eff && col < p.N)
-            res[it] = *reinterpret_cast<const float4*>(p.resid +
-                                                       static_cast<size_t>(grow) * p.ld_res + col);
-        }
-      }
+      __syncwarp();
 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(acc * BN + half * HALF);
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         uint32_t r[32];
         tmem_ld32(t_row + c * 32, r);
+        // residual rows of this chunk (coalesced layout, see below): in flight during the math
+        float4 res[8];
+        if constexpr (EPI == EPI_BIAS_RESID) {
+          const int col = n0 + c * 32 + (lane & 7) * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int grow = m0 + q * 32 + it * 4 + (lane >> 3);
+            res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grow < m_eff && col < p.N)
+              res[it] = *reinterpret_cast<const float4*>(p.resid +
+                                                         static_cast<size_t>(grow) * p.ld_res + col);
+          }
+        }
         tmem_ld_wait();
         if (c == NCH - 1) {
           // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
@@ -253,81 +268,78 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
-        {
-          const uint32_t rowp = slab + lane * 128;
+        // ---- arithmetic in the TMEM layout: this thread = row (q*32 + lane), 32 columns ----
+        uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts128(rowp + ((j ^ (lane & 7)) << 4),
-                   make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
-        }
-        __syncwarp();
-        const int col = n0 + c * 32 + cl * 4;
-        const bool col_ok = col < p.N;
-        float4 a[8];
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const uint4 bq = lds128(bias_s + (c * 32 + j4 * 4) * 4);  // broadcast: same for all lanes
+          const float bj[4] = {__uint_as_float(bq.x), __uint_as_float(bq.y), __uint_as_float(bq.z),
+                               __uint_as_float(bq.w)};
+          float v[4];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + rsub;
-          const uint4 u = lds128(slab + rr * 128 + ((cl ^ (rr & 7)) << 4));
-          a[it] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z),
-                              __uint_as_float(u.w));
-        }
-        __syncwarp();  // slab may be overwritten by the next chunk
-        // prefetch the next chunk's residual while this chunk is processed
-        float4 res_next[8];
-        if constexpr (EPI == EPI_BIAS_RESID) {
-          if (c + 1 < NCH) {
-            const int ncol = col + 32;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int grow = row_base + it * 4;
-              res_next[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (grow < m_eff && ncol < p.N)
-                res_next[it] = *reinterpret_cast<const float4*>(
-                    p.resid + static_cast<size_t>(grow) * p.ld_res + ncol);
+          for (int k = 0; k < 4; ++k) {
+            float t = round_f16(__uint_as_float(r[j4 * 4 + k]) + bj[k]);
+            if constexpr (EPI == EPI_BIAS_GELU) t = gelu_erf(t);
+            if constexpr (EPI == EPI_BIAS_RELU) t = fmaxf(t, 0.f);
+            if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_RESID) {
+              if (p.scale != 1.0f) t = round_f16(t * p.scale);
             }
+            v[k] = t;
           }
+          pk[j4 * 2] = pack_half2(v[0], v[1]);
+          pk[j4 * 2 + 1] = pack_half2(v[2], v[3]);
         }
+        // ---- fp16 transpose through the slab ----
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int grow = row_base + it * 4;
-          if (grow < m_eff && col_ok) {
-            float v0 = round_f16(a[it].x + bias_r[c][0]), v1 = round_f16(a[it].y + bias_r[c][1]);
-            float v2 = round_f16(a[it].z + bias_r[c][2]), v3 = round_f16(a[it].w + bias_r[c][3]);
-            if constexpr (EPI == EPI_BIAS) {
-              if (p.scale != 1.0f) {
-                v0 = round_f16(v0 * p.scale); v1 = round_f16(v1 * p.scale);
-                v2 = round_f16(v2 * p.scale); v3 = round_f16(v3 * p.scale);
-              }
-            }
-            if constexpr (EPI == EPI_BIAS_GELU) {
-              v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
-            } else if constexpr (EPI == EPI_BIAS_RELU) {
-              v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
-            }
-            if constexpr (EPI == EPI_BIAS_RESID) {
-              if (p.scale != 1.0f) {
-                v0 = round_f16(v0 * p.scale); v1 = round_f16(v1 * p.scale);
-                v2 = round_f16(v2 * p.scale); v3 = round_f16(v3 * p.scale);
-              }
-              const float4 o = make_float4(res[it].x + v0, res[it].y + v1, res[it].z + v2,
-                                           res[it].w + v3);
+        for (int k = 0; k < 4; ++k)
+          sts128(my_row + ((k ^ swz_w) << 4),
+                 make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
+        __syncwarp();
+        if constexpr (EPI == EPI_BIAS_RESID) {
+          // lane -> (row it*4 + lane/8, columns (lane%8)*4 .. +3): 128-byte fp32 row segments
+          const int col = n0 + c * 32 + (lane & 7) * 4;
+          const int p8 = lane & 7;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3);
+            const int grow = m0 + q * 32 + rr;
+            uint2 hv;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];"
+                         : "=r"(hv.x), "=r"(hv.y)
+                         : "r"(slab + rr * 64 + (((p8 >> 1) ^ ((rr >> 1) & 3)) << 4) + (p8 & 1) * 8)
+                         : "memory");
+            if (grow < m_eff && col < p.N) {
+              const float2 v01 = __half22float2(*reinterpret_cast<const __half2*>(&hv.x));
+              const float2 v23 = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
+              const float4 o = make_float4(res[it].x + v01.x, res[it].y + v01.y, res[it].z + v23.x,
+                                           res[it].w + v23.y);
               *reinterpret_cast<float4*>(p.out_f + static_cast<size_t>(grow) * p.ldo_f + col) = o;
               if (p.out_h != nullptr) {
                 const uint2 oh = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
                 *reinterpret_cast<uint2*>(p.out_h + static_cast<size_t>(grow) * p.ldo_h + col) = oh;
               }
-            } else {
-              const uint2 oh = make_uint2(pack_half2(v0, v1), pack_half2(v2, v3));
-              *reinterpret_cast<uint2*>(p.out_h + static_cast<size_t>(grow) * p.ldo_h + col) = oh;
+            }
+          }
+        } else {
+          // lane -> (row it*8 + lane/4, columns (lane%4)*8 .. +7): 64-byte fp16 row segments
+          const int col = n0 + c * 32 + (lane & 3) * 8;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2);
+            const int grow = m0 + q * 32 + rr;
+            const uint4 hv = lds128(slab + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+            if (grow < m_eff && col < p.N) {
+              __half* dst = p.out_h + static_cast<size_t>(grow) * p.ldo_h + col;
+              if (p.vec8) {
+                *reinterpret_cast<uint4*>(dst) = hv;
+              } else {  // row pitch / column count only 8-byte aligned
+                *reinterpret_cast<uint2*>(dst) = make_uint2(hv.x, hv.y);
+                if (col + 4 < p.N) *reinterpret_cast<uint2*>(dst + 4) = make_uint2(hv.z, hv.w);
+              }
             }
           }
         }
-        if constexpr (EPI == EPI_BIAS_RESID) {
-          if (c + 1 < NCH) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) res[it] = res_next[it];
-          }
-        }
+        __syncwarp();  // the slab is overwritten by the next chunk
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -336,6 +348,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // no CTA exits while its peer can still multicast into it
   if (warp_idx == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
