@@ -3,11 +3,12 @@
 //   B : fp16 row-major nn.Linear weight [out,in]=[N,K]    -> TMA, 128B-swizzled K-major smem tiles
 //   D : fp32 accumulators in TMEM, two stages of BN columns so the epilogue of tile i overlaps the
 //       MMA main loop of tile i+1.
-// CTAs run as clusters of two that work on vertically adjacent tiles (m, n) / (m+1, n): each CTA
-// fetches its own A tile and one half of the shared B tile, multicast into both CTAs' shared
-// memory, which cuts the L2 -> SM operand traffic by a third (the kernel is bound by that traffic,
-// not by HBM or the tensor pipe: 48 KB per 128x256x64 MMA block per SM otherwise).  A smem stage is
-// recycled once the MMAs of both CTAs have read it (tcgen05.commit multicast to both producers).
+// CTA pairs (clusters of two, tcgen05 cta_group::2) work on one 256 x BN tile: each CTA stages its
+// own 128 rows of A and one half of the B tile, the leader CTA issues M = 256 MMAs that read both
+// CTAs' shared memory and accumulate each CTA's 128 rows in its own TMEM.  Per 128xBNx64 MMA block
+// an SM then receives A + B/2 instead of A + B: with BN = 256 that is 32 KB per 512 tensor-clocks,
+// which the ~70 B/clk an SM can take in sustains; a lone CTA (48 KB) is capped at ~2/3 of the
+// tensor peak, and multicasting B inside a cluster of two does not help (same bytes per SM).
 // Warp roles (384 threads): warp0 = TMA producer, warp1 = MMA issuer (one elected thread),
 // warp2 = TMEM allocator, warps4-11 = epilogue: two warps per TMEM lane quarter, each owning half
 // of the tile's columns.  The epilogue arithmetic (bias / GELU / ReLU / scale, one rounding to
@@ -52,9 +53,9 @@ template <int BN>
 struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 64;  // 64 halves = 128 B = one swizzle row
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int A_BYTES = BM * BK * 2;         // this CTA's 128 rows of A
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;   // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_WARPS = 8;
   static constexpr int THREADS = 128 + EPI_WARPS * 32;
@@ -121,18 +122,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 2);  // the MMA warps of both CTAs of the cluster
+      mbar_init(&full_bar[s], 1);   // used in the leader CTA: its producer's expect_tx arrival
+      mbar_init(&empty_bar[s], 1);  // the leader's commit, multicast to both CTAs
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], Cfg::EPI_WARPS);
+      mbar_init(&tmem_full_bar[a], 1);                       // the leader's commit, multicast
+      mbar_init(&tmem_empty_bar[a], 2 * Cfg::EPI_WARPS);     // leader CTA: epilogue warps of both CTAs
     }
     fence_mbar_init();
   }
   if (warp_idx == 2) {
-    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc_cg2(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish_cg2();
   }
   tc_fence_before();
   __syncthreads();
@@ -154,10 +155,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES + cta_rank * (Cfg::B_BYTES / 2);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);  // A + both halves of B
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
-          tma_load_2d_mc(sb, &tmap_b, &full_bar[stage], kb * BK, n0 + cta_rank * (BN / 2), 0x3);
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          // all four boxes of the pair (2 x A, 2 x B half) complete on the leader's barrier
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          tma_load_2d_cg2(sa, &tmap_a, lead_bar, kb * BK, m0);
+          tma_load_2d_cg2(sb, &tmap_b, lead_bar, kb * BK, n0 + cta_rank * (BN / 2));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -170,7 +173,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // The whole warp walks the pipeline with warp-uniform state (descriptors in uniform registers)
     // and one elected lane issues; issuing from inside an `if (lane == 0)` region makes the
     // compiler wrap every tcgen05.mma in a lane-serialising loop (~100 clk of scalar code each).
-    constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
+    constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN, 0, 0);  // M = 256 over the CTA pair
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
     const int tiles_u = __shfl_sync(0xffffffffu, total_tiles, 0);
@@ -178,7 +181,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < tiles_u; tile += num_clusters) {
+    for (int tile = cluster_id; cta_rank == 0 && tile < tiles_u; tile += num_clusters) {
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(acc * BN);
@@ -192,9 +195,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 halves = 32 B along K inside the swizzle row: +2 in 16-byte units
-            umma_ss_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_ss_f16_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit_mc(&empty_bar[stage], 0x3);  // to both producers, once these MMAs retire
+          umma_commit_cg2_mc(&empty_bar[stage], 0x3);  // to both producers, once these MMAs retire
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -202,7 +205,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           phase ^= 1;
         }
       }
-      if (elect_one()) umma_commit(&tmem_full_bar[acc]);  // accumulator ready for the epilogue
+      if (elect_one()) umma_commit_cg2_mc(&tmem_full_bar[acc], 0x3);  // both CTAs' epilogues
       __syncwarp();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -261,28 +264,35 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                          static_cast<size_t>(grow) * p.ld_res + col);
           }
         }
+        // bias of the chunk's 32 columns: warp-wide broadcast loads, in flight with the TMEM load
+        uint4 bq[8];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) bq[j4] = lds128(bias_s + (c * 32 + j4 * 4) * 4);
         tmem_ld_wait();
         if (c == NCH - 1) {
           // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
         }
         // ---- arithmetic in the TMEM layout: this thread = row (q*32 + lane), 32 columns ----
         uint32_t pk[16];
+        const bool plain = (EPI == EPI_BIAS) && p.scale == 1.0f;  // one rounding, no round trip
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const uint4 bq = lds128(bias_s + (c * 32 + j4 * 4) * 4);  // broadcast: same for all lanes
-          const float bj[4] = {__uint_as_float(bq.x), __uint_as_float(bq.y), __uint_as_float(bq.z),
-                               __uint_as_float(bq.w)};
+          const float bj[4] = {__uint_as_float(bq[j4].x), __uint_as_float(bq[j4].y),
+                               __uint_as_float(bq[j4].z), __uint_as_float(bq[j4].w)};
           float v[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            float t = round_f16(__uint_as_float(r[j4 * 4 + k]) + bj[k]);
-            if constexpr (EPI == EPI_BIAS_GELU) t = gelu_erf(t);
-            if constexpr (EPI == EPI_BIAS_RELU) t = fmaxf(t, 0.f);
-            if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_RESID) {
-              if (p.scale != 1.0f) t = round_f16(t * p.scale);
+            float t = __uint_as_float(r[j4 * 4 + k]) + bj[k];
+            if (!plain) {
+              t = round_f16(t);
+              if constexpr (EPI == EPI_BIAS_GELU) t = gelu_erf(t);
+              if constexpr (EPI == EPI_BIAS_RELU) t = fmaxf(t, 0.f);
+              if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_RESID) {
+                if (p.scale != 1.0f) t = round_f16(t * p.scale);
+              }
             }
             v[k] = t;
           }
@@ -351,7 +361,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   cluster_sync_all();  // no CTA exits while its peer can still multicast into it
   if (warp_idx == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

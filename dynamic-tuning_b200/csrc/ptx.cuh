@@ -170,9 +170,36 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap
       : "memory");
 }
 
+// 2-D tiled load issued by either CTA of a CTA pair (cta_group::2): the box lands in the issuing
+// CTA's shared memory, complete_tx goes to the mbarrier at cluster address bar_cluster_addr (the
+// leader CTA's barrier, see mapa_shared()).
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* m,
+                                                uint32_t bar_cluster_addr, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0),
+        "r"(c1)
+      : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // thread-block clusters
 // ---------------------------------------------------------------------------------------------
+// shared::cluster address of the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta));
+  return r;
+}
+// Relaxed: the accesses this arrival publishes are TMEM reads, ordered by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync; a release here would also drain the warp's global stores
+// (a MEMBAR -- measured as the top stall of the GEMM epilogue).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -201,6 +228,20 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
                : "memory");
 }
+// CTA-pair (cta_group::2) variants: executed by the same warp of both CTAs of the pair
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_cg2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -219,6 +260,20 @@ __device__ __forceinline__ void umma_ss_f16(uint32_t d_tmem, uint64_t a_desc, ui
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// CTA-pair MMA (issued by the leader CTA): M = 256 rows split over the two CTAs' TMEM, A rows and
+// B columns split over the two CTAs' shared memory at the descriptors' offsets.
+__device__ __forceinline__ void umma_ss_f16_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n"
       :
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
@@ -249,6 +304,16 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
+// CTA-pair commit: arrives on the barrier at this offset in every CTA of cta_mask once all MMAs
+// issued so far by this thread (for the pair) have retired.
+__device__ __forceinline__ void umma_commit_cg2_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
       "h"(cta_mask)
       : "memory");
