@@ -7,11 +7,11 @@
 
 namespace dyt {
 
-template <int BN, int EPI>
+template <int BN, int EPI, int EW>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tn_kernel<BN, EPI>;
+  using Cfg = GemmCfg<BN, EW>;
+  auto kern = gemm_tn_kernel<BN, EPI, EW>;
   static bool configured = false;
   if (!configured) {
     DYT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -42,11 +42,23 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 template <int BN>
 static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb,
                         const GemmParams& p, cudaStream_t s) {
+  // sixteen epilogue warps where the epilogue, not the main loop, sets the pace
+  if constexpr (BN >= 128) {
+    if (epi == EPI_BIAS_GELU) return launch_gemm<BN, EPI_BIAS_GELU, 16>(ta, tb, p, s);
+    if (p.K <= 128) {
+      switch (epi) {
+        case EPI_BIAS: return launch_gemm<BN, EPI_BIAS, 16>(ta, tb, p, s);
+        case EPI_BIAS_RELU: return launch_gemm<BN, EPI_BIAS_RELU, 16>(ta, tb, p, s);
+        case EPI_BIAS_RESID: return launch_gemm<BN, EPI_BIAS_RESID, 16>(ta, tb, p, s);
+        default: return fail(DYT_EINVAL, "unknown epilogue %d", epi);
+      }
+    }
+  }
   switch (epi) {
-    case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(ta, tb, p, s);
-    case EPI_BIAS_GELU: return launch_gemm<BN, EPI_BIAS_GELU>(ta, tb, p, s);
-    case EPI_BIAS_RELU: return launch_gemm<BN, EPI_BIAS_RELU>(ta, tb, p, s);
-    case EPI_BIAS_RESID: return launch_gemm<BN, EPI_BIAS_RESID>(ta, tb, p, s);
+    case EPI_BIAS: return launch_gemm<BN, EPI_BIAS, 8>(ta, tb, p, s);
+    case EPI_BIAS_GELU: return launch_gemm<BN, EPI_BIAS_GELU, 8>(ta, tb, p, s);
+    case EPI_BIAS_RELU: return launch_gemm<BN, EPI_BIAS_RELU, 8>(ta, tb, p, s);
+    case EPI_BIAS_RESID: return launch_gemm<BN, EPI_BIAS_RESID, 8>(ta, tb, p, s);
     default: return fail(DYT_EINVAL, "unknown epilogue %d", epi);
   }
 }

@@ -10,8 +10,8 @@
 // which the ~70 B/clk an SM can take in sustains; a lone CTA (48 KB) is capped at ~2/3 of the
 // tensor peak, and multicasting B inside a cluster of two does not help (same bytes per SM).
 // Warp roles (384 threads): warp0 = TMA producer, warp1 = MMA issuer (one elected thread),
-// warp2 = TMEM allocator, warps4-11 = epilogue: two warps per TMEM lane quarter, each owning half
-// of the tile's columns.  The epilogue arithmetic (bias / GELU / ReLU / scale, one rounding to
+// warp2 = TMEM allocator, warps4.. = epilogue: two or four warps per TMEM lane quarter, each
+// owning a slice of the tile's columns.  The epilogue arithmetic (bias / GELU / ReLU / scale, one rounding to
 // fp16 per Linear output) runs in the TMEM register layout (thread = row, 32 columns); only the
 // fp16 result goes through a bank-conflict-free smem transpose (64-byte rows, 16-byte chunks XORed
 // with (row>>1)&3) to reach coalesced 128-bit global accesses.  The main loop's operand reads
@@ -49,18 +49,23 @@ struct GemmParams {
   int vec8;    // 1: out_h rows are 16-byte aligned and N % 8 == 0 -> 128-bit fp16 stores
 };
 
-template <int BN>
+// EW = epilogue warps: 8 (two per TMEM lane quarter) or 16 (four per quarter, for epilogue-bound
+// shapes: GELU, K <= 128 -- the arithmetic epilogue is latency-bound and wants more warps in flight)
+template <int BN, int EW = 8>
 struct GemmCfg {
+  static_assert(EW == 8 || (EW == 16 && BN >= 128), "epilogue warps: 8, or 16 for BN >= 128");
   static constexpr int BM = 128;
   static constexpr int BK = 64;  // 64 halves = 128 B = one swizzle row
-  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int STAGES = (BN == 256) ? (EW == 16 ? 5 : 6) : (BN == 128 && EW == 16 ? 7 : 8);
   static constexpr int A_BYTES = BM * BK * 2;         // this CTA's 128 rows of A
   static constexpr int B_BYTES = (BN / 2) * BK * 2;   // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_WARPS = 8;
+  static constexpr int EPI_WARPS = EW;
+  static constexpr int PARTS = EW / 4;          // column slices of the tile, one per warp of a quarter
+  static constexpr int PART_COLS = BN / PARTS;  // columns owned by one epilogue warp
   static constexpr int THREADS = 128 + EPI_WARPS * 32;
   static constexpr int SLAB_BYTES = 32 * 64;   // 32 rows x 32 fp16 (one 32-column chunk), per warp
-  static constexpr int BIAS_BYTES = (BN / 2) * 4;  // fp32 bias of the warp's half of the tile
+  static constexpr int BIAS_BYTES = PART_COLS * 4;  // fp32 bias of the warp's columns
   static constexpr int EPI_BYTES = EPI_WARPS * (SLAB_BYTES + BIAS_BYTES);
   static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: all powers of two
   static constexpr int BAR_BYTES = 256;
@@ -95,11 +100,11 @@ __device__ __forceinline__ float gelu_f16(float x) {
   return fmaf(-a, q, relu);
 }
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
+template <int BN, int EPI, int EW>
+__global__ void __launch_bounds__(GemmCfg<BN, EW>::THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EW>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -224,11 +229,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
-    constexpr int HALF = BN / 2;      // columns owned by this warp
-    constexpr int NCH = HALF / 32;    // 32-column chunks per warp per tile
+    constexpr int HALF = Cfg::PART_COLS;  // columns owned by this warp
+    constexpr int NCH = HALF / 32;        // 32-column chunks per warp per tile
     const int e = warp_idx - 4;
     const int q = e & 3;              // == warp_idx % 4: TMEM lane quarter this warp may access
-    const int half = e >> 2;
+    const int half = e >> 2;          // which column slice of the tile
     const uint32_t slab = smem_u32(epi_smem) + e * (Cfg::SLAB_BYTES + Cfg::BIAS_BYTES);
     const uint32_t bias_s = slab + Cfg::SLAB_BYTES;
     const uint32_t my_row = slab + lane * 64;
