@@ -33,6 +33,7 @@ struct BlockWorkspace {
   int* token_pos;   // [T]
   int* cu_seqlens;  // [B+1]
   int* n_kept;      // [1]
+  float* score_part;  // [T, slices] selector score partial sums from the proj epilogue
   void* dispatch_ws;
   size_t total;
 };
@@ -60,6 +61,7 @@ static BlockWorkspace carve(const dyt_block_shape* s, void* base) {
   w.mlp = static_cast<__half*>(take(T * C * 2));
   w.down = static_cast<__half*>(take(T * static_cast<size_t>(s->bottleneck) * 2));
   w.adapt = static_cast<__half*>(take(T * C * 2));
+  w.score_part = static_cast<float*>(take(T * static_cast<size_t>(gemm_tn_dot_slices(s->C)) * 4));
   w.packed_idx = static_cast<int*>(take(T * 4));
   w.token_pos = static_cast<int*>(take(T * 4));
   w.cu_seqlens = static_cast<int*>(take((static_cast<size_t>(s->B) + 1) * 4));
@@ -133,14 +135,18 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   // 3. attention (uniform sequences of N tokens)
   DYT_TRY(attn_varlen_fwd(w.qkv, 3 * C, nullptr, B, N, N, T, H, 64, w.attn_o, C, stream));
   // 4. proj + residual -> x1 (fp32) and its fp16 copy
+  // (the token selector's score Linear rides in the epilogue: per-row partial dot products)
+  const int slices = gemm_tn_dot_slices(C);
+  const bool fuse_score = C > 128;
   DYT_TRY(gemm_tn(w.attn_o, C, HP(wt->proj_w), C, T, C, C, nullptr, EPI_BIAS_RESID,
-                  HP(wt->proj_b), w.x1h, C, w.x1, C, x, C, 1.0f, stream));
+                  HP(wt->proj_b), w.x1h, C, w.x1, C, x, C, 1.0f, stream,
+                  fuse_score ? wt->sel_w : nullptr, w.score_part, slices, opt->logit_fp16));
   // 5. dispatcher: score, gate, compaction, LN2 of kept rows
-  DYT_TRY(dyt_dispatch_fwd(w.x1, C, wt->sel_w, wt->sel_b, opt->logit_fp16, opt->min_kept,
-                           opt->noise1, opt->noise2, opt->tau, B, N, C, wt->ln2_w, wt->ln2_b,
-                           opt->eps, opt->forced_mask, mask_out, opt->gate_out, logits_out, w.packed_idx,
-                           w.token_pos, w.cu_seqlens, w.n_kept, w.packed, C, w.dispatch_ws,
-                           stream_));
+  DYT_TRY(dispatch_fwd(w.x1, C, wt->sel_w, wt->sel_b, opt->logit_fp16, opt->min_kept,
+                       opt->noise1, opt->noise2, opt->tau, B, N, C, wt->ln2_w, wt->ln2_b,
+                       opt->eps, opt->forced_mask, mask_out, opt->gate_out, logits_out, w.packed_idx,
+                       w.token_pos, w.cu_seqlens, w.n_kept, w.packed, C, w.dispatch_ws, stream_,
+                       fuse_score ? w.score_part : nullptr, slices));
   // 6./7. MLP on the kept rows only (row count read from device memory)
   DYT_TRY(gemm_tn(w.packed, C, HP(wt->fc1_w), C, T, shape->hidden, C, w.n_kept, EPI_BIAS_GELU,
                   HP(wt->fc1_b), w.hidden, shape->hidden, nullptr, 0, nullptr, 0, 1.0f, stream));

@@ -48,12 +48,15 @@ struct DispatchParams {
   int* n_kept;          // [1]      out
   __half* packed;       // [B*N, ldp] out: LayerNorm2 of the kept rows, fp16
   int ldp;
+  const float* partials;  // optional [B*N, n_partials]: the score dot products, already computed in
+  int n_partials;         // column slices by the producer of x1 (proj GEMM epilogue); summed in order
   int* counts;          // [B] workspace (see dispatch_kernel)
   unsigned int* sync;   // [2] workspace; zero before the first launch, left zeroed by the kernel
 };
 
 constexpr int DISPATCH_MAX_N = 2048;
-constexpr int DISPATCH_CHUNK = 16;  // rows per phase-2 work item
+constexpr int DISPATCH_CHUNK = 32;   // tokens per phase-2 (compaction) work item
+constexpr int DISPATCH_SMEM_B = 1024;  // largest batch whose per-image prefix lives in smem
 
 __device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
 
@@ -95,6 +98,40 @@ dispatch_kernel(const DispatchParams p) {
   }
 
   // ------------------------------- phase 1: score + gate -------------------------------
+  if (p.partials != nullptr) {
+    // the dot products come from the proj GEMM epilogue: one thread per token, no pass over x1
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+      const int b = t / N;
+      const int n = t - b * N;
+      if (n == 0) {
+        p.mask[t] = 1.0f;
+        if (p.gate_out != nullptr) p.gate_out[t] = 1.0f;
+        atomicAdd(cur + b, 1);
+        continue;
+      }
+      float acc = 0.f;
+      for (int i = 0; i < p.n_partials; ++i) acc += p.partials[static_cast<size_t>(t) * p.n_partials + i];
+      float logit = acc + bias;
+      if (p.logit_fp16) logit = r16(logit);
+      float g = logit;
+      const size_t li = static_cast<size_t>(b) * (N - 1) + (n - 1);
+      if (p.noise1 != nullptr) {
+        if (p.logit_fp16) {
+          g = r16(g + r16(p.noise1[li]));
+          g = r16(g - r16(p.noise2[li]));
+          g = r16(g / r16(p.tau));
+        } else {
+          g = ((g + p.noise1[li]) - p.noise2[li]) / p.tau;
+        }
+      }
+      bool keep = g >= p.min_kept;
+      if (p.gate_out != nullptr) p.gate_out[t] = keep ? 1.0f : 0.0f;
+      if (p.forced_mask != nullptr) keep = p.forced_mask[t] != 0.0f;
+      p.logits[li] = logit;
+      p.mask[t] = keep ? 1.0f : 0.0f;
+      if (keep) atomicAdd(cur + b, 1);
+    }
+  } else
   for (int t = gw; t < T; t += nw) {
     const int b = t / N;
     const int n = t - b * N;
@@ -152,40 +189,75 @@ dispatch_kernel(const DispatchParams p) {
   }
 
   // ------------------------------- grid barrier -------------------------------
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(&p.sync[0], 1u);
-    const long long t0 = clock64();
-    while (atomicAdd(&p.sync[0], 0u) < gridDim.x) {
-      __nanosleep(100);
-      if (clock64() - t0 > 4000000000ll) {
-        printf("dyt: dispatcher grid barrier timeout (block %d)\n", (int)blockIdx.x);
-        __trap();
+  // (monotonic arrival counter: the k-th barrier waits for k * gridDim.x arrivals)
+  auto grid_barrier = [&](unsigned int k) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(&p.sync[0], 1u);
+      const long long t0 = clock64();
+      while (atomicAdd(&p.sync[0], 0u) < k * gridDim.x) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000ll) {
+          printf("dyt: dispatcher grid barrier timeout (block %d)\n", (int)blockIdx.x);
+          __trap();
+        }
       }
+      __threadfence();
     }
-    __threadfence();
-  }
-  __syncthreads();
+    __syncthreads();
+  };
+  grid_barrier(1u);
 
   // ------------------------------- phase 2: compact + pack -------------------------------
+  // exclusive prefix of the per-image counts, once per CTA (falls back to a per-item sum for
+  // batches beyond the smem table)
+  __shared__ int s_base[DISPATCH_SMEM_B + 1];
+  const bool smem_base = p.B <= DISPATCH_SMEM_B;
+  if (smem_base) {
+    __shared__ int s_warp[8];
+    int carry = 0;
+    for (int b0 = 0; b0 < p.B; b0 += 256) {
+      const int i = b0 + threadIdx.x;
+      const int c = i < p.B ? __ldcg(cur + i) : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) s_warp[warp] = incl;
+      __syncthreads();
+      int woff = 0;
+      for (int w = 0; w < warp; ++w) woff += s_warp[w];
+      if (i < p.B) s_base[i] = carry + woff + incl - c;
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += s_warp[w];
+      carry += tot;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) s_base[p.B] = carry;
+    __syncthreads();
+  }
   const int cpi = (N + DISPATCH_CHUNK - 1) / DISPATCH_CHUNK;  // chunks per image
   const int items = p.B * cpi;
   for (int item = gw; item < items; item += nw) {
     const int b = item / cpi;
     const int n0 = (item - b * cpi) * DISPATCH_CHUNK;
     // packed base of the image = kept tokens of all previous images
-    int part = 0;
-    for (int i = lane; i < b; i += 32) part += __ldcg(cur + i);
-    const int base = warp_sum_int(part);
-    // kept tokens of this image before the chunk
-    const float* mrow = p.mask + static_cast<size_t>(b) * N;
-    int before = 0;
-    for (int i0 = 0; i0 < n0; i0 += 32) {
-      const int n = i0 + lane;
-      const bool k = (n < n0) && (__ldcg(mrow + n) != 0.0f);
-      before += __popc(__ballot_sync(0xffffffffu, k));
+    int base;
+    if (smem_base) {
+      base = s_base[b];
+    } else {
+      int part = 0;
+      for (int i = lane; i < b; i += 32) part += __ldcg(cur + i);
+      base = warp_sum_int(part);
     }
+    // kept tokens of this image before the chunk: every lane counts its share of the mask row
+    const float* mrow = p.mask + static_cast<size_t>(b) * N;
+    int mine = 0;
+    for (int n = lane; n < n0; n += 32) mine += (__ldcg(mrow + n) != 0.0f) ? 1 : 0;
+    const int before = warp_sum_int(mine);
     const int n = n0 + lane;
     const bool valid = lane < DISPATCH_CHUNK && n < N;
     const bool keep = valid && (__ldcg(mrow + n) != 0.0f);
@@ -209,16 +281,31 @@ dispatch_kernel(const DispatchParams p) {
         p.n_kept[0] = total;
       }
     }
-    if (p.packed != nullptr) {
-      int j = first;
-      while (ballot != 0u) {
-        const int l = __ffs(ballot) - 1;
-        ballot &= ballot - 1u;
-        float4 v[NV];
-        load_row_f32<NV>(p.x1 + (static_cast<size_t>(b) * N + n0 + l) * p.ldx, lane, v);
-        row_layernorm<NV>(v, p.ln_w, p.ln_b, p.eps, lane);
-        store_row_f16<NV>(p.packed + static_cast<size_t>(j) * p.ldp, lane, v);
-        ++j;
+  }
+
+  // ------------------------------- phase 3: pack -------------------------------
+  // LayerNorm2 of the kept rows into the packed fp16 buffer: warps stride over packed positions
+  // (perfectly balanced, whatever the per-image keep counts), two rows in flight per warp.
+  if (p.packed != nullptr) {
+    grid_barrier(2u);
+    int total;
+    if (smem_base) {
+      total = s_base[p.B];
+    } else {
+      total = __ldcg(p.n_kept);
+    }
+    for (int j = gw; j < total; j += 2 * nw) {
+      const int j1 = j + nw;
+      const int t0 = __ldcg(p.packed_idx + j);
+      const int t1 = j1 < total ? __ldcg(p.packed_idx + j1) : -1;
+      float4 v0[NV], v1[NV];
+      load_row_f32<NV>(p.x1 + static_cast<size_t>(t0) * p.ldx, lane, v0);
+      if (t1 >= 0) load_row_f32<NV>(p.x1 + static_cast<size_t>(t1) * p.ldx, lane, v1);
+      row_layernorm<NV>(v0, p.ln_w, p.ln_b, p.eps, lane);
+      store_row_f16<NV>(p.packed + static_cast<size_t>(j) * p.ldp, lane, v0);
+      if (t1 >= 0) {
+        row_layernorm<NV>(v1, p.ln_w, p.ln_b, p.eps, lane);
+        store_row_f16<NV>(p.packed + static_cast<size_t>(j1) * p.ldp, lane, v1);
       }
     }
   }
@@ -263,6 +350,15 @@ extern "C" size_t dyt_dispatch_workspace_bytes(int B) {
   return static_cast<size_t>(B) * sizeof(int) + 64;
 }
 
+namespace dyt {
+int dispatch_fwd(const float* x1, int ldx, const float* sel_w, const float* sel_b, int logit_fp16,
+                 float min_kept, const float* noise1, const float* noise2, float tau, int B, int N,
+                 int C, const float* ln_w, const float* ln_b, float eps, const float* forced_mask,
+                 float* mask, float* gate_out, float* logits, int* packed_idx, int* token_pos,
+                 int* cu_seqlens, int* n_kept, void* packed_f16, int ldp, void* workspace,
+                 void* stream, const float* partials, int n_partials);
+}
+
 extern "C" int dyt_dispatch_fwd(const float* x1, int ldx, const float* sel_w, const float* sel_b,
                                 int logit_fp16, float min_kept, const float* noise1,
                                 const float* noise2, float tau, int B, int N, int C,
@@ -270,6 +366,20 @@ extern "C" int dyt_dispatch_fwd(const float* x1, int ldx, const float* sel_w, co
                                 const float* forced_mask, float* mask, float* gate_out,
                                 float* logits, int* packed_idx, int* token_pos, int* cu_seqlens, int* n_kept,
                                 void* packed_f16, int ldp, void* workspace, void* stream) {
+  return dyt::dispatch_fwd(x1, ldx, sel_w, sel_b, logit_fp16, min_kept, noise1, noise2, tau, B, N, C,
+                           ln_w, ln_b, eps, forced_mask, mask, gate_out, logits, packed_idx, token_pos,
+                           cu_seqlens, n_kept, packed_f16, ldp, workspace, stream, nullptr, 0);
+}
+
+// Internal entry: `partials` ([B*N, n_partials] fp32) replaces the score pass over x1 by the column
+// partial sums the proj GEMM epilogue has already produced (block.cu).
+int dyt::dispatch_fwd(const float* x1, int ldx, const float* sel_w, const float* sel_b,
+                      int logit_fp16, float min_kept, const float* noise1, const float* noise2,
+                      float tau, int B, int N, int C, const float* ln_w, const float* ln_b,
+                      float eps, const float* forced_mask, float* mask, float* gate_out,
+                      float* logits, int* packed_idx, int* token_pos, int* cu_seqlens, int* n_kept,
+                      void* packed_f16, int ldp, void* workspace, void* stream,
+                      const float* partials, int n_partials) {
   using namespace dyt;
   DYT_CHECK_ARG(x1 && sel_w && sel_b && mask && logits && packed_idx && token_pos && cu_seqlens &&
                     n_kept && workspace,
@@ -290,6 +400,7 @@ extern "C" int dyt_dispatch_fwd(const float* x1, int ldx, const float* sel_w, co
   p.mask = mask; p.gate_out = gate_out; p.logits = logits; p.packed_idx = packed_idx; p.token_pos = token_pos;
   p.cu_seqlens = cu_seqlens; p.n_kept = n_kept;
   p.packed = static_cast<__half*>(packed_f16); p.ldp = ldp;
+  p.partials = partials; p.n_partials = n_partials;
   p.sync = static_cast<unsigned int*>(workspace);
   p.counts = reinterpret_cast<int*>(static_cast<char*>(workspace) + 64);
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -64,9 +64,15 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb,
 }
 
 // Internal entry used by the composite block forward as well.
+int gemm_tn_dot_slices(int N) {
+  const int bn = (N <= 64) ? 64 : ((N <= 128 || (N % 256 != 0 && N % 128 == 0)) ? 128 : 256);
+  return ((N + bn - 1) / bn) * 2;  // RESID epilogues with K > 128 run two column slices per tile
+}
+
 int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, int K,
             const int* m_dev, int epi, const __half* bias, __half* out_h, int ldo_h, float* out_f,
-            int ldo_f, const float* resid, int ld_res, float scale, cudaStream_t stream) {
+            int ldo_f, const float* resid, int ld_res, float scale, cudaStream_t stream,
+            const float* dot_w, float* dot_out, int dot_ld, int dot_f16) {
   DYT_CHECK_ARG(a != nullptr && w != nullptr, "gemm: null operand");
   DYT_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   DYT_CHECK_ARG(N % 8 == 0 && K % 8 == 0, "gemm: N and K must be multiples of 8 (N=%d K=%d)", N, K);
@@ -101,6 +107,12 @@ int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, in
   p.out_h = out_h; p.out_f = out_f; p.resid = resid;
   p.ldo_h = ldo_h; p.ldo_f = ldo_f; p.ld_res = ld_res;
   p.scale = scale;
+  p.dot_w = dot_w; p.dot_out = dot_out; p.dot_ld = dot_ld; p.dot_f16 = dot_f16;
+  if (dot_w != nullptr) {
+    DYT_CHECK_ARG(epi == EPI_BIAS_RESID && K > 128 && dot_out != nullptr && N % 4 == 0 &&
+                      dot_ld >= gemm_tn_dot_slices(N),
+                  "gemm: the fused row-dot needs the residual epilogue, K > 128 and dot_ld >= slices");
+  }
   p.vec8 = (out_h != nullptr && ldo_h % 8 == 0 && N % 8 == 0 &&
             (reinterpret_cast<uintptr_t>(out_h) & 15) == 0) ? 1 : 0;
   switch (bn) {
@@ -119,5 +131,5 @@ extern "C" int dyt_linear_f16(const void* x, int ldx, const void* w, int ldw, in
   return dyt::gemm_tn(static_cast<const __half*>(x), ldx, static_cast<const __half*>(w), ldw, M, N,
                       K, m_dev, epilogue, static_cast<const __half*>(bias),
                       static_cast<__half*>(out_f16), ldo_f16, out_f32, ldo_f32, resid, ld_resid,
-                      scale, static_cast<cudaStream_t>(stream));
+                      scale, static_cast<cudaStream_t>(stream), nullptr, nullptr, 0, 0);
 }

@@ -47,6 +47,14 @@ struct GemmParams {
   int ld_res;  // row stride of resid
   float scale;
   int vec8;    // 1: out_h rows are 16-byte aligned and N % 8 == 0 -> 128-bit fp16 stores
+  // EPI_BIAS_RESID only, optional: per-row dot products <out row, dot_w> accumulated over each
+  // epilogue warp's column slice (the token selector's score Linear fused into the proj GEMM,
+  // reference models/dynamic_adapter.py:70-72).  dot_out[row * dot_ld + slice], slice =
+  // n_tile * PARTS + part; dot_f16 = 1 rounds the row values to fp16 first (autocast policy).
+  const float* dot_w;  // [N] fp32 or nullptr
+  float* dot_out;
+  int dot_ld;
+  int dot_f16;
 };
 
 // EW = epilogue warps: 8 (two per TMEM lane quarter) or 16 (four per quarter, for epilogue-bound
@@ -264,6 +272,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(acc * BN + half * HALF);
+      float dot_acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // RESID row-dot partials
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         uint32_t r[32];
@@ -325,6 +334,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           // lane -> (row it*4 + lane/8, columns (lane%8)*4 .. +3): 128-byte fp32 row segments
           const int col = n0 + c * 32 + (lane & 7) * 4;
           const int p8 = lane & 7;
+          float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.dot_w != nullptr && col < p.N) {
+            dw = *reinterpret_cast<const float4*>(p.dot_w + col);
+            if (p.dot_f16)
+              dw = make_float4(round_f16(dw.x), round_f16(dw.y), round_f16(dw.z), round_f16(dw.w));
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + (lane >> 3);
@@ -340,9 +355,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
               const float4 o = make_float4(res[it].x + v01.x, res[it].y + v01.y, res[it].z + v23.x,
                                            res[it].w + v23.y);
               *reinterpret_cast<float4*>(p.out_f + static_cast<size_t>(grow) * p.ldo_f + col) = o;
-              if (p.out_h != nullptr) {
-                const uint2 oh = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+              const uint2 oh = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+              if (p.out_h != nullptr)
                 *reinterpret_cast<uint2*>(p.out_h + static_cast<size_t>(grow) * p.ldo_h + col) = oh;
+              if (p.dot_w != nullptr) {
+                float4 s = o;
+                if (p.dot_f16) {
+                  const float2 s01 = __half22float2(*reinterpret_cast<const __half2*>(&oh.x));
+                  const float2 s23 = __half22float2(*reinterpret_cast<const __half2*>(&oh.y));
+                  s = make_float4(s01.x, s01.y, s23.x, s23.y);
+                }
+                dot_acc[it] = fmaf(s.x, dw.x, fmaf(s.y, dw.y, fmaf(s.z, dw.z, fmaf(s.w, dw.w, dot_acc[it]))));
               }
             }
           }
@@ -366,6 +389,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
         __syncwarp();  // the slab is overwritten by the next chunk
+      }
+      if constexpr (EPI == EPI_BIAS_RESID) {
+        if (p.dot_w != nullptr) {
+          // the eight lanes that share a row add up their column partials, lane%8 == 0 stores
+          const int slice = (tile % n_tiles) * Cfg::PARTS + half;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            float v = dot_acc[it];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            const int grow = m0 + q * 32 + it * 4 + (lane >> 3);
+            if ((lane & 7) == 0 && grow < m_eff)
+              p.dot_out[static_cast<size_t>(grow) * p.dot_ld + slice] = v;
+          }
+        }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;

@@ -7,7 +7,10 @@ namespace dyt {
 
 int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, int K,
             const int* m_dev, int epi, const __half* bias, __half* out_h, int ldo_h, float* out_f,
-            int ldo_f, const float* resid, int ld_res, float scale, cudaStream_t stream);
+            int ldo_f, const float* resid, int ld_res, float scale, cudaStream_t stream,
+            const float* dot_w = nullptr, float* dot_out = nullptr, int dot_ld = 0, int dot_f16 = 0);
+// number of per-row partial sums the fused row-dot of a residual-epilogue GEMM writes (N columns)
+int gemm_tn_dot_slices(int N);
 
 int attn_varlen_fwd(const __half* qkv, int ld_qkv, const int* cu_seqlens, int num_seqs,
                     int uniform_len, int max_seqlen, int total_tokens, int num_heads, int head_dim,
@@ -21,5 +24,12 @@ int scatter_merge(const float* x1, int ldx, const __half* adapt, int lda, const 
                   int ldm, const int* token_pos, int n_rows, int C, float* out, int ldo,
                   const float* nln_w, const float* nln_b, float eps, __half* nln_out, int ldn,
                   cudaStream_t stream);
+
+int dispatch_fwd(const float* x1, int ldx, const float* sel_w, const float* sel_b, int logit_fp16,
+                 float min_kept, const float* noise1, const float* noise2, float tau, int B, int N,
+                 int C, const float* ln_w, const float* ln_b, float eps, const float* forced_mask,
+                 float* mask, float* gate_out, float* logits, int* packed_idx, int* token_pos,
+                 int* cu_seqlens, int* n_kept, void* packed_f16, int ldp, void* workspace,
+                 void* stream, const float* partials, int n_partials);
 
 }  // namespace dyt
