@@ -373,7 +373,8 @@ def run_ours(args, world, rank, local):
         "steps": args.steps, "warmup": warm, "ms_per_step": sec / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
-        "config": {"workload": "ViT-B/16 DyT inference bs256 224x224 r~0.5 on 1xB200 (speed.py path)",
+        "config": {"workload": "ViT-B/16 DyT inference bs256 224x224 r~0.5 per B200 (speed.py path; "
+                               "BASELINE configs[1]), images sharded over the GPUs",
                    "batch_per_gpu": BATCH, "keep_rate": round(keep_rate, 4),
                    "kept_tokens_per_image_layer": round(kept_tokens, 2),
                    "l2": "per-step working set ~1.1 GB of activations >> 126 MB L2 (no flush needed)",
@@ -393,9 +394,13 @@ def run_ours(args, world, rank, local):
     if world == 1:
         rows = kernel_table(model, x0, kept_tokens * BATCH, peaks, device)
         top = max((r for r in rows if r["bound"] == "tensor"), key=lambda r: r["us"])
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed
+        # ncu --set full capture (profiles/r1e_ncu_full_one_layer.md), per launch
+        traffic = {"gemm qkv [T,768]x[2304,768]": 261.9e6, "gemm fc1 + GELU (kept rows)": 147.9e6,
+                   "gemm fc2 (kept rows)": 189.9e6}.get(top["kernel"])
         line["roofline"] = {"kernel": top["kernel"], "bound": "tensor", "achieved": top["achieved"],
                             "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": top["frac"],
-                            "traffic": None, "us_per_launch": top["us"],
+                            "traffic": traffic, "us_per_launch": top["us"],
                             "peak_source": peaks["source"] + " bf16 burst (kernel timed alone)"}
         line["kernels"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()}
                            for r in rows]
