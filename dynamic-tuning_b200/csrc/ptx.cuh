@@ -128,11 +128,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((n & 4095u) == 0u) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
-      if (now - t0 > DYT_WAIT_TIMEOUT_CYCLES) {
-        printf("dyt: mbarrier wait timeout block=%d thread=%d bar=%u parity=%u\n", (int)blockIdx.x,
-               (int)threadIdx.x, smem_u32(bar), parity);
-        __trap();
-      }
+      // no printf here: a call in this (inlined everywhere) function makes the compiler keep
+      // caller-saved values such as the TMEM base in local memory, which showed up as LDL stalls
+      // inside the attention softmax loops
+      if (now - t0 > DYT_WAIT_TIMEOUT_CYCLES) __trap();
     }
   }
 }

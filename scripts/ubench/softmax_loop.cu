@@ -49,7 +49,7 @@ __global__ void k(long long* out, float* sink, int units, int nfull, int mma_mod
   tc_fence_before(); __syncthreads(); tc_fence_after();
   if (warp == 8) {
     // background MMA stream (one elected lane): mode 1 = PV-like TS 128x64x16 x13, mode 2 = S-like SS 128x208x16 x4, 3 = both
-    if (mma_mode != 0) {
+    if ((mma_mode & 15) != 0) {
     const uint32_t tm = __shfl_sync(0xffffffffu, tptr, 0);
     const uint32_t sm = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
     uint32_t ph = 0;
@@ -69,6 +69,7 @@ __global__ void k(long long* out, float* sink, int units, int nfull, int mma_mod
     }
   } else if (warp < (int)gridDim.y * 0 + nw_soft) {
   const uint32_t s_addr = tptr + (uint32_t((warp & 3) * 32) << 16) + (warp >= 4 ? 256 : 0);
+  const uint32_t p_base = (mma_mode & 16) ? (s_addr ^ 256u) : s_addr;
   float sum4[4] = {0, 0, 0, 0};
   const float sl2 = 0.18f, mb = 1.0f;
   long long t0 = clock64();
@@ -79,11 +80,11 @@ __global__ void k(long long* out, float* sink, int units, int nfull, int mma_mod
 #pragma unroll 1
     for (int c = 0; c < nfull; c += 2) {
       if (c + 1 < nfull) tmem_ld32(s_addr + (c + 1) * 32, rb);
-      if (VARIANT == 0) exp32(ra, sl2, mb, sum4, s_addr + c * 16); else exp32b(ra, sl2, mb, sum4, s_addr + c * 16);
+      if (VARIANT == 0) exp32(ra, sl2, mb, sum4, p_base + c * 16); else exp32b(ra, sl2, mb, sum4, p_base + c * 16);
       tmem_ld_wait();
       if (c + 1 < nfull) {
         if (c + 2 < nfull) tmem_ld32(s_addr + (c + 2) * 32, ra);
-        if (VARIANT == 0) exp32(rb, sl2, mb, sum4, s_addr + (c + 1) * 16); else exp32b(rb, sl2, mb, sum4, s_addr + (c + 1) * 16);
+        if (VARIANT == 0) exp32(rb, sl2, mb, sum4, p_base + (c + 1) * 16); else exp32b(rb, sl2, mb, sum4, p_base + (c + 1) * 16);
         tmem_ld_wait();
       }
     }
@@ -104,7 +105,7 @@ int main() {
   long long h[64];
   const int units = 50, nfull = 6;
   cudaFuncSetAttribute(k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 70 * 1024);
-  for (int variant = 0; variant < 4; ++variant)
+  for (int variant : {0, 16, 3, 19})
     for (int nw : {4, 8}) {
       for (int rep = 0; rep < 2; ++rep) {
         k<0><<<1, 9 * 32, 70 * 1024>>>(d, sink, units, nfull, variant, nw);   // 8 softmax warps slots + MMA warp

@@ -105,6 +105,34 @@ def test_block_matches_oracle(dev, vitb_sd, B):
         assert _rel(logits[0].unsqueeze(-1), ref["logits"]) <= 2e-3
 
 
+def test_fused_selector_score_matches_standalone_dispatcher(dev, vitb_sd):
+    """The block computes the selector logits inside the proj GEMM epilogue (column partial sums);
+    the standalone dispatcher on the block's own x1 buffer must give the same logits (fp32
+    summation order differs: <= 1 fp16 ulp) and the same mask except on threshold ties."""
+    g, sd, img = vitb_sd
+    m = _speed_model(sd, dev)
+    from dyt_b200 import engine, ops
+    import ctypes as C
+    B = 4
+    x = torch.randn(B, 197, 768, generator=torch.Generator().manual_seed(11)) * 0.7
+    blk = m.blocks[5]
+    out, masks, logits, _ = engine.run_blocks(x.to(dev), [blk], fuse_next_ln=False)
+    shape = engine.block_shape_of(blk, B, 197)
+    ws = engine._workspace(shape, dev)
+    bufs = engine.workspace_buffers(shape, ws)
+    off = bufs.x1 - ws.data_ptr()
+    x1 = ws[off:off + B * 197 * 768 * 4].view(torch.float32).reshape(B, 197, 768).clone()
+    d = ops.dispatch(x1, blk.mlp_token_select.mlp_head.weight.detach(),
+                     blk.mlp_token_select.mlp_head.bias.detach(), pack=False)
+    l_ref, l_got = d["logits"][..., 0], logits[0]
+    assert float((l_ref - l_got).abs().max()) <= 2e-3 * float(l_ref.abs().max())
+    mism = d["mask"][..., 0] != masks[0]
+    if bool(mism.any()):
+        thr = O.min_kept_logit(torch.float16)
+        assert bool(((l_ref[mism[:, 1:]] - thr).abs() <= 2e-3).all())
+    assert int(mism.sum()) <= 2
+
+
 def test_block_imposed_mask_config1(dev, vitb_sd):
     """BASELINE configs[0] on the GPU path: fixed 50 % keep mask, block output vs oracle."""
     g, sd, img = vitb_sd

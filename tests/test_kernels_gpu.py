@@ -81,6 +81,48 @@ def test_linear_residual_and_device_row_count(dev):
     assert bool((buf[123:] == -7.0).all())
 
 
+def test_gelu_epilogue_exhaustive_fp16(dev):
+    """Every finite fp16 value through the fc1 epilogue (identity weight, zero bias): the Gaussian-tail
+    polynomial GELU must land on the correctly rounded fp16 GELU (float64 erf) or its fp16 neighbour.
+    (torch's own fp32 formula 0.5*x*(1+erf(x/sqrt2)) cancels catastrophically for x < -3 and is
+    itself several fp16 ulps off there, so it is only checked with an absolute bound.)"""
+    from dyt_b200 import ops, _lib
+    bits = torch.arange(65536, dtype=torch.int32).to(torch.int16).view(torch.float16)
+    x = bits[torch.isfinite(bits)]
+    pad = (-x.numel()) % 8
+    x = torch.cat([x, torch.zeros(pad, dtype=torch.float16)]).reshape(-1, 8)
+    w = torch.eye(8, dtype=torch.float16)
+    out, _ = ops.linear_f16(x.to(dev), w.to(dev), torch.zeros(8, dtype=torch.float16, device=dev),
+                            epilogue=_lib.EPI_BIAS_GELU)
+    ref = torch.nn.functional.gelu(x.double()).half()
+    got = out.cpu()
+    ref32 = torch.nn.functional.gelu(x.float()).half()        # what autocast does to nn.GELU
+    fin = torch.isfinite(ref32.float()) & torch.isfinite(got.float())
+    err32 = (got.float() - ref32.float()).abs()[fin]
+    tol32 = 1.5e-6 + 2e-3 * ref32.float().abs()[fin]
+    assert bool((err32 <= tol32).all()), "GELU differs from torch's fp32 GELU beyond its own noise"
+    d = (got.view(torch.int16).int() - ref.view(torch.int16).int()).abs()
+    d = torch.where((got == 0) & (ref == 0), torch.zeros_like(d), d)   # +0 / -0
+    assert int(d.max()) <= 1, f"GELU off by {int(d.max())} fp16 ulps"
+    assert int((d > 0).sum()) <= 400, f"{int((d > 0).sum())} of {x.numel()} values differ"
+
+
+@pytest.mark.parametrize("M,N,K", [(129, 256, 64), (255, 512, 128), (1000, 768, 768), (257, 2304, 64)])
+def test_linear_cta_pair_edges(dev, M, N, K):
+    """Tile rows that are odd in count (the CTA pair's second tile is a dummy), rows past M and
+    the short-K shapes that take the sixteen-warp epilogue."""
+    from dyt_b200 import ops, _lib
+    g = _gen(M + N + K)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    ref = O.linear(x, w, b, "amp16")
+    out, _ = ops.linear_f16(x.half().to(dev), w.half().to(dev), b.half().to(dev))
+    _close(out, ref, atol=1e-3, rtol=2e-3)
+    out2, _ = ops.linear_f16(x.half().to(dev), w.half().to(dev), b.half().to(dev), scale=0.1)
+    _close(out2, O._r16(ref * 0.1), atol=1e-3, rtol=3e-3)
+
+
 def test_linear_rejects_bad_arguments(dev):
     from dyt_b200 import ops, DytError
     with pytest.raises(DytError):
