@@ -380,12 +380,14 @@ def run_ours(args, world, rank, local):
                    "l2": "per-step working set ~1.1 GB of activations >> 126 MB L2 (no flush needed)",
                    "weights": "random init seed 0, selector bias calibrated on the GPU path",
                    "stem_head": "patch embed = own im2col + tcgen05 GEMM + assemble kernels; final LN "
-                                "(cls rows) and the 768x100 head via torch library ops"},
+                                "(cls rows, own row-gather LayerNorm kernel) + 768x100 head (own "
+                                "tcgen05 GEMM, classes zero-padded to 104)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s",
                 "h2d_bytes_per_step": host_images.numel() * 4,
                 "d2h_bytes_per_step": host_logits.numel() * 2},
-        "gpu_launches": args.steps * (DEPTH * 9 + 1 + 3),   # 9 per block + LN1 + 3 stem kernels
+        # 9 per block + first LN1 + 3 stem kernels + final LN + head GEMM
+        "gpu_launches": args.steps * (DEPTH * 9 + 1 + 3 + 2),
         "model_flops_per_image": fl_img,
         "model_tflops": value / world * fl_img / 1e12,
         "frac_of_r_scaled_compute_roofline": value / world * fl_img / 1e12 / peaks["tf_sust"],

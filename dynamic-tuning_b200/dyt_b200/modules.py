@@ -362,6 +362,41 @@ class VisionTransformer(nn.Module):
             return self.head_drop(self.norm(x[:, 0]))
         return None
 
+    def _cls_head(self, tokens):
+        """Final LayerNorm of the cls rows + classifier head on the sm_100a kernels (reference
+        vision_transformer_IN21K.py:371-380 / model_speed_test.py:483-491 under fp16 autocast):
+        row-gathering LayerNorm kernel -> tcgen05 GEMM.  Returns None when the configuration is not
+        the plain 'token' pool + nn.Linear head under fp16 autocast (then the caller falls back to
+        the generic module path)."""
+        if not (self.global_pool == "token" and isinstance(self.fc_norm, nn.Identity) and
+                isinstance(self.norm, nn.LayerNorm) and isinstance(self.head, nn.Linear) and
+                _act_dtype() == torch.float16 and self.head.bias is not None and
+                not (self.training and self.head_drop.p > 0)):
+            return None
+        B, N, Cd = tokens.shape
+        key = (self.head.weight.data_ptr(), self.head.weight._version, self.head.bias._version)
+        cache = self.__dict__.get("_dyt_head")
+        if cache is None or cache[0] != key:
+            nc = self.head.out_features
+            n8 = (nc + 7) // 8 * 8          # the GEMM wants N % 8 == 0: zero-padded classes
+            w16 = torch.zeros((n8, Cd), dtype=torch.float16, device=tokens.device)
+            b16 = torch.zeros((n8,), dtype=torch.float16, device=tokens.device)
+            w16[:nc] = self.head.weight.detach().to(torch.float16)
+            b16[:nc] = self.head.bias.detach().to(torch.float16)
+            cache = (key, w16, b16, nc)
+            self.__dict__["_dyt_head"] = cache
+        _, w16, b16, nc = cache
+        ikey = (B, N, tokens.device)
+        icache = self.__dict__.get("_dyt_cls_idx")
+        if icache is None or icache[0] != ikey:
+            icache = (ikey, torch.arange(B, device=tokens.device, dtype=torch.int32) * N)
+            self.__dict__["_dyt_cls_idx"] = icache
+        idx = icache[1]
+        cls_n = ops.layernorm_f16(tokens.float(), self.norm.weight.detach().float(),
+                                  self.norm.bias.detach().float(), float(self.norm.eps), row_idx=idx)
+        logits, _ = ops.linear_f16(cls_n, w16, b16)
+        return logits[:, :nc]
+
     def _blocks(self, x, complete_model=False):
         if self.training and torch.is_grad_enabled():
             raise NotImplementedError("dyt_b200: train-mode forward/backward is the next scope row; "
@@ -398,6 +433,9 @@ class SpeedVisionTransformer(VisionTransformer):
 
     def forward(self, x):
         tokens, _, _ = self._blocks(self._embed(x))
+        logits = self._cls_head(tokens)
+        if logits is not None:
+            return logits
         pooled = self._pooled_norm(tokens)
         if pooled is not None:
             return self.head(pooled)
@@ -421,6 +459,9 @@ class TrainVisionTransformer(VisionTransformer):
         dt = _act_dtype()
         token_select = dict(token_select=masks.permute(1, 0, 2)[:, :, 1:].unsqueeze(-1).to(dt),
                             token_logits=logits.permute(1, 0, 2).unsqueeze(-1).to(dt))
+        cls_logits = self._cls_head(tokens)
+        if cls_logits is not None:
+            return cls_logits, token_select
         pooled = self._pooled_norm(tokens)
         if pooled is not None:
             return self.head(pooled), token_select

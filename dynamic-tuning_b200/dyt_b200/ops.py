@@ -196,6 +196,7 @@ def scatter_merge(x1: torch.Tensor, adapt: torch.Tensor, mlp_packed: torch.Tenso
 
 
 _stem_ws = {}
+_stem_params = {}
 
 
 def patch_embed(img: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torch.Tensor],
@@ -207,10 +208,17 @@ def patch_embed(img: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torch.
     B, Cin, H, W = img.shape
     Cdim = conv_w.shape[0]
     L = (H // patch) * (W // patch)
-    w16 = conv_w.detach().reshape(Cdim, -1).to(torch.float16).contiguous()
-    b16 = None if conv_b is None else conv_b.detach().to(torch.float16).contiguous()
-    cls = cls_token.detach().reshape(-1).to(torch.float32).contiguous()
-    pos = pos_embed.detach().reshape(L + 1, Cdim).to(torch.float32).contiguous()
+    # fp16 copies of the (frozen) stem parameters, rebuilt only when a parameter changes
+    key = (conv_w.data_ptr(), conv_w._version, None if conv_b is None else conv_b._version,
+           cls_token.data_ptr(), cls_token._version, pos_embed.data_ptr(), pos_embed._version)
+    cached = _stem_params.get(conv_w.data_ptr())
+    if cached is None or cached[0] != key:
+        w16 = conv_w.detach().reshape(Cdim, -1).to(torch.float16).contiguous()
+        b16 = None if conv_b is None else conv_b.detach().to(torch.float16).contiguous()
+        cls = cls_token.detach().reshape(-1).to(torch.float32).contiguous()
+        pos = pos_embed.detach().reshape(L + 1, Cdim).to(torch.float32).contiguous()
+        _stem_params[conv_w.data_ptr()] = cached = (key, w16, b16, cls, pos)
+    _, w16, b16, cls, pos = cached
     need = int(_lib.lib().dyt_patch_embed_workspace_bytes(B, H, W, patch, Cin, Cdim))
     if need == 0:
         raise DytError(f"patch_embed: unsupported geometry H={H} W={W} P={patch}")
