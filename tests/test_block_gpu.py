@@ -215,6 +215,34 @@ def test_model_config1_imposed_mask_vs_golden(dev, vitb_sd):
     assert _rel(logits, ref["logits"]) <= 5e-3
 
 
+def test_vit_large_block_matches_oracle(dev):
+    """BASELINE configs[3] shape (ViT-L/16: C = 1024, 16 heads, hidden 4096; the MoE-adapter of that
+    config does not exist in the reference): one block and a 2-layer model against
+    the oracle, which is the reference Block re-parameterised (vision_transformer_IN21K.py:199-231)."""
+    from models.model_speed_test import VisionTransformer
+    from dyt_b200 import engine
+    tuning, select = configs(d_model=1024)
+    sd = O.synthetic_state_dict(embed_dim=1024, depth=2, num_heads=16, seed=3)
+    img = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(0))
+    sd = O.calibrate_selector_bias(sd, img, 2, 16, 0.1, 0.7)
+    m = VisionTransformer(embed_dim=1024, depth=2, num_heads=16, num_classes=100,
+                          tuning_config=tuning, select_config=select)
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().to(dev)
+    x = torch.randn(2, 197, 1024, generator=torch.Generator().manual_seed(5)) * 0.7
+    ref = O.block_sparse(x, sd, "blocks.1.", 16, 0.1, "amp16")
+    out, masks, logits, _ = engine.run_blocks(x.to(dev), [m.blocks[1]], fuse_next_ln=False)
+    flips = _check_masks(masks[0].unsqueeze(-1).cpu(), ref["mask"], ref["logits"], max_flips=1)
+    if flips == 0:
+        assert _rel(out, ref["out"]) <= 1e-3
+    keep = float(masks[0][:, 1:].mean())
+    assert 0.4 < keep < 0.95
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        got = m(img.to(dev))
+    full = O.vit_forward(img, sd, 2, 16, 0.1, policy="amp16", sparse=True)
+    assert _rel(got.float(), full["logits"]) <= 2e-2
+
+
 def test_tiny_dims_unsupported_are_loud(dev):
     """head_dim != 64 is outside the implemented kernels: must raise, never fall back."""
     from dyt_b200 import DytError
