@@ -70,6 +70,61 @@ int layernorm_f16(const float* x, int ldx, const int* row_idx, const int* n_rows
 }
 
 // ---------------------------------------------------------------------------------------------
+// Video pooling head input: k_in = f16(LN_k(LN(x))), v_in = f16(LN_v(LN(x))) for every token
+// (reference video_models/video_vision_transformer_IN21K.py:474 `self.norm`, :44-45 `norm_k` /
+// `norm_v` of AttentiveBlock; all three LayerNorms run in fp32 under autocast, the consumer Linear
+// casts to fp16).  One pass over the fp32 stream instead of three.
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+double_layernorm_f16_kernel(const float* __restrict__ x, int ldx, int n_rows,
+                            const float* __restrict__ g0, const float* __restrict__ b0,
+                            const float* __restrict__ gk, const float* __restrict__ bk,
+                            const float* __restrict__ gv, const float* __restrict__ bv, float eps,
+                            __half* __restrict__ out_k, __half* __restrict__ out_v, int ldo) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n_rows;
+       r += gridDim.x * warps_per_block) {
+    float4 v[NV], k[NV];
+    load_row_f32<NV>(x + static_cast<size_t>(r) * ldx, lane, v);
+    row_layernorm<NV>(v, g0, b0, eps, lane);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) k[i] = v[i];
+    row_layernorm<NV>(k, gk, bk, eps, lane);
+    store_row_f16<NV>(out_k + static_cast<size_t>(r) * ldo, lane, k);
+    row_layernorm<NV>(v, gv, bv, eps, lane);
+    store_row_f16<NV>(out_v + static_cast<size_t>(r) * ldo, lane, v);
+  }
+}
+
+int double_layernorm_f16(const float* x, int ldx, int n_rows, int C, const float* g0,
+                         const float* b0, const float* gk, const float* bk, const float* gv,
+                         const float* bv, float eps, __half* out_k, __half* out_v, int ldo,
+                         cudaStream_t stream) {
+  DYT_CHECK_ARG(x && g0 && b0 && gk && bk && gv && bv && out_k && out_v, "double_layernorm: null buffer");
+  DYT_CHECK_ARG(n_rows >= 0 && ldx >= C && ldo >= C && ldx % 4 == 0 && ldo % 4 == 0,
+                "double_layernorm: bad sizes");
+  if (n_rows == 0) return DYT_OK;
+  int grid = (n_rows + 7) / 8;
+  const int cap = sm_count() * 16;
+  if (grid > cap) grid = cap;
+#define DYT_LAUNCH_DLN(NV)                                                                          \
+  double_layernorm_f16_kernel<NV><<<grid, 256, 0, stream>>>(x, ldx, n_rows, g0, b0, gk, bk, gv, bv, \
+                                                            eps, out_k, out_v, ldo)
+  switch (C) {
+    case 768: DYT_LAUNCH_DLN(6); break;
+    case 1024: DYT_LAUNCH_DLN(8); break;
+    case 384: DYT_LAUNCH_DLN(3); break;
+    case 128: DYT_LAUNCH_DLN(1); break;
+    default:
+      return fail(DYT_EUNSUPPORTED, "double_layernorm: embed dim %d not instantiated", C);
+  }
+#undef DYT_LAUNCH_DLN
+  return cuda_status(cudaGetLastError(), "double_layernorm_f16_kernel launch");
+}
+
+// ---------------------------------------------------------------------------------------------
 // scatter-merge: out[t] = adapt[t] + (x1[t] + (kept(t) ? mlp_packed[pos[t]] : 0))
 // Replaces zeros() + index_put + two adds (reference models/model_speed_test.py:302-308).
 // Optionally also emits LayerNorm(out) in fp16 with the NEXT block's norm1 (or the final norm), so
@@ -152,6 +207,15 @@ extern "C" int dyt_layernorm_f16(const float* x, int ldx, const int* row_idx, co
                                  void* out_f16, int ldo, void* stream) {
   return dyt::layernorm_f16(x, ldx, row_idx, n_rows_dev, n_rows, C, gamma, beta, eps,
                             static_cast<__half*>(out_f16), ldo, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dyt_pool_layernorm_f16(const float* x, int ldx, int n_rows, int C, const float* g0,
+                                      const float* b0, const float* gk, const float* bk,
+                                      const float* gv, const float* bv, float eps, void* out_k_f16,
+                                      void* out_v_f16, int ldo, void* stream) {
+  return dyt::double_layernorm_f16(x, ldx, n_rows, C, g0, b0, gk, bk, gv, bv, eps,
+                                   static_cast<__half*>(out_k_f16), static_cast<__half*>(out_v_f16),
+                                   ldo, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dyt_scatter_merge_fwd(const float* x1, int ldx, const void* adapt_f16, int lda,

@@ -63,6 +63,8 @@ SIGNATURES = {
                                    _vp, _i, _vp]),
     "dyt_patch_embed_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "dyt_patch_embed_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "dyt_pool_layernorm_f16": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp]),
+    "dyt_query_attn_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "dyt_block_workspace_bytes": (_sz, [C.POINTER(BlockShape)]),
     "dyt_block_workspace_layout": (_i, [C.POINTER(BlockShape), _vp, C.POINTER(BlockBuffers)]),
     "dyt_block_fwd": (_i, [C.POINTER(BlockShape), C.POINTER(BlockWeights), C.POINTER(BlockOpts),

@@ -466,3 +466,140 @@ class TrainVisionTransformer(VisionTransformer):
         if pooled is not None:
             return self.head(pooled), token_select
         return self.forward_head(self.norm(tokens)), token_select
+
+
+# ---------------------------------------------------------------------------------------------
+# video model (reference video_models/video_vision_transformer_IN21K.py): the image blocks applied
+# to every frame, then an attentive pooling head over all t*N tokens of a clip
+# ---------------------------------------------------------------------------------------------
+class CrossAttention(nn.Module):
+    """Parameter container + kernel-backed forward of the reference CrossAttention (:52-110)."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0.0,
+                 proj_drop=0.0, attn_head_dim=None):
+        super().__init__()
+        self.num_heads = num_heads
+        head_dim = dim // num_heads if attn_head_dim is None else attn_head_dim
+        if head_dim != 64:
+            raise NotImplementedError("dyt_b200 pooling head implements head_dim 64")
+        if attn_drop > 0 or proj_drop > 0:
+            raise NotImplementedError("dyt_b200 pooling head: dropout is inference-dead (p = 0)")
+        all_head_dim = head_dim * num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        self.q = nn.Linear(dim, all_head_dim, bias=False)
+        self.k = nn.Linear(dim, all_head_dim, bias=False)
+        self.v = nn.Linear(dim, all_head_dim, bias=False)
+        if qkv_bias:
+            self.q_bias = nn.Parameter(torch.zeros(all_head_dim))
+            self.v_bias = nn.Parameter(torch.zeros(all_head_dim))
+        else:
+            self.q_bias = None
+            self.k_bias = None
+            self.v_bias = None
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(all_head_dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+
+    def forward(self, x, k=None, v=None):
+        """x [b, 1, C] fp16/fp32 normalised query tokens, k / v [b, n_keys, C] fp16 normalised tokens."""
+        _no_backward("CrossAttention", x, self.q.weight)
+        h16 = torch.float16
+        b = k.shape[0]
+        if x.shape[1] != 1:
+            raise NotImplementedError("dyt_b200 pooling head implements one query token per clip")
+        qb = None if self.q_bias is None else self.q_bias.to(h16)
+        vb = None if self.v_bias is None else self.v_bias.to(h16)
+        zb = None if vb is None else torch.zeros_like(vb)
+        q, _ = ops.linear_f16(x.reshape(b, -1).to(h16), self.q.weight.to(h16), qb)
+        q = (q * self.scale).to(h16)                       # fp16 tensor * python float (:101)
+        kk, _ = ops.linear_f16(k.to(h16), self.k.weight.to(h16), zb)
+        vv, _ = ops.linear_f16(v.to(h16), self.v.weight.to(h16), vb)
+        o = ops.query_attn(q, kk, vv, self.num_heads)
+        out, _ = ops.linear_f16(o, self.proj.weight.to(h16), self.proj.bias.to(h16))
+        out = out.reshape(b, 1, -1)
+        return out if _act_dtype() == h16 else out.float()
+
+
+class AttentiveBlock(nn.Module):
+    """Reference AttentiveBlock (:27-49): norm_q / norm_k / norm_v + CrossAttention."""
+
+    def __init__(self, dim, num_heads, qkv_bias=False, qk_scale=None, drop=0.0, attn_drop=0.0,
+                 drop_path=0.0, norm_layer=nn.LayerNorm, attn_head_dim=None):
+        super().__init__()
+        self.norm_q = norm_layer(dim)
+        self.norm_k = norm_layer(dim)
+        self.norm_v = norm_layer(dim)
+        self.cross_attn = CrossAttention(dim, num_heads=num_heads, qkv_bias=qkv_bias,
+                                         qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop,
+                                         attn_head_dim=attn_head_dim)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+
+    def forward(self, x_q, x_kv, _pre_norm=None):
+        """x_q [b, 1, C]; x_kv [b, n_keys, C] fp32 tokens.  `_pre_norm` = (weight, bias) of a
+        LayerNorm to apply to x_kv first inside the same kernel (the model's final `norm`)."""
+        if not x_kv.is_cuda:
+            raise DytError("dyt_b200 AttentiveBlock needs CUDA tensors (no CPU fallback)")
+        eps = float(self.norm_k.eps)
+        if _pre_norm is None:
+            raise NotImplementedError("dyt_b200 AttentiveBlock is driven by the video model "
+                                      "(final norm fused with norm_k / norm_v)")
+        xk, xv = ops.pool_layernorm_f16(x_kv.float(), _pre_norm, (self.norm_k.weight, self.norm_k.bias),
+                                        (self.norm_v.weight, self.norm_v.bias), eps)
+        q_in = ops.layernorm_f16(x_q.float().contiguous(), self.norm_q.weight.detach().float(),
+                                 self.norm_q.bias.detach().float(), eps)
+        return self.cross_attn(q_in, k=xk, v=xv)
+
+
+class VideoVisionTransformer(TrainVisionTransformer):
+    """Reference video VisionTransformer (:279-483): forward(x [b, c, t, h, w], complete_model) ->
+    (logits, dict(token_select [b*t, L, N-1, 1], token_logits))."""
+    flavour = "video"
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        embed_dim = self.embed_dim
+        num_heads = self.blocks[0].attn.num_heads
+        self.query_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        norm_layer = type(self.blocks[0].norm1)
+        eps = float(self.blocks[0].norm1.eps)
+        self.attentive_blocks = AttentiveBlock(
+            dim=embed_dim, num_heads=num_heads, qkv_bias=self.blocks[0].attn.qkv.bias is not None,
+            qk_scale=None, drop=0.0, attn_drop=0.0, drop_path=0,
+            norm_layer=lambda d: norm_layer(d, eps=eps))
+        for m in self.attentive_blocks.modules():
+            if isinstance(m, nn.Linear):
+                trunc_normal_(m.weight, std=0.02)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+
+    def forward_features(self, x, complete_model=False):
+        b, c, t, h, w = x.shape
+        frames = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)     # "b c t h w -> (b t) c h w"
+        return super().forward_features(frames, complete_model)
+
+    def forward(self, x, complete_model=False):
+        b, c, t, h, w = x.shape
+        frames = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+        tokens, masks, logits = self._blocks(self._embed(frames), complete_model)
+        dt = _act_dtype()
+        token_select = dict(token_select=masks.permute(1, 0, 2)[:, :, 1:].unsqueeze(-1).to(dt),
+                            token_logits=logits.permute(1, 0, 2).unsqueeze(-1).to(dt))
+        if not isinstance(self.norm, nn.LayerNorm) or not isinstance(self.fc_norm, nn.Identity):
+            raise NotImplementedError("dyt_b200 video head implements norm = LayerNorm, fc_norm = Identity")
+        n_tok = tokens.shape[1]
+        kv = tokens.reshape(b, t * n_tok, tokens.shape[2])            # "(b t) tokens c -> b (t tokens) c"
+        pooled = self.attentive_blocks(self.query_token.expand(b, -1, -1), kv,
+                                       _pre_norm=(self.norm.weight, self.norm.bias))[:, 0, :]
+        h16 = torch.float16
+        if isinstance(self.head, nn.Linear):
+            nc = self.head.out_features
+            n8 = (nc + 7) // 8 * 8
+            w16 = torch.zeros((n8, self.embed_dim), dtype=h16, device=pooled.device)
+            b16 = torch.zeros((n8,), dtype=h16, device=pooled.device)
+            w16[:nc] = self.head.weight.detach().to(h16)
+            if self.head.bias is not None:
+                b16[:nc] = self.head.bias.detach().to(h16)
+            out, _ = ops.linear_f16(pooled.to(h16).contiguous(), w16, b16)
+            out = out[:, :nc]
+            return (out if dt == h16 else out.float()), token_select
+        return self.head(pooled), token_select

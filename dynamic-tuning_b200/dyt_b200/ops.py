@@ -233,3 +233,40 @@ def patch_embed(img: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torch.
         pos.data_ptr(), Cdim, x.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
         "dyt_patch_embed_fwd")
     return x
+
+
+def pool_layernorm_f16(x: torch.Tensor, norm0, norm_k, norm_v, eps: float = 1e-6):
+    """(f16(LN_k(LN_0(x))), f16(LN_v(LN_0(x)))) for fp32 rows x [..., C]; norm* = (weight, bias)."""
+    _need_cuda(x, *norm0, *norm_k, *norm_v)
+    if x.dtype != torch.float32:
+        raise DytError("pool_layernorm_f16 expects the fp32 token stream")
+    x2 = _rows2d(x)
+    T, Cdim = x2.shape
+    outk = torch.empty((T, Cdim), dtype=torch.float16, device=x.device)
+    outv = torch.empty((T, Cdim), dtype=torch.float16, device=x.device)
+    f = lambda t: t.detach().to(torch.float32).contiguous()
+    prm = [f(t) for t in (*norm0, *norm_k, *norm_v)]
+    check(_lib.lib().dyt_pool_layernorm_f16(
+        x2.data_ptr(), x2.stride(0), T, Cdim, *[t.data_ptr() for t in prm], float(eps),
+        outk.data_ptr(), outv.data_ptr(), Cdim, _stream()), "dyt_pool_layernorm_f16")
+    return outk.reshape(*x.shape[:-1], Cdim), outv.reshape(*x.shape[:-1], Cdim)
+
+
+def query_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int) -> torch.Tensor:
+    """Single-query cross attention.  q fp16 [C] or [b, C] (pre-scaled), k / v fp16 [b, n_keys, C].
+    Returns fp16 [b, C]."""
+    _need_cuda(q, k, v)
+    if any(t.dtype != torch.float16 for t in (q, k, v)):
+        raise DytError("query_attn expects fp16 operands")
+    b, nk, Cdim = k.shape
+    k2, v2 = _rows2d(k), _rows2d(v)
+    if k2.stride(0) != v2.stride(0):
+        v2 = v2.contiguous()
+        k2 = k2.contiguous()
+    q = q.contiguous()
+    ldq = 0 if q.dim() == 1 or q.shape[0] == 1 else q.stride(0)
+    out = torch.empty((b, Cdim), dtype=torch.float16, device=k.device)
+    check(_lib.lib().dyt_query_attn_fwd(
+        q.data_ptr(), ldq, k2.data_ptr(), v2.data_ptr(), k2.stride(0), b, nk, num_heads,
+        Cdim // num_heads, out.data_ptr(), Cdim, _stream()), "dyt_query_attn_fwd")
+    return out

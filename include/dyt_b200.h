@@ -115,6 +115,22 @@ int dyt_patch_embed_fwd(const float* img, int B, int Cin, int H, int W, int P, c
                         const void* bias_f16, const float* cls, const float* pos, int C,
                         float* x_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- video pooling head (reference video_models/video_vision_transformer_IN21K.py:27-110, :474-481) ----
+ * dyt_pool_layernorm_f16: out_k = f16(LN_k(LN_0(x))), out_v = f16(LN_v(LN_0(x))) per row: the model's
+ * final `norm` followed by AttentiveBlock.norm_k / norm_v, one pass over the fp32 token stream.
+ * dyt_query_attn_fwd: single-query cross attention per clip and head.  q fp16 [num_clips, H*64] (row
+ * stride ldq; ldq = 0 broadcasts one query to every clip), already scaled by head_dim^-0.5;
+ * k, v fp16 [num_clips * n_keys, H*64] (row stride ld_kv); out fp16 [num_clips, H*64].
+ * Rounding points of CrossAttention.forward under fp16 autocast: fp16 scores, fp32 softmax, fp16
+ * probabilities, fp32 accumulation, fp16 output. */
+int dyt_pool_layernorm_f16(const float* x, int ldx, int n_rows, int C, const float* g0,
+                           const float* b0, const float* gk, const float* bk, const float* gv,
+                           const float* bv, float eps, void* out_k_f16, void* out_v_f16, int ldo,
+                           void* stream);
+int dyt_query_attn_fwd(const void* q_f16, int ldq, const void* k_f16, const void* v_f16, int ld_kv,
+                       int num_clips, int n_keys, int num_heads, int head_dim, void* out_f16, int ldo,
+                       void* stream);
+
 /* ---- whole block: Block.batch_forward (reference models/model_speed_test.py:274-310) ---------- */
 typedef struct dyt_block_shape {
   int B;          /* images (sequences) */

@@ -285,6 +285,53 @@ def vit_forward(img: Tensor, p: Dict[str, Tensor], depth: int, num_heads: int, s
 # ----------------------------------------------------------------------------------------------
 # deterministic synthetic parameters (shared by the golden generator, the tests and bench.py)
 # ----------------------------------------------------------------------------------------------
+def attentive_pool(tokens: Tensor, p: Dict[str, Tensor], num_heads: int,
+                   policy: str = "fp32") -> Tensor:
+    """Video pooling head: AttentiveBlock + CrossAttention with one learned query per clip
+    (reference video_models/video_vision_transformer_IN21K.py:27-110, called at :479-480).
+    tokens [b, t*N, C] = norm(x) of all frames (fp32).  Returns [b, C]."""
+    pre = "attentive_blocks."
+    b, nk, c = tokens.shape
+    d = c // num_heads
+    xq = layer_norm(p["query_token"].expand(b, -1, -1), p[pre + "norm_q.weight"], p[pre + "norm_q.bias"])
+    xk = layer_norm(tokens, p[pre + "norm_k.weight"], p[pre + "norm_k.bias"])
+    xv = layer_norm(tokens, p[pre + "norm_v.weight"], p[pre + "norm_v.bias"])
+    qb = p.get(pre + "cross_attn.q_bias")
+    vb = p.get(pre + "cross_attn.v_bias")
+    q = linear(xq, p[pre + "cross_attn.q.weight"], qb, policy)                      # :92
+    k = linear(xk, p[pre + "cross_attn.k.weight"], None if qb is None else torch.zeros_like(vb), policy)
+    v = linear(xv, p[pre + "cross_attn.v.weight"], vb, policy)
+    q = q.reshape(b, 1, num_heads, d).permute(0, 2, 1, 3)
+    k = k.reshape(b, nk, num_heads, d).permute(0, 2, 1, 3)
+    v = v.reshape(b, nk, num_heads, d).permute(0, 2, 1, 3)
+    q = q * d ** -0.5                                                                # :101
+    if policy == "amp16":
+        q = _r16(q)
+        attn = _r16(q @ k.transpose(-2, -1)).softmax(dim=-1)                        # fp16 matmul out, fp32 softmax
+        o = _r16(_r16(attn) @ v)
+    else:
+        attn = (q @ k.transpose(-2, -1)).softmax(dim=-1)
+        o = attn @ v
+    o = o.transpose(1, 2).reshape(b, 1, c)
+    return linear(o, p[pre + "cross_attn.proj.weight"], p[pre + "cross_attn.proj.bias"], policy)[:, 0]
+
+
+def video_forward(clip: Tensor, p: Dict[str, Tensor], depth: int, num_heads: int, scale: float,
+                  policy: str = "fp32", patch: int = 16) -> Dict[str, Tensor]:
+    """Video model, eval mode (reference video_models/video_vision_transformer_IN21K.py:435-483):
+    every frame goes through the image blocks independently (dense masked block == the sparse
+    block in eval), then norm -> [b, t*N, C] -> attentive pooling -> head."""
+    b, ch, t, h, w = clip.shape
+    frames = clip.permute(0, 2, 1, 3, 4).reshape(b * t, ch, h, w)
+    r = vit_forward(frames, p, depth, num_heads, scale, policy=policy, sparse=True, patch=patch)
+    xn = layer_norm(r["x_final"], p["norm.weight"], p["norm.bias"])
+    tokens = xn.reshape(b, t * xn.shape[1], xn.shape[2])
+    pooled = attentive_pool(tokens, p, num_heads, policy)
+    logits = linear(pooled, p["head.weight"], p["head.bias"], policy)
+    return dict(logits=logits, token_select=r["token_select"], token_logits=r["token_logits"],
+                pooled=pooled)
+
+
 def synthetic_state_dict(embed_dim: int = 768, depth: int = 12, num_heads: int = 12,
                          mlp_ratio: float = 4.0, bottleneck: int = 64, num_classes: int = 100,
                          img_size: int = 224, patch: int = 16, seed: int = 0) -> Dict[str, Tensor]:

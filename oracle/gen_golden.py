@@ -10,6 +10,8 @@ itself are the pins of the oracle (oracle/dyt_oracle.py):
   gumbel_train.pt   train-mode hard Gumbel gate given the RNG draws (fp32 and fp16 logits)
   tiny_vit.pt       a 2-layer dim-128 ViT (reference generic ctor): full state_dict, inputs, every
                     model-level output of both reference models + per-block activations
+  video_tiny.pt     a 2-layer dim-128 video model (reference video ctor): state_dict incl. the
+                    attentive pooling head, a 3x2-frame clip, logits / masks / pooled features
   vitb_b2.pt        ViT-B/16, synthetic seed-0 weights (regenerated from the seed, not stored),
                     calibrated selector biases, B=2: logits / masks / token logits of the speed model
                     and the train model (eval, complete_model on/off), config-1 imposed-mask logits
@@ -136,6 +138,55 @@ def vitb_b2(ref_speed, ref_train):
     return out
 
 
+def video_state_dict(sd, embed_dim, seed):
+    """Adds the pooling-head parameters of the video model (query_token, attentive_blocks.*) to an
+    image-model state_dict, drawn like synthetic_state_dict draws the others."""
+    c = embed_dim
+    g = torch.Generator().manual_seed(1000 + seed)
+    rn = lambda *shape, std=0.02: torch.randn(*shape, generator=g) * std
+    pre = "attentive_blocks."
+    sd = dict(sd)
+    sd["query_token"] = rn(1, 1, c, std=0.5)
+    for n in ("norm_q", "norm_k", "norm_v"):
+        sd[pre + n + ".weight"] = 1.0 + rn(c, std=0.1)
+        sd[pre + n + ".bias"] = rn(c)
+    for n in ("q", "k", "v"):
+        sd[pre + f"cross_attn.{n}.weight"] = rn(c, c, std=0.05)
+    sd[pre + "cross_attn.q_bias"] = rn(c)
+    sd[pre + "cross_attn.v_bias"] = rn(c)
+    sd[pre + "cross_attn.proj.weight"] = rn(c, c, std=0.05)
+    sd[pre + "cross_attn.proj.bias"] = rn(c)
+    return sd
+
+
+def tiny_video(ref_video):
+    """2-layer dim-128 video model (reference video_models/video_vision_transformer_IN21K.py generic
+    ctor), 3 clips of 2 frames of 32x32: full state_dict, clip, logits, masks, pooled features."""
+    dims = dict(embed_dim=128, depth=2, num_heads=2, bottleneck=16, num_classes=10, img_size=32)
+    sd = O.synthetic_state_dict(seed=5, **dims)
+    g = torch.Generator().manual_seed(21)
+    clip = torch.randn(3, 3, 2, 32, 32, generator=g)
+    frames = clip.permute(0, 2, 1, 3, 4).reshape(6, 3, 32, 32)
+    sd = O.calibrate_selector_bias(sd, frames, 2, 2, 0.1, 0.5)
+    sd = video_state_dict(sd, 128, 5)
+    tuning, select = ref_shim.reference_configs(ffn_num=16, scalar="0.1", d_model=128)
+    m = ref_video.VisionTransformer(img_size=32, patch_size=16, embed_dim=128, depth=2, num_heads=2,
+                                    mlp_ratio=4.0, qkv_bias=True, num_classes=10,
+                                    tuning_config=tuning, select_config=select)
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    m = m.eval()
+    out = dict(dims=dims, scale=0.1, state_dict=sd, clip=clip, keys=sorted(m.state_dict().keys()))
+    with torch.no_grad():
+        lg, d = m(clip)
+        out["logits"], out["token_select"], out["token_logits"] = lg, d["token_select"], d["token_logits"]
+        x, _ = m.forward_features(clip)
+        tokens = x.reshape(3, -1, 128)
+        out["tokens"] = tokens
+        out["pooled"] = m.attentive_blocks(m.query_token.expand(3, -1, -1), tokens)[:, 0, :]
+    return out
+
+
 def main():
     assert ref_shim.reference_available(), "needs the reference checkout at " + ref_shim.REFERENCE_ROOT
     torch.set_num_threads(os.cpu_count())
@@ -147,6 +198,8 @@ def main():
     torch.save(gumbel_train(ref_dyn), os.path.join(OUT, "gumbel_train.pt"))
     torch.save(tiny_vit(ref_speed, ref_train), os.path.join(OUT, "tiny_vit.pt"))
     torch.save(vitb_b2(ref_speed, ref_train), os.path.join(OUT, "vitb_b2.pt"))
+    ref_video = ref_shim.import_reference("video_models.video_vision_transformer_IN21K")
+    torch.save(tiny_video(ref_video), os.path.join(OUT, "video_tiny.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 

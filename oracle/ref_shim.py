@@ -132,7 +132,9 @@ def import_reference(module: str):
     """import e.g. 'models.model_speed_test' from the reference checkout, isolated from any other
     package called `models` (the product ships a drop-in package of the same name)."""
     install()
-    saved = {k: v for k, v in sys.modules.items() if k == "models" or k.startswith("models.")}
+    def _ours(k):
+        return k in ("models", "video_models") or k.startswith(("models.", "video_models."))
+    saved = {k: v for k, v in sys.modules.items() if _ours(k)}
     for k in saved:
         del sys.modules[k]
     sys.path.insert(0, REFERENCE_ROOT)
@@ -140,7 +142,7 @@ def import_reference(module: str):
         mod = importlib.import_module(module)
     finally:
         sys.path.remove(REFERENCE_ROOT)
-        ref_mods = {k: v for k, v in sys.modules.items() if k == "models" or k.startswith("models.")}
+        ref_mods = {k: v for k, v in sys.modules.items() if _ours(k)}
         for k in ref_mods:
             del sys.modules[k]
         sys.modules.update(saved)

@@ -311,3 +311,59 @@ def test_full_batch_properties(dev, vitb_sd):
     assert int(m0.sum()) == B and int(m1.sum()) == B * 197
     assert bool(torch.isfinite(o0).all()) and bool(torch.isfinite(o1).all())
     assert torch.equal(o0[:, 0], o1[:, 0])          # cls rows are kept in both
+
+
+# ---------------------------------------------------------------------------------------------
+# video model: per-frame DyT blocks + attentive pooling head
+# ---------------------------------------------------------------------------------------------
+def test_pooling_head_kernels_match_oracle(dev):
+    """Fused final-norm + norm_k / norm_v LayerNorm kernel and the single-query attention kernel
+    against the oracle's restatement of AttentiveBlock / CrossAttention (amp16 policy)."""
+    from dyt_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    b, nk, C, H = 3, 2 * 197, 768, 12
+    x = torch.randn(b, nk, C, generator=g) * 1.5 + 0.2
+    n0 = (1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g))
+    nk_ = (1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g))
+    nv_ = (1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g))
+    xn = O.layer_norm(x, n0[0], n0[1])
+    ref_k, ref_v = O._r16(O.layer_norm(xn, *nk_)), O._r16(O.layer_norm(xn, *nv_))
+    to = lambda t: tuple(u.to(dev) for u in t)
+    outk, outv = ops.pool_layernorm_f16(x.to(dev), to(n0), to(nk_), to(nv_), 1e-6)
+    assert float((outk.float().cpu() - ref_k).abs().max()) <= 4e-3      # one fp16 ulp at |x| ~ 4
+    assert float((outv.float().cpu() - ref_v).abs().max()) <= 4e-3
+    q = O._r16(torch.randn(C, generator=g) * 0.5)
+    k = O._r16(torch.randn(b, nk, C, generator=g))
+    v = O._r16(torch.randn(b, nk, C, generator=g))
+    qh = q.reshape(1, H, 1, 64)
+    kh = k.reshape(b, nk, H, 64).permute(0, 2, 1, 3)
+    vh = v.reshape(b, nk, H, 64).permute(0, 2, 1, 3)
+    attn = O._r16(qh @ kh.transpose(-2, -1)).softmax(dim=-1)
+    ref = O._r16(O._r16(attn) @ vh).transpose(1, 2).reshape(b, C)
+    out = ops.query_attn(q.half().to(dev), k.half().to(dev), v.half().to(dev), H)
+    assert float((out.float().cpu() - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-3
+
+
+def test_tiny_video_model_vs_reference_golden(dev):
+    """The drop-in video model on the reference's own tiny video model outputs (fp32 golden) and on
+    the oracle (amp16): logits, per-frame token masks, pooled features."""
+    from video_models.video_vision_transformer_IN21K import VisionTransformer
+    g = load_golden("video_tiny.pt")
+    d = g["dims"]
+    tuning, select = configs(ffn_num=d["bottleneck"], d_model=d["embed_dim"])
+    m = VisionTransformer(img_size=d["img_size"], patch_size=16, embed_dim=d["embed_dim"],
+                          depth=d["depth"], num_heads=d["num_heads"], mlp_ratio=4.0, qkv_bias=True,
+                          num_classes=d["num_classes"], tuning_config=tuning, select_config=select)
+    m.load_state_dict(g["state_dict"], strict=True)
+    m = m.eval().to(dev)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        logits, ts = m(g["clip"].to(dev))
+    assert logits.shape == g["logits"].shape and logits.dtype == torch.float16
+    assert ts["token_select"].shape == g["token_select"].shape
+    ref16 = O.video_forward(g["clip"], g["state_dict"], d["depth"], d["num_heads"], g["scale"],
+                            policy="amp16")
+    mism = int((ts["token_select"].float().cpu() != ref16["token_select"].float()).sum())
+    assert mism <= 1
+    if mism == 0:
+        assert _rel(logits.float(), ref16["logits"]) <= 1e-2
+        assert _rel(logits.float(), g["logits"]) <= 3e-2

@@ -105,3 +105,23 @@ def test_gate_threshold_table_product_side():
     assert min_kept_logit(torch.float16, 0.5) == 2.0 ** -10 * (1 + 2.0 ** -10)
     assert min_kept_logit(torch.float16, 0.7) > 0.8            # sigmoid(l) > 0.7  <=>  l > 0.847
     assert 0 < min_kept_logit(torch.float32, 0.5) < 2e-7
+
+
+def test_video_model_state_dict_keys_match_reference():
+    """video_models.video_vision_transformer_IN21K (main_video.py:29): same parameter names as the
+    reference video model (golden key list generated from the reference ctor), strict load works."""
+    from conftest import load_golden
+    from video_models.video_vision_transformer_IN21K import (AttentiveBlock, CrossAttention,  # noqa: F401
+                                                             VisionTransformer, vit_base_patch16_224_in21k)
+    g = load_golden("video_tiny.pt")
+    d = g["dims"]
+    tuning, select = _cfgs(ffn_num=d["bottleneck"], d_model=d["embed_dim"])
+    m = VisionTransformer(img_size=d["img_size"], patch_size=16, embed_dim=d["embed_dim"],
+                          depth=d["depth"], num_heads=d["num_heads"], mlp_ratio=4.0, qkv_bias=True,
+                          num_classes=d["num_classes"], tuning_config=tuning, select_config=select)
+    assert sorted(m.state_dict().keys()) == g["keys"]
+    res = m.load_state_dict(g["state_dict"], strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    import pytest, torch
+    with pytest.raises(Exception):          # CPU tensors: no fallback
+        m.eval()(torch.zeros(1, 3, 2, 32, 32))
