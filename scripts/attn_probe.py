@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.join(ROOT, "dynamic-tuning_b200"))
 import torch
 from dyt_b200 import ops
 dev = torch.device("cuda:0")
-B, H, N = 256, 12, int(os.environ.get("ATTN_N", "197"))
+B, H, N = int(os.environ.get("ATTN_B", "256")), int(os.environ.get("ATTN_H", "12")), int(os.environ.get("ATTN_N", "197"))
 qkv = torch.randn(B, N, 3 * H * 64, device=dev, dtype=torch.float16)
 def run(n):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
