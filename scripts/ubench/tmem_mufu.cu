@@ -105,6 +105,15 @@ __global__ void k_mufu(long long* out, float* sink, int iters, int mode) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) x[2*j] += __uint_as_float(pk[j] & 0x7fff) * 1e-30f;
       x[1] += s * 1e-30f;
+    } else if (mode == 3 || mode == 4) {   // ex2 on wide-range negative inputs (like attention scores), no feedback
+      const float span = mode == 3 ? -24.0f : -0.9f;
+      float acc2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float t = span * __uint_as_float(0x3f800000u | (((i * 32 + j) * 2654435761u + lane * 40503u) >> 9)) - span;  // span*[1,2) - span = span*[0,1)
+        acc2 += ex2_approx(t);
+      }
+      x[i & 1] += acc2;
     } else {                  // fmnmx3
       float m0 = x[0], m1 = x[1];
 #pragma unroll
@@ -137,14 +146,14 @@ int main() {
              (double)mx / iters / (mode >= 2 ? 1 : 2));
       printf("  err: %s\n", cudaGetErrorString(cudaGetLastError()));
     }
-  for (int mode = 0; mode < 3; ++mode)
+  for (int mode = 0; mode < 5; ++mode)
     for (int nw : {1, 4, 8, 16}) {
       k_mufu<<<1, nw * 32>>>(d, sink, iters, mode); cudaDeviceSynchronize();
       k_mufu<<<1, nw * 32>>>(d, sink, iters, mode); cudaDeviceSynchronize();
       cudaMemcpy(h, d, 64 * 8, cudaMemcpyDeviceToHost);
       long long mx = 0; for (int i = 0; i < nw; ++i) mx = h[i] > mx ? h[i] : mx;
       printf("alu mode %d (%s) warps %2d: %lld clk, %.2f clk per warp-element (per SMSP: %.2f)\n", mode,
-             mode == 0 ? "ex2 only" : mode == 1 ? "ffma+ex2+sum+pack" : "fmnmx3", nw, mx,
+             mode == 0 ? "ex2 only" : mode == 1 ? "ffma+ex2+sum+pack" : mode == 2 ? "fmnmx3" : mode == 3 ? "ex2 inputs in [-24,0]" : "ex2 inputs in [-0.9,0]", nw, mx,
              (double)mx / iters / 32, (double)mx / iters / 32 / ((nw + 3) / 4));
     }
   return 0;
