@@ -1,17 +1,20 @@
-// Fused token dispatcher (sm_100a, HBM-bound): one persistent kernel, no host sync.
-//   phase 1  score  : logit[b,n] = <x1[b,n,:], w> + bias for the N-1 patch tokens (warp per token,
-//                     128-bit coalesced row loads, fp16-rounded operands / fp32 accumulate / one
-//                     rounding of the logit when the activation dtype is fp16)
-//            gate   : keep = sigmoid(logit) > threshold evaluated in the logit dtype, implemented as
-//                     the equivalent monotone test `logit >= min_kept` (the host derives min_kept
-//                     from torch's own sigmoid, see dyt_b200/gate.py); train mode adds the two
-//                     caller-drawn Gumbel terms and the temperature first.  cls token always kept.
-//   grid barrier    : all CTAs are co-resident (grid <= occupancy * #SMs)
-//   phase 2  compact: per-image exclusive base from the per-image counts, ballot/popc warp scan of
-//                     the keep flags -> packed_idx (ascending flat index == nonzero() order),
-//                     token_pos (inverse map), cu_seqlens, n_kept
-//            pack   : for every kept token LayerNorm2(x1 row) -> fp16 row of the packed buffer
-//                     (the A operand of the MLP fc1 GEMM)
+// Fused token dispatcher (sm_100a, HBM-bound): one kernel, one CTA per image, no host sync and no
+// grid-wide barrier.
+//   gate    : logit[b,n] = <x1[b,n,:], w> + bias for the N-1 patch tokens -- inside a block the dot
+//             products arrive as column partial sums from the proj GEMM epilogue, stand-alone the
+//             CTA's warps compute them (128-bit coalesced row loads, fp16-rounded operands / fp32
+//             accumulate / one rounding of the logit when the activation dtype is fp16);
+//             keep = sigmoid(logit) > threshold evaluated in the logit dtype, implemented as the
+//             equivalent monotone test `logit >= min_kept` (the host derives min_kept from torch's
+//             own sigmoid, see dyt_b200/gate.py); train mode adds the two caller-drawn Gumbel terms
+//             and the temperature first.  cls token always kept.
+//   prefix  : the image's packed base = kept tokens of all previous images, by decoupled look-back
+//             over per-image status words (aggregate / inclusive prefix, tagged with a launch
+//             epoch kept in the workspace, images taken in ticket order so predecessors always run)
+//   compact : ballot/popc ranks -> packed_idx (ascending flat index == nonzero() order), token_pos
+//             (inverse map), cu_seqlens, n_kept
+//   pack    : for every kept token LayerNorm2(x1 row) -> fp16 row of the packed buffer (the A
+//             operand of the MLP fc1 GEMM), the CTA's warps striding over the image's kept rows
 //
 // Replaces TokenSelect.forward + _gumbel_sigmoid (reference models/dynamic_adapter.py:25-77,
 // models/model_speed_test.py:27-60), the nonzero()/gather glue (models/model_speed_test.py:297-301)
@@ -50,13 +53,11 @@ struct DispatchParams {
   int ldp;
   const float* partials;  // optional [B*N, n_partials]: the score dot products, already computed in
   int n_partials;         // column slices by the producer of x1 (proj GEMM epilogue); summed in order
-  int* counts;          // [B] workspace (see dispatch_kernel)
-  unsigned int* sync;   // [2] workspace; zero before the first launch, left zeroed by the kernel
+  unsigned int* ctl;            // workspace: [0] ticket, [1] finished CTAs, [2] launch epoch
+  unsigned long long* status;   // workspace: [B] per-image (epoch tag << 32 | flag << 30 | count)
 };
 
 constexpr int DISPATCH_MAX_N = 2048;
-constexpr int DISPATCH_CHUNK = 32;   // tokens per phase-2 (compaction) work item
-constexpr int DISPATCH_SMEM_B = 1024;  // largest batch whose per-image prefix lives in smem
 
 __device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
 
@@ -66,104 +67,49 @@ __device__ __forceinline__ int warp_sum_int(int v) {
   return v;
 }
 
-// Work distribution: phase 1 strides warps over all B*N rows (consecutive warps read consecutive
-// rows); phase 2 strides warps over (image, 16-row chunk) items, each warp deriving the packed
-// base of its image from the per-image counts and its rank inside the image from the mask.
-// Workspace: sync[0] barrier arrivals, sync[1] finished CTAs, counts[B] kept tokens per image.
-// All of it must be zero at launch; the last CTA to finish zeroes it again, so a workspace that was
-// zero-filled once stays valid for every later launch, whatever its B.
+constexpr unsigned long long ST_AGG = 1ull << 30;     // count of this image only
+constexpr unsigned long long ST_PREFIX = 2ull << 30;  // inclusive count up to this image
+constexpr unsigned int ST_VALUE_MASK = (1u << 30) - 1u;
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Workspace: ctl[0] image ticket, ctl[1] finished CTAs, ctl[2] launch epoch, status[B].  It must
+// be zero before the first launch; the last CTA of a launch resets ticket / finished and bumps the
+// epoch, so stale status words of earlier launches never match (graph-replay safe: no host state).
 template <int NV>
 __global__ void __launch_bounds__(256)
 dispatch_kernel(const DispatchParams p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int N = p.N;
-  const int gw = blockIdx.x * 8 + warp;
-  const int nw = gridDim.x * 8;
-  const int T = p.B * N;
 
-  __shared__ int s_last;
-  int* cur = p.counts;
+  __shared__ int s_b, s_cnt, s_base;
+  __shared__ unsigned int s_tag;
+  __shared__ short s_list[DISPATCH_MAX_N];       // kept token indices of the image, ascending
+  __shared__ unsigned char s_keep[DISPATCH_MAX_N];
+  __shared__ int s_wsum[8];
 
-  // selector weight in registers, laid out like a row
-  float4 w[NV];
-  load_row_f32<NV>(p.sel_w, lane, w);
-  float bias = p.sel_b[0];
-  if (p.logit_fp16) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      w[i].x = r16(w[i].x); w[i].y = r16(w[i].y); w[i].z = r16(w[i].z); w[i].w = r16(w[i].w);
-    }
-    bias = r16(bias);
+  if (threadIdx.x == 0) {
+    s_b = static_cast<int>(atomicAdd(&p.ctl[0], 1u));   // ticket order: predecessors are running
+    s_tag = *reinterpret_cast<volatile unsigned int*>(&p.ctl[2]) + 1u;
   }
+  __syncthreads();
+  const int b = s_b;
+  const unsigned long long tag = static_cast<unsigned long long>(s_tag) << 32;
+  float bias = p.sel_b[0];
+  if (p.logit_fp16) bias = r16(bias);
+  const float* x_img = p.x1 + static_cast<size_t>(b) * N * p.ldx;
 
-  // ------------------------------- phase 1: score + gate -------------------------------
-  if (p.partials != nullptr) {
-    // the dot products come from the proj GEMM epilogue: one thread per token, no pass over x1
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
-      const int b = t / N;
-      const int n = t - b * N;
-      if (n == 0) {
-        p.mask[t] = 1.0f;
-        if (p.gate_out != nullptr) p.gate_out[t] = 1.0f;
-        atomicAdd(cur + b, 1);
-        continue;
-      }
-      float acc = 0.f;
-      for (int i = 0; i < p.n_partials; ++i) acc += p.partials[static_cast<size_t>(t) * p.n_partials + i];
-      float logit = acc + bias;
-      if (p.logit_fp16) logit = r16(logit);
-      float g = logit;
-      const size_t li = static_cast<size_t>(b) * (N - 1) + (n - 1);
-      if (p.noise1 != nullptr) {
-        if (p.logit_fp16) {
-          g = r16(g + r16(p.noise1[li]));
-          g = r16(g - r16(p.noise2[li]));
-          g = r16(g / r16(p.tau));
-        } else {
-          g = ((g + p.noise1[li]) - p.noise2[li]) / p.tau;
-        }
-      }
-      bool keep = g >= p.min_kept;
-      if (p.gate_out != nullptr) p.gate_out[t] = keep ? 1.0f : 0.0f;
-      if (p.forced_mask != nullptr) keep = p.forced_mask[t] != 0.0f;
-      p.logits[li] = logit;
-      p.mask[t] = keep ? 1.0f : 0.0f;
-      if (keep) atomicAdd(cur + b, 1);
-    }
-  } else
-  for (int t = gw; t < T; t += nw) {
-    const int b = t / N;
-    const int n = t - b * N;
-    if (n == 0) {
-      if (lane == 0) {
-        p.mask[t] = 1.0f;
-        if (p.gate_out != nullptr) p.gate_out[t] = 1.0f;
-        atomicAdd(cur + b, 1);
-      }
-      continue;
-    }
-    float4 v[NV];
-    load_row_f32<NV>(p.x1 + static_cast<size_t>(t) * p.ldx, lane, v);
-    float acc = 0.f;
-    if (p.logit_fp16) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        acc = fmaf(r16(v[i].x), w[i].x, acc);
-        acc = fmaf(r16(v[i].y), w[i].y, acc);
-        acc = fmaf(r16(v[i].z), w[i].z, acc);
-        acc = fmaf(r16(v[i].w), w[i].w, acc);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        acc = fmaf(v[i].x, w[i].x, acc);
-        acc = fmaf(v[i].y, w[i].y, acc);
-        acc = fmaf(v[i].z, w[i].z, acc);
-        acc = fmaf(v[i].w, w[i].w, acc);
-      }
-    }
-    acc = warp_sum(acc);
+  // ------------------------------- gate -------------------------------
+  auto decide = [&](int n, float acc) {   // one thread per token: logit -> keep flag + outputs
+    const size_t t = static_cast<size_t>(b) * N + n;
     float logit = acc + bias;
     if (p.logit_fp16) logit = r16(logit);
     float g = logit;
@@ -179,175 +125,164 @@ dispatch_kernel(const DispatchParams p) {
       }
     }
     bool keep = g >= p.min_kept;  // NaN -> dropped, +inf -> kept
-    if (lane == 0 && p.gate_out != nullptr) p.gate_out[t] = keep ? 1.0f : 0.0f;
+    if (p.gate_out != nullptr) p.gate_out[t] = keep ? 1.0f : 0.0f;
     if (p.forced_mask != nullptr) keep = p.forced_mask[t] != 0.0f;
-    if (lane == 0) {
-      p.logits[li] = logit;
-      p.mask[t] = keep ? 1.0f : 0.0f;
-      if (keep) atomicAdd(cur + b, 1);
-    }
+    p.logits[li] = logit;
+    p.mask[t] = keep ? 1.0f : 0.0f;
+    s_keep[n] = keep ? 1 : 0;
+  };
+  if (threadIdx.x == 0) {
+    p.mask[static_cast<size_t>(b) * N] = 1.0f;
+    if (p.gate_out != nullptr) p.gate_out[static_cast<size_t>(b) * N] = 1.0f;
+    s_keep[0] = 1;
   }
-
-  // ------------------------------- grid barrier -------------------------------
-  // (monotonic arrival counter: the k-th barrier waits for k * gridDim.x arrivals)
-  auto grid_barrier = [&](unsigned int k) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      atomicAdd(&p.sync[0], 1u);
-      const long long t0 = clock64();
-      while (atomicAdd(&p.sync[0], 0u) < k * gridDim.x) {
-        __nanosleep(64);
-        if (clock64() - t0 > 4000000000ll) {
-          printf("dyt: dispatcher grid barrier timeout (block %d)\n", (int)blockIdx.x);
-          __trap();
+  if (p.partials != nullptr) {
+    // the dot products come from the proj GEMM epilogue as column partial sums
+    for (int n = 1 + threadIdx.x; n < N; n += 256) {
+      const float* pp = p.partials + (static_cast<size_t>(b) * N + n) * p.n_partials;
+      float acc = 0.f;
+      for (int i = 0; i < p.n_partials; ++i) acc += pp[i];
+      decide(n, acc);
+    }
+  } else {
+    float4 w[NV];
+    load_row_f32<NV>(p.sel_w, lane, w);
+    if (p.logit_fp16) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        w[i].x = r16(w[i].x); w[i].y = r16(w[i].y); w[i].z = r16(w[i].z); w[i].w = r16(w[i].w);
+      }
+    }
+    for (int n = 1 + warp; n < N; n += 8) {
+      float4 v[NV];
+      load_row_f32<NV>(x_img + static_cast<size_t>(n) * p.ldx, lane, v);
+      float acc = 0.f;
+      if (p.logit_fp16) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          acc = fmaf(r16(v[i].x), w[i].x, acc);
+          acc = fmaf(r16(v[i].y), w[i].y, acc);
+          acc = fmaf(r16(v[i].z), w[i].z, acc);
+          acc = fmaf(r16(v[i].w), w[i].w, acc);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          acc = fmaf(v[i].x, w[i].x, acc);
+          acc = fmaf(v[i].y, w[i].y, acc);
+          acc = fmaf(v[i].z, w[i].z, acc);
+          acc = fmaf(v[i].w, w[i].w, acc);
         }
       }
-      __threadfence();
+      acc = warp_sum(acc);
+      if (lane == 0) decide(n, acc);
     }
-    __syncthreads();
-  };
-  grid_barrier(1u);
-
-  // ------------------------------- phase 2: compact + pack -------------------------------
-  // exclusive prefix of the per-image counts, once per CTA (falls back to a per-item sum for
-  // batches beyond the smem table)
-  __shared__ int s_base[DISPATCH_SMEM_B + 1];
-  const bool smem_base = p.B <= DISPATCH_SMEM_B;
-  if (smem_base) {
-    __shared__ int s_warp[8];
-    int carry = 0;
-    for (int b0 = 0; b0 < p.B; b0 += 256) {
-      const int i = b0 + threadIdx.x;
-      const int c = i < p.B ? __ldcg(cur + i) : 0;
-      int incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      if (lane == 31) s_warp[warp] = incl;
-      __syncthreads();
-      int woff = 0;
-      for (int w = 0; w < warp; ++w) woff += s_warp[w];
-      if (i < p.B) s_base[i] = carry + woff + incl - c;
-      int tot = 0;
-      for (int w = 0; w < 8; ++w) tot += s_warp[w];
-      carry += tot;
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) s_base[p.B] = carry;
-    __syncthreads();
   }
-  const int cpi = (N + DISPATCH_CHUNK - 1) / DISPATCH_CHUNK;  // chunks per image
-  const int items = p.B * cpi;
-  for (int item = gw; item < items; item += nw) {
-    const int b = item / cpi;
-    const int n0 = (item - b * cpi) * DISPATCH_CHUNK;
-    // packed base of the image = kept tokens of all previous images
-    int base;
-    if (smem_base) {
-      base = s_base[b];
-    } else {
-      int part = 0;
-      for (int i = lane; i < b; i += 32) part += __ldcg(cur + i);
-      base = warp_sum_int(part);
+  __syncthreads();
+
+  // ------------------------------- compact (inside the image) -------------------------------
+  if (warp == 0) {
+    int cnt = 0;
+    for (int n0 = 0; n0 < N; n0 += 32) {
+      const int n = n0 + lane;
+      const bool k = n < N && s_keep[n] != 0;
+      const unsigned ballot = __ballot_sync(0xffffffffu, k);
+      if (k) s_list[cnt + __popc(ballot & ((1u << lane) - 1u))] = static_cast<short>(n);
+      cnt += __popc(ballot);
     }
-    // kept tokens of this image before the chunk: every lane counts its share of the mask row
-    const float* mrow = p.mask + static_cast<size_t>(b) * N;
-    int mine = 0;
-    for (int n = lane; n < n0; n += 32) mine += (__ldcg(mrow + n) != 0.0f) ? 1 : 0;
-    const int before = warp_sum_int(mine);
-    const int n = n0 + lane;
-    const bool valid = lane < DISPATCH_CHUNK && n < N;
-    const bool keep = valid && (__ldcg(mrow + n) != 0.0f);
-    unsigned ballot = __ballot_sync(0xffffffffu, keep);
-    const int rank = __popc(ballot & ((1u << lane) - 1u));
-    const int first = base + before;
-    if (valid) {
-      const size_t t = static_cast<size_t>(b) * N + n;
-      if (keep) {
-        p.packed_idx[first + rank] = static_cast<int>(t);
-        p.token_pos[t] = first + rank;
-      } else {
-        p.token_pos[t] = -1;
+    // ------------------------------- prefix over the images: decoupled look-back ----------------
+    int excl = 0;
+    if (b > 0) {
+      if (lane == 0) st_status(&p.status[b], tag | ST_AGG | static_cast<unsigned int>(cnt));
+      int j = b - 1;
+      long long t0 = 0;
+      while (j >= 0) {
+        const int idx = j - lane;
+        unsigned long long s = 0;
+        bool ready;
+        unsigned int polls = 0;
+        do {  // all (valid) lanes of the window have published something in this launch
+          if (idx >= 0) s = ld_status(&p.status[idx]);
+          ready = idx < 0 || (s >> 32) == (tag >> 32);
+          if ((++polls & 1023u) == 0u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 4000000000ll) __trap();
+          }
+        } while (!__all_sync(0xffffffffu, ready));
+        const bool is_prefix = idx >= 0 && (s & ST_PREFIX) != 0;
+        const unsigned pb = __ballot_sync(0xffffffffu, is_prefix);
+        const int first = pb ? __ffs(pb) - 1 : 32;   // nearest predecessor holding a prefix
+        const int val = (idx >= 0 && lane <= first) ? static_cast<int>(s & ST_VALUE_MASK) : 0;
+        excl += warp_sum_int(val);
+        if (pb) break;
+        j -= 32;
       }
     }
-    if (n0 == 0 && lane == 0) {
-      p.cu_seqlens[b] = base;
+    if (lane == 0) {
+      st_status(&p.status[b], tag | ST_PREFIX | static_cast<unsigned int>(excl + cnt));
+      s_cnt = cnt;
+      s_base = excl;
+      p.cu_seqlens[b] = excl;
       if (b == p.B - 1) {
-        const int total = base + __ldcg(cur + b);
-        p.cu_seqlens[p.B] = total;
-        p.n_kept[0] = total;
+        p.cu_seqlens[p.B] = excl + cnt;
+        p.n_kept[0] = excl + cnt;
       }
     }
   }
+  __syncthreads();
+  const int cnt = s_cnt, base = s_base;
 
-  // ------------------------------- phase 3: pack -------------------------------
-  // LayerNorm2 of the kept rows into the packed fp16 buffer: warps stride over packed positions
-  // (perfectly balanced, whatever the per-image keep counts), two rows in flight per warp.
+  // ------------------------------- index maps -------------------------------
+  for (int n = threadIdx.x; n < N; n += 256) p.token_pos[static_cast<size_t>(b) * N + n] = -1;
+  __syncthreads();
+  for (int r = threadIdx.x; r < cnt; r += 256) {
+    const int t = b * N + s_list[r];
+    p.packed_idx[base + r] = t;
+    p.token_pos[t] = base + r;
+  }
+
+  // ------------------------------- pack -------------------------------
+  // LayerNorm2 of the kept rows into the packed fp16 buffer, two rows in flight per warp
   if (p.packed != nullptr) {
-    grid_barrier(2u);
-    int total;
-    if (smem_base) {
-      total = s_base[p.B];
-    } else {
-      total = __ldcg(p.n_kept);
-    }
-    for (int j = gw; j < total; j += 2 * nw) {
-      const int j1 = j + nw;
-      const int t0 = __ldcg(p.packed_idx + j);
-      const int t1 = j1 < total ? __ldcg(p.packed_idx + j1) : -1;
+    for (int r = warp; r < cnt; r += 16) {
+      const int r1 = r + 8;
       float4 v0[NV], v1[NV];
-      load_row_f32<NV>(p.x1 + static_cast<size_t>(t0) * p.ldx, lane, v0);
-      if (t1 >= 0) load_row_f32<NV>(p.x1 + static_cast<size_t>(t1) * p.ldx, lane, v1);
+      load_row_f32<NV>(x_img + static_cast<size_t>(s_list[r]) * p.ldx, lane, v0);
+      if (r1 < cnt) load_row_f32<NV>(x_img + static_cast<size_t>(s_list[r1]) * p.ldx, lane, v1);
       row_layernorm<NV>(v0, p.ln_w, p.ln_b, p.eps, lane);
-      store_row_f16<NV>(p.packed + static_cast<size_t>(j) * p.ldp, lane, v0);
-      if (t1 >= 0) {
+      store_row_f16<NV>(p.packed + static_cast<size_t>(base + r) * p.ldp, lane, v0);
+      if (r1 < cnt) {
         row_layernorm<NV>(v1, p.ln_w, p.ln_b, p.eps, lane);
-        store_row_f16<NV>(p.packed + static_cast<size_t>(j1) * p.ldp, lane, v1);
+        store_row_f16<NV>(p.packed + static_cast<size_t>(base + r1) * p.ldp, lane, v1);
       }
     }
   }
 
-  // last CTA out: leave the workspace zeroed for the next launch
+  // last CTA out: next launch starts with ticket 0 and a new epoch
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned prev = atomicAdd(&p.sync[1], 1u);
-    s_last = (prev == gridDim.x - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  if (s_last) {
-    for (int i = threadIdx.x; i < p.B; i += blockDim.x) cur[i] = 0;
-    if (threadIdx.x == 0) {
-      p.sync[0] = 0u;
-      p.sync[1] = 0u;
+    const unsigned prev = atomicAdd(&p.ctl[1], 1u);
+    if (prev == gridDim.x - 1) {
+      p.ctl[0] = 0u;
+      p.ctl[1] = 0u;
+      p.ctl[2] = s_tag;   // epoch + 1
+      __threadfence();
     }
-    __threadfence();
   }
 }
 
 template <int NV>
 static int launch_dispatch(const DispatchParams& p, cudaStream_t stream) {
-  static int max_blocks = 0;
-  if (max_blocks == 0) {
-    int per_sm = 0;
-    DYT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dispatch_kernel<NV>, 256, 0));
-    if (per_sm < 1) return fail(DYT_EDRIVER, "dispatch kernel does not fit on an SM");
-    if (per_sm > 4) per_sm = 4;
-    max_blocks = per_sm * sm_count();  // all CTAs co-resident: required by the grid barrier
-  }
-  const int want = (p.B * p.N + 7) / 8;
-  const int grid = want < max_blocks ? want : max_blocks;
-  dispatch_kernel<NV><<<grid, 256, 0, stream>>>(p);
+  dispatch_kernel<NV><<<p.B, 256, 0, stream>>>(p);   // one CTA per image, taken in ticket order
   return cuda_status(cudaGetLastError(), "dispatch_kernel launch");
 }
 
 }  // namespace dyt
 
 extern "C" size_t dyt_dispatch_workspace_bytes(int B) {
-  return static_cast<size_t>(B) * sizeof(int) + 64;
+  return static_cast<size_t>(B) * sizeof(unsigned long long) + 64;
 }
 
 namespace dyt {
@@ -401,8 +336,8 @@ int dyt::dispatch_fwd(const float* x1, int ldx, const float* sel_w, const float*
   p.cu_seqlens = cu_seqlens; p.n_kept = n_kept;
   p.packed = static_cast<__half*>(packed_f16); p.ldp = ldp;
   p.partials = partials; p.n_partials = n_partials;
-  p.sync = static_cast<unsigned int*>(workspace);
-  p.counts = reinterpret_cast<int*>(static_cast<char*>(workspace) + 64);
+  p.ctl = static_cast<unsigned int*>(workspace);
+  p.status = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + 64);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (C) {
     case 768: return launch_dispatch<6>(p, s);
