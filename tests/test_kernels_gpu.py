@@ -246,6 +246,34 @@ def test_dispatch_matches_oracle(dev, B, N, C, policy):
     _close(r["packed"][:n_kept], ref_rows, atol=1e-3, rtol=1e-3)
 
 
+def test_dispatch_many_images_lookback(dev):
+    """More images than CTAs can be co-resident (video batches: b*t frame-sequences): the per-image
+    CTAs take tickets in launch order and chain their packed bases by decoupled look-back over
+    several 32-image windows; bookkeeping must equal torch's nonzero() order, twice in a row on the
+    same workspace (epoch reuse)."""
+    from dyt_b200 import ops
+    B, N, C = 1500, 9, 128
+    g = _gen(77)
+    x = torch.randn(B, N, C, generator=g)
+    w = torch.randn(1, C, generator=g) * 0.3
+    b = torch.zeros(1)
+    lw, lb = torch.ones(C), torch.zeros(C)
+    for _ in range(2):
+        d = ops.dispatch(x.to(dev), w.to(dev), b.to(dev), ln_w=lw.to(dev), ln_b=lb.to(dev))
+        mask = d["mask"][..., 0].cpu()
+        nz = torch.nonzero(mask.reshape(-1))[:, 0].to(torch.int32)
+        n_kept = int(d["n_kept"].cpu())
+        assert n_kept == nz.numel() and 0 < n_kept < B * N
+        assert torch.equal(d["packed_idx"].cpu()[:n_kept], nz)
+        cu = torch.cat([torch.zeros(1), mask.sum(1).cumsum(0)]).to(torch.int32)
+        assert torch.equal(d["cu_seqlens"].cpu(), cu)
+        pos = d["token_pos"].cpu()
+        assert torch.equal(pos[nz.long()], torch.arange(n_kept, dtype=torch.int32))
+        assert bool((pos[mask.reshape(-1) == 0] == -1).all())
+        ref = O._r16(O.layer_norm(x.reshape(-1, C)[nz.long()], lw, lb))
+        _close(d["packed"].cpu()[:n_kept], ref, atol=2e-3, rtol=2e-3)
+
+
 def test_dispatch_gate_exhaustive_fp16(dev):
     """Every fp16 bit pattern as a logit: x1 rows are one-hot * value, w = e_0, bias 0, so the
     kernel's logit IS the pattern; the mask must equal the reference gate's truth table (golden,
