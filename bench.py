@@ -420,6 +420,52 @@ def run_ours(args, world, rank, local):
     print(json.dumps(line), flush=True)
 
 
+def run_extra(args, world, rank, local):
+    """Extra workloads (not the headline line): the other single-GPU BASELINE configs, same timing
+    rules (CUDA events, >= 3 warm-up steps, inputs in HBM, working set >> L2)."""
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    from dyt_b200 import synthetic
+    if args.workload == "vit_l16":
+        model = synthetic.build_vit_l16(device, seed=0)
+        batch, rate, units, name = 128, 0.7, "images/s", "ViT-L/16 DyT inference bs128 224x224 r~0.7 (no MoE-adapter: not in the reference)"
+        images = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(rank)).to(device)
+        cal = images[:32]
+        per_step = batch
+    else:
+        model = synthetic.build_video_b16(device, seed=0)
+        clips = 32 if world == 1 else 8   # BASELINE: 64 clips over 8 GPUs; one GPU alone takes 32
+        batch, rate, units, name = clips, 0.5, "clips/s", f"video ViT-B DyT, {clips} clips x 8 x 224x224 per GPU, r~0.5"
+        images = torch.randn(clips, 3, 8, 224, 224, generator=torch.Generator().manual_seed(rank)).to(device)
+        cal = images[:4].permute(0, 2, 1, 3, 4).reshape(-1, 3, 224, 224)
+        per_step = clips
+    keep = synthetic.calibrate_keep_rate(model, cal, rate)
+
+    def forward():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            return model(images)
+
+    warm = max(3, args.warmup)
+    for _ in range(warm):
+        forward()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        forward()
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    sec = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, world, device)
+    if rank == 0:
+        print(json.dumps({"metric": f"extra workload {args.workload}", "value": per_step * world * args.steps / sec,
+                          "unit": units, "n_gpus": world, "steps": args.steps, "warmup": warm,
+                          "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                          "config": {"workload": name, "keep_rate_calibration": round(keep, 4)}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -427,6 +473,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="vit_b16", choices=["vit_b16", "vit_l16", "video_b16"],
+                    help="vit_b16 = the BASELINE metric (default); the others are extra lines")
     args = ap.parse_args()
     if args.impl == "reference":
         # CPU arm: rank 0 alone works, nobody needs a process group
@@ -434,7 +482,10 @@ def main():
         return
     world, rank, local = dist_setup(args.gpus)
     try:
-        run_ours(args, world, rank, local)
+        if args.workload != "vit_b16":
+            run_extra(args, world, rank, local)
+        else:
+            run_ours(args, world, rank, local)
     finally:
         if world > 1:
             import torch.distributed as dist

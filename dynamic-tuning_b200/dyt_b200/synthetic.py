@@ -42,6 +42,45 @@ def build_vit_b16(device, num_classes: int = 100, seed: int = 0, flavour: str = 
     return model.eval().to(device)
 
 
+def _randomise_dyt_parts(model, seed: int):
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for blk in model.blocks:
+            blk.adaptmlp.up_proj.weight.copy_(
+                0.02 * torch.randn(blk.adaptmlp.up_proj.weight.shape, generator=g))
+            blk.mlp_token_select.mlp_head.weight.copy_(
+                0.5 * torch.randn(blk.mlp_token_select.mlp_head.weight.shape, generator=g))
+
+
+def build_vit_l16(device, num_classes: int = 100, seed: int = 0, ffn_num: int = 64,
+                  scalar: str = "0.1"):
+    """BASELINE configs[3] backbone: ViT-L/16 (C = 1024, depth 24, 16 heads) with DyT blocks via the
+    reference's generic ctor (vision_transformer_IN21K.py:199-231); the MoE-adapter of that config
+    does not exist in the reference."""
+    from models.model_speed_test import VisionTransformer
+    tuning, select = reference_configs(ffn_num=ffn_num, scalar=scalar, d_model=1024, ratio=0.7)
+    torch.manual_seed(seed)
+    model = VisionTransformer(patch_size=16, embed_dim=1024, depth=24, num_heads=16, mlp_ratio=4.0,
+                              qkv_bias=True, num_classes=num_classes, drop_path_rate=0.0,
+                              tuning_config=tuning, select_config=select)
+    _randomise_dyt_parts(model, seed)
+    return model.eval().to(device)
+
+
+def build_video_b16(device, num_classes: int = 174, seed: int = 0, ffn_num: int = 64,
+                    scalar: str = "0.1"):
+    """BASELINE configs[4] model: per-frame ViT-B/16 DyT + attentive pooling head."""
+    from video_models.video_vision_transformer_IN21K import vit_base_patch16_224_in21k as ctor
+    tuning, select = reference_configs(ffn_num=ffn_num, scalar=scalar)
+    torch.manual_seed(seed)
+    model = ctor(num_classes=num_classes, drop_path_rate=0.0, tuning_config=tuning,
+                 select_config=select)
+    _randomise_dyt_parts(model, seed)
+    with torch.no_grad():
+        model.query_token.normal_(std=0.5, generator=torch.Generator().manual_seed(seed + 2))
+    return model.eval().to(device)
+
+
 @torch.no_grad()
 def calibrate_keep_rate(model, images: torch.Tensor, rate: float) -> float:
     """Layer by layer: bias_i = -quantile(logits_i, 1 - rate) on `images`, using the kernels."""
