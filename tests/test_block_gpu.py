@@ -367,3 +367,33 @@ def test_tiny_video_model_vs_reference_golden(dev):
     if mism == 0:
         assert _rel(logits.float(), ref16["logits"]) <= 1e-2
         assert _rel(logits.float(), g["logits"]) <= 3e-2
+
+
+def test_forward_is_cuda_graph_capturable_and_replay_safe(dev, vitb_sd):
+    """No host synchronisation, no allocation inside the C ABI: the whole forward captures into a
+    CUDA graph; replays with new input contents reproduce the eager results (the dispatcher's
+    launch epoch lives in the workspace, so replays do not see stale look-back state)."""
+    g, sd, img = vitb_sd
+    m = _speed_model(sd, dev)
+    imgs = [torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(s)).to(dev)
+            for s in (1, 2, 3)]
+
+    def fwd(x):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            return m(x)
+
+    eager = [fwd(x).clone() for x in imgs]
+    static_in = imgs[0].clone()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            fwd(static_in)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_out = fwd(static_in)
+    for x, ref in zip(imgs, eager):
+        static_in.copy_(x)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(static_out, ref)
