@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libdyt_b200.so")
 ABI_VERSION = 1
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_BIAS_RESID = 0, 1, 2, 3
+EW_GELU_FWD, EW_GELU_BWD, EW_RELU_DROP_BWD, EW_MUL = 0, 1, 2, 3
 
 
 class DytError(RuntimeError):
@@ -65,6 +66,14 @@ SIGNATURES = {
     "dyt_patch_embed_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "dyt_pool_layernorm_f16": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp]),
     "dyt_query_attn_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "dyt_layernorm_bwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _vp, _f, _vp, _i, _vp, _vp, _vp, _i,
+                               _vp, _i, _vp]),
+    "dyt_merge_bwd": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _vp, _i,
+                           _vp, _i, _vp, _vp]),
+    "dyt_rowscale_colsum": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "dyt_eltwise_f16": (_i, [_i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dyt_wgrad_f16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _i, _vp, _vp]),
+    "dyt_attn_varlen_bwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "dyt_block_workspace_bytes": (_sz, [C.POINTER(BlockShape)]),
     "dyt_block_workspace_layout": (_i, [C.POINTER(BlockShape), _vp, C.POINTER(BlockBuffers)]),
     "dyt_block_fwd": (_i, [C.POINTER(BlockShape), C.POINTER(BlockWeights), C.POINTER(BlockOpts),

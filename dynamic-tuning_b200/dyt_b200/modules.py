@@ -18,7 +18,7 @@ from typing import Callable, Optional, Tuple, Union
 import torch
 import torch.nn as nn
 
-from . import _lib, engine, ops
+from . import _lib, engine, ops, train
 from ._lib import DytError
 from .layers import DropPath, Mlp, PatchDropout, PatchEmbed, trunc_normal_, use_fused_attn
 
@@ -36,6 +36,13 @@ def _no_backward(what: str, *tensors) -> None:
         raise NotImplementedError(
             f"dyt_b200 {what}: only the forward pass is implemented (backward is the next scope "
             "row, SURVEY.md section 8f); call under torch.no_grad()")
+
+
+def _wants_grad(module: nn.Module, x: torch.Tensor) -> bool:
+    """True when the call must be differentiable: autograd on and the input or a parameter of the
+    module requires grad (the reference's fine-tuning step, engine_finetune.py:47-76)."""
+    return torch.is_grad_enabled() and (x.requires_grad or
+                                        any(p.requires_grad for p in module.parameters()))
 
 
 def _gumbel_sigmoid(logits, tau=1, hard=False, eps=1e-10, training=True, threshold=0.5):
@@ -197,12 +204,6 @@ class _BlockBase(nn.Module):
         return float(self.norm1.eps)
 
     def _run(self, x, forced_mask=None, report_gate=False):
-        _no_backward("Block", x, *self.parameters())
-        if self.training and torch.is_grad_enabled():
-            # train() mode = Gumbel gate + adapter dropout + dense masked MLP with autograd: the
-            # backward kernels are the next scope row.
-            raise NotImplementedError("dyt_b200 Block: train-mode forward/backward is not "
-                                      "implemented yet; use model.eval() / torch.no_grad()")
         out, masks, logits, _ = engine.run_blocks(
             x, [self], eps=self._eps(), forced_masks=None if forced_mask is None else [forced_mask],
             fuse_next_ln=False, report_gate=report_gate)
@@ -224,6 +225,8 @@ class SpeedBlock(_BlockBase):
         if not hasattr(self, "mlp_token_select"):
             raise AttributeError("'Block' object has no attribute 'mlp_token_select' "
                                  "(select=False; every reference entry script uses keep_layers=0)")
+        _no_backward("Block (speed flavour: inference only; fine-tune with "
+                     "models.vision_transformer_IN21K)", x, *self.parameters())
         out, _, _ = self._run(x)
         return out
 
@@ -247,6 +250,12 @@ class TrainBlock(_BlockBase):
         if self.count_flops:
             return self.forward_count_flops(x)
         B, N, _ = x.shape
+        if _wants_grad(self, x):
+            # fine-tuning: dense masked block with autograd (Gumbel gate + adapter dropout in
+            # train() mode), forward and backward on the sm_100a kernels (dyt_b200.train)
+            out, sel, logit = train.block_train(self, x, complete_model)
+            dt = _act_dtype()
+            return out, dict(sub_token_select=sel.to(dt), token_logits=logit.to(dt))
         if complete_model:
             # teacher pass: MLP on every token; the selector's own decision is still reported
             out, sel, logit = self._run(x, forced_mask=torch.ones(B, N, device=x.device),
@@ -341,9 +350,11 @@ class VisionTransformer(nn.Module):
 
     # -- stem: patch embedding + cls + position through the sm_100a im2col / GEMM / assemble path --
     def _embed(self, x):
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("dyt_b200: train-mode forward/backward is the next scope row; "
-                                      "call model.eval() under torch.no_grad()")
+        if torch.is_grad_enabled() and (x.requires_grad or any(
+                p.requires_grad for p in (self.cls_token, self.pos_embed, *self.patch_embed.parameters()))):
+            raise NotImplementedError("dyt_b200 fine-tuning keeps the stem frozen (patch_embed, "
+                                      "cls_token, pos_embed: main_image.py:242-256) and has no "
+                                      "gradient w.r.t. the pixels")
         if not x.is_cuda:
             raise DytError("dyt_b200 VisionTransformer needs CUDA inputs (no CPU fallback)")
         pe = self.patch_embed
@@ -398,9 +409,7 @@ class VisionTransformer(nn.Module):
         return logits[:, :nc]
 
     def _blocks(self, x, complete_model=False):
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("dyt_b200: train-mode forward/backward is the next scope row; "
-                                      "call model.eval() under torch.no_grad()")
+        _no_backward("VisionTransformer (inference path)", x, *self.blocks.parameters())
         for blk in self.blocks:
             if not hasattr(blk, "mlp_token_select"):
                 raise AttributeError("'Block' object has no attribute 'mlp_token_select'")
@@ -447,6 +456,9 @@ class TrainVisionTransformer(VisionTransformer):
     block_cls = TrainBlock
 
     def forward_features(self, x, complete_model=False):
+        if _wants_grad(self, x):
+            raise NotImplementedError("dyt_b200: differentiable forward_features is not built; the "
+                                      "fine-tuning step goes through forward()")
         x, masks, logits = self._blocks(self._embed(x), complete_model)
         dt = _act_dtype()
         # [L, B, N] -> [B, L, N-1, 1] without the cls slot (vision_transformer_IN21K.py:367-368)
@@ -454,7 +466,28 @@ class TrainVisionTransformer(VisionTransformer):
         token_logits = logits.permute(1, 0, 2).unsqueeze(-1).to(dt)
         return self.norm(x), dict(token_select=token_select, token_logits=token_logits)
 
+    def _forward_finetune(self, x, complete_model=False):
+        """The differentiable path of the fine-tuning step (engine_finetune.py:47-76): student
+        (complete_model=False) and teacher (True) passes both carry gradients to the adapters."""
+        x = self._embed(x)
+        sels, lgs = [], []
+        for blk in self.blocks:
+            x, sel, lg = train.block_train(blk, x, complete_model)
+            sels.append(sel[:, 1:])
+            lgs.append(lg)
+        dt = _act_dtype()
+        token_select = dict(token_select=torch.stack(sels, dim=1).to(dt),
+                            token_logits=torch.stack(lgs, dim=1).to(dt))
+        return x, token_select
+
     def forward(self, x, complete_model=False):
+        if _wants_grad(self, x):
+            if not (self.global_pool == "token" and isinstance(self.fc_norm, nn.Identity) and
+                    isinstance(self.head, nn.Linear) and self.head_drop.p == 0):
+                raise NotImplementedError("dyt_b200 fine-tuning implements the reference head: token "
+                                          "pool, final norm, nn.Linear head, no head dropout")
+            tokens, token_select = self._forward_finetune(x, complete_model)
+            return train.head_train(self, tokens).to(_act_dtype()), token_select
         tokens, masks, logits = self._blocks(self._embed(x), complete_model)
         dt = _act_dtype()
         token_select = dict(token_select=masks.permute(1, 0, 2)[:, :, 1:].unsqueeze(-1).to(dt),

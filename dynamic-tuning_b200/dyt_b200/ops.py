@@ -270,3 +270,146 @@ def query_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int
         q.data_ptr(), ldq, k2.data_ptr(), v2.data_ptr(), k2.stride(0), b, nk, num_heads,
         Cdim // num_heads, out.data_ptr(), Cdim, _stream()), "dyt_query_attn_fwd")
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# backward kernels (include/dyt_b200.h "backward of the block"); used by dyt_b200.train
+# --------------------------------------------------------------------------------------------
+def eltwise_f16(op: int, a: torch.Tensor, b: Optional[torch.Tensor] = None,
+                c: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Elementwise fp16 kernels (GELU forward / backward, ReLU+dropout backward, product)."""
+    _need_cuda(a, b, c)
+    for t in (a, b, c):
+        if t is not None and (t.dtype != torch.float16 or not t.is_contiguous()):
+            raise DytError("eltwise_f16 expects contiguous fp16 tensors")
+        if t is not None and t.shape != a.shape:
+            raise DytError("eltwise_f16 operands must have one shape")
+    out = torch.empty_like(a)
+    check(_lib.lib().dyt_eltwise_f16(op, a.data_ptr(), _ptr(b), _ptr(c), out.data_ptr(), a.numel(),
+                                     _stream()), "dyt_eltwise_f16")
+    return out
+
+
+def layernorm_bwd(gy: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6,
+                  resid: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
+                  axpy: Optional[torch.Tensor] = None, row_idx: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None, want_f16_copy: bool = False):
+    """g_x = resid + dLN(g_y) (+ row_scale[:, None] * axpy).  gy fp16 [R, C]; x fp32 rows (all rows
+    of the stream when row_idx selects R of them); returns (fp32 like x, fp16 copy or None)."""
+    _need_cuda(gy, x, weight, resid, row_scale, axpy, row_idx, out)
+    if gy.dtype != torch.float16 or x.dtype != torch.float32:
+        raise DytError("layernorm_bwd expects an fp16 gradient and the fp32 forward input")
+    g2, x2 = _rows2d(gy), _rows2d(x)
+    R, Cdim = g2.shape
+    if row_idx is None and x2.shape[0] != R:
+        raise DytError("layernorm_bwd: gradient / input row counts differ")
+    if out is None:
+        if row_idx is not None:
+            raise DytError("layernorm_bwd with row_idx writes into a caller-provided buffer")
+        out = torch.empty_like(x2)
+    o2 = _rows2d(out)
+    r2 = None if resid is None else _rows2d(resid)
+    oh = torch.empty(x2.shape, dtype=torch.float16, device=x.device) if want_f16_copy else None
+    w = weight.detach().to(torch.float32).contiguous()
+    rs = None if row_scale is None else row_scale.reshape(-1).to(torch.float32).contiguous()
+    ax = None if axpy is None else axpy.reshape(-1).to(torch.float32).contiguous()
+    check(_lib.lib().dyt_layernorm_bwd(
+        g2.data_ptr(), g2.stride(0), x2.data_ptr(), x2.stride(0), _ptr(row_idx), R, Cdim,
+        w.data_ptr(), float(eps), _ptr(r2), 0 if r2 is None else r2.stride(0), _ptr(rs), _ptr(ax),
+        o2.data_ptr(), o2.stride(0), _ptr(oh), Cdim, _stream()), "dyt_layernorm_bwd")
+    return out.reshape(x.shape), (None if oh is None else oh.reshape(x.shape))
+
+
+def merge_bwd(g_out: torch.Tensor, N: int, mlp_x: Optional[torch.Tensor] = None,
+              mask: Optional[torch.Tensor] = None, logits: Optional[torch.Tensor] = None,
+              noise: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, tau: float = 5.0,
+              g_token_select: Optional[torch.Tensor] = None,
+              g_token_logits: Optional[torch.Tensor] = None, masked: bool = True):
+    """Backward of the merge + straight-through gate.  g_out fp32 [B*N, C].  Returns
+    (g16, g_masked16 or None, g_logit [B*N] fp32 or None)."""
+    _need_cuda(g_out, mlp_x, mask, logits, g_token_select, g_token_logits)
+    if g_out.dtype != torch.float32:
+        raise DytError("merge_bwd expects the fp32 stream gradient")
+    g2 = _rows2d(g_out)
+    T, Cdim = g2.shape
+    B = T // N
+    dev = g_out.device
+    g16 = torch.empty((T, Cdim), dtype=torch.float16, device=dev)
+    gm16 = gl = m2 = None
+    mk = lg = n1 = n2 = gs = gle = None
+    if masked:
+        if mlp_x is None or mask is None or logits is None:
+            raise DytError("merge_bwd(masked=True) needs mlp_x, mask and logits")
+        m2 = _rows2d(mlp_x)
+        gm16 = torch.empty((T, Cdim), dtype=torch.float16, device=dev)
+        gl = torch.empty((T,), dtype=torch.float32, device=dev)
+        mk = mask.reshape(-1).to(torch.float32).contiguous()
+        lg = logits.reshape(-1).to(torch.float32).contiguous()
+        if noise is not None:
+            n1 = noise[0].reshape(-1).to(torch.float32).contiguous()
+            n2 = noise[1].reshape(-1).to(torch.float32).contiguous()
+        if g_token_select is not None:
+            gs = g_token_select.reshape(-1).to(torch.float32).contiguous()
+        if g_token_logits is not None:
+            gle = g_token_logits.reshape(-1).to(torch.float32).contiguous()
+    check(_lib.lib().dyt_merge_bwd(
+        g2.data_ptr(), g2.stride(0), _ptr(m2), 0 if m2 is None else m2.stride(0), _ptr(mk),
+        _ptr(lg), _ptr(n1), _ptr(n2), float(tau), _ptr(gs), _ptr(gle), B, N, Cdim, g16.data_ptr(),
+        Cdim, _ptr(gm16), Cdim, _ptr(gl), _stream()), "dyt_merge_bwd")
+    return g16, gm16, gl
+
+
+def rowscale_colsum(s: torch.Tensor, x16: torch.Tensor, out_w: torch.Tensor,
+                    out_b: Optional[torch.Tensor]) -> None:
+    """out_w[:] += sum_t s[t] * x16[t, :], out_b += sum_t s[t] (fp32 accumulators, in place)."""
+    _need_cuda(s, x16, out_w, out_b)
+    x2 = _rows2d(x16)
+    if x2.dtype != torch.float16 or s.dtype != torch.float32 or out_w.dtype != torch.float32:
+        raise DytError("rowscale_colsum: s fp32, x fp16, out fp32")
+    check(_lib.lib().dyt_rowscale_colsum(s.data_ptr(), x2.data_ptr(), x2.stride(0), x2.shape[0],
+                                         x2.shape[1], out_w.data_ptr(), _ptr(out_b), _stream()),
+          "dyt_rowscale_colsum")
+
+
+def wgrad_f16(g16: torch.Tensor, x16: torch.Tensor, n_out: Optional[int] = None,
+              alpha: float = 1.0, want_bias: bool = True):
+    """(dW [n_out, K] fp32, db [n_out] fp32 or None) = alpha * (g^T x, colsum g); g [T, >= n_out]."""
+    _need_cuda(g16, x16)
+    g2, x2 = _rows2d(g16), _rows2d(x16)
+    if g2.dtype != torch.float16 or x2.dtype != torch.float16 or g2.shape[0] != x2.shape[0]:
+        raise DytError("wgrad_f16 expects fp16 [T, Nout] and [T, K]")
+    n_out = g2.shape[1] if n_out is None else n_out
+    T, K = x2.shape
+    dW = torch.zeros((n_out, K), dtype=torch.float32, device=g16.device)
+    db = torch.zeros((n_out,), dtype=torch.float32, device=g16.device) if want_bias else None
+    check(_lib.lib().dyt_wgrad_f16(g2.data_ptr(), g2.stride(0), x2.data_ptr(), x2.stride(0), T,
+                                   n_out, K, float(alpha), dW.data_ptr(), K, _ptr(db), _stream()),
+          "dyt_wgrad_f16")
+    return dW, db
+
+
+def attn_varlen_bwd(qkv: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, num_heads: int,
+                    cu_seqlens: Optional[torch.Tensor] = None, num_seqs: Optional[int] = None,
+                    max_seqlen: Optional[int] = None) -> torch.Tensor:
+    """d_qkv (fp16, like qkv) of attn_varlen."""
+    _need_cuda(qkv, out, d_out, cu_seqlens)
+    if any(t.dtype != torch.float16 for t in (qkv, out, d_out)):
+        raise DytError("attn_varlen_bwd expects fp16 tensors")
+    C3 = qkv.shape[-1]
+    Cdim = C3 // 3
+    q2, o2, g2 = _rows2d(qkv), _rows2d(out), _rows2d(d_out)
+    if cu_seqlens is None:
+        if qkv.dim() != 3:
+            raise DytError("uniform attention expects qkv [B, N, 3C]")
+        nseq, uni, mx = qkv.shape[0], qkv.shape[1], qkv.shape[1]
+    else:
+        nseq = int(num_seqs if num_seqs is not None else cu_seqlens.numel() - 1)
+        if max_seqlen is None:
+            raise DytError("varlen attention needs max_seqlen (no host sync is done here)")
+        uni, mx = 0, int(max_seqlen)
+    dqkv = torch.empty_like(q2)
+    check(_lib.lib().dyt_attn_varlen_bwd(
+        q2.data_ptr(), q2.stride(0), o2.data_ptr(), o2.stride(0), g2.data_ptr(), g2.stride(0),
+        _ptr(cu_seqlens), nseq, uni, mx, num_heads, Cdim // num_heads, dqkv.data_ptr(),
+        dqkv.stride(0), _stream()), "dyt_attn_varlen_bwd")
+    return dqkv.reshape(qkv.shape)

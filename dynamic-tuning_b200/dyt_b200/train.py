@@ -1,0 +1,300 @@
+"""Train-mode forward and backward of the DyT block for parameter-efficient fine-tuning.
+
+Reference behaviour:
+  * models/vision_transformer_IN21K.py:144-165  Block.forward in train mode: dense MLP on every
+    token, `x = residual + token_select * mlp_x + adapt_x`; `complete_model=True` (the teacher pass of
+    engine_finetune.py:49) drops the mask.
+  * models/dynamic_adapter.py:25-54  hard Gumbel-sigmoid gate with the straight-through estimator.
+  * models/dynamic_adapter.py:127-130  Adapter with train-time dropout (p = 0.1).
+  * main_image.py:242-256  only adaptmlp.*, mlp_token_select.* and head.* are trainable: the backward
+    is data gradients through the frozen backbone plus weight gradients of those parameters.
+
+Everything runs on the sm_100a kernels through the C ABI (ops.*); torch.autograd only routes the
+gradients between the per-block Functions.  There is no CPU / eager fallback.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib, ops
+from ._lib import DytError
+
+_FROZEN = {
+    "qkv": "attn.qkv", "proj": "attn.proj", "fc1": "mlp.fc1", "fc2": "mlp.fc2",
+}
+_TRAINABLE_PREFIXES = ("adaptmlp.", "mlp_token_select.")
+
+
+def _get(module, dotted):
+    obj = module
+    for part in dotted.split("."):
+        obj = getattr(obj, part)
+    return obj
+
+
+class FrozenWeights:
+    """fp16 copies (and transposes, for the data-gradient GEMMs) of a block's frozen Linears and the
+    fp32 LayerNorm parameters; rebuilt only if a frozen parameter changes."""
+
+    def __init__(self, block):
+        self.block = block
+        self.key = None
+        self.t: Dict[str, torch.Tensor] = {}
+
+    def get(self) -> Dict[str, torch.Tensor]:
+        blk = self.block
+        params = [_get(blk, d).weight for d in _FROZEN.values()] + [blk.norm1.weight, blk.norm2.weight]
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key != self.key:
+            for name, p in blk.named_parameters():
+                if p.requires_grad and not name.startswith(_TRAINABLE_PREFIXES):
+                    raise NotImplementedError(
+                        f"dyt_b200 fine-tuning implements the reference's PEFT setting (frozen "
+                        f"backbone, main_image.py:242-256); '{name}' requires grad")
+            with torch.no_grad():
+                h16 = torch.float16
+                for short, dotted in _FROZEN.items():
+                    lin = _get(blk, dotted)
+                    if not lin.weight.is_cuda:
+                        raise DytError("dyt_b200: block parameters must live on a CUDA device")
+                    w = lin.weight.detach().to(h16).contiguous()
+                    self.t[short + "_w"] = w
+                    self.t[short + "_wT"] = w.t().contiguous()
+                    self.t[short + "_b"] = None if lin.bias is None else lin.bias.detach().to(h16).contiguous()
+                for short, ln in (("ln1", blk.norm1), ("ln2", blk.norm2)):
+                    self.t[short + "_w"] = ln.weight.detach().float().contiguous()
+                    self.t[short + "_b"] = ln.bias.detach().float().contiguous()
+            self.key = key
+        return self.t
+
+
+def _frozen(block) -> Dict[str, torch.Tensor]:
+    fw = block.__dict__.get("_dyt_frozen")
+    if fw is None:
+        fw = FrozenWeights(block)
+        block.__dict__["_dyt_frozen"] = fw
+    return fw.get()
+
+
+def _scale_of(block) -> float:
+    s = block.adaptmlp.scale
+    if torch.is_tensor(s):
+        if s.requires_grad:
+            raise NotImplementedError("dyt_b200: adapter_scalar='learnable_scalar' is not used by any "
+                                      "reference entry script and has no backward here")
+        return float(s.item())
+    return float(s)
+
+
+class DytBlockFn(torch.autograd.Function):
+    """One DyT block in train mode.  Inputs: x fp32 [B, N, C] and the six trainable tensors of the
+    block; outputs: (x_out fp32, token_select [B, N, 1] fp32, token_logits [B, N-1, 1] fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, down_w, down_b, up_w, up_b, sel_w, sel_b, block, complete_model, noise,
+                drop_mult, eps, training_gate):
+        ctx.set_materialize_grads(False)
+        fz = _frozen(block)
+        h16 = torch.float16
+        B, N, Cd = x.shape
+        H = block.attn.num_heads
+        if Cd != 64 * H:
+            raise DytError(f"dyt_b200 attention kernels need head_dim 64 (C={Cd}, heads={H})")
+        x = x.detach().to(torch.float32).contiguous()
+        scale = _scale_of(block)
+        tau = float(getattr(block.mlp_token_select, "tau", 5.0))
+        thr = float(getattr(block.mlp_token_select, "threshold", 0.5))
+        dw16 = down_w.detach().to(h16).contiguous()
+        db16 = down_b.detach().to(h16).contiguous()
+        uw16 = up_w.detach().to(h16).contiguous()
+        ub16 = up_b.detach().to(h16).contiguous()
+
+        xn = ops.layernorm_f16(x, fz["ln1_w"], fz["ln1_b"], eps)
+        qkv, _ = ops.linear_f16(xn, fz["qkv_w"], fz["qkv_b"])
+        o = ops.attn_varlen(qkv.reshape(B, N, -1), H)
+        x1, x1h = ops.linear_f16(o, fz["proj_w"], fz["proj_b"], epilogue=_lib.EPI_BIAS_RESID,
+                                 resid=x, want_f16_copy=True)
+        d = ops.dispatch(x1.reshape(B, N, Cd), sel_w.detach(), sel_b.detach(),
+                         logit_dtype=torch.float16, threshold=thr,
+                         noise=noise if training_gate else None, tau=tau, pack=False)
+        mask, logits = d["mask"], d["logits"]
+        ln2 = ops.layernorm_f16(x1, fz["ln2_w"], fz["ln2_b"], eps)
+        pre, _ = ops.linear_f16(ln2, fz["fc1_w"], fz["fc1_b"])
+        hdn = ops.eltwise_f16(_lib.EW_GELU_FWD, pre)
+        mlp_x, _ = ops.linear_f16(hdn, fz["fc2_w"], fz["fc2_b"])
+        hd, _ = ops.linear_f16(x1h, dw16, db16, epilogue=_lib.EPI_BIAS_RELU)
+        if drop_mult is not None:
+            hd = ops.eltwise_f16(_lib.EW_MUL, hd, drop_mult.reshape(hd.shape))
+        up, _ = ops.linear_f16(hd, uw16, ub16, epilogue=_lib.EPI_BIAS, scale=scale)
+        T = B * N
+        ar = torch.arange(T, device=x.device, dtype=torch.int32)
+        if complete_model:
+            token_pos = ar
+        else:
+            token_pos = torch.where(mask.reshape(-1) > 0, ar, torch.full_like(ar, -1))
+        out, _ = ops.scatter_merge(x1.reshape(B, N, Cd), up.reshape(B, N, Cd), mlp_x.reshape(T, Cd),
+                                   token_pos)
+        ctx.block = block
+        ctx.meta = (B, N, Cd, H, scale, tau, eps, bool(complete_model), bool(training_gate))
+        ctx.noise = noise if training_gate else None
+        ctx.drop_mult = drop_mult
+        ctx.save_for_backward(x, qkv, o, x1, x1h, mask, logits, pre, mlp_x, hd, dw16, uw16,
+                              sel_w.detach())
+        return out, mask, logits
+
+    @staticmethod
+    def backward(ctx, g_out, g_sel, g_logits):
+        (x, qkv, o, x1, x1h, mask, logits, pre, mlp_x, hd, dw16, uw16, sel_w) = ctx.saved_tensors
+        B, N, Cd, H, scale, tau, eps, complete_model, training_gate = ctx.meta
+        fz = _frozen(ctx.block)
+        T = B * N
+        if g_out is None:
+            g_out = torch.zeros((T, Cd), dtype=torch.float32, device=x.device)
+        g_out = g_out.to(torch.float32).contiguous().reshape(T, Cd)
+        g16, gm16, g_l = ops.merge_bwd(
+            g_out, N, mlp_x=mlp_x, mask=mask, logits=logits, noise=ctx.noise, tau=tau,
+            g_token_select=None if complete_model else g_sel,
+            g_token_logits=None if complete_model else g_logits, masked=not complete_model)
+        if complete_model:
+            gm16 = g16
+        # ---- adapter: up dgrad, wgrads, ReLU / dropout, (down dgrad further below) ----
+        g_hd, _ = ops.linear_f16(g16, uw16.t().contiguous(), None, epilogue=_lib.EPI_BIAS, scale=scale)
+        d_up_w, d_up_b = ops.wgrad_f16(g16, hd.reshape(T, -1), alpha=scale)
+        dm = None if ctx.drop_mult is None else ctx.drop_mult.reshape(T, -1)
+        g_hp = ops.eltwise_f16(_lib.EW_RELU_DROP_BWD, g_hd.reshape(T, -1), hd.reshape(T, -1), dm)
+        d_down_w, d_down_b = ops.wgrad_f16(g_hp, x1h.reshape(T, Cd))
+        # ---- frozen MLP: fc2 dgrad, GELU', fc1 dgrad, LayerNorm2 backward ----
+        g_h, _ = ops.linear_f16(gm16, fz["fc2_wT"], None)
+        g_pre = ops.eltwise_f16(_lib.EW_GELU_BWD, g_h.reshape(pre.shape), pre)
+        g_ln2, _ = ops.linear_f16(g_pre, fz["fc1_wT"], None)
+        d_sel_w = d_sel_b = None
+        if complete_model:
+            g_x1, _ = ops.layernorm_bwd(g_ln2.reshape(T, Cd), x1.reshape(T, Cd), fz["ln2_w"], eps,
+                                        resid=g_out)
+        else:
+            # selector: data gradient g_l * w folded into the LayerNorm-backward pass
+            g_x1, _ = ops.layernorm_bwd(g_ln2.reshape(T, Cd), x1.reshape(T, Cd), fz["ln2_w"], eps,
+                                        resid=g_out, row_scale=g_l, axpy=sel_w)
+            d_sel_w = torch.zeros(Cd, dtype=torch.float32, device=x.device)
+            d_sel_b = torch.zeros(1, dtype=torch.float32, device=x.device)
+            ops.rowscale_colsum(g_l, x1h.reshape(T, Cd), d_sel_w, d_sel_b)
+            d_sel_w = d_sel_w.reshape(1, Cd)
+        need_x = ctx.needs_input_grad[0]
+        g_x = None
+        if need_x:
+            g_x1, g_x1h = ops.linear_f16(g_hp, dw16.t().contiguous(), None,
+                                         epilogue=_lib.EPI_BIAS_RESID, resid=g_x1, want_f16_copy=True)
+            g_o, _ = ops.linear_f16(g_x1h, fz["proj_wT"], None)
+            g_qkv = ops.attn_varlen_bwd(qkv.reshape(B, N, -1), o.reshape(B, N, Cd),
+                                        g_o.reshape(B, N, Cd), H)
+            g_xn, _ = ops.linear_f16(g_qkv.reshape(T, -1), fz["qkv_wT"], None)
+            g_x, _ = ops.layernorm_bwd(g_xn.reshape(T, Cd), x.reshape(T, Cd), fz["ln1_w"], eps,
+                                       resid=g_x1.reshape(T, Cd))
+            g_x = g_x.reshape(B, N, Cd)
+        return (g_x, d_down_w, d_down_b, d_up_w, d_up_b, d_sel_w, d_sel_b,
+                None, None, None, None, None, None)
+
+
+_fixed = {"noises": None, "drop_mults": None}
+
+
+class fixed_randomness:
+    """Context manager that feeds recorded Gumbel draws / dropout multipliers to successive
+    block_train calls (one entry per block call, in call order) instead of drawing them: lets a test
+    share the randomness with the reference."""
+
+    def __init__(self, noises=None, drop_mults=None):
+        self.new = {"noises": None if noises is None else list(noises),
+                    "drop_mults": None if drop_mults is None else list(drop_mults)}
+
+    def __enter__(self):
+        self.old = dict(_fixed)
+        _fixed.update(self.new)
+        return self
+
+    def __exit__(self, *exc):
+        _fixed.update(self.old)
+        return False
+
+
+def block_train(block, x: torch.Tensor, complete_model: bool = False,
+                noise: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                drop_mult: Optional[torch.Tensor] = None):
+    """Train-mode block with autograd.  `noise` = the two Gumbel draws [B, N-1, 1] (drawn here in the
+    reference's order when None and the block is in train mode); `drop_mult` = the adapter dropout
+    multiplier keep / (1 - p), fp16 [B, N, bottleneck] (drawn here when None and p > 0)."""
+    if not x.is_cuda:
+        raise DytError("dyt_b200 needs CUDA tensors (no CPU fallback)")
+    if not hasattr(block, "mlp_token_select"):
+        raise AttributeError("'Block' object has no attribute 'mlp_token_select'")
+    B, N, _ = x.shape
+    training_gate = bool(block.training)
+    if noise is None and _fixed["noises"]:
+        noise = tuple(t.to(x.device) for t in _fixed["noises"].pop(0))
+    if drop_mult is None and _fixed["drop_mults"]:
+        drop_mult = _fixed["drop_mults"].pop(0)
+    if training_gate and noise is None:
+        from .modules import draw_gumbel_pair
+        noise = draw_gumbel_pair((B, N - 1, 1), torch.float16, x.device)
+    p = float(block.adaptmlp.dropout)
+    if block.training and p > 0 and drop_mult is None:
+        keep = torch.rand((B, N, block.adaptmlp.down_proj.out_features), device=x.device) >= p
+        drop_mult = keep.to(torch.float16) / (1.0 - p)
+    if drop_mult is not None:
+        drop_mult = drop_mult.to(device=x.device, dtype=torch.float16).contiguous()
+    a, s = block.adaptmlp, block.mlp_token_select.mlp_head
+    sel_b = s.bias if s.bias is not None else torch.zeros(1, device=x.device)
+    return DytBlockFn.apply(x, a.down_proj.weight, a.down_proj.bias, a.up_proj.weight,
+                            a.up_proj.bias, s.weight, sel_b, block, bool(complete_model), noise,
+                            drop_mult, float(block.norm1.eps), training_gate)
+
+
+class DytHeadFn(torch.autograd.Function):
+    """Final LayerNorm of the cls rows + classifier (reference vision_transformer_IN21K.py:371-380);
+    `norm` is frozen, `head` is trainable (main_image.py:247)."""
+
+    @staticmethod
+    def forward(ctx, tokens, head_w, head_b, norm_w, norm_b, eps):
+        B, N, Cd = tokens.shape
+        dev = tokens.device
+        tokens = tokens.detach().to(torch.float32).contiguous()
+        nc = head_w.shape[0]
+        n8 = (nc + 7) // 8 * 8
+        w16 = torch.zeros((n8, Cd), dtype=torch.float16, device=dev)
+        b16 = torch.zeros((n8,), dtype=torch.float16, device=dev)
+        w16[:nc] = head_w.detach().to(torch.float16)
+        if head_b is not None:
+            b16[:nc] = head_b.detach().to(torch.float16)
+        idx = torch.arange(B, device=dev, dtype=torch.int32) * N
+        nw = norm_w.detach().float().contiguous()
+        cls_n = ops.layernorm_f16(tokens, nw, norm_b.detach().float().contiguous(), eps, row_idx=idx)
+        logits, _ = ops.linear_f16(cls_n, w16, b16)
+        ctx.save_for_backward(tokens, cls_n, w16, idx, nw)
+        ctx.meta = (B, N, Cd, nc, n8, eps, head_b is not None)
+        return logits[:, :nc]
+
+    @staticmethod
+    def backward(ctx, g_logits):
+        tokens, cls_n, w16, idx, nw = ctx.saved_tensors
+        B, N, Cd, nc, n8, eps, has_bias = ctx.meta
+        g16 = torch.zeros((B, n8), dtype=torch.float16, device=tokens.device)
+        g16[:, :nc] = g_logits.to(torch.float16)
+        d_w, d_b = ops.wgrad_f16(g16, cls_n, n_out=nc, want_bias=has_bias)
+        g_tok = None
+        if ctx.needs_input_grad[0]:
+            g_cls, _ = ops.linear_f16(g16, w16.t().contiguous(), None)
+            g_tok = torch.zeros((B * N, Cd), dtype=torch.float32, device=tokens.device)
+            ops.layernorm_bwd(g_cls, tokens.reshape(B * N, Cd), nw, eps, row_idx=idx, out=g_tok)
+            g_tok = g_tok.reshape(B, N, Cd)
+        return g_tok, d_w, d_b, None, None, None
+
+
+def head_train(model, tokens: torch.Tensor) -> torch.Tensor:
+    for name, p in (("norm.weight", model.norm.weight), ("norm.bias", model.norm.bias)):
+        if p.requires_grad:
+            raise NotImplementedError(f"dyt_b200 fine-tuning keeps the final norm frozen ('{name}' "
+                                      "requires grad)")
+    return DytHeadFn.apply(tokens, model.head.weight, model.head.bias, model.norm.weight,
+                           model.norm.bias, float(model.norm.eps))

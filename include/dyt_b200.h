@@ -131,6 +131,67 @@ int dyt_query_attn_fwd(const void* q_f16, int ldq, const void* k_f16, const void
                        int num_clips, int n_keys, int num_heads, int head_dim, void* out_f16, int ldo,
                        void* stream);
 
+/* ---- backward of the block for parameter-efficient fine-tuning ----
+ * The backbone is frozen (main_image.py:242-256: only adaptmlp.*, mlp_token_select.* and head.* are
+ * trained), so the backward needs data gradients through every frozen op and weight gradients for
+ * the adapter, the selector and the head only.  Data gradients through a frozen Linear are
+ * dyt_linear_f16 calls with the transposed weight (g_x = g_y W == g_y (W^T)^T).  Under fp16 autocast
+ * the gradients of fp16 tensors are fp16, the gradient of the fp32 residual stream is fp32. */
+
+/* g_x = resid + dLayerNorm(g_y) [+ row_scale[r] * axpy[:]]   (fp32), optional fp16 copy.
+ * g_y fp16 [n_rows, C] (the dgrad GEMM output), x fp32 = the forward input of the LayerNorm
+ * (statistics are recomputed).  With row_idx, gradient row r belongs to x / resid / out row
+ * row_idx[r] (final norm on the cls rows).  resid may alias out.  row_scale/axpy add the selector's
+ * data gradient g_logit[t] * mlp_head.weight in the same pass.
+ * Backward of nn.LayerNorm norm1 / norm2 / norm (models/vision_transformer_IN21K.py:110, :123, :316). */
+int dyt_layernorm_bwd(const void* gy_f16, int ldg, const float* x, int ldx, const int* row_idx,
+                      int n_rows, int C, const float* gamma, float eps, const float* resid, int ldr,
+                      const float* row_scale, const float* axpy, float* out, int ldo, void* out_f16,
+                      int ldoh, void* stream);
+
+/* Backward of  x = residual + token_select * mlp_x + adapt_x  (models/vision_transformer_IN21K.py:
+ * 161-163) and of the straight-through hard gate (models/dynamic_adapter.py:46-51):
+ *   g_f16        = f16(g_out)                                  gradient of adapt_x (and of mlp_x
+ *                                                              when complete_model=True)
+ *   g_masked_f16 = mask * g_f16                                gradient of mlp_x
+ *   g_logit[t]   = (<g_f16[t], mlp_x[t]> + g_token_select[t]) * y(1-y) * (1/tau in train form)
+ *                  + g_token_logits, 0 for the cls slot; y = sigmoid((l + n1 - n2)/tau) or sigmoid(l)
+ * g_out fp32 [B*N, C]; mask [B*N]; logits / noise* / g_token_logits [B*(N-1)]; g_token_select [B*N]
+ * (gradient arriving on the returned sub_token_select, may be NULL).  g_masked_f16 == NULL selects
+ * the complete_model form (only g_f16 is written). */
+int dyt_merge_bwd(const float* g_out, int ldg, const void* mlp_f16, int ldm, const float* mask,
+                  const float* logits, const float* noise1, const float* noise2, float tau,
+                  const float* g_token_select, const float* g_token_logits, int B, int N, int C,
+                  void* g_f16, int ld16, void* g_masked_f16, int ldgm, float* g_logit, void* stream);
+
+/* out_w[c] += sum_t s[t] * x[t, c];  out_b += sum_t s[t]: weight / bias gradient of the selector's
+ * Linear(C -> 1) (TokenSelect.mlp_head, models/dynamic_adapter.py:60).  fp32 atomics: the caller
+ * zero-fills (or carries) out_w / out_b. */
+int dyt_rowscale_colsum(const float* s, const void* x_f16, int ldx, int T, int C, float* out_w,
+                        float* out_b, void* stream);
+
+/* Elementwise fp16 ops on contiguous, 16-byte aligned buffers of n elements (n % 8 == 0). */
+#define DYT_EW_GELU_FWD 0      /* out = gelu_erf(a)                      timm Mlp.act (train path keeps the pre-activation) */
+#define DYT_EW_GELU_BWD 1      /* out = a * gelu'(b)                     a = g_h, b = pre-activation */
+#define DYT_EW_RELU_DROP_BWD 2 /* out = b > 0 ? a * c : 0  (c NULL = 1)  Adapter ReLU + dropout backward */
+#define DYT_EW_MUL 3           /* out = a * b                            Adapter dropout forward (b = keep/(1-p)) */
+int dyt_eltwise_f16(int op, const void* a, const void* b, const void* c, void* out, size_t n,
+                    void* stream);
+
+/* dW[Nout, Kin] += alpha * g[T, Nout]^T x[T, Kin],  db[Nout] += alpha * colsum(g)  (db may be NULL):
+ * weight gradient of a trainable nn.Linear (Adapter.down_proj / up_proj, head).  g, x fp16; dW, db
+ * fp32, accumulated with atomics (caller zero-fills). */
+int dyt_wgrad_f16(const void* g_f16, int ldg, const void* x_f16, int ldx, int T, int Nout, int Kin,
+                  float alpha, float* dW, int ldw, float* db, void* stream);
+
+/* Backward of dyt_attn_varlen_fwd: d_qkv [total_tokens, 3, H, 64] fp16 from qkv, the forward output
+ * `out` and its gradient d_out ([total_tokens, H*64] fp16).  Probabilities are recomputed.
+ * Sequences up to 208 tokens. */
+int dyt_attn_varlen_bwd(const void* qkv, int ld_qkv, const void* out, int ldo, const void* d_out,
+                        int ld_do, const int* cu_seqlens, int num_seqs, int uniform_len,
+                        int max_seqlen, int num_heads, int head_dim, void* d_qkv, int ld_dqkv,
+                        void* stream);
+
 /* ---- whole block: Block.batch_forward (reference models/model_speed_test.py:274-310) ---------- */
 typedef struct dyt_block_shape {
   int B;          /* images (sequences) */

@@ -244,6 +244,90 @@ def block_dense(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int, sc
 
 
 # ----------------------------------------------------------------------------------------------
+# a2 / a4 / a5 in train mode, differentiable (fp32): the dense masked block with the hard
+# straight-through Gumbel gate and adapter dropout (reference models/vision_transformer_IN21K.py:
+# 144-165, models/dynamic_adapter.py:25-54, :127-130).  Gradients come from torch.autograd on this
+# restatement; the random draws are inputs so the kernels can share them.
+# ----------------------------------------------------------------------------------------------
+def gumbel_sigmoid_st(logits: Tensor, tau: float = 5.0, threshold: float = 0.5,
+                      training: bool = True, noise: Optional[Tuple[Tensor, Tensor]] = None,
+                      hard_override: Optional[Tensor] = None) -> Tensor:
+    """models/dynamic_adapter.py:25-54 with hard=True: ret = y_hard - y_soft.detach() + y_soft.
+    hard_override (tests only) imposes y_hard, e.g. the decisions of a lower-precision run whose
+    borderline tokens rounded the other way."""
+    if training:
+        g1, g2 = noise
+        y_soft = ((logits + g1 - g2) / tau).sigmoid()
+    else:
+        y_soft = logits.sigmoid()
+    y_hard = torch.zeros_like(logits).masked_fill(y_soft > threshold, 1.0)
+    if hard_override is not None:
+        y_hard = hard_override.to(y_hard.dtype).reshape(y_hard.shape)
+    return y_hard - y_soft.detach() + y_soft
+
+
+def block_train(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int, scale: float,
+                noise: Optional[Tuple[Tensor, Tensor]] = None, drop_mult: Optional[Tensor] = None,
+                complete_model: bool = False, training: bool = True, tau: float = 5.0,
+                threshold: float = 0.5, hard_override: Optional[Tensor] = None) -> Dict[str, Tensor]:
+    """Block.forward of the train model (fp32).  drop_mult = keep / (1 - p) multiplier of the adapter
+    dropout (None = no dropout).  Returns dict(out, mask [B,N,1] (differentiable), logits)."""
+    x1 = x + attention(layer_norm(x, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"]), p,
+                       prefix + "attn.", num_heads, "fp32")                        # :148
+    logits = F.linear(x1[:, 1:, :], p[prefix + "mlp_token_select.mlp_head.weight"],
+                      p[prefix + "mlp_token_select.mlp_head.bias"])                # dynamic_adapter.py:72
+    sel = gumbel_sigmoid_st(logits, tau, threshold, training, noise, hard_override)  # :74
+    sel = torch.cat([sel.new_ones(x.shape[0], 1, 1), sel], dim=1)                  # :75
+    pre = prefix + "adaptmlp."
+    down = F.relu(F.linear(x1, p[pre + "down_proj.weight"], p[pre + "down_proj.bias"]))
+    if drop_mult is not None:
+        down = down * drop_mult                                                    # dynamic_adapter.py:129
+    adapt_x = F.linear(down, p[pre + "up_proj.weight"], p[pre + "up_proj.bias"]) * scale
+    mlp_x = mlp(layer_norm(x1, p[prefix + "norm2.weight"], p[prefix + "norm2.bias"]), p,
+                prefix + "mlp.", "fp32")                                           # :159
+    if not complete_model:
+        mlp_x = sel * mlp_x                                                        # :161-162
+    out = x1 + mlp_x + adapt_x                                                     # :163
+    return dict(out=out, mask=sel, logits=logits, x1=x1)
+
+
+def vit_train_forward(img: Tensor, p: Dict[str, Tensor], depth: int, num_heads: int, scale: float,
+                      noises=None, drop_mults=None, complete_model: bool = False,
+                      training: bool = True, patch: int = 16) -> Dict[str, Tensor]:
+    """Train model forward (reference models/vision_transformer_IN21K.py:343-385), fp32."""
+    x = patch_embed(img, p, patch, "fp32")
+    x = torch.cat((p["cls_token"].expand(x.shape[0], -1, -1), x), dim=1) + p["pos_embed"]
+    sels, logs = [], []
+    for i in range(depth):
+        r = block_train(x, p, f"blocks.{i}.", num_heads, scale,
+                        None if noises is None else noises[i],
+                        None if drop_mults is None else drop_mults[i], complete_model, training)
+        x = r["out"]
+        sels.append(r["mask"])
+        logs.append(r["logits"])
+    xn = layer_norm(x, p["norm.weight"], p["norm.bias"])
+    logits = F.linear(xn[:, 0], p["head.weight"], p["head.bias"])
+    return dict(logits=logits, token_select=torch.stack(sels, dim=1)[:, :, 1:, :],
+                token_logits=torch.stack(logs, dim=1))
+
+
+def finetune_loss(student_logits: Tensor, token_select: Tensor, teacher_logits: Tensor,
+                  targets: Tensor, token_target_ratio: float = 0.5, token_loss_ratio: float = 2.0,
+                  token_minimal: float = 0.1, token_minimal_weight: float = 1.0) -> Tensor:
+    """The loss of the fine-tuning step (reference engine_finetune.py:47-65 with models/losses.py:
+    50-82 AdaLoss over a cross-entropy base criterion)."""
+    kl = F.kl_div(F.log_softmax(student_logits, dim=-1),
+                  F.log_softmax(teacher_logits.detach(), dim=-1), reduction="batchmean",
+                  log_target=True)
+    teacher = F.cross_entropy(teacher_logits, targets)
+    base = F.cross_entropy(student_logits, targets)
+    flops = ((token_select.mean() - token_target_ratio) ** 2).mean()              # losses.py:71-74
+    minimal = (token_minimal - token_select.mean(-1)).clamp(min=0.0).sum()        # :77-78
+    token_loss = flops + token_minimal_weight * minimal
+    return base + token_loss_ratio * token_loss + teacher + kl
+
+
+# ----------------------------------------------------------------------------------------------
 # a10: VisionTransformer.forward (reference models/model_speed_test.py:467-496 and
 #      models/vision_transformer_IN21K.py:343-385)
 # ----------------------------------------------------------------------------------------------

@@ -12,6 +12,10 @@ itself are the pins of the oracle (oracle/dyt_oracle.py):
                     model-level output of both reference models + per-block activations
   video_tiny.pt     a 2-layer dim-128 video model (reference video ctor): state_dict incl. the
                     attentive pooling head, a 3x2-frame clip, logits / masks / pooled features
+  finetune_tiny.pt  one fine-tuning step (student + teacher pass, AdaLoss + teacher CE + KL, backward)
+                    of the reference train model in train() mode on the tiny ViT: inputs, the
+                    replayed Gumbel draws, dropout multipliers, loss, outputs and every trainable
+                    parameter's gradient
   vitb_b2.pt        ViT-B/16, synthetic seed-0 weights (regenerated from the seed, not stored),
                     calibrated selector biases, B=2: logits / masks / token logits of the speed model
                     and the train model (eval, complete_model on/off), config-1 imposed-mask logits
@@ -187,6 +191,79 @@ def tiny_video(ref_video):
     return out
 
 
+def tiny_finetune(ref_train, ref_losses):
+    """One fine-tuning step of the reference train model (engine_finetune.py:47-76: student pass,
+    teacher pass, AdaLoss + teacher CE + KL, backward) on the 2-layer dim-128 model in train() mode.
+    The reference draws its randomness from the global RNG; to share it with the kernels the two
+    Gumbel draws per layer and pass are replayed from the seed (models/dynamic_adapter.py:30-39) and
+    nn.functional.dropout is swapped for a multiplication by recorded keep/(1-p) multipliers while
+    the reference runs (p = 0 calls pass through)."""
+    dims = dict(embed_dim=128, depth=2, num_heads=2, bottleneck=16, num_classes=10, img_size=32)
+    sd = O.synthetic_state_dict(seed=9, **dims)
+    g = torch.Generator().manual_seed(31)
+    img = torch.randn(4, 3, 32, 32, generator=g)
+    targets = torch.tensor([1, 7, 3, 3])
+    sd = O.calibrate_selector_bias(sd, img, 2, 2, 0.1, 0.5)
+    tuning, select = ref_shim.reference_configs(ffn_num=16, scalar="0.1", d_model=128)
+    m = ref_train.VisionTransformer(img_size=32, patch_size=16, embed_dim=128, depth=2, num_heads=2,
+                                    mlp_ratio=4.0, qkv_bias=True, num_classes=10,
+                                    tuning_config=tuning, select_config=select)
+    m.load_state_dict(sd, strict=True)
+    trainable = []
+    for name, prm in m.named_parameters():      # main_image.py:242-256 freeze logic
+        prm.requires_grad = ("adaptmlp" in name) or ("mlp_token_select" in name) or name.startswith("head.")
+        if prm.requires_grad:
+            trainable.append(name)
+    m.train()
+    B, N = 4, 5
+    drop_mults = [(torch.rand(B, N, 16, generator=g) >= 0.1).float() / 0.9 for _ in range(4)]
+    queue = list(drop_mults)
+    import torch.nn.functional as F
+    orig_dropout = F.dropout
+
+    def fixed_dropout(x, p=0.5, training=True, inplace=False):
+        if p == 0.0 or not training:
+            return x
+        return x * queue.pop(0)
+
+    F.dropout = fixed_dropout
+    torch.nn.functional.dropout = fixed_dropout
+    try:
+        torch.manual_seed(777)
+        out_s, ts = m(img)
+        out_t, _ = m(img, complete_model=True)
+        crit = ref_losses.AdaLoss(torch.nn.CrossEntropyLoss(), token_target_ratio=0.5,
+                                  token_loss_ratio=2.0, token_minimal=0.1, token_minimal_weight=1.0)
+        kl = F.kl_div(F.log_softmax(out_s, dim=-1), F.log_softmax(out_t.detach(), dim=-1),
+                      reduction="batchmean", log_target=True)
+        teacher_loss = crit.base_criterion(out_t, targets)
+        loss, _ = crit(dict(prediction=out_s, **ts), targets)
+        loss = loss + teacher_loss + kl
+        loss.backward()
+    finally:
+        F.dropout = orig_dropout
+        torch.nn.functional.dropout = orig_dropout
+    assert not queue, "dropout call count differs from the recorded multipliers"
+    torch.manual_seed(777)     # replay: student layers 0..1, then teacher layers 0..1
+    noises = []
+    for _ in range(4):
+        e = torch.empty(B, N - 1, 1)
+        g1 = -e.clone().exponential_().log()
+        g2 = -e.clone().exponential_().log()
+        noises.append((g1, g2))
+    grads = {n: prm.grad.clone() for n, prm in m.named_parameters() if prm.requires_grad}
+    margin = min(float(((lg + n1 - n2) / 5).abs().min()) for lg, (n1, n2) in
+                 zip(ts["token_logits"].unbind(1), noises[:2]))
+    print("tiny_finetune: loss", float(loss), "keep", float(ts["token_select"].mean()),
+          "gate margin", margin)
+    assert margin > 5e-3, "a gate decision sits too close to the threshold for a cross-precision pin"
+    return dict(dims=dims, scale=0.1, state_dict=sd, img=img, targets=targets, noises=noises,
+                drop_mults=drop_mults, trainable=trainable, loss=loss.detach(),
+                student_logits=out_s.detach(), teacher_logits=out_t.detach(),
+                token_select=ts["token_select"].detach(), token_logits=ts["token_logits"].detach(),
+                grads=grads)
+
+
 def main():
     assert ref_shim.reference_available(), "needs the reference checkout at " + ref_shim.REFERENCE_ROOT
     torch.set_num_threads(os.cpu_count())
@@ -200,6 +277,8 @@ def main():
     torch.save(vitb_b2(ref_speed, ref_train), os.path.join(OUT, "vitb_b2.pt"))
     ref_video = ref_shim.import_reference("video_models.video_vision_transformer_IN21K")
     torch.save(tiny_video(ref_video), os.path.join(OUT, "video_tiny.pt"))
+    ref_losses = ref_shim.import_reference("models.losses")
+    torch.save(tiny_finetune(ref_train, ref_losses), os.path.join(OUT, "finetune_tiny.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 

@@ -122,6 +122,15 @@ def install() -> None:
     _module("timm.models.layers", **layers)
     _module("timm.models.registry", register_model=ident_deco)
     _module("easydict", EasyDict=EasyDict)
+    # models/losses.py:1-3 imports three names it never uses
+    timm.loss = _module("timm.loss")
+    _module("timm.data.transforms_factory", transforms_imagenet_train=dummy)
+    if "numpy.lib.arraysetops" not in sys.modules:
+        try:
+            importlib.import_module("numpy.lib.arraysetops")
+        except ImportError:
+            import numpy as _np
+            _module("numpy.lib.arraysetops", isin=_np.isin)
 
 
 def reference_available() -> bool:

@@ -84,13 +84,30 @@ def test_no_cpu_fallback_anywhere():
             m(torch.zeros(1, 3, 224, 224))
 
 
-def test_training_mode_is_refused_loudly_until_backward_exists():
+def test_training_mode_has_no_cpu_fallback_and_refuses_unfrozen_backbone():
+    """Fine-tuning runs on the CUDA kernels only (dyt_b200.train): CPU tensors raise; the speed
+    flavour is inference-only; a trainable stem is refused (the reference freezes it)."""
+    from dyt_b200 import DytError
     from models.vision_transformer_IN21K import VisionTransformer
+    from models.model_speed_test import VisionTransformer as SpeedViT
     tuning, select = _cfgs(16, 128)
-    m = VisionTransformer(img_size=32, patch_size=16, embed_dim=128, depth=1, num_heads=2,
-                          num_classes=10, tuning_config=tuning, select_config=select).train()
-    with pytest.raises(NotImplementedError):
+    kw = dict(img_size=32, patch_size=16, embed_dim=128, depth=1, num_heads=2, num_classes=10,
+              tuning_config=tuning, select_config=select)
+    m = VisionTransformer(**kw).train()
+    with pytest.raises(NotImplementedError):     # stem parameters still require grad
         m(torch.zeros(2, 3, 32, 32))
+    for n, p in m.named_parameters():
+        p.requires_grad = ("adaptmlp" in n) or ("mlp_token_select" in n) or n.startswith("head.")
+    with pytest.raises(DytError):                # frozen like main_image.py:242-256, but on the CPU
+        m(torch.zeros(2, 3, 32, 32))
+    with pytest.raises(DytError):
+        m.blocks[0](torch.zeros(2, 5, 128))
+    s = SpeedViT(**kw).train()
+    for p in s.parameters():
+        p.requires_grad = False
+    s.blocks[0].adaptmlp.up_proj.weight.requires_grad = True
+    with pytest.raises((NotImplementedError, DytError)):
+        s.blocks[0](torch.zeros(2, 5, 128))
 
 
 def test_gate_threshold_table_product_side():
