@@ -208,11 +208,13 @@ rowscale_colsum_kernel(const float* __restrict__ s, const __half* __restrict__ X
 // ---------------------------------------------------------------------------------------------
 enum { EW_GELU_FWD = 0, EW_GELU_BWD = 1, EW_RELU_DROP_BWD = 2, EW_MUL = 3 };
 
+// Phi(x) = erfc(-x / sqrt 2) / 2: erfc keeps its relative accuracy in the negative tail, where
+// 1 + erf(x / sqrt 2) cancels
 __device__ __forceinline__ float gelu_exact(float x) {
-  return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+  return 0.5f * x * erfcf(-x * 0.70710678118654752f);
 }
 __device__ __forceinline__ float gelu_grad(float x) {
-  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  const float cdf = 0.5f * erfcf(-x * 0.70710678118654752f);
   const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }

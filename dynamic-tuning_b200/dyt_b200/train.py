@@ -142,6 +142,8 @@ class DytBlockFn(torch.autograd.Function):
         ctx.drop_mult = drop_mult
         ctx.save_for_backward(x, qkv, o, x1, x1h, mask, logits, pre, mlp_x, hd, dw16, uw16,
                               sel_w.detach())
+        if debug_keep is not None:   # tests: look at the forward intermediates
+            debug_keep.update(x1=x1, x1h=x1h, pre=pre, mlp_x=mlp_x, hd=hd, qkv=qkv, o=o)
         return out, mask, logits
 
     @staticmethod
@@ -198,6 +200,7 @@ class DytBlockFn(torch.autograd.Function):
 
 
 _fixed = {"noises": None, "drop_mults": None}
+debug_keep: Optional[dict] = None   # set to a dict to receive the last block forward's intermediates
 
 
 class fixed_randomness:

@@ -269,7 +269,8 @@ def gumbel_sigmoid_st(logits: Tensor, tau: float = 5.0, threshold: float = 0.5,
 def block_train(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int, scale: float,
                 noise: Optional[Tuple[Tensor, Tensor]] = None, drop_mult: Optional[Tensor] = None,
                 complete_model: bool = False, training: bool = True, tau: float = 5.0,
-                threshold: float = 0.5, hard_override: Optional[Tensor] = None) -> Dict[str, Tensor]:
+                threshold: float = 0.5, hard_override: Optional[Tensor] = None,
+                relu_override: Optional[Tensor] = None) -> Dict[str, Tensor]:
     """Block.forward of the train model (fp32).  drop_mult = keep / (1 - p) multiplier of the adapter
     dropout (None = no dropout).  Returns dict(out, mask [B,N,1] (differentiable), logits)."""
     x1 = x + attention(layer_norm(x, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"]), p,
@@ -279,7 +280,13 @@ def block_train(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int, sc
     sel = gumbel_sigmoid_st(logits, tau, threshold, training, noise, hard_override)  # :74
     sel = torch.cat([sel.new_ones(x.shape[0], 1, 1), sel], dim=1)                  # :75
     pre = prefix + "adaptmlp."
-    down = F.relu(F.linear(x1, p[pre + "down_proj.weight"], p[pre + "down_proj.bias"]))
+    down_pre = F.linear(x1, p[pre + "down_proj.weight"], p[pre + "down_proj.bias"])
+    if relu_override is None:
+        down = F.relu(down_pre)
+    else:
+        # tests only: the ReLU's on/off pattern of a lower-precision run (the derivative is a step, so
+        # a pre-activation that rounds across zero changes the gradient by a whole term)
+        down = down_pre * relu_override.to(down_pre.dtype)
     if drop_mult is not None:
         down = down * drop_mult                                                    # dynamic_adapter.py:129
     adapt_x = F.linear(down, p[pre + "up_proj.weight"], p[pre + "up_proj.bias"]) * scale
@@ -288,7 +295,7 @@ def block_train(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int, sc
     if not complete_model:
         mlp_x = sel * mlp_x                                                        # :161-162
     out = x1 + mlp_x + adapt_x                                                     # :163
-    return dict(out=out, mask=sel, logits=logits, x1=x1)
+    return dict(out=out, mask=sel, logits=logits, x1=x1, down_pre=down_pre)
 
 
 def vit_train_forward(img: Tensor, p: Dict[str, Tensor], depth: int, num_heads: int, scale: float,

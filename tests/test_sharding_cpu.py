@@ -50,3 +50,46 @@ def test_flops_model_matches_survey():
     import bench
     assert bench.flops_per_image(197) / 1e9 == pytest.approx(35.60, abs=0.02)   # dense ViT-B
     assert bench.flops_per_image(99) / 1e9 == pytest.approx(24.50, abs=0.02)    # r = 0.5
+
+
+def _arena_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, os.path.join(ROOT, "dynamic-tuning_b200"))
+    from dyt_b200.ddp import GradArena
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
+    lin[0].bias.requires_grad = False                      # frozen tensors stay out of the arena
+    arena = GradArena(lin.parameters())
+    assert len(arena.params) == 3 and arena.nbytes == (36 + 16 + 4) * 4
+    x = torch.full((4, 7), float(rank + 1))
+    for step in range(2):
+        arena.zero()
+        lin(x).sum().backward()                            # autograd accumulates into the arena views
+        assert all(p.grad.data_ptr() == arena.flat.data_ptr() + 4 * o
+                   for p, o in zip(arena.params, arena.offsets))
+        local = [p.grad.clone() for p in arena.params]
+        arena.all_reduce_mean()
+    q.put((rank, [g.tolist() for g in local], [p.grad.tolist() for p in arena.params]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_arena_allreduce():
+    """BASELINE configs[2] exchange step: one flat arena, one all-reduce, mean
+    over ranks; equals the average of the per-rank gradients."""
+    world, port = 2, 29531
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_arena_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, l0, a0), (_, l1, a1) = res
+    assert a0 == a1                                         # both ranks hold the same averaged grads
+    for g0, g1, avg in zip(l0, l1, a0):
+        want = (torch.tensor(g0) + torch.tensor(g1)) / 2
+        assert torch.allclose(torch.tensor(avg), want, rtol=1e-6, atol=1e-7)
