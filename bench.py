@@ -466,6 +466,53 @@ def run_extra(args, world, rank, local):
                           "config": {"workload": name, "keep_rate_calibration": round(keep, 4)}}), flush=True)
 
 
+def run_finetune(args, world, rank, local):
+    """BASELINE configs[2]: ViT-B/16 DyT fine-tune step on synthetic VTAB-shape data, 64 images per
+    GPU (512 global at 8), ffn_num 16, adapter scale 1 (train_vtab.sh:8, main_vtab.py:351).  One step
+    = student pass + teacher pass + loss + backward + ONE gradient all-reduce (NCCL, flat 74-tensor
+    arena) + AdamW step, as engine_finetune.py:47-76."""
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    from dyt_b200 import synthetic
+    from dyt_b200.ddp import GradArena, trainable_parameters
+    from dyt_b200.finetune import FinetuneStep
+    batch = 64
+    model = synthetic.build_vit_b16(device, flavour="train", ffn_num=16, scalar="1.0", seed=0)
+    gen = torch.Generator().manual_seed(rank)
+    images = torch.randn(batch, 3, 224, 224, generator=gen).to(device)
+    targets = torch.randint(0, NUM_CLASSES, (batch,), generator=gen).to(device)
+    keep = synthetic.calibrate_keep_rate(model, images, RATE)
+    params = trainable_parameters(model)
+    model.train()
+    arena = GradArena(params)
+    step = FinetuneStep(model, torch.optim.AdamW(params, lr=1e-3, weight_decay=0.05), arena)
+    warm = max(6, args.warmup)          # the dynamic loss scale settles within the first steps
+    for _ in range(warm):
+        loss = step(images, targets)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        loss = step(images, targets)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    sec = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, world, device)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "extra workload finetune_b16", "value": batch * world * args.steps / sec,
+            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "ViT-B/16 DyT fine-tune step (student + teacher forward, backward, "
+                                   "grad all-reduce, AdamW), 64 images per GPU, ffn_num 16, scale 1",
+                       "keep_rate_calibration": round(keep, 4), "loss": float(loss),
+                       "loss_scale": float(step.scaler.get_scale()),
+                       "allreduce_bytes_per_step": arena.nbytes if world > 1 else 0,
+                       "trainable_tensors": len(arena.params)}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -473,7 +520,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="vit_b16", choices=["vit_b16", "vit_l16", "video_b16"],
+    ap.add_argument("--workload", default="vit_b16", choices=["vit_b16", "vit_l16", "video_b16", "finetune_b16"],
                     help="vit_b16 = the BASELINE metric (default); the others are extra lines")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -482,7 +529,9 @@ def main():
         return
     world, rank, local = dist_setup(args.gpus)
     try:
-        if args.workload != "vit_b16":
+        if args.workload == "finetune_b16":
+            run_finetune(args, world, rank, local)
+        elif args.workload != "vit_b16":
             run_extra(args, world, rank, local)
         else:
             run_ours(args, world, rank, local)

@@ -1,0 +1,62 @@
+"""One fine-tuning step of the reference's recipe on the sm_100a path.
+
+Mirrors engine_finetune.py:47-76 (train_one_epoch inner loop): student pass, teacher pass
+(complete_model=True), AdaLoss (models/losses.py:50-82: cross-entropy + token_loss_ratio * keep-rate
+loss) + teacher cross-entropy + KL(student || teacher), scaled backward, gradient all-reduce,
+optimizer step.  The loss itself is a handful of torch ops on [B, classes] logits and the [B, L,
+N-1, 1] masks (host-side glue in the reference too); forward / backward of the model are kernels.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from .ddp import GradArena
+
+
+def ada_loss(student_logits, token_select, targets, token_target_ratio=0.5, token_loss_ratio=2.0,
+             token_minimal=0.1, token_minimal_weight=1.0):
+    """models/losses.py:50-82 with a cross-entropy base criterion."""
+    base = F.cross_entropy(student_logits, targets)
+    flops = ((token_select.mean() - token_target_ratio) ** 2).mean()
+    minimal = (token_minimal - token_select.mean(-1)).clamp(min=0.0).sum()
+    return base + token_loss_ratio * (flops + token_minimal_weight * minimal)
+
+
+def finetune_loss(student_logits, token_select, teacher_logits, targets, **kw):
+    """engine_finetune.py:52-65."""
+    kl = F.kl_div(F.log_softmax(student_logits, dim=-1),
+                  F.log_softmax(teacher_logits.detach(), dim=-1), reduction="batchmean",
+                  log_target=True)
+    teacher = F.cross_entropy(teacher_logits, targets)
+    return ada_loss(student_logits, token_select, targets, **kw) + teacher + kl
+
+
+class FinetuneStep:
+    """model: TrainVisionTransformer with the reference's freeze rule applied; optimizer over the
+    trainable parameters; arena: their flat gradient buffer (all-reduced once per step).  Loss scaling
+    is torch's dynamic GradScaler, as in the reference (util/misc.py NativeScalerWithGradNormCount):
+    the keep-rate loss puts a gradient of token_loss_ratio * scale on every dropped token's fp16
+    mask entry, which overflows at the initial scale 65536; the scaler skips those steps and backs
+    off exactly as it does for the reference."""
+
+    def __init__(self, model, optimizer, arena: GradArena, token_target_ratio: float = 0.5,
+                 init_scale: float = 65536.0):
+        self.model, self.opt, self.arena = model, optimizer, arena
+        self.scaler = torch.amp.GradScaler("cuda", init_scale=init_scale)
+        self.ratio = token_target_ratio
+
+    def __call__(self, images: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        self.arena.zero()
+        with torch.autocast("cuda", dtype=torch.float16):
+            out_s, ts = self.model(images)
+            out_t, _ = self.model(images, complete_model=True)
+            loss = finetune_loss(out_s.float(), ts["token_select"].float(), out_t.float(), targets,
+                                 token_target_ratio=self.ratio)
+        self.scaler.scale(loss).backward()
+        self.arena.all_reduce_mean()          # the step's only collective (sum of scaled grads / world)
+        self.scaler.step(self.opt)            # unscale, skip on inf / nan
+        self.scaler.update()
+        return loss.detach()
