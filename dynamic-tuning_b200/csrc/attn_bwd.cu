@@ -2,7 +2,7 @@
 // recomputing the probabilities from Q and K instead of saving them (reference
 // models/vision_transformer_IN21K.py:61-65, the backward of F.scaled_dot_product_attention).
 //
-// One CTA (8 warps) per (sequence, head); Q, K, V, dO of the head and the whole P / dS matrix stay
+// One CTA (16 warps) per (sequence, head); Q, K, V, dO of the head and the whole P / dS matrix stay
 // in shared memory (fp16), every contraction runs on HMMA through nvcuda::wmma with fp32
 // accumulation, and accumulator tiles pass through a small per-warp fp32 staging tile for the row
 // arithmetic.  Phases (separated by CTA barriers):
@@ -24,7 +24,7 @@ namespace dyt {
 constexpr int AB_MAXN = 208;   // padded sequence length held in shared memory
 constexpr int AB_LDQ = 72;     // row stride (halves) of the Q / K / V / dO tiles
 constexpr int AB_LDP = 216;    // row stride (halves) of the P / dS matrix
-constexpr int AB_WARPS = 8;
+constexpr int AB_WARPS = 16;
 constexpr int AB_STG = 16 * 20;  // floats per warp staging tile
 constexpr size_t AB_QBYTES = static_cast<size_t>(AB_MAXN) * AB_LDQ * 2;
 constexpr size_t AB_PBYTES = static_cast<size_t>(AB_MAXN) * AB_LDP * 2;

@@ -14,6 +14,7 @@
 #include <stdarg.h>
 
 #include "../../include/dyt_b200.h"
+#include "gelu.cuh"
 #include "host_utils.h"
 #include "rowwise.cuh"
 
@@ -208,17 +209,6 @@ rowscale_colsum_kernel(const float* __restrict__ s, const __half* __restrict__ X
 // ---------------------------------------------------------------------------------------------
 enum { EW_GELU_FWD = 0, EW_GELU_BWD = 1, EW_RELU_DROP_BWD = 2, EW_MUL = 3 };
 
-// Phi(x) = erfc(-x / sqrt 2) / 2: erfc keeps its relative accuracy in the negative tail, where
-// 1 + erf(x / sqrt 2) cancels
-__device__ __forceinline__ float gelu_exact(float x) {
-  return 0.5f * x * erfcf(-x * 0.70710678118654752f);
-}
-__device__ __forceinline__ float gelu_grad(float x) {
-  const float cdf = 0.5f * erfcf(-x * 0.70710678118654752f);
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
-}
-
 template <int OP>
 __global__ void __launch_bounds__(256)
 eltwise_f16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
@@ -240,11 +230,11 @@ eltwise_f16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
       const float2 fb = __half22float2(pb[j]);
       float2 r;
       if (OP == EW_GELU_FWD) {            // a = pre-activation
-        r.x = gelu_exact(fa.x);
-        r.y = gelu_exact(fa.y);
+        r.x = gelu_f16(fa.x);
+        r.y = gelu_f16(fa.y);
       } else if (OP == EW_GELU_BWD) {     // a = g_h, b = pre-activation
-        r.x = fa.x * gelu_grad(fb.x);
-        r.y = fa.y * gelu_grad(fb.y);
+        r.x = fa.x * gelu_grad_f16(fb.x);
+        r.y = fa.y * gelu_grad_f16(fb.y);
       } else if (OP == EW_RELU_DROP_BWD) {  // a = g, b = relu output (after dropout), c = multiplier
         float2 fc = make_float2(1.f, 1.f);
         if (c != nullptr) fc = __half22float2(pc[j]);

@@ -21,6 +21,7 @@
 // Replaces the cuBLASLt calls behind nn.Linear in the reference block
 // (reference models/model_speed_test.py:147 qkv, :164 proj, :106-111 adapter, timm Mlp fc1/fc2).
 #pragma once
+#include "gelu.cuh"
 #include "ptx.cuh"
 
 namespace dyt {
@@ -79,34 +80,6 @@ struct GemmCfg {
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
 };
-
-// exact-erf GELU of an fp16 value, for an fp16 result:  gelu(x) = max(x, 0) - |x| * Q(|x|) with the
-// Gaussian upper tail Q(a) = erfc(a / sqrt 2) / 2 = 2^P(a), P a degree-7 polynomial fitted to
-// log2 Q on [0, 5.75] (relative error of Q <= 3.3e-6; beyond 5.75 the tail term is below half the
-// smallest fp16 subnormal).  Over all 63488 finite fp16 inputs the fp16-rounded result equals that
-// of an fp32 erf evaluation except for 162 inputs that land on the neighbouring fp16 value (the
-// same order as fp32 erf itself against float64).  9 FMA-pipe instructions + 1 MUFU per element:
-// the fc1 epilogue is bound by instruction issue, so this is what sets that GEMM's speed.
-// NaN propagates (max.NaN), +-inf give +inf / -0.
-__device__ __forceinline__ float gelu_f16(float x) {
-  constexpr float kC[8] = {
-      -9.999953348e-01f,
-      -1.151250054e+00f,
-      -4.584681700e-01f,
-      -5.395489181e-02f,
-      8.504621978e-03f,
-      -9.294938285e-04f,
-      6.144065649e-05f,
-      -1.825521560e-06f};
-  const float a = fminf(fabsf(x), 5.75f);
-  float pl = kC[7];
-#pragma unroll
-  for (int i = 6; i >= 0; --i) pl = fmaf(pl, a, kC[i]);
-  const float q = ex2_approx(pl);
-  float relu;
-  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(relu) : "f"(x));
-  return fmaf(-a, q, relu);
-}
 
 template <int BN, int EPI, int EW>
 __global__ void __launch_bounds__(GemmCfg<BN, EW>::THREADS, 1)

@@ -43,12 +43,14 @@ class FinetuneStep:
     off exactly as it does for the reference."""
 
     def __init__(self, model, optimizer, arena: GradArena, token_target_ratio: float = 0.5,
-                 init_scale: float = 65536.0):
+                 init_scale: float = 65536.0, cuda_graph: bool = False):
         self.model, self.opt, self.arena = model, optimizer, arena
         self.scaler = torch.amp.GradScaler("cuda", init_scale=init_scale)
         self.ratio = token_target_ratio
+        self.cuda_graph = cuda_graph
+        self._graph = None
 
-    def __call__(self, images: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    def _forward_backward(self, images, targets):
         self.arena.zero()
         with torch.autocast("cuda", dtype=torch.float16):
             out_s, ts = self.model(images)
@@ -56,7 +58,34 @@ class FinetuneStep:
             loss = finetune_loss(out_s.float(), ts["token_select"].float(), out_t.float(), targets,
                                  token_target_ratio=self.ratio)
         self.scaler.scale(loss).backward()
+        return loss.detach()
+
+    def _capture(self, images, targets):
+        """Whole forward + backward of the step as ONE CUDA graph (the launch-bound part: ~1100 kernel
+        launches per step); the random draws (Gumbel noise, dropout) advance with every replay
+        through torch's graph-safe generator, the loss scale is read from device memory."""
+        self._img, self._tgt = images.clone(), targets.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):                       # warm-up off the capture: caches, workspaces
+                self._forward_backward(self._img, self._tgt)
+        torch.cuda.current_stream().wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._loss = self._forward_backward(self._img, self._tgt)
+
+    def __call__(self, images: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        if self.cuda_graph:
+            if self._graph is None:
+                self._capture(images, targets)
+            self._img.copy_(images, non_blocking=True)
+            self._tgt.copy_(targets, non_blocking=True)
+            self._graph.replay()
+            loss = self._loss
+        else:
+            loss = self._forward_backward(images, targets)
         self.arena.all_reduce_mean()          # the step's only collective (sum of scaled grads / world)
         self.scaler.step(self.opt)            # unscale, skip on inf / nan
         self.scaler.update()
-        return loss.detach()
+        return loss

@@ -23,8 +23,8 @@ params = trainable_parameters(model)
 model.train()
 arena = GradArena(params)
 opt = torch.optim.AdamW(params, lr=1e-3)
-step = FinetuneStep(model, opt, arena)
-for _ in range(3):
+step = FinetuneStep(model, opt, arena, cuda_graph=os.environ.get("TRAIN_GRAPH", "0") == "1")
+for _ in range(6):
     loss = step(img, tgt)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
