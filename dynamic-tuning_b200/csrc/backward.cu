@@ -259,6 +259,19 @@ eltwise_f16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
 // ---------------------------------------------------------------------------------------------
 constexpr int WG_TILE = 64, WG_TOK = 32, WG_LD = 72;
 
+// up to 8 halves starting at p (only the first `remaining` exist), missing ones read as zero
+__device__ __forceinline__ uint4 load8_guarded(const __half* p, int remaining, bool vec) {
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (remaining >= 8 && vec) {
+    v = *reinterpret_cast<const uint4*>(p);
+  } else if (remaining > 0) {
+    __half* h = reinterpret_cast<__half*>(&v);
+    for (int i = 0; i < 8; ++i)
+      if (i < remaining) h[i] = p[i];
+  }
+  return v;
+}
+
 __global__ void __launch_bounds__(128)
 wgrad_kernel(const __half* __restrict__ G, int ldg, const __half* __restrict__ X, int ldx, int T,
              int Nout, int Kin, int tok_per_cta, float alpha, float* __restrict__ dW, int ldw,
@@ -279,15 +292,21 @@ wgrad_kernel(const __half* __restrict__ G, int ldg, const __half* __restrict__ X
 #pragma unroll
     for (int j = 0; j < 2; ++j) wmma::fill_fragment(acc[i][j], 0.f);
   float bsum = 0.f;  // thread c < 64 sums column n0 + c of G (only the k-tile 0 CTAs report it)
-  const __half hz = __float2half(0.f);
+  const bool g_vec = (ldg % 8 == 0) && ((reinterpret_cast<uintptr_t>(G) & 15) == 0);
+  const bool x_vec = (ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
   for (int t0 = t_begin; t0 < t_end; t0 += WG_TOK) {
-    // stage G[t0..t0+32, n0..n0+64] and X[t0..t0+32, k0..k0+64], zero outside the matrices
-    for (int e = threadIdx.x; e < WG_TOK * WG_TILE; e += 128) {
-      const int r = e >> 6, c = e & 63;
+    // stage G[t0..t0+32, n0..n0+64] and X[t0..t0+32, k0..k0+64], zero outside the matrices:
+    // 8 halves (16 bytes) per access
+    for (int e = threadIdx.x; e < WG_TOK * 8; e += 128) {
+      const int r = e >> 3, cg = (e & 7) * 8;
       const int t = t0 + r;
-      const bool tin = t < t_end;
-      Gs[r * WG_LD + c] = (tin && n0 + c < Nout) ? G[static_cast<size_t>(t) * ldg + n0 + c] : hz;
-      Xs[r * WG_LD + c] = (tin && k0 + c < Kin) ? X[static_cast<size_t>(t) * ldx + k0 + c] : hz;
+      uint4 gv = make_uint4(0, 0, 0, 0), xv = gv;
+      if (t < t_end) {
+        gv = load8_guarded(G + static_cast<size_t>(t) * ldg + n0 + cg, Nout - (n0 + cg), g_vec);
+        xv = load8_guarded(X + static_cast<size_t>(t) * ldx + k0 + cg, Kin - (k0 + cg), x_vec);
+      }
+      *reinterpret_cast<uint4*>(Gs + r * WG_LD + cg) = gv;
+      *reinterpret_cast<uint4*>(Xs + r * WG_LD + cg) = xv;
     }
     __syncthreads();
     if (db != nullptr && blockIdx.x == 0 && threadIdx.x < WG_TILE) {
