@@ -4,8 +4,11 @@
 //
 // One CTA (16 warps) per (sequence, head); Q, K, V, dO of the head and the whole P / dS matrix stay
 // in shared memory (fp16), every contraction runs on HMMA through nvcuda::wmma with fp32
-// accumulation, and accumulator tiles pass through a small per-warp fp32 staging tile for the row
-// arithmetic.  Phases (separated by CTA barriers):
+// accumulation.  The softmax / dS row arithmetic works directly on the accumulator registers (the
+// m16n16k16 fp32 accumulator layout of two m16n8 HMMAs: lane (g = lane/4, t = lane%4) holds rows g and
+// g+8, columns 2t, 2t+1, 8+2t, 9+2t; verified at run time against wmma::load_matrix_sync, trap on
+// mismatch); only the [16 x 64] output tiles pass through a per-warp fp32 staging tile.
+// Phases (separated by CTA barriers):
 //   1  per 16-query block: S = Q K^T twice (row max / sum, then P = exp(S - m) / l  -> smem)
 //   2  per 16-key block:   dV = P^T dO
 //   3  per 16-query block: D = rowsum(dO o O); dP = dO V^T; dS = P o (dP - D) * scale -> smem
@@ -104,13 +107,33 @@ attn_bwd_kernel(const __half* __restrict__ qkv, int ld_qkv, const __half* __rest
   }
   __syncthreads();
 
+  // ---- accumulator layout self-check (warp 0): element i of lane (g, t) is (g + 8*((i>>1)&1),
+  //      2t + (i&1) + 8*(i>>2)) ----
+  const int g = lane >> 2, t4 = lane & 3;
+  if (warp == 0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) stg[rr * 20 + cb + c] = static_cast<float>(rr * 16 + cb + c);
+    __syncwarp();
+    FragC chk;
+    wmma::load_matrix_sync(chk, stg, 20, wmma::mem_row_major);
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      ok = ok && chk.x[i] == static_cast<float>((g + 8 * ((i >> 1) & 1)) * 16 + 2 * t4 + (i & 1) + 8 * (i >> 2));
+    if (!ok) __trap();
+    __syncwarp();
+  }
+
   // ---- phase 1: P ----
   for (int ib = warp; ib < nb; ib += AB_WARPS) {
     const int i0 = ib * 16;
     FragA aq[4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) wmma::load_matrix_sync(aq[kk], Qs + i0 * AB_LDQ + kk * 16, AB_LDQ);
-    float m = -1e30f, l = 0.f, inv_l = 0.f;
+    float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f, inv0 = 0.f, inv1 = 0.f;
+    const bool live0 = i0 + g < n, live1 = i0 + g + 8 < n;
+    __half* prow0 = Ps + (i0 + g) * AB_LDP + 2 * t4;
+    __half* prow1 = prow0 + 8 * AB_LDP;
     for (int pass = 0; pass < 2; ++pass) {
       for (int jb = 0; jb < nb; ++jb) {
         FragC acc;
@@ -121,45 +144,50 @@ attn_bwd_kernel(const __half* __restrict__ qkv, int ld_qkv, const __half* __rest
           wmma::load_matrix_sync(bk, Ks + jb * 16 * AB_LDQ + kk * 16, AB_LDQ);
           wmma::mma_sync(acc, aq[kk], bk, acc);
         }
-        wmma::store_matrix_sync(stg, acc, 20, wmma::mem_row_major);
-        __syncwarp();
-        float s[8];
+        float sv[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int j = jb * 16 + cb + c;
-          s[c] = j < n ? stg[rr * 20 + cb + c] * scale : -1e30f;
+        for (int i = 0; i < 8; ++i) {
+          const int j = jb * 16 + 8 * (i >> 2) + 2 * t4 + (i & 1);
+          sv[i] = j < n ? acc.x[i] * scale : -1e30f;
         }
         if (pass == 0) {
-          float mx = s[0];
-#pragma unroll
-          for (int c = 1; c < 8; ++c) mx = fmaxf(mx, s[c]);
-          const float mn = fmaxf(m, mx);
-          float add = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) add += __expf(s[c] - mn);
-          l = l * __expf(m - mn) + add;
-          m = mn;
+          const float mx0 = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[4], sv[5]));
+          const float mx1 = fmaxf(fmaxf(sv[2], sv[3]), fmaxf(sv[6], sv[7]));
+          const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+          l0 = l0 * __expf(m0 - mn0) + (__expf(sv[0] - mn0) + __expf(sv[1] - mn0)) +
+               (__expf(sv[4] - mn0) + __expf(sv[5] - mn0));
+          l1 = l1 * __expf(m1 - mn1) + (__expf(sv[2] - mn1) + __expf(sv[3] - mn1)) +
+               (__expf(sv[6] - mn1) + __expf(sv[7] - mn1));
+          m0 = mn0;
+          m1 = mn1;
         } else {
-          uint4 u;
-          __half2* hp = reinterpret_cast<__half2*>(&u);
-          const bool live = i0 + rr < n;
+          float pv[8];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float p0 = live ? __expf(s[2 * c] - m) * inv_l : 0.f;
-            const float p1 = live ? __expf(s[2 * c + 1] - m) * inv_l : 0.f;
-            hp[c] = __floats2half2_rn(p0, p1);
+          for (int i = 0; i < 8; ++i) {
+            const bool r1 = (i >> 1) & 1;
+            pv[i] = (r1 ? live1 : live0) ? __expf(sv[i] - (r1 ? m1 : m0)) * (r1 ? inv1 : inv0) : 0.f;
           }
-          *reinterpret_cast<uint4*>(Ps + (i0 + rr) * AB_LDP + jb * 16 + cb) = u;
+          *reinterpret_cast<__half2*>(prow0 + jb * 16) = __floats2half2_rn(pv[0], pv[1]);
+          *reinterpret_cast<__half2*>(prow0 + jb * 16 + 8) = __floats2half2_rn(pv[4], pv[5]);
+          *reinterpret_cast<__half2*>(prow1 + jb * 16) = __floats2half2_rn(pv[2], pv[3]);
+          *reinterpret_cast<__half2*>(prow1 + jb * 16 + 8) = __floats2half2_rn(pv[6], pv[7]);
         }
-        __syncwarp();
       }
-      if (pass == 0) {  // merge the two lanes that share a row
-        const float mo = __shfl_xor_sync(0xffffffffu, m, 1);
-        const float lo = __shfl_xor_sync(0xffffffffu, l, 1);
-        const float mt = fmaxf(m, mo);
-        l = l * __expf(m - mt) + lo * __expf(mo - mt);
-        m = mt;
-        inv_l = 1.f / l;
+      if (pass == 0) {  // merge the four lanes that share rows g and g + 8
+#pragma unroll
+        for (int off = 1; off <= 2; off <<= 1) {
+          const float mo0 = __shfl_xor_sync(0xffffffffu, m0, off);
+          const float lo0 = __shfl_xor_sync(0xffffffffu, l0, off);
+          const float mo1 = __shfl_xor_sync(0xffffffffu, m1, off);
+          const float lo1 = __shfl_xor_sync(0xffffffffu, l1, off);
+          const float mt0 = fmaxf(m0, mo0), mt1 = fmaxf(m1, mo1);
+          l0 = l0 * __expf(m0 - mt0) + lo0 * __expf(mo0 - mt0);
+          l1 = l1 * __expf(m1 - mt1) + lo1 * __expf(mo1 - mt1);
+          m0 = mt0;
+          m1 = mt1;
+        }
+        inv0 = 1.f / l0;
+        inv1 = 1.f / l1;
       }
     }
   }
@@ -191,29 +219,36 @@ attn_bwd_kernel(const __half* __restrict__ qkv, int ld_qkv, const __half* __rest
   // ---- phase 3: dS (in place of P) and dQ ----
   for (int ib = warp; ib < nb; ib += AB_WARPS) {
     const int i0 = ib * 16;
-    // D_i = sum_d dO[i, d] * O[i, d]; lane pair (2r, 2r+1) covers row r, 32 columns each
-    float dsum = 0.f;
-    if (i0 + rr < n) {
-      const __half* orow = o + static_cast<size_t>(start + i0 + rr) * ldo + h * 64 + (lane & 1) * 32;
-      const __half* grow = Gs + (i0 + rr) * AB_LDQ + (lane & 1) * 32;
+    // D = sum_d dO[row, d] * O[row, d] for rows g and g + 8; lane t covers 16 of the 64 columns
+    float dsum[2] = {0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 uo = *reinterpret_cast<const uint4*>(orow + c * 8);
-        const uint4 ug = *reinterpret_cast<const uint4*>(grow + c * 8);
-        const __half2* po = reinterpret_cast<const __half2*>(&uo);
-        const __half2* pg = reinterpret_cast<const __half2*>(&ug);
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int row = i0 + g + 8 * hrow;
+      if (row < n) {
+        const __half* orow = o + static_cast<size_t>(start + row) * ldo + h * 64 + t4 * 16;
+        const __half* grow = Gs + row * AB_LDQ + t4 * 16;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 fo = __half22float2(po[e]);
-          const float2 fg = __half22float2(pg[e]);
-          dsum += fo.x * fg.x + fo.y * fg.y;
+        for (int c = 0; c < 2; ++c) {
+          const uint4 uo = *reinterpret_cast<const uint4*>(orow + c * 8);
+          const uint4 ug = *reinterpret_cast<const uint4*>(grow + c * 8);
+          const __half2* po = reinterpret_cast<const __half2*>(&uo);
+          const __half2* pg = reinterpret_cast<const __half2*>(&ug);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 fo = __half22float2(po[e]);
+            const float2 fg = __half22float2(pg[e]);
+            dsum[hrow] += fo.x * fg.x + fo.y * fg.y;
+          }
         }
       }
+      dsum[hrow] += __shfl_xor_sync(0xffffffffu, dsum[hrow], 1);
+      dsum[hrow] += __shfl_xor_sync(0xffffffffu, dsum[hrow], 2);
     }
-    dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
     FragA ag[4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) wmma::load_matrix_sync(ag[kk], Gs + i0 * AB_LDQ + kk * 16, AB_LDQ);
+    __half* prow0 = Ps + (i0 + g) * AB_LDP + 2 * t4;
+    __half* prow1 = prow0 + 8 * AB_LDP;
     for (int jb = 0; jb < nb; ++jb) {
       FragC acc;
       wmma::fill_fragment(acc, 0.f);
@@ -223,21 +258,18 @@ attn_bwd_kernel(const __half* __restrict__ qkv, int ld_qkv, const __half* __rest
         wmma::load_matrix_sync(bv, Vs + jb * 16 * AB_LDQ + kk * 16, AB_LDQ);
         wmma::mma_sync(acc, ag[kk], bv, acc);
       }
-      wmma::store_matrix_sync(stg, acc, 20, wmma::mem_row_major);
-      __syncwarp();
-      __half* prow = Ps + (i0 + rr) * AB_LDP + jb * 16 + cb;
-      uint4 u = *reinterpret_cast<const uint4*>(prow);
-      __half2* hp = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float2 p = __half22float2(hp[c]);
-        const float d0 = p.x * (stg[rr * 20 + cb + 2 * c] - dsum) * scale;
-        const float d1 = p.y * (stg[rr * 20 + cb + 2 * c + 1] - dsum) * scale;
-        hp[c] = __floats2half2_rn(d0, d1);
-      }
-      *reinterpret_cast<uint4*>(prow) = u;
-      __syncwarp();
+      __half2* q00 = reinterpret_cast<__half2*>(prow0 + jb * 16);
+      __half2* q01 = reinterpret_cast<__half2*>(prow0 + jb * 16 + 8);
+      __half2* q10 = reinterpret_cast<__half2*>(prow1 + jb * 16);
+      __half2* q11 = reinterpret_cast<__half2*>(prow1 + jb * 16 + 8);
+      const float2 p00 = __half22float2(*q00), p01 = __half22float2(*q01);
+      const float2 p10 = __half22float2(*q10), p11 = __half22float2(*q11);
+      *q00 = __floats2half2_rn(p00.x * (acc.x[0] - dsum[0]) * scale, p00.y * (acc.x[1] - dsum[0]) * scale);
+      *q01 = __floats2half2_rn(p01.x * (acc.x[4] - dsum[0]) * scale, p01.y * (acc.x[5] - dsum[0]) * scale);
+      *q10 = __floats2half2_rn(p10.x * (acc.x[2] - dsum[1]) * scale, p10.y * (acc.x[3] - dsum[1]) * scale);
+      *q11 = __floats2half2_rn(p11.x * (acc.x[6] - dsum[1]) * scale, p11.y * (acc.x[7] - dsum[1]) * scale);
     }
+    __syncwarp();  // this warp's dS rows are complete before its fragment loads read them
     FragC acc[4];
 #pragma unroll
     for (int dn = 0; dn < 4; ++dn) wmma::fill_fragment(acc[dn], 0.f);

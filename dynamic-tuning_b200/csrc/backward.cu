@@ -294,21 +294,32 @@ wgrad_kernel(const __half* __restrict__ G, int ldg, const __half* __restrict__ X
   float bsum = 0.f;  // thread c < 64 sums column n0 + c of G (only the k-tile 0 CTAs report it)
   const bool g_vec = (ldg % 8 == 0) && ((reinterpret_cast<uintptr_t>(G) & 15) == 0);
   const bool x_vec = (ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-  for (int t0 = t_begin; t0 < t_end; t0 += WG_TOK) {
-    // stage G[t0..t0+32, n0..n0+64] and X[t0..t0+32, k0..k0+64], zero outside the matrices:
-    // 8 halves (16 bytes) per access
-    for (int e = threadIdx.x; e < WG_TOK * 8; e += 128) {
-      const int r = e >> 3, cg = (e & 7) * 8;
-      const int t = t0 + r;
-      uint4 gv = make_uint4(0, 0, 0, 0), xv = gv;
+  // each thread stages two 16-byte groups of G and of X per 32-token tile; the next tile's global
+  // loads are issued before the current tile's MMAs (register double buffering)
+  const int sr0 = threadIdx.x >> 3, scg = (threadIdx.x & 7) * 8;  // rows sr0 and sr0 + 16
+  uint4 pg[2], px[2];
+  auto fetch = [&](int t0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int t = t0 + sr0 + h * 16;
+      pg[h] = make_uint4(0, 0, 0, 0);
+      px[h] = pg[h];
       if (t < t_end) {
-        gv = load8_guarded(G + static_cast<size_t>(t) * ldg + n0 + cg, Nout - (n0 + cg), g_vec);
-        xv = load8_guarded(X + static_cast<size_t>(t) * ldx + k0 + cg, Kin - (k0 + cg), x_vec);
+        pg[h] = load8_guarded(G + static_cast<size_t>(t) * ldg + n0 + scg, Nout - (n0 + scg), g_vec);
+        px[h] = load8_guarded(X + static_cast<size_t>(t) * ldx + k0 + scg, Kin - (k0 + scg), x_vec);
       }
-      *reinterpret_cast<uint4*>(Gs + r * WG_LD + cg) = gv;
-      *reinterpret_cast<uint4*>(Xs + r * WG_LD + cg) = xv;
+    }
+  };
+  fetch(t_begin);
+  for (int t0 = t_begin; t0 < t_end; t0 += WG_TOK) {
+    // stage G[t0..t0+32, n0..n0+64] and X[t0..t0+32, k0..k0+64] (zero outside the matrices)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      *reinterpret_cast<uint4*>(Gs + (sr0 + h * 16) * WG_LD + scg) = pg[h];
+      *reinterpret_cast<uint4*>(Xs + (sr0 + h * 16) * WG_LD + scg) = px[h];
     }
     __syncthreads();
+    if (t0 + WG_TOK < t_end) fetch(t0 + WG_TOK);
     if (db != nullptr && blockIdx.x == 0 && threadIdx.x < WG_TILE) {
 #pragma unroll 8
       for (int r = 0; r < WG_TOK; ++r) bsum += __half2float(Gs[r * WG_LD + threadIdx.x]);

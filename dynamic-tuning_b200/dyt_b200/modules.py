@@ -471,8 +471,12 @@ class TrainVisionTransformer(VisionTransformer):
         (complete_model=False) and teacher (True) passes both carry gradients to the adapters."""
         x = self._embed(x)
         sels, lgs = [], []
-        for blk in self.blocks:
-            x, sel, lg = train.block_train(blk, x, complete_model)
+        B, N, _ = x.shape
+        noises = mults = [None] * len(self.blocks)
+        if self.training and not (train._fixed["noises"] or train._fixed["drop_mults"]):
+            noises, mults = train.draw_pass_randomness(list(self.blocks), B, N, x.device)
+        for i, blk in enumerate(self.blocks):
+            x, sel, lg = train.block_train(blk, x, complete_model, noises[i], mults[i])
             sels.append(sel[:, 1:])
             lgs.append(lg)
         dt = _act_dtype()

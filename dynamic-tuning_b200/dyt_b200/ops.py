@@ -372,16 +372,22 @@ def rowscale_colsum(s: torch.Tensor, x16: torch.Tensor, out_w: torch.Tensor,
 
 
 def wgrad_f16(g16: torch.Tensor, x16: torch.Tensor, n_out: Optional[int] = None,
-              alpha: float = 1.0, want_bias: bool = True):
-    """(dW [n_out, K] fp32, db [n_out] fp32 or None) = alpha * (g^T x, colsum g); g [T, >= n_out]."""
+              alpha: float = 1.0, want_bias: bool = True, out=None):
+    """(dW [n_out, K] fp32, db [n_out] fp32 or None) = alpha * (g^T x, colsum g); g [T, >= n_out].
+    out = (dW, db): accumulate into caller-provided (zero-filled or carried) contiguous buffers."""
     _need_cuda(g16, x16)
     g2, x2 = _rows2d(g16), _rows2d(x16)
     if g2.dtype != torch.float16 or x2.dtype != torch.float16 or g2.shape[0] != x2.shape[0]:
         raise DytError("wgrad_f16 expects fp16 [T, Nout] and [T, K]")
     n_out = g2.shape[1] if n_out is None else n_out
     T, K = x2.shape
-    dW = torch.zeros((n_out, K), dtype=torch.float32, device=g16.device)
-    db = torch.zeros((n_out,), dtype=torch.float32, device=g16.device) if want_bias else None
+    if out is not None:
+        dW, db = out
+        if dW.shape != (n_out, K) or not dW.is_contiguous() or dW.dtype != torch.float32:
+            raise DytError("wgrad_f16: out[0] must be a contiguous fp32 [n_out, K] buffer")
+    else:
+        dW = torch.zeros((n_out, K), dtype=torch.float32, device=g16.device)
+        db = torch.zeros((n_out,), dtype=torch.float32, device=g16.device) if want_bias else None
     check(_lib.lib().dyt_wgrad_f16(g2.data_ptr(), g2.stride(0), x2.data_ptr(), x2.stride(0), T,
                                    n_out, K, float(alpha), dW.data_ptr(), K, _ptr(db), _stream()),
           "dyt_wgrad_f16")

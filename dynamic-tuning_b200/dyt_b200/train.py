@@ -78,6 +78,25 @@ def _frozen(block) -> Dict[str, torch.Tensor]:
     return fw.get()
 
 
+def _adapter_f16(block, down_w, down_b, up_w, up_b):
+    """fp16 copies and transposes of the trainable adapter parameters: rebuilt when a parameter
+    changes (once per optimizer step), shared by the student and the teacher pass of a step."""
+    key = tuple((p.data_ptr(), p._version) for p in (down_w, down_b, up_w, up_b))
+    c = block.__dict__.get("_dyt_adapter_f16")
+    capturing = torch.cuda.is_current_stream_capturing()
+    if c is None or c[0] != key or c[2] != capturing:
+        h16 = torch.float16
+        with torch.no_grad():
+            dw = down_w.detach().to(h16).contiguous()
+            uw = up_w.detach().to(h16).contiguous()
+            t = dict(dw=dw, db=down_b.detach().to(h16).contiguous(), uw=uw,
+                     ub=up_b.detach().to(h16).contiguous(), dwT=dw.t().contiguous(),
+                     uwT=uw.t().contiguous())
+        c = (key, t, capturing)
+        block.__dict__["_dyt_adapter_f16"] = c
+    return c[1]
+
+
 def _scale_of(block) -> float:
     s = block.adaptmlp.scale
     if torch.is_tensor(s):
@@ -106,10 +125,8 @@ class DytBlockFn(torch.autograd.Function):
         scale = _scale_of(block)
         tau = float(getattr(block.mlp_token_select, "tau", 5.0))
         thr = float(getattr(block.mlp_token_select, "threshold", 0.5))
-        dw16 = down_w.detach().to(h16).contiguous()
-        db16 = down_b.detach().to(h16).contiguous()
-        uw16 = up_w.detach().to(h16).contiguous()
-        ub16 = up_b.detach().to(h16).contiguous()
+        ad = _adapter_f16(block, down_w, down_b, up_w, up_b)
+        dw16, db16, uw16, ub16 = ad["dw"], ad["db"], ad["uw"], ad["ub"]
 
         xn = ops.layernorm_f16(x, fz["ln1_w"], fz["ln1_b"], eps)
         qkv, _ = ops.linear_f16(xn, fz["qkv_w"], fz["qkv_b"])
@@ -140,7 +157,7 @@ class DytBlockFn(torch.autograd.Function):
         ctx.meta = (B, N, Cd, H, scale, tau, eps, bool(complete_model), bool(training_gate))
         ctx.noise = noise if training_gate else None
         ctx.drop_mult = drop_mult
-        ctx.save_for_backward(x, qkv, o, x1, x1h, mask, logits, pre, mlp_x, hd, dw16, uw16,
+        ctx.save_for_backward(x, qkv, o, x1, x1h, mask, logits, pre, mlp_x, hd, ad["dwT"], ad["uwT"],
                               sel_w.detach())
         if debug_keep is not None:   # tests: look at the forward intermediates
             debug_keep.update(x1=x1, x1h=x1h, pre=pre, mlp_x=mlp_x, hd=hd, qkv=qkv, o=o)
@@ -148,7 +165,7 @@ class DytBlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out, g_sel, g_logits):
-        (x, qkv, o, x1, x1h, mask, logits, pre, mlp_x, hd, dw16, uw16, sel_w) = ctx.saved_tensors
+        (x, qkv, o, x1, x1h, mask, logits, pre, mlp_x, hd, dwT, uwT, sel_w) = ctx.saved_tensors
         B, N, Cd, H, scale, tau, eps, complete_model, training_gate = ctx.meta
         fz = _frozen(ctx.block)
         T = B * N
@@ -162,11 +179,17 @@ class DytBlockFn(torch.autograd.Function):
         if complete_model:
             gm16 = g16
         # ---- adapter: up dgrad, wgrads, ReLU / dropout, (down dgrad further below) ----
-        g_hd, _ = ops.linear_f16(g16, uw16.t().contiguous(), None, epilogue=_lib.EPI_BIAS, scale=scale)
-        d_up_w, d_up_b = ops.wgrad_f16(g16, hd.reshape(T, -1), alpha=scale)
+        g_hd, _ = ops.linear_f16(g16, uwT, None, epilogue=_lib.EPI_BIAS, scale=scale)
+        bott = hd.shape[-1]
+        n_w = Cd * bott
+        zbuf = torch.zeros(2 * n_w + Cd + bott + Cd + 4, dtype=torch.float32, device=x.device)
+        d_up_w, d_up_b = zbuf[:n_w].view(Cd, bott), zbuf[2 * n_w:2 * n_w + Cd]
+        d_down_w = zbuf[n_w:2 * n_w].view(bott, Cd)
+        d_down_b = zbuf[2 * n_w + Cd:2 * n_w + Cd + bott]
+        ops.wgrad_f16(g16, hd.reshape(T, -1), alpha=scale, out=(d_up_w, d_up_b))
         dm = None if ctx.drop_mult is None else ctx.drop_mult.reshape(T, -1)
         g_hp = ops.eltwise_f16(_lib.EW_RELU_DROP_BWD, g_hd.reshape(T, -1), hd.reshape(T, -1), dm)
-        d_down_w, d_down_b = ops.wgrad_f16(g_hp, x1h.reshape(T, Cd))
+        ops.wgrad_f16(g_hp, x1h.reshape(T, Cd), out=(d_down_w, d_down_b))
         # ---- frozen MLP: fc2 dgrad, GELU', fc1 dgrad, LayerNorm2 backward ----
         g_h, _ = ops.linear_f16(gm16, fz["fc2_wT"], None)
         g_pre = ops.eltwise_f16(_lib.EW_GELU_BWD, g_h.reshape(pre.shape), pre)
@@ -179,14 +202,14 @@ class DytBlockFn(torch.autograd.Function):
             # selector: data gradient g_l * w folded into the LayerNorm-backward pass
             g_x1, _ = ops.layernorm_bwd(g_ln2.reshape(T, Cd), x1.reshape(T, Cd), fz["ln2_w"], eps,
                                         resid=g_out, row_scale=g_l, axpy=sel_w)
-            d_sel_w = torch.zeros(Cd, dtype=torch.float32, device=x.device)
-            d_sel_b = torch.zeros(1, dtype=torch.float32, device=x.device)
+            off = 2 * n_w + Cd + bott
+            d_sel_w, d_sel_b = zbuf[off:off + Cd], zbuf[off + Cd:off + Cd + 1]
             ops.rowscale_colsum(g_l, x1h.reshape(T, Cd), d_sel_w, d_sel_b)
             d_sel_w = d_sel_w.reshape(1, Cd)
         need_x = ctx.needs_input_grad[0]
         g_x = None
         if need_x:
-            g_x1, g_x1h = ops.linear_f16(g_hp, dw16.t().contiguous(), None,
+            g_x1, g_x1h = ops.linear_f16(g_hp, dwT, None,
                                          epilogue=_lib.EPI_BIAS_RESID, resid=g_x1, want_f16_copy=True)
             g_o, _ = ops.linear_f16(g_x1h, fz["proj_wT"], None)
             g_qkv = ops.attn_varlen_bwd(qkv.reshape(B, N, -1), o.reshape(B, N, Cd),
@@ -220,6 +243,27 @@ class fixed_randomness:
     def __exit__(self, *exc):
         _fixed.update(self.old)
         return False
+
+
+def draw_pass_randomness(blocks, B: int, N: int, device):
+    """All Gumbel draws and dropout multipliers of one pass (every block) in a handful of launches:
+    returns per-block lists (noise pairs as fp32 [B, N-1, 1] holding fp16 values, the dtype the
+    reference draws them in under autocast; multipliers fp16 [B, N, bottleneck])."""
+    L = len(blocks)
+    from .modules import draw_gumbel_pair
+    g1, g2 = draw_gumbel_pair((L, B, N - 1, 1), torch.float16, device)
+    g1, g2 = g1.float(), g2.float()
+    noises = [(g1[i], g2[i]) for i in range(L)]
+    p = float(blocks[0].adaptmlp.dropout)
+    bott = blocks[0].adaptmlp.down_proj.out_features
+    if p > 0 and all(float(b.adaptmlp.dropout) == p and b.adaptmlp.down_proj.out_features == bott
+                     for b in blocks):
+        keep = torch.rand((L, B, N, bott), device=device) >= p
+        mult = keep.to(torch.float16) * (1.0 / (1.0 - p))
+        mults = [mult[i] for i in range(L)]
+    else:
+        mults = [None] * L
+    return noises, mults
 
 
 def block_train(block, x: torch.Tensor, complete_model: bool = False,
