@@ -192,6 +192,17 @@ int dyt_attn_varlen_bwd(const void* qkv, int ld_qkv, const void* out, int ldo, c
                         int max_seqlen, int num_heads, int head_dim, void* d_qkv, int ld_dqkv,
                         void* stream);
 
+/* ---- evaluation analytics ----------------------------------------
+ * Per-image FLOPs and per-layer kept-token counters of one batch, on the device.
+ * token_select fp32 [B, L, Np] (the model's token_select output, cls stripped, 0/1).
+ *   image_flops[b] = base_flops + (block_num - L) * table[Np + 1] + sum_l table[count(b, l) + 1]
+ * (reference block_flops_dict.py:57-83, additions in the same order), optional;
+ *   counters[l] += sum_b count(b, l) for l < L, counters[L] += B   (uint64, caller zero-fills;
+ * replaces the padded all_gather of every mask, engine_finetune.py:245-252, :446-480), optional. */
+int dyt_keep_stats(const float* token_select, int B, int L, int Np, const float* flops_table,
+                   int table_len, int block_num, float base_flops, float* image_flops,
+                   unsigned long long* counters, void* stream);
+
 /* ---- whole block: Block.batch_forward (reference models/model_speed_test.py:274-310) ---------- */
 typedef struct dyt_block_shape {
   int B;          /* images (sequences) */

@@ -374,6 +374,31 @@ def vit_forward(img: Tensor, p: Dict[str, Tensor], depth: int, num_heads: int, s
 
 
 # ----------------------------------------------------------------------------------------------
+# evaluation analytics (reference block_flops_dict.py:57-83, engine_finetune.py:341-352)
+# ----------------------------------------------------------------------------------------------
+def batch_select_flops(flops_dict: Tensor, token_select: Tensor, block_num: int = 12,
+                       base_flops: float = 0.116) -> Tensor:
+    """token_select [B, L, N-1, 1] -> per-image GFLOPs [B]: base + sum over the block_num layers of
+    flops_dict[kept patch tokens + 1] (layers without a selector count all tokens); fp32 additions
+    in layer order, like the reference's loop over torch scalars."""
+    ts = token_select.squeeze(-1).float()
+    out = []
+    for img in ts:                                                  # :80-81
+        t = img.shape[1]
+        counts = [t] * (block_num - img.shape[0]) + img.sum(-1).int().tolist()   # :63-64
+        f = torch.tensor(base_flops, dtype=torch.float32)
+        for c in counts:
+            f = f + flops_dict[c + 1].float()                       # :66-70
+        out.append(f)
+    return torch.stack(out)
+
+
+def layer_keep_rates(token_select: Tensor) -> Tensor:
+    """engine_finetune.py:349-351: mean of token_select[:, layer] per layer."""
+    return token_select.float().mean(dim=(0, 2, 3))
+
+
+# ----------------------------------------------------------------------------------------------
 # deterministic synthetic parameters (shared by the golden generator, the tests and bench.py)
 # ----------------------------------------------------------------------------------------------
 def attentive_pool(tokens: Tensor, p: Dict[str, Tensor], num_heads: int,

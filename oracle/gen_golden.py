@@ -16,6 +16,8 @@ itself are the pins of the oracle (oracle/dyt_oracle.py):
                     of the reference train model in train() mode on the tiny ViT: inputs, the
                     replayed Gumbel draws, dropout multipliers, loss, outputs and every trainable
                     parameter's gradient
+  flops_accounting.pt  per-image GFLOPs of block_flops_dict.batch_select_flops and per-layer keep rates
+                    for random masks / a random table
   vitb_b2.pt        ViT-B/16, synthetic seed-0 weights (regenerated from the seed, not stored),
                     calibrated selector biases, B=2: logits / masks / token logits of the speed model
                     and the train model (eval, complete_model on/off), config-1 imposed-mask logits
@@ -264,6 +266,31 @@ def tiny_finetune(ref_train, ref_losses):
                 grads=grads)
 
 
+def flops_accounting():
+    """block_flops_dict.batch_select_flops of the reference (its module imports fvcore / timm.models
+    at the top, stubbed here: neither is used by the two accounting functions) on random masks and a
+    random table; plus the per-layer rates engine_finetune.py:349-351 logs."""
+    import types
+    ref_shim.install()
+    for name, attrs in (("fvcore", {}), ("fvcore.nn", {"FlopCountAnalysis": object}),
+                        ("timm.models", {"create_model": None})):
+        m = sys.modules.get(name) or types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+    sys.modules["fvcore"].nn = sys.modules["fvcore.nn"]
+    ref = ref_shim.import_reference("block_flops_dict")
+    g = torch.Generator().manual_seed(5)
+    table = torch.rand(198, generator=g) * 1.5
+    ts = (torch.rand(37, 12, 196, 1, generator=g) < torch.rand(1, 12, 1, 1, generator=g)).float()
+    ts[3] = 0.0
+    ts[4] = 1.0
+    out = dict(table=table, token_select=ts.to(torch.uint8))
+    out["flops_12"] = ref.batch_select_flops(37, table, ts, block_num=12, base_flops=0.116)
+    out["flops_10of12"] = ref.batch_select_flops(37, table, ts[:, 2:], block_num=12, base_flops=0.25)
+    out["layer_rates"] = torch.stack([ts[:, l].mean() for l in range(12)])
+    return out
+
+
 def main():
     assert ref_shim.reference_available(), "needs the reference checkout at " + ref_shim.REFERENCE_ROOT
     torch.set_num_threads(os.cpu_count())
@@ -277,6 +304,7 @@ def main():
     torch.save(vitb_b2(ref_speed, ref_train), os.path.join(OUT, "vitb_b2.pt"))
     ref_video = ref_shim.import_reference("video_models.video_vision_transformer_IN21K")
     torch.save(tiny_video(ref_video), os.path.join(OUT, "video_tiny.pt"))
+    torch.save(flops_accounting(), os.path.join(OUT, "flops_accounting.pt"))
     ref_losses = ref_shim.import_reference("models.losses")
     torch.save(tiny_finetune(ref_train, ref_losses), os.path.join(OUT, "finetune_tiny.pt"))
     for f in sorted(os.listdir(OUT)):

@@ -353,3 +353,28 @@ def test_scatter_merge(dev):
                                 next_ln=(lw.to(dev), lb.to(dev)))
     assert torch.equal(out.cpu(), ref)                          # same fp32 additions: bit-exact
     _close(ln, O._r16(O.layer_norm(ref, lw, lb)), atol=1e-3, rtol=1e-3)
+
+
+def test_keep_stats_kernel_matches_reference_accounting():
+    """dyt_keep_stats / dyt_b200.flops.batch_select_flops against the reference's
+    block_flops_dict.batch_select_flops (golden, bit-equal: same fp32 additions in the same order) and
+    the per-layer keep rates of engine_finetune.py:349-351; the drop-in module keeps the names."""
+    from conftest import load_golden
+    from dyt_b200 import flops
+    import block_flops_dict as drop_in
+    g = load_golden("flops_accounting.pt")
+    dev = torch.device("cuda:0")
+    ts = g["token_select"].float().to(dev)
+    a = flops.batch_select_flops(37, g["table"], ts, block_num=12, base_flops=0.116)
+    assert torch.equal(a.cpu(), g["flops_12"])
+    b = drop_in.batch_select_flops(37, g["table"].to(dev), ts[:, 2:].half(), block_num=12, base_flops=0.25)
+    assert torch.equal(b.cpu(), g["flops_10of12"])
+    st = flops.KeepStats(12, 196, dev)
+    st.update(ts[:20])
+    st.update(ts[20:])
+    assert int(st.counters[12]) == 37
+    assert torch.equal(st.counters[:12].cpu(), g["token_select"].long().sum(dim=(0, 2, 3)))
+    assert torch.allclose(st.layer_rates().cpu(), g["layer_rates"], atol=1e-6)
+    assert drop_in.get_block_flops().shape == (198,) and abs(drop_in.get_base_flops() - 0.1157) < 2e-3
+    with pytest.raises(Exception):
+        flops.batch_select_flops(1, g["table"], g["token_select"].float())      # CPU tensor: no fallback
