@@ -45,6 +45,8 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb,
   // sixteen epilogue warps where the epilogue, not the main loop, sets the pace
   if constexpr (BN >= 128) {
     if (epi == EPI_BIAS_GELU) return launch_gemm<BN, EPI_BIAS_GELU, 16>(ta, tb, p, s);
+    if (epi == EPI_BIAS_GELU_KEEP) return launch_gemm<BN, EPI_BIAS_GELU_KEEP, 16>(ta, tb, p, s);
+    if (epi == EPI_DGELU) return launch_gemm<BN, EPI_DGELU, 16>(ta, tb, p, s);
     if (p.K <= 128) {
       switch (epi) {
         case EPI_BIAS: return launch_gemm<BN, EPI_BIAS, 16>(ta, tb, p, s);
@@ -54,6 +56,8 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb,
       }
     }
   }
+  if (epi == EPI_BIAS_GELU_KEEP || epi == EPI_DGELU)
+    return fail(DYT_EUNSUPPORTED, "gemm: the fused GELU training epilogues need N > 64");
   switch (epi) {
     case EPI_BIAS: return launch_gemm<BN, EPI_BIAS, 8>(ta, tb, p, s);
     case EPI_BIAS_GELU: return launch_gemm<BN, EPI_BIAS_GELU, 8>(ta, tb, p, s);
@@ -72,7 +76,7 @@ int gemm_tn_dot_slices(int N) {
 int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, int K,
             const int* m_dev, int epi, const __half* bias, __half* out_h, int ldo_h, float* out_f,
             int ldo_f, const float* resid, int ld_res, float scale, cudaStream_t stream,
-            const float* dot_w, float* dot_out, int dot_ld, int dot_f16) {
+            const float* dot_w, float* dot_out, int dot_ld, int dot_f16, __half* aux, int ld_aux) {
   DYT_CHECK_ARG(a != nullptr && w != nullptr, "gemm: null operand");
   DYT_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   DYT_CHECK_ARG(N % 8 == 0 && K % 8 == 0, "gemm: N and K must be multiples of 8 (N=%d K=%d)", N, K);
@@ -108,6 +112,13 @@ int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, in
   p.ldo_h = ldo_h; p.ldo_f = ldo_f; p.ld_res = ld_res;
   p.scale = scale;
   p.dot_w = dot_w; p.dot_out = dot_out; p.dot_ld = dot_ld; p.dot_f16 = dot_f16;
+  p.aux = aux; p.ld_aux = ld_aux;
+  if (epi == EPI_BIAS_GELU_KEEP || epi == EPI_DGELU) {
+    DYT_CHECK_ARG(aux != nullptr && ld_aux >= N && ld_aux % 8 == 0 && N % 8 == 0 &&
+                      (reinterpret_cast<uintptr_t>(aux) & 15) == 0 && ldo_h % 8 == 0 &&
+                      (reinterpret_cast<uintptr_t>(out_h) & 15) == 0,
+                  "gemm: the GELU training epilogues need 16-byte aligned aux / out rows");
+  }
   if (dot_w != nullptr) {
     DYT_CHECK_ARG(epi == EPI_BIAS_RESID && K > 128 && dot_out != nullptr && N % 4 == 0 &&
                       dot_ld >= gemm_tn_dot_slices(N),
@@ -131,5 +142,17 @@ extern "C" int dyt_linear_f16(const void* x, int ldx, const void* w, int ldw, in
   return dyt::gemm_tn(static_cast<const __half*>(x), ldx, static_cast<const __half*>(w), ldw, M, N,
                       K, m_dev, epilogue, static_cast<const __half*>(bias),
                       static_cast<__half*>(out_f16), ldo_f16, out_f32, ldo_f32, resid, ld_resid,
-                      scale, static_cast<cudaStream_t>(stream), nullptr, nullptr, 0, 0);
+                      scale, static_cast<cudaStream_t>(stream), nullptr, nullptr, 0, 0, nullptr, 0);
+}
+
+extern "C" int dyt_linear_f16_aux(const void* x, int ldx, const void* w, int ldw, int M, int N, int K,
+                                  const int* m_dev, int epilogue, const void* bias, void* out_f16,
+                                  int ldo_f16, void* aux_f16, int ld_aux, void* stream) {
+  if (epilogue != dyt::EPI_BIAS_GELU_KEEP && epilogue != dyt::EPI_DGELU)
+    return dyt::fail(dyt::DYT_EINVAL, "linear_f16_aux: epilogue must be GELU_KEEP (4) or DGELU (5)");
+  return dyt::gemm_tn(static_cast<const __half*>(x), ldx, static_cast<const __half*>(w), ldw, M, N,
+                      K, m_dev, epilogue, static_cast<const __half*>(bias),
+                      static_cast<__half*>(out_f16), ldo_f16, nullptr, 0, nullptr, 0, 1.0f,
+                      static_cast<cudaStream_t>(stream), nullptr, nullptr, 0, 0,
+                      static_cast<__half*>(aux_f16), ld_aux);
 }

@@ -32,6 +32,10 @@ enum GemmEpilogue : int {
   EPI_BIAS_RELU = 2,   // out_h = f16(relu(f16(acc + bias)))
   EPI_BIAS_RESID = 3,  // v = f16(acc + bias); if scale != 1: v = f16(v * scale);
                        // out_f = resid + v   (fp32 residual stream); optional out_h = f16(out_f)
+  EPI_BIAS_GELU_KEEP = 4,  // like EPI_BIAS_GELU, and aux = f16(acc + bias): the pre-activation the
+                           // backward needs (train-mode fc1)
+  EPI_DGELU = 5,       // out_h = f16(f16(acc + bias) * gelu'(aux)): fc2 data gradient times the
+                       // GELU derivative at the saved pre-activation
 };
 
 struct GemmParams {
@@ -56,6 +60,8 @@ struct GemmParams {
   float* dot_out;
   int dot_ld;
   int dot_f16;
+  __half* aux;   // EPI_BIAS_GELU_KEEP: written; EPI_DGELU: read ([M, N] fp16, row stride ld_aux)
+  int ld_aux;
 };
 
 // EW = epilogue warps: 8 (two per TMEM lane quarter) or 16 (four per quarter, for epilogue-bound
@@ -267,6 +273,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint4 bq[8];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) bq[j4] = lds128(bias_s + (c * 32 + j4 * 4) * 4);
+        // EPI_DGELU: the saved pre-activations of this thread's row (TMEM layout: 32 columns = 64 B)
+        uint4 ax[4];
+        if constexpr (EPI == EPI_DGELU) {
+          const int grow = m0 + q * 32 + lane;
+          const int col = n0 + c * 32;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            ax[k] = make_uint4(0, 0, 0, 0);
+            if (grow < m_eff && col + k * 8 < p.N)
+              ax[k] = *reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(grow) * p.ld_aux +
+                                                      col + k * 8);
+          }
+        }
         tmem_ld_wait();
         if (c == NCH - 1) {
           // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
@@ -278,6 +297,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // Per pair of columns: one F2FP rounds both Linear outputs to fp16 (the single rounding of
         // the autocast Linear); activations that need the rounded value unpack it again.
         uint32_t pk[16];
+        uint32_t keep[EPI == EPI_BIAS_GELU_KEEP ? 16 : 1];
         const bool plain = (EPI == EPI_BIAS || EPI == EPI_BIAS_RESID) && p.scale == 1.0f;
 #pragma unroll
         for (int j2 = 0; j2 < 16; ++j2) {
@@ -289,8 +309,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           __half2 o = h;
           if constexpr (EPI == EPI_BIAS_RELU) {
             o = __hmax2(h, __float2half2_rn(0.f));
-          } else if constexpr (EPI == EPI_BIAS_GELU) {
+          } else if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_GELU_KEEP) {
             o = __floats2half2_rn(gelu_f16(__low2float(h)), gelu_f16(__high2float(h)));
+            if constexpr (EPI == EPI_BIAS_GELU_KEEP) keep[j2] = *reinterpret_cast<const uint32_t*>(&h);
+          } else if constexpr (EPI == EPI_DGELU) {
+            const uint4 av = ax[j2 >> 2];
+            const uint32_t aw = (j2 & 3) == 0 ? av.x : ((j2 & 3) == 1 ? av.y : ((j2 & 3) == 2 ? av.z : av.w));
+            const float2 pre = __half22float2(*reinterpret_cast<const __half2*>(&aw));
+            o = __floats2half2_rn(__low2float(h) * gelu_grad_f16(pre.x),
+                                  __high2float(h) * gelu_grad_f16(pre.y));
           } else {
             if (!plain)  // f16(f16(v) * scale), the multiply in fp32 like torch's fp16-tensor * float
               o = __floats2half2_rn(__low2float(h) * p.scale, __high2float(h) * p.scale);
@@ -298,11 +325,33 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           pk[j2] = *reinterpret_cast<const uint32_t*>(&o);
         }
         // ---- fp16 transpose through the slab ----
+        auto slab_write = [&](const uint32_t* v) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          sts128(my_row + ((k ^ swz_w) << 4),
-                 make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
-        __syncwarp();
+          for (int k = 0; k < 4; ++k)
+            sts128(my_row + ((k ^ swz_w) << 4),
+                   make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+          __syncwarp();
+        };
+        // lane -> (row it*8 + lane/4, columns (lane%4)*8 .. +7): 64-byte fp16 row segments
+        auto slab_to_global = [&](__half* base, int ld) {
+          const int col = n0 + c * 32 + (lane & 3) * 8;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2);
+            const int grow = m0 + q * 32 + rr;
+            const uint4 hv = lds128(slab + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+            if (grow < m_eff && col < p.N) {
+              __half* dst = base + static_cast<size_t>(grow) * ld + col;
+              if (p.vec8) {
+                *reinterpret_cast<uint4*>(dst) = hv;
+              } else {  // row pitch / column count only 8-byte aligned
+                *reinterpret_cast<uint2*>(dst) = make_uint2(hv.x, hv.y);
+                if (col + 4 < p.N) *reinterpret_cast<uint2*>(dst + 4) = make_uint2(hv.z, hv.w);
+              }
+            }
+          }
+        };
+        slab_write(pk);
         if constexpr (EPI == EPI_BIAS_RESID) {
           // lane -> (row it*4 + lane/8, columns (lane%8)*4 .. +3): 128-byte fp32 row segments
           const int col = n0 + c * 32 + (lane & 7) * 4;
@@ -343,22 +392,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           }
         } else {
-          // lane -> (row it*8 + lane/4, columns (lane%4)*8 .. +7): 64-byte fp16 row segments
-          const int col = n0 + c * 32 + (lane & 3) * 8;
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rr = it * 8 + (lane >> 2);
-            const int grow = m0 + q * 32 + rr;
-            const uint4 hv = lds128(slab + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
-            if (grow < m_eff && col < p.N) {
-              __half* dst = p.out_h + static_cast<size_t>(grow) * p.ldo_h + col;
-              if (p.vec8) {
-                *reinterpret_cast<uint4*>(dst) = hv;
-              } else {  // row pitch / column count only 8-byte aligned
-                *reinterpret_cast<uint2*>(dst) = make_uint2(hv.x, hv.y);
-                if (col + 4 < p.N) *reinterpret_cast<uint2*>(dst + 4) = make_uint2(hv.z, hv.w);
-              }
-            }
+          slab_to_global(p.out_h, p.ldo_h);
+          if constexpr (EPI == EPI_BIAS_GELU_KEEP) {
+            __syncwarp();  // every lane has read the activations before the slab is reused
+            slab_write(keep);
+            slab_to_global(p.aux, p.ld_aux);
           }
         }
         __syncwarp();  // the slab is overwritten by the next chunk

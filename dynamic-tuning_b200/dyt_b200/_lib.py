@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libdyt_b200.so")
 ABI_VERSION = 1
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_BIAS_RESID = 0, 1, 2, 3
+EPI_BIAS_GELU_KEEP, EPI_DGELU = 4, 5
 EW_GELU_FWD, EW_GELU_BWD, EW_RELU_DROP_BWD, EW_MUL = 0, 1, 2, 3
 
 
@@ -55,6 +56,7 @@ SIGNATURES = {
     "dyt_last_error": (C.c_char_p, []),
     "dyt_linear_f16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i,
                             _f, _vp]),
+    "dyt_linear_f16_aux": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "dyt_attn_varlen_fwd": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "dyt_layernorm_f16": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _f, _vp, _i, _vp]),
     "dyt_dispatch_workspace_bytes": (_sz, [_i]),

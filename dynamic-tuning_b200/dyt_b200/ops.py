@@ -67,6 +67,32 @@ def linear_f16(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = 
     return out_h.reshape(*lead, N), None
 
 
+def linear_f16_aux(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int,
+                   aux: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Train-mode MLP GEMMs.  EPI_BIAS_GELU_KEEP: returns (gelu(x W^T + b), pre-activation);
+    EPI_DGELU: returns ((x W^T + b) * gelu'(aux), aux).  All fp16."""
+    _need_cuda(x, w, bias, aux)
+    if x.dtype != torch.float16 or w.dtype != torch.float16:
+        raise DytError("linear_f16_aux expects fp16 operands")
+    x2 = _rows2d(x)
+    M, K = x2.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    if epilogue == _lib.EPI_BIAS_GELU_KEEP:
+        aux2 = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    else:
+        if aux is None or aux.dtype != torch.float16:
+            raise DytError("EPI_DGELU needs the fp16 pre-activation")
+        aux2 = _rows2d(aux)
+        if aux2.shape != (M, N):
+            raise DytError("EPI_DGELU: pre-activation shape mismatch")
+    check(_lib.lib().dyt_linear_f16_aux(
+        x2.data_ptr(), x2.stride(0), w.data_ptr(), w.stride(0), M, N, K, None, epilogue, _ptr(bias),
+        out.data_ptr(), N, aux2.data_ptr(), aux2.stride(0), _stream()), "dyt_linear_f16_aux")
+    lead = x.shape[:-1]
+    return out.reshape(*lead, N), aux2.reshape(*lead, N)
+
+
 def attn_varlen(qkv: torch.Tensor, num_heads: int, cu_seqlens: Optional[torch.Tensor] = None,
                 num_seqs: Optional[int] = None, max_seqlen: Optional[int] = None) -> torch.Tensor:
     """qkv: fp16 [B, N, 3*C] (uniform) or [T, 3*C] with int32 cu_seqlens [num_seqs+1].

@@ -138,8 +138,11 @@ class DytBlockFn(torch.autograd.Function):
                          noise=noise if training_gate else None, tau=tau, pack=False)
         mask, logits = d["mask"], d["logits"]
         ln2 = ops.layernorm_f16(x1, fz["ln2_w"], fz["ln2_b"], eps)
-        pre, _ = ops.linear_f16(ln2, fz["fc1_w"], fz["fc1_b"])
-        hdn = ops.eltwise_f16(_lib.EW_GELU_FWD, pre)
+        if fz["fc1_w"].shape[0] > 64:      # fc1 + GELU, keeping the pre-activation (one kernel)
+            hdn, pre = ops.linear_f16_aux(ln2, fz["fc1_w"], fz["fc1_b"], _lib.EPI_BIAS_GELU_KEEP)
+        else:
+            pre, _ = ops.linear_f16(ln2, fz["fc1_w"], fz["fc1_b"])
+            hdn = ops.eltwise_f16(_lib.EW_GELU_FWD, pre)
         mlp_x, _ = ops.linear_f16(hdn, fz["fc2_w"], fz["fc2_b"])
         hd, _ = ops.linear_f16(x1h, dw16, db16, epilogue=_lib.EPI_BIAS_RELU)
         if drop_mult is not None:
@@ -191,8 +194,12 @@ class DytBlockFn(torch.autograd.Function):
         g_hp = ops.eltwise_f16(_lib.EW_RELU_DROP_BWD, g_hd.reshape(T, -1), hd.reshape(T, -1), dm)
         ops.wgrad_f16(g_hp, x1h.reshape(T, Cd), out=(d_down_w, d_down_b))
         # ---- frozen MLP: fc2 dgrad, GELU', fc1 dgrad, LayerNorm2 backward ----
-        g_h, _ = ops.linear_f16(gm16, fz["fc2_wT"], None)
-        g_pre = ops.eltwise_f16(_lib.EW_GELU_BWD, g_h.reshape(pre.shape), pre)
+        if fz["fc2_wT"].shape[0] > 64:     # fc2 dgrad * gelu'(pre) in the GEMM epilogue
+            g_pre, _ = ops.linear_f16_aux(gm16, fz["fc2_wT"], None, _lib.EPI_DGELU,
+                                          aux=pre.reshape(T, -1))
+        else:
+            g_h, _ = ops.linear_f16(gm16, fz["fc2_wT"], None)
+            g_pre = ops.eltwise_f16(_lib.EW_GELU_BWD, g_h.reshape(pre.shape), pre)
         g_ln2, _ = ops.linear_f16(g_pre, fz["fc1_wT"], None)
         d_sel_w = d_sel_b = None
         if complete_model:

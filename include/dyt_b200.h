@@ -50,6 +50,18 @@ int dyt_linear_f16(const void* x, int ldx, const void* w, int ldw, int M, int N,
                    float* out_f32, int ldo_f32, const float* resid, int ld_resid, float scale,
                    void* stream);
 
+/* dyt_linear_f16 with an auxiliary fp16 [M, N] operand, for the train-mode MLP:
+ *   DYT_EPI_BIAS_GELU_KEEP: out = f16(gelu(f16(x W^T + b))) and aux = f16(x W^T + b) (written):
+ *     fc1 + GELU keeping the pre-activation for the backward;
+ *   DYT_EPI_DGELU: out = f16(f16(x W^T + b) * gelu'(aux)) (aux read): the fc2 data gradient
+ *     (x = g_mlp, W = fc2.weight^T) times the GELU derivative at the saved pre-activation.
+ * N > 64, rows of out / aux 16-byte aligned. */
+#define DYT_EPI_BIAS_GELU_KEEP 4
+#define DYT_EPI_DGELU 5
+int dyt_linear_f16_aux(const void* x, int ldx, const void* w, int ldw, int M, int N, int K,
+                       const int* m_dev, int epilogue, const void* bias, void* out_f16, int ldo_f16,
+                       void* aux_f16, int ld_aux, void* stream);
+
 /* Multi-head attention over packed variable-length sequences.
  * Replaces F.scaled_dot_product_attention(q, k, v) in Attention.forward (reference
  * models/model_speed_test.py:145-166 == models/vision_transformer_IN21K.py:54-75): non-causal,
