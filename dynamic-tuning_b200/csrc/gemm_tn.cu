@@ -43,7 +43,7 @@ template <int BN>
 static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb,
                         const GemmParams& p, cudaStream_t s) {
   // sixteen epilogue warps where the epilogue, not the main loop, sets the pace
-  if constexpr (BN >= 128) {
+  if constexpr (BN == 128 || BN == 256) {
     if (epi == EPI_BIAS_GELU) return launch_gemm<BN, EPI_BIAS_GELU, 16>(ta, tb, p, s);
     if (epi == EPI_BIAS_GELU_KEEP) return launch_gemm<BN, EPI_BIAS_GELU_KEEP, 16>(ta, tb, p, s);
     if (epi == EPI_DGELU) return launch_gemm<BN, EPI_DGELU, 16>(ta, tb, p, s);
@@ -94,6 +94,20 @@ int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, in
   int bn = 256;
   if (N <= 64) bn = 64;
   else if (N <= 128 || (N % 256 != 0 && N % 128 == 0)) bn = 128;
+  // Wave quantisation: the persistent grid runs ceil(tiles / clusters) rounds of equal-cost tiles.
+  // When the row count is known on the host (no device-side count, no fused row-dot whose slice
+  // layout is tied to BN = 256) and N splits into 192-wide tiles, take them if rounds x width is
+  // smaller: e.g. M = 12608, N = 768: 150 tiles of 256 = 3 rounds, 200 tiles of 192 = 3 rounds of
+  // 3/4 the cost.  (A 192-wide tile pair still takes in A + B/2 = 28 KB per 384 tensor clocks.)
+  // The GELU epilogues and K <= 128 keep BN = 256 with sixteen epilogue warps.
+  if (bn == 256 && m_dev == nullptr && dot_w == nullptr && N % 192 == 0 && K > 128 &&
+      (epi == EPI_BIAS || epi == EPI_BIAS_RELU || epi == EPI_BIAS_RESID)) {
+    const long pairs = (M + 255) / 256;
+    const long clusters = sm_count() / 2;
+    const long r256 = (pairs * ((N + 255) / 256) + clusters - 1) / clusters;
+    const long r192 = (pairs * (N / 192) + clusters - 1) / clusters;
+    if (r192 * 192 * 10 <= r256 * 256 * 9) bn = 192;  // only for a clear (>= 10 %) saving
+  }
 
   CUtensorMap ta, tb;
   int s = make_tmap_f16_sw128(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(K),
@@ -129,6 +143,7 @@ int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, in
   switch (bn) {
     case 64: return dispatch_epi<64>(epi, ta, tb, p, stream);
     case 128: return dispatch_epi<128>(epi, ta, tb, p, stream);
+    case 192: return dispatch_epi<192>(epi, ta, tb, p, stream);
     default: return dispatch_epi<256>(epi, ta, tb, p, stream);
   }
 }

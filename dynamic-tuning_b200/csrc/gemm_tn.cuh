@@ -68,10 +68,13 @@ struct GemmParams {
 // shapes: GELU, K <= 128 -- the arithmetic epilogue is latency-bound and wants more warps in flight)
 template <int BN, int EW = 8>
 struct GemmCfg {
-  static_assert(EW == 8 || (EW == 16 && BN >= 128), "epilogue warps: 8, or 16 for BN >= 128");
+  static_assert(BN == 64 || BN == 128 || BN == 192 || BN == 256, "tile widths: 64 / 128 / 192 / 256");
+  static_assert(EW == 8 || (EW == 16 && (BN == 128 || BN == 256)),
+                "epilogue warps: 8, or 16 for BN = 128 / 256 (column slices of 32-column chunks)");
   static constexpr int BM = 128;
   static constexpr int BK = 64;  // 64 halves = 128 B = one swizzle row
-  static constexpr int STAGES = (BN == 256) ? (EW == 16 ? 5 : 6) : (BN == 128 && EW == 16 ? 7 : 8);
+  static constexpr int STAGES =
+      (BN == 256) ? (EW == 16 ? 5 : 6) : (BN == 192 ? 7 : (BN == 128 && EW == 16 ? 7 : 8));
   static constexpr int A_BYTES = BM * BK * 2;         // this CTA's 128 rows of A
   static constexpr int B_BYTES = (BN / 2) * BK * 2;   // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -82,7 +85,7 @@ struct GemmCfg {
   static constexpr int SLAB_BYTES = 32 * 64;   // 32 rows x 32 fp16 (one 32-column chunk), per warp
   static constexpr int BIAS_BYTES = PART_COLS * 4;  // fp32 bias of the warp's columns
   static constexpr int EPI_BYTES = EPI_WARPS * (SLAB_BYTES + BIAS_BYTES);
-  static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: all powers of two
+  static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);  // power of two
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
 };

@@ -107,10 +107,12 @@ def test_gelu_epilogue_exhaustive_fp16(dev):
     assert int((d > 0).sum()) <= 400, f"{int((d > 0).sum())} of {x.numel()} values differ"
 
 
-@pytest.mark.parametrize("M,N,K", [(129, 256, 64), (255, 512, 128), (1000, 768, 768), (257, 2304, 64)])
+@pytest.mark.parametrize("M,N,K", [(129, 256, 64), (255, 512, 128), (1000, 768, 768), (257, 2304, 64),
+                                   (12608, 768, 3072), (5000, 2304, 768), (12608, 3072, 768)])
 def test_linear_cta_pair_edges(dev, M, N, K):
-    """Tile rows that are odd in count (the CTA pair's second tile is a dummy), rows past M and
-    the short-K shapes that take the sixteen-warp epilogue."""
+    """Tile rows that are odd in count (the CTA pair's second tile is a dummy), rows past M, the
+    short-K shapes that take the sixteen-warp epilogue, and the shapes whose wave count picks the
+    192-wide tile (N % 192 == 0, row count known on the host)."""
     from dyt_b200 import ops, _lib
     g = _gen(M + N + K)
     x = torch.randn(M, K, generator=g)
