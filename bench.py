@@ -167,6 +167,49 @@ def cpu_reference_run(state_dict, steps: int, warmup: int, sample_batch: int, se
                        f"torch {torch.__version__} CPU, {cores} threads")
 
 
+def cpu_finetune_run(state_dict, sample_batch: int = 8, seed: int = 0):
+    """CPU baseline of the fine-tune step: the oracle's train-mode restatement (student + teacher
+    forward, loss, autograd backward through the frozen backbone) on a bounded sample, fp32, all
+    host threads; one untimed + one timed step."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dyt_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(sample_batch, 3, 224, 224, generator=g)
+    tgt = torch.randint(0, NUM_CLASSES, (sample_batch,), generator=g)
+    sd = {}
+    for k, v in state_dict.items():
+        v = v.detach().float().cpu().clone()
+        if ("adaptmlp" in k) or ("mlp_token_select" in k) or k.startswith("head."):
+            v.requires_grad_(True)
+        sd[k] = v
+    n_tok = sd["pos_embed"].shape[1]
+    bott = sd["blocks.0.adaptmlp.down_proj.weight"].shape[0]
+
+    def step():
+        noises = [(-torch.empty(sample_batch, n_tok - 1, 1).exponential_(generator=g).log(),
+                   -torch.empty(sample_batch, n_tok - 1, 1).exponential_(generator=g).log())
+                  for _ in range(2 * DEPTH)]
+        drops = [(torch.rand(sample_batch, n_tok, bott, generator=g) >= 0.1).float() / 0.9
+                 for _ in range(2 * DEPTH)]
+        s = O.vit_train_forward(img, sd, DEPTH, HEADS, 1.0, noises[:DEPTH], drops[:DEPTH], False)
+        t = O.vit_train_forward(img, sd, DEPTH, HEADS, 1.0, noises[DEPTH:], drops[DEPTH:], True)
+        loss = O.finetune_loss(s["logits"], s["token_select"], t["logits"], tgt)
+        loss.backward()
+        for v in sd.values():
+            v.grad = None
+
+    step()
+    t0 = time.perf_counter()
+    step()
+    dt = time.perf_counter() - t0
+    return dict(value=sample_batch / dt, unit="images/s", cores=cores, kind="port",
+                sample=f"1 fine-tune step (student + teacher forward, backward) of {sample_batch} "
+                       f"images, fp32 autograd through the oracle, torch {torch.__version__} CPU, "
+                       f"{cores} threads")
+
+
 def synthetic_cpu_state_dict(seed: int = 0):
     """Same construction as dyt_b200.synthetic.build_vit_b16 but on the CPU, with the selector bias
     calibrated by the oracle (used when no GPU is present, i.e. the pure reference arm)."""
@@ -501,6 +544,9 @@ def run_finetune(args, world, rank, local):
     barrier(world)
     sec = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, world, device)
     if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu = cpu_finetune_run(model.state_dict())
         print(json.dumps({
             "metric": "extra workload finetune_b16", "value": batch * world * args.steps / sec,
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
@@ -512,7 +558,8 @@ def run_finetune(args, world, rank, local):
                        "loss_scale": float(step.scaler.get_scale()),
                        "cuda_graph": "forward + backward of the step replayed as one CUDA graph",
                        "allreduce_bytes_per_step": arena.nbytes if world > 1 else 0,
-                       "trainable_tensors": len(arena.params)}}), flush=True)
+                       "trainable_tensors": len(arena.params)},
+            "cpu_baseline": cpu}), flush=True)
 
 
 def main():
