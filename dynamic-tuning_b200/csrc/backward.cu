@@ -29,13 +29,17 @@ namespace dyt {
 template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const __half* __restrict__ gy, int ldg, const float* __restrict__ x, int ldx,
-                     const int* __restrict__ row_idx, int n_rows, const float* __restrict__ gamma,
-                     float eps, const float* resid, int ldr, const float* __restrict__ row_scale,
-                     const float* __restrict__ axpy, float* out, int ldo, __half* __restrict__ out_h,
-                     int ldoh) {
+                     const int* __restrict__ row_idx, const int* __restrict__ n_rows_dev, int n_rows,
+                     const float* __restrict__ gamma, float eps, const float* resid, int ldr,
+                     const float* __restrict__ row_scale, const float* __restrict__ axpy, float* out,
+                     int ldo, __half* __restrict__ out_h, int ldoh) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   constexpr float inv_c = 1.0f / static_cast<float>(NV * 128);
+  if (n_rows_dev != nullptr) {
+    const int nd = *n_rows_dev;
+    n_rows = nd < n_rows ? nd : n_rows;
+  }
   for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n_rows;
        r += gridDim.x * warps_per_block) {
     const size_t src = row_idx != nullptr ? static_cast<size_t>(row_idx[r]) : static_cast<size_t>(r);
@@ -97,11 +101,13 @@ layernorm_bwd_kernel(const __half* __restrict__ gy, int ldg, const float* __rest
 
 template <int NV>
 static void launch_ln_bwd(int grid, cudaStream_t st, const __half* gy, int ldg, const float* x,
-                          int ldx, const int* row_idx, int n_rows, const float* gamma, float eps,
-                          const float* resid, int ldr, const float* row_scale, const float* axpy,
-                          float* out, int ldo, __half* out_h, int ldoh) {
-  layernorm_bwd_kernel<NV><<<grid, 256, 0, st>>>(gy, ldg, x, ldx, row_idx, n_rows, gamma, eps,
-                                                 resid, ldr, row_scale, axpy, out, ldo, out_h, ldoh);
+                          int ldx, const int* row_idx, const int* n_rows_dev, int n_rows,
+                          const float* gamma, float eps, const float* resid, int ldr,
+                          const float* row_scale, const float* axpy, float* out, int ldo,
+                          __half* out_h, int ldoh) {
+  layernorm_bwd_kernel<NV><<<grid, 256, 0, st>>>(gy, ldg, x, ldx, row_idx, n_rows_dev, n_rows, gamma,
+                                                 eps, resid, ldr, row_scale, axpy, out, ldo, out_h,
+                                                 ldoh);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -116,13 +122,19 @@ merge_bwd_kernel(const float* __restrict__ g_out, int ldg, const __half* __restr
                  const float* __restrict__ n1, const float* __restrict__ n2, float tau,
                  const float* __restrict__ g_sel, const float* __restrict__ g_logits_ext, int T,
                  int N, __half* __restrict__ g16, int ld16, __half* __restrict__ gm16, int ldgm,
-                 float* __restrict__ g_logit) {
+                 float* __restrict__ g_logit, const int* __restrict__ token_pos,
+                 const float* __restrict__ sel_w, float* __restrict__ gx_init, int ldgx) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   for (int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5); t < T;
        t += gridDim.x * warps_per_block) {
     float4 v[NV];
     load_row_f32<NV>(g_out + static_cast<size_t>(t) * ldg, lane, v);
+    float4 raw[NV];
+    if (gx_init != nullptr) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) raw[i] = v[i];
+    }
     // the gradient reaching the fp16 tensors (mlp_x, adapt) is g_out rounded to fp16
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -145,7 +157,13 @@ merge_bwd_kernel(const float* __restrict__ g_out, int ldg, const __half* __restr
       v[i].x *= m; v[i].y *= m; v[i].z *= m; v[i].w *= m;
     }
     dot = warp_sum(dot);
-    store_row_f16<NV>(gm16 + static_cast<size_t>(t) * ldgm, lane, v);
+    if (token_pos == nullptr) {
+      store_row_f16<NV>(gm16 + static_cast<size_t>(t) * ldgm, lane, v);
+    } else {  // packed: kept rows only, at their position in the compacted order
+      const int pos = token_pos[t];
+      if (pos >= 0) store_row_f16<NV>(gm16 + static_cast<size_t>(pos) * ldgm, lane, v);
+    }
+    float gl_row = 0.f;
     if (lane == 0) {
       const int n = t % N;
       float gl = 0.f;
@@ -163,6 +181,50 @@ merge_bwd_kernel(const float* __restrict__ g_out, int ldg, const __half* __restr
         if (g_logits_ext != nullptr) gl += g_logits_ext[li];
       }
       g_logit[t] = gl;
+      gl_row = gl;
+    }
+    if (gx_init != nullptr) {
+      // start of the x1 gradient: residual path + the selector's data gradient g_logit * w
+      gl_row = __shfl_sync(0xffffffffu, gl_row, 0);
+      const float4* w4 = reinterpret_cast<const float4*>(sel_w);
+      float4* o4 = reinterpret_cast<float4*>(gx_init + static_cast<size_t>(t) * ldgx);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 w = w4[i * 32 + lane];
+        o4[i * 32 + lane] = make_float4(raw[i].x + gl_row * w.x, raw[i].y + gl_row * w.y,
+                                        raw[i].z + gl_row * w.z, raw[i].w + gl_row * w.w);
+      }
+    }
+  }
+}
+
+// out[r, :] = a[r, :] * gelu'(pre[row_idx[r], :]) for the first *n_rows_dev packed rows
+__global__ void __launch_bounds__(256)
+gelu_bwd_rows_kernel(const __half* __restrict__ a, int lda, const __half* __restrict__ pre, int ldp,
+                     const int* __restrict__ row_idx, const int* __restrict__ n_rows_dev, int n_rows,
+                     int H, __half* __restrict__ out, int ldo) {
+  if (n_rows_dev != nullptr) {
+    const int nd = *n_rows_dev;
+    n_rows = nd < n_rows ? nd : n_rows;
+  }
+  const int groups = H >> 3;
+  for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    const uint4* pa = reinterpret_cast<const uint4*>(a + static_cast<size_t>(r) * lda);
+    const uint4* pp = reinterpret_cast<const uint4*>(pre + static_cast<size_t>(row_idx[r]) * ldp);
+    uint4* po = reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * ldo);
+    for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
+      const uint4 ua = pa[gi], up = pp[gi];
+      const __half2* ha = reinterpret_cast<const __half2*>(&ua);
+      const __half2* hp = reinterpret_cast<const __half2*>(&up);
+      uint4 uo;
+      __half2* ho = reinterpret_cast<__half2*>(&uo);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fa = __half22float2(ha[j]);
+        const float2 fp = __half22float2(hp[j]);
+        ho[j] = __floats2half2_rn(fa.x * gelu_grad_f16(fp.x), fa.y * gelu_grad_f16(fp.y));
+      }
+      po[gi] = uo;
     }
   }
 }
@@ -374,7 +436,8 @@ static int row_grid(int n_rows) {
 using namespace dyt;
 
 extern "C" int dyt_layernorm_bwd(const void* gy_f16, int ldg, const float* x, int ldx,
-                                 const int* row_idx, int n_rows, int C, const float* gamma,
+                                 const int* row_idx, const int* n_rows_dev, int n_rows, int C,
+                                 const float* gamma,
                                  float eps, const float* resid, int ldr, const float* row_scale,
                                  const float* axpy, float* out, int ldo, void* out_f16, int ldoh,
                                  void* stream) {
@@ -391,8 +454,8 @@ extern "C" int dyt_layernorm_bwd(const void* gy_f16, int ldg, const float* x, in
   __half* oh = static_cast<__half*>(out_f16);
   const int grid = row_grid(n_rows);
 #define DYT_LNB(NV)                                                                              \
-  launch_ln_bwd<NV>(grid, st, gy, ldg, x, ldx, row_idx, n_rows, gamma, eps, resid, ldr, row_scale, \
-                    axpy, out, ldo, oh, ldoh)
+  launch_ln_bwd<NV>(grid, st, gy, ldg, x, ldx, row_idx, n_rows_dev, n_rows, gamma, eps, resid, ldr, \
+                    row_scale, axpy, out, ldo, oh, ldoh)
   switch (C) {
     case 768: DYT_LNB(6); break;
     case 1024: DYT_LNB(8); break;
@@ -409,7 +472,8 @@ extern "C" int dyt_merge_bwd(const float* g_out, int ldg, const void* mlp_f16, i
                              const float* mask, const float* logits, const float* noise1,
                              const float* noise2, float tau, const float* g_token_select,
                              const float* g_token_logits, int B, int N, int C, void* g_f16, int ld16,
-                             void* g_masked_f16, int ldgm, float* g_logit, void* stream) {
+                             void* g_masked_f16, int ldgm, float* g_logit, const int* token_pos,
+                             const float* sel_w, float* gx_init, int ldgx, void* stream) {
   DYT_CHECK_ARG(g_out && g_f16, "merge_bwd: null buffer");
   DYT_CHECK_ARG(B >= 0 && N >= 1 && ldg >= C && ld16 >= C && ldg % 4 == 0 && ld16 % 4 == 0,
                 "merge_bwd: bad sizes");
@@ -419,7 +483,12 @@ extern "C" int dyt_merge_bwd(const float* g_out, int ldg, const void* mlp_f16, i
                   "merge_bwd: the masked path needs mlp / mask / logits / g_logit");
     DYT_CHECK_ARG((noise1 == nullptr) == (noise2 == nullptr), "merge_bwd: noise1 and noise2 go together");
     DYT_CHECK_ARG(noise1 == nullptr || tau > 0.f, "merge_bwd: tau must be positive");
+  } else {
+    DYT_CHECK_ARG(token_pos == nullptr && gx_init == nullptr,
+                  "merge_bwd: token_pos / gx_init belong to the masked form");
   }
+  DYT_CHECK_ARG(gx_init == nullptr || (sel_w != nullptr && ldgx >= C && ldgx % 4 == 0),
+                "merge_bwd: gx_init needs the selector weight and a valid stride");
   const int T = B * N;
   if (T == 0) return DYT_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -428,7 +497,7 @@ extern "C" int dyt_merge_bwd(const float* g_out, int ldg, const void* mlp_f16, i
   merge_bwd_kernel<NV><<<grid, 256, 0, st>>>(                                                      \
       g_out, ldg, static_cast<const __half*>(mlp_f16), ldm, mask, logits, noise1, noise2, tau,     \
       g_token_select, g_token_logits, T, N, static_cast<__half*>(g_f16), ld16,                     \
-      static_cast<__half*>(g_masked_f16), ldgm, g_logit)
+      static_cast<__half*>(g_masked_f16), ldgm, g_logit, token_pos, sel_w, gx_init, ldgx)
   switch (C) {
     case 768: DYT_MB(6); break;
     case 1024: DYT_MB(8); break;
@@ -484,6 +553,26 @@ extern "C" int dyt_eltwise_f16(int op, const void* a, const void* b, const void*
     default: return fail(DYT_EINVAL, "eltwise: unknown op %d", op);
   }
   return cuda_status(cudaGetLastError(), "eltwise_f16_kernel launch");
+}
+
+extern "C" int dyt_gelu_bwd_rows(const void* g_f16, int ldg, const void* pre_f16, int ldp,
+                                 const int* row_idx, const int* n_rows_dev, int n_rows, int H,
+                                 void* out_f16, int ldo, void* stream) {
+  DYT_CHECK_ARG(g_f16 && pre_f16 && row_idx && out_f16, "gelu_bwd_rows: null buffer");
+  DYT_CHECK_ARG(n_rows >= 0 && H > 0 && H % 8 == 0 && ldg >= H && ldp >= H && ldo >= H &&
+                    ldg % 8 == 0 && ldp % 8 == 0 && ldo % 8 == 0,
+                "gelu_bwd_rows: H and the strides must be multiples of 8");
+  DYT_CHECK_ARG(((reinterpret_cast<uintptr_t>(g_f16) | reinterpret_cast<uintptr_t>(pre_f16) |
+                  reinterpret_cast<uintptr_t>(out_f16)) & 15) == 0,
+                "gelu_bwd_rows: buffers must be 16-byte aligned");
+  if (n_rows == 0) return DYT_OK;
+  int grid = n_rows;
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  gelu_bwd_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(g_f16), ldg, static_cast<const __half*>(pre_f16), ldp, row_idx,
+      n_rows_dev, n_rows, H, static_cast<__half*>(out_f16), ldo);
+  return cuda_status(cudaGetLastError(), "gelu_bwd_rows_kernel launch");
 }
 
 extern "C" int dyt_wgrad_f16(const void* g_f16, int ldg, const void* x_f16, int ldx, int T, int Nout,

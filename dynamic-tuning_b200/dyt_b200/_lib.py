@@ -68,10 +68,11 @@ SIGNATURES = {
     "dyt_patch_embed_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "dyt_pool_layernorm_f16": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp]),
     "dyt_query_attn_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
-    "dyt_layernorm_bwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _vp, _f, _vp, _i, _vp, _vp, _vp, _i,
-                               _vp, _i, _vp]),
+    "dyt_layernorm_bwd": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _f, _vp, _i, _vp, _vp, _vp,
+                               _i, _vp, _i, _vp]),
     "dyt_merge_bwd": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _vp, _i,
-                           _vp, _i, _vp, _vp]),
+                           _vp, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "dyt_gelu_bwd_rows": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _i, _vp]),
     "dyt_rowscale_colsum": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "dyt_eltwise_f16": (_i, [_i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dyt_wgrad_f16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _i, _vp, _vp]),

@@ -319,7 +319,8 @@ def eltwise_f16(op: int, a: torch.Tensor, b: Optional[torch.Tensor] = None,
 def layernorm_bwd(gy: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6,
                   resid: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
                   axpy: Optional[torch.Tensor] = None, row_idx: Optional[torch.Tensor] = None,
-                  out: Optional[torch.Tensor] = None, want_f16_copy: bool = False):
+                  out: Optional[torch.Tensor] = None, want_f16_copy: bool = False,
+                  n_rows_dev: Optional[torch.Tensor] = None):
     """g_x = resid + dLN(g_y) (+ row_scale[:, None] * axpy).  gy fp16 [R, C]; x fp32 rows (all rows
     of the stream when row_idx selects R of them); returns (fp32 like x, fp16 copy or None)."""
     _need_cuda(gy, x, weight, resid, row_scale, axpy, row_idx, out)
@@ -340,8 +341,8 @@ def layernorm_bwd(gy: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, eps: 
     rs = None if row_scale is None else row_scale.reshape(-1).to(torch.float32).contiguous()
     ax = None if axpy is None else axpy.reshape(-1).to(torch.float32).contiguous()
     check(_lib.lib().dyt_layernorm_bwd(
-        g2.data_ptr(), g2.stride(0), x2.data_ptr(), x2.stride(0), _ptr(row_idx), R, Cdim,
-        w.data_ptr(), float(eps), _ptr(r2), 0 if r2 is None else r2.stride(0), _ptr(rs), _ptr(ax),
+        g2.data_ptr(), g2.stride(0), x2.data_ptr(), x2.stride(0), _ptr(row_idx), _ptr(n_rows_dev), R,
+        Cdim, w.data_ptr(), float(eps), _ptr(r2), 0 if r2 is None else r2.stride(0), _ptr(rs), _ptr(ax),
         o2.data_ptr(), o2.stride(0), _ptr(oh), Cdim, _stream()), "dyt_layernorm_bwd")
     return out.reshape(x.shape), (None if oh is None else oh.reshape(x.shape))
 
@@ -350,9 +351,12 @@ def merge_bwd(g_out: torch.Tensor, N: int, mlp_x: Optional[torch.Tensor] = None,
               mask: Optional[torch.Tensor] = None, logits: Optional[torch.Tensor] = None,
               noise: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, tau: float = 5.0,
               g_token_select: Optional[torch.Tensor] = None,
-              g_token_logits: Optional[torch.Tensor] = None, masked: bool = True):
+              g_token_logits: Optional[torch.Tensor] = None, masked: bool = True,
+              token_pos: Optional[torch.Tensor] = None, sel_w: Optional[torch.Tensor] = None):
     """Backward of the merge + straight-through gate.  g_out fp32 [B*N, C].  Returns
-    (g16, g_masked16 or None, g_logit [B*N] fp32 or None)."""
+    (g16, g_masked16 or None, g_logit [B*N] fp32 or None, gx_init or None).  With token_pos the
+    masked gradient is packed (kept rows only, compacted order); with sel_w the kernel also returns
+    gx_init = g_out + g_logit * sel_w (fp32)."""
     _need_cuda(g_out, mlp_x, mask, logits, g_token_select, g_token_logits)
     if g_out.dtype != torch.float32:
         raise DytError("merge_bwd expects the fp32 stream gradient")
@@ -378,11 +382,32 @@ def merge_bwd(g_out: torch.Tensor, N: int, mlp_x: Optional[torch.Tensor] = None,
             gs = g_token_select.reshape(-1).to(torch.float32).contiguous()
         if g_token_logits is not None:
             gle = g_token_logits.reshape(-1).to(torch.float32).contiguous()
+    gx = sw = None
+    if masked and sel_w is not None:
+        sw = sel_w.reshape(-1).to(torch.float32).contiguous()
+        gx = torch.empty((T, Cdim), dtype=torch.float32, device=dev)
+    tp = token_pos if masked else None
     check(_lib.lib().dyt_merge_bwd(
         g2.data_ptr(), g2.stride(0), _ptr(m2), 0 if m2 is None else m2.stride(0), _ptr(mk),
         _ptr(lg), _ptr(n1), _ptr(n2), float(tau), _ptr(gs), _ptr(gle), B, N, Cdim, g16.data_ptr(),
-        Cdim, _ptr(gm16), Cdim, _ptr(gl), _stream()), "dyt_merge_bwd")
-    return g16, gm16, gl
+        Cdim, _ptr(gm16), Cdim, _ptr(gl), _ptr(tp), _ptr(sw), _ptr(gx), Cdim, _stream()),
+        "dyt_merge_bwd")
+    return g16, gm16, gl, gx
+
+
+def gelu_bwd_rows(g16: torch.Tensor, pre: torch.Tensor, row_idx: torch.Tensor,
+                  n_rows_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r] = g16[r] * gelu'(pre[row_idx[r]]) for the packed rows (count on the device)."""
+    _need_cuda(g16, pre, row_idx, n_rows_dev)
+    g2, p2 = _rows2d(g16), _rows2d(pre)
+    if g2.dtype != torch.float16 or p2.dtype != torch.float16 or g2.shape[1] != p2.shape[1]:
+        raise DytError("gelu_bwd_rows expects fp16 [R, H] and [T, H]")
+    out = torch.empty_like(g2)
+    check(_lib.lib().dyt_gelu_bwd_rows(g2.data_ptr(), g2.stride(0), p2.data_ptr(), p2.stride(0),
+                                       row_idx.data_ptr(), _ptr(n_rows_dev), g2.shape[0],
+                                       g2.shape[1], out.data_ptr(), out.stride(0), _stream()),
+          "dyt_gelu_bwd_rows")
+    return out
 
 
 def rowscale_colsum(s: torch.Tensor, x16: torch.Tensor, out_w: torch.Tensor,

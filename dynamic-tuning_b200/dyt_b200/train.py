@@ -161,24 +161,30 @@ class DytBlockFn(torch.autograd.Function):
         ctx.noise = noise if training_gate else None
         ctx.drop_mult = drop_mult
         ctx.save_for_backward(x, qkv, o, x1, x1h, mask, logits, pre, mlp_x, hd, ad["dwT"], ad["uwT"],
-                              sel_w.detach())
+                              sel_w.detach(), d["token_pos"], d["packed_idx"], d["n_kept"])
         if debug_keep is not None:   # tests: look at the forward intermediates
             debug_keep.update(x1=x1, x1h=x1h, pre=pre, mlp_x=mlp_x, hd=hd, qkv=qkv, o=o)
         return out, mask, logits
 
     @staticmethod
     def backward(ctx, g_out, g_sel, g_logits):
-        (x, qkv, o, x1, x1h, mask, logits, pre, mlp_x, hd, dwT, uwT, sel_w) = ctx.saved_tensors
+        (x, qkv, o, x1, x1h, mask, logits, pre, mlp_x, hd, dwT, uwT, sel_w, token_pos, packed_idx,
+         n_kept) = ctx.saved_tensors
         B, N, Cd, H, scale, tau, eps, complete_model, training_gate = ctx.meta
         fz = _frozen(ctx.block)
         T = B * N
         if g_out is None:
             g_out = torch.zeros((T, Cd), dtype=torch.float32, device=x.device)
         g_out = g_out.to(torch.float32).contiguous().reshape(T, Cd)
-        g16, gm16, g_l = ops.merge_bwd(
+        # student pass: the masked MLP gradient is zero on dropped rows, so the frozen MLP's backward
+        # can run on the kept rows only (packed, count on the device, like the inference forward).
+        # Kept as an option (SPARSE_STUDENT_MIN_TOKENS): see the measurement next to that constant.
+        sparse = (not complete_model) and T >= SPARSE_STUDENT_MIN_TOKENS
+        g16, gm16, g_l, g_x1 = ops.merge_bwd(
             g_out, N, mlp_x=mlp_x, mask=mask, logits=logits, noise=ctx.noise, tau=tau,
             g_token_select=None if complete_model else g_sel,
-            g_token_logits=None if complete_model else g_logits, masked=not complete_model)
+            g_token_logits=None if complete_model else g_logits, masked=not complete_model,
+            token_pos=token_pos if sparse else None, sel_w=sel_w if sparse else None)
         if complete_model:
             gm16 = g16
         # ---- adapter: up dgrad, wgrads, ReLU / dropout, (down dgrad further below) ----
@@ -198,17 +204,28 @@ class DytBlockFn(torch.autograd.Function):
         # DYT_EPI_DGELU epilogue (76 us vs 35 + 36 us at 12.6k rows: the derivative costs two MUFU +
         # a polynomial per element and holds the accumulator stage, and the plain GEMM can take
         # the 192-wide tile)
-        g_h, _ = ops.linear_f16(gm16, fz["fc2_wT"], None)
-        g_pre = ops.eltwise_f16(_lib.EW_GELU_BWD, g_h.reshape(pre.shape), pre)
-        g_ln2, _ = ops.linear_f16(g_pre, fz["fc1_wT"], None)
         d_sel_w = d_sel_b = None
         if complete_model:
+            g_h, _ = ops.linear_f16(gm16, fz["fc2_wT"], None)
+            g_pre = ops.eltwise_f16(_lib.EW_GELU_BWD, g_h.reshape(pre.shape), pre)
+            g_ln2, _ = ops.linear_f16(g_pre, fz["fc1_wT"], None)
             g_x1, _ = ops.layernorm_bwd(g_ln2.reshape(T, Cd), x1.reshape(T, Cd), fz["ln2_w"], eps,
                                         resid=g_out)
         else:
-            # selector: data gradient g_l * w folded into the LayerNorm-backward pass
-            g_x1, _ = ops.layernorm_bwd(g_ln2.reshape(T, Cd), x1.reshape(T, Cd), fz["ln2_w"], eps,
-                                        resid=g_out, row_scale=g_l, axpy=sel_w)
+            if sparse:
+                g_h, _ = ops.linear_f16(gm16, fz["fc2_wT"], None, m_dev=n_kept)
+                g_pre = ops.gelu_bwd_rows(g_h, pre.reshape(T, -1), packed_idx, n_kept)
+                g_ln2, _ = ops.linear_f16(g_pre, fz["fc1_wT"], None, m_dev=n_kept)
+                # g_x1 = g_out + g_l * w_sel (from merge_bwd) + dLN2 on the kept rows, in place
+                ops.layernorm_bwd(g_ln2.reshape(T, Cd), x1.reshape(T, Cd), fz["ln2_w"], eps,
+                                  resid=g_x1, out=g_x1, row_idx=packed_idx, n_rows_dev=n_kept)
+            else:
+                g_h, _ = ops.linear_f16(gm16, fz["fc2_wT"], None)
+                g_pre = ops.eltwise_f16(_lib.EW_GELU_BWD, g_h.reshape(pre.shape), pre)
+                g_ln2, _ = ops.linear_f16(g_pre, fz["fc1_wT"], None)
+                # selector: data gradient g_l * w folded into the LayerNorm-backward pass
+                g_x1, _ = ops.layernorm_bwd(g_ln2.reshape(T, Cd), x1.reshape(T, Cd), fz["ln2_w"],
+                                            eps, resid=g_out, row_scale=g_l, axpy=sel_w)
             off = 2 * n_w + Cd + bott
             d_sel_w, d_sel_b = zbuf[off:off + Cd], zbuf[off + Cd:off + Cd + 1]
             ops.rowscale_colsum(g_l, x1h.reshape(T, Cd), d_sel_w, d_sel_b)
@@ -230,6 +247,11 @@ class DytBlockFn(torch.autograd.Function):
 
 
 _fixed = {"noises": None, "drop_mults": None}
+# B * N from which the student pass runs the frozen MLP's backward on the kept rows only.  Off by
+# default: measured on one B200 it is a wash (64 images 21.19 vs 21.10 ms per step, 256 images
+# 72.96 vs 72.47 ms): the packed GEMMs save half the tiles, but at these sizes that is at most one
+# round of the persistent grid, and the packed form needs an extra fp32 pass over the stream.
+SPARSE_STUDENT_MIN_TOKENS = 1 << 30
 debug_keep: Optional[dict] = None   # set to a dict to receive the last block forward's intermediates
 
 

@@ -153,11 +153,13 @@ int dyt_query_attn_fwd(const void* q_f16, int ldq, const void* k_f16, const void
 /* g_x = resid + dLayerNorm(g_y) [+ row_scale[r] * axpy[:]]   (fp32), optional fp16 copy.
  * g_y fp16 [n_rows, C] (the dgrad GEMM output), x fp32 = the forward input of the LayerNorm
  * (statistics are recomputed).  With row_idx, gradient row r belongs to x / resid / out row
- * row_idx[r] (final norm on the cls rows).  resid may alias out.  row_scale/axpy add the selector's
+ * row_idx[r] (final norm on the cls rows; the kept rows of the student pass, whose count
+ * n_rows_dev stays on the device).  resid may alias out.  row_scale/axpy add the selector's
  * data gradient g_logit[t] * mlp_head.weight in the same pass.
  * Backward of nn.LayerNorm norm1 / norm2 / norm (models/vision_transformer_IN21K.py:110, :123, :316). */
 int dyt_layernorm_bwd(const void* gy_f16, int ldg, const float* x, int ldx, const int* row_idx,
-                      int n_rows, int C, const float* gamma, float eps, const float* resid, int ldr,
+                      const int* n_rows_dev, int n_rows, int C, const float* gamma, float eps,
+                      const float* resid, int ldr,
                       const float* row_scale, const float* axpy, float* out, int ldo, void* out_f16,
                       int ldoh, void* stream);
 
@@ -170,11 +172,22 @@ int dyt_layernorm_bwd(const void* gy_f16, int ldg, const float* x, int ldx, cons
  *                  + g_token_logits, 0 for the cls slot; y = sigmoid((l + n1 - n2)/tau) or sigmoid(l)
  * g_out fp32 [B*N, C]; mask [B*N]; logits / noise* / g_token_logits [B*(N-1)]; g_token_select [B*N]
  * (gradient arriving on the returned sub_token_select, may be NULL).  g_masked_f16 == NULL selects
- * the complete_model form (only g_f16 is written). */
+ * the complete_model form (only g_f16 is written).
+ * Sparse student backward (g_mlp is zero on dropped rows, so the frozen MLP's backward only needs
+ * the kept rows): with token_pos (from dyt_dispatch_fwd) the masked gradient is written PACKED,
+ * row token_pos[t] for kept tokens only; with gx_init (+ sel_w = mlp_head.weight [C]) the kernel
+ * also writes gx_init[t] = g_out[t] + g_logit[t] * sel_w, the x1 gradient before the LayerNorm2
+ * term that dyt_layernorm_bwd then adds on the kept rows (row_idx = packed_idx). */
 int dyt_merge_bwd(const float* g_out, int ldg, const void* mlp_f16, int ldm, const float* mask,
                   const float* logits, const float* noise1, const float* noise2, float tau,
                   const float* g_token_select, const float* g_token_logits, int B, int N, int C,
-                  void* g_f16, int ld16, void* g_masked_f16, int ldgm, float* g_logit, void* stream);
+                  void* g_f16, int ld16, void* g_masked_f16, int ldgm, float* g_logit,
+                  const int* token_pos, const float* sel_w, float* gx_init, int ldgx, void* stream);
+
+/* out[r] = g[r] * gelu'(pre[row_idx[r]]) for the first min(n_rows, *n_rows_dev) packed rows of H
+ * fp16 columns: GELU backward of the kept rows, gathering the saved pre-activation. */
+int dyt_gelu_bwd_rows(const void* g_f16, int ldg, const void* pre_f16, int ldp, const int* row_idx,
+                      const int* n_rows_dev, int n_rows, int H, void* out_f16, int ldo, void* stream);
 
 /* out_w[c] += sum_t s[t] * x[t, c];  out_b += sum_t s[t]: weight / bias gradient of the selector's
  * Linear(C -> 1) (TokenSelect.mlp_head, models/dynamic_adapter.py:60).  fp32 atomics: the caller

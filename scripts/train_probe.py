@@ -13,6 +13,9 @@ from dyt_b200.ddp import GradArena, trainable_parameters  # noqa: E402
 from dyt_b200.finetune import FinetuneStep  # noqa: E402
 
 B = int(os.environ.get("TRAIN_B", "64"))
+if "TRAIN_SPARSE_MIN" in os.environ:
+    from dyt_b200 import train as _train
+    _train.SPARSE_STUDENT_MIN_TOKENS = int(os.environ["TRAIN_SPARSE_MIN"])
 dev = torch.device("cuda:0")
 model = synthetic.build_vit_b16(dev, flavour="train", ffn_num=16, scalar="1.0")
 g = torch.Generator().manual_seed(0)
