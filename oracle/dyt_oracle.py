@@ -134,7 +134,7 @@ def compact(mask: Tensor) -> Tuple[Tensor, Tensor]:
     flat = mask.reshape(bsz * n)
     packed_idx = flat.nonzero()[:, 0]
     counts = mask.reshape(bsz, n).sum(dim=1).to(torch.int32)
-    cu = torch.zeros(bsz + 1, dtype=torch.int32)
+    cu = torch.zeros(bsz + 1, dtype=torch.int32, device=mask.device)
     cu[1:] = torch.cumsum(counts, 0)
     return packed_idx, cu
 
@@ -213,10 +213,11 @@ def block_sparse(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int, s
     packed_idx, cu = compact(mask)                                                # :297-300
     flat = x1.reshape(bsz * n, c)
     gather_x = flat[packed_idx, :]                                                # :301
-    mlp_x = torch.zeros_like(flat)                                                # :302
-    mlp_x[packed_idx, :] = mlp(layer_norm(gather_x, p[prefix + "norm2.weight"],
-                                          p[prefix + "norm2.bias"]), p, prefix + "mlp.",
-                               policy)                                            # :303-304
+    kept = mlp(layer_norm(gather_x, p[prefix + "norm2.weight"], p[prefix + "norm2.bias"]), p,
+               prefix + "mlp.", policy)                                           # :303
+    # :302 allocates zeros in the mask's dtype (fp16 under autocast, like the MLP output)
+    mlp_x = torch.zeros(flat.shape, dtype=kept.dtype, device=flat.device)
+    mlp_x[packed_idx, :] = kept                                                   # :304
     out = adapt_x + (x1 + mlp_x.reshape(bsz, n, c))                               # :305-308
     return dict(out=out, x1=x1, mask=mask, logits=logits, packed_idx=packed_idx, cu_seqlens=cu)
 
