@@ -281,6 +281,111 @@ static int launch_dispatch(const DispatchParams& p, cudaStream_t stream) {
 
 }  // namespace dyt
 
+namespace dyt {
+// ---------------------------------------------------------------------------------------------
+// TokenSelect.forward alone (score + gate, no compaction): one warp per token over the whole grid.
+// Same arithmetic as the dispatcher's gate above; used by the train-mode forward, where the dense
+// masked block needs only the mask and the logits (models/dynamic_adapter.py:70-77) and a batch of
+// 64 images would leave most SMs idle under the one-CTA-per-image dispatcher.
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+token_select_kernel(const float* __restrict__ x1, int ldx, const float* __restrict__ sel_w,
+                    const float* __restrict__ sel_b, int logit_fp16, float min_kept,
+                    const float* __restrict__ noise1, const float* __restrict__ noise2, float tau,
+                    int T, int N, float* __restrict__ mask, float* __restrict__ logits) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  float bias = sel_b[0];
+  if (logit_fp16) bias = r16(bias);
+  float4 w[NV];
+  load_row_f32<NV>(sel_w, lane, w);
+  if (logit_fp16) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      w[i].x = r16(w[i].x); w[i].y = r16(w[i].y); w[i].z = r16(w[i].z); w[i].w = r16(w[i].w);
+    }
+  }
+  for (int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5); t < T;
+       t += gridDim.x * warps_per_block) {
+    const int n = t % N;
+    if (n == 0) {  // cls: always kept, no logit
+      if (lane == 0) mask[t] = 1.0f;
+      continue;
+    }
+    float4 v[NV];
+    load_row_f32<NV>(x1 + static_cast<size_t>(t) * ldx, lane, v);
+    float acc = 0.f;
+    if (logit_fp16) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        acc = fmaf(r16(v[i].x), w[i].x, acc);
+        acc = fmaf(r16(v[i].y), w[i].y, acc);
+        acc = fmaf(r16(v[i].z), w[i].z, acc);
+        acc = fmaf(r16(v[i].w), w[i].w, acc);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        acc = fmaf(v[i].x, w[i].x, acc);
+        acc = fmaf(v[i].y, w[i].y, acc);
+        acc = fmaf(v[i].z, w[i].z, acc);
+        acc = fmaf(v[i].w, w[i].w, acc);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float logit = acc + bias;
+      if (logit_fp16) logit = r16(logit);
+      float g = logit;
+      const size_t li = static_cast<size_t>(t / N) * (N - 1) + (n - 1);
+      if (noise1 != nullptr) {
+        if (logit_fp16) {
+          g = r16(g + r16(noise1[li]));
+          g = r16(g - r16(noise2[li]));
+          g = r16(g / r16(tau));
+        } else {
+          g = ((g + noise1[li]) - noise2[li]) / tau;
+        }
+      }
+      logits[li] = logit;
+      mask[t] = g >= min_kept ? 1.0f : 0.0f;
+    }
+  }
+}
+
+}  // namespace dyt
+
+extern "C" int dyt_token_select_fwd(const float* x1, int ldx, const float* sel_w, const float* sel_b,
+                                    int logit_fp16, float min_kept, const float* noise1,
+                                    const float* noise2, float tau, int B, int N, int C, float* mask,
+                                    float* logits, void* stream) {
+  using namespace dyt;
+  DYT_CHECK_ARG(x1 && sel_w && sel_b && mask && logits, "token_select: null buffer");
+  DYT_CHECK_ARG(B >= 0 && N >= 2 && ldx >= C && ldx % 4 == 0, "token_select: bad sizes");
+  DYT_CHECK_ARG((noise1 == nullptr) == (noise2 == nullptr), "token_select: need both noise tensors");
+  DYT_CHECK_ARG(noise1 == nullptr || tau > 0.f, "token_select: tau must be positive");
+  const int T = B * N;
+  if (T == 0) return DYT_OK;
+  int grid = (T + 7) / 8;
+  const int cap = sm_count() * 16;
+  if (grid > cap) grid = cap;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define DYT_TS(NV)                                                                                 \
+  token_select_kernel<NV><<<grid, 256, 0, st>>>(x1, ldx, sel_w, sel_b, logit_fp16, min_kept, noise1, \
+                                                noise2, tau, T, N, mask, logits)
+  switch (C) {
+    case 768: DYT_TS(6); break;
+    case 1024: DYT_TS(8); break;
+    case 384: DYT_TS(3); break;
+    case 128: DYT_TS(1); break;
+    default:
+      return fail(DYT_EUNSUPPORTED, "token_select: embed dim %d not instantiated (128/384/768/1024)", C);
+  }
+#undef DYT_TS
+  return cuda_status(cudaGetLastError(), "token_select_kernel launch");
+}
+
 extern "C" size_t dyt_dispatch_workspace_bytes(int B) {
   return static_cast<size_t>(B) * sizeof(unsigned long long) + 64;
 }

@@ -198,6 +198,31 @@ def dispatch(x1: torch.Tensor, sel_w: torch.Tensor, sel_b: torch.Tensor, *,
                 cu_seqlens=cu, n_kept=n_kept, packed=packed)
 
 
+def token_select(x1: torch.Tensor, sel_w: torch.Tensor, sel_b: torch.Tensor, *,
+                 logit_dtype: torch.dtype = torch.float16, threshold: float = 0.5,
+                 noise: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, tau: float = 5.0):
+    """Score + gate without compaction: (mask [B, N, 1] f32, logits [B, N-1, 1] f32)."""
+    _need_cuda(x1, sel_w, sel_b)
+    if x1.dtype != torch.float32 or x1.dim() != 3:
+        raise DytError("token_select expects x1 [B, N, C] fp32")
+    x1 = x1.contiguous()
+    B, N, Cdim = x1.shape
+    mask = torch.empty((B, N, 1), dtype=torch.float32, device=x1.device)
+    logits = torch.empty((B, N - 1, 1), dtype=torch.float32, device=x1.device)
+    n1 = n2 = None
+    if noise is not None:
+        n1 = noise[0].to(torch.float32).contiguous()
+        n2 = noise[1].to(torch.float32).contiguous()
+    sw = sel_w.reshape(-1).to(torch.float32).contiguous()
+    sb = sel_b.reshape(-1).to(torch.float32).contiguous()
+    check(_lib.lib().dyt_token_select_fwd(
+        x1.data_ptr(), Cdim, sw.data_ptr(), sb.data_ptr(),
+        1 if logit_dtype == torch.float16 else 0, float(min_kept_logit(logit_dtype, threshold)),
+        _ptr(n1), _ptr(n2), float(tau), B, N, Cdim, mask.data_ptr(), logits.data_ptr(), _stream()),
+        "dyt_token_select_fwd")
+    return mask, logits
+
+
 def scatter_merge(x1: torch.Tensor, adapt: torch.Tensor, mlp_packed: torch.Tensor,
                   token_pos: torch.Tensor, next_ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
                   eps: float = 1e-6):

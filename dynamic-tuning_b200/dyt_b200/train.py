@@ -133,10 +133,20 @@ class DytBlockFn(torch.autograd.Function):
         o = ops.attn_varlen(qkv.reshape(B, N, -1), H)
         x1, x1h = ops.linear_f16(o, fz["proj_w"], fz["proj_b"], epilogue=_lib.EPI_BIAS_RESID,
                                  resid=x, want_f16_copy=True)
-        d = ops.dispatch(x1.reshape(B, N, Cd), sel_w.detach(), sel_b.detach(),
-                         logit_dtype=torch.float16, threshold=thr,
-                         noise=noise if training_gate else None, tau=tau, pack=False)
-        mask, logits = d["mask"], d["logits"]
+        T = B * N
+        sparse_bwd = (not complete_model) and T >= SPARSE_STUDENT_MIN_TOKENS
+        if sparse_bwd:   # the kept-rows-only backward needs the compaction as well
+            d = ops.dispatch(x1.reshape(B, N, Cd), sel_w.detach(), sel_b.detach(),
+                             logit_dtype=torch.float16, threshold=thr,
+                             noise=noise if training_gate else None, tau=tau, pack=False)
+            mask, logits = d["mask"], d["logits"]
+            compaction = (d["token_pos"], d["packed_idx"], d["n_kept"])
+        else:
+            mask, logits = ops.token_select(x1.reshape(B, N, Cd), sel_w.detach(), sel_b.detach(),
+                                            logit_dtype=torch.float16, threshold=thr,
+                                            noise=noise if training_gate else None, tau=tau)
+            empty = torch.empty(0, dtype=torch.int32, device=x.device)
+            compaction = (empty, empty, empty)
         ln2 = ops.layernorm_f16(x1, fz["ln2_w"], fz["ln2_b"], eps)
         if fz["fc1_w"].shape[0] > 64:      # fc1 + GELU, keeping the pre-activation (one kernel)
             hdn, pre = ops.linear_f16_aux(ln2, fz["fc1_w"], fz["fc1_b"], _lib.EPI_BIAS_GELU_KEEP)
@@ -148,7 +158,6 @@ class DytBlockFn(torch.autograd.Function):
         if drop_mult is not None:
             hd = ops.eltwise_f16(_lib.EW_MUL, hd, drop_mult.reshape(hd.shape))
         up, _ = ops.linear_f16(hd, uw16, ub16, epilogue=_lib.EPI_BIAS, scale=scale)
-        T = B * N
         ar = torch.arange(T, device=x.device, dtype=torch.int32)
         if complete_model:
             token_pos = ar
@@ -161,7 +170,7 @@ class DytBlockFn(torch.autograd.Function):
         ctx.noise = noise if training_gate else None
         ctx.drop_mult = drop_mult
         ctx.save_for_backward(x, qkv, o, x1, x1h, mask, logits, pre, mlp_x, hd, ad["dwT"], ad["uwT"],
-                              sel_w.detach(), d["token_pos"], d["packed_idx"], d["n_kept"])
+                              sel_w.detach(), *compaction)
         if debug_keep is not None:   # tests: look at the forward intermediates
             debug_keep.update(x1=x1, x1h=x1h, pre=pre, mlp_x=mlp_x, hd=hd, qkv=qkv, o=o)
         return out, mask, logits
@@ -179,7 +188,7 @@ class DytBlockFn(torch.autograd.Function):
         # student pass: the masked MLP gradient is zero on dropped rows, so the frozen MLP's backward
         # can run on the kept rows only (packed, count on the device, like the inference forward).
         # Kept as an option (SPARSE_STUDENT_MIN_TOKENS): see the measurement next to that constant.
-        sparse = (not complete_model) and T >= SPARSE_STUDENT_MIN_TOKENS
+        sparse = (not complete_model) and token_pos.numel() > 0
         g16, gm16, g_l, g_x1 = ops.merge_bwd(
             g_out, N, mlp_x=mlp_x, mask=mask, logits=logits, noise=ctx.noise, tau=tau,
             g_token_select=None if complete_model else g_sel,

@@ -3,9 +3,9 @@
 scaled_dot_product_attention, nonzero + index gather / scatter) run ON THE B200 under
 torch.autocast(fp16), i.e. cuBLAS / cuDNN-flash / ATen kernels, timed like bench.py (CUDA events,
 6 warm-up + 15 timed steps, batch resident in HBM).  /root/reference itself is not on the GPU box;
-the oracle is pinned to it by tests/golden.  Not part of the product or of bench.py.
+the oracle is pinned to it by tests/golden.  Test infrastructure (it runs the oracle): not part of the product or of bench.py.
 
-  python scripts/torch_eager_baseline.py            # inference bs256 + fine-tune step bs64
+  python tests/baseline_torch_eager_b200.py            # inference bs256 + fine-tune step bs64
 """
 import os
 import sys
