@@ -1,5 +1,6 @@
 // Host launcher + C-ABI entry for the tcgen05 GEMM (see gemm_tn.cuh).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/dyt_b200.h"
 #include "gemm_tn.cuh"
@@ -109,6 +110,12 @@ int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, in
     if (r192 * 192 * 10 <= r256 * 256 * 9) bn = 192;  // only for a clear (>= 10 %) saving
   }
 
+  {  // experiment hook (scripts/gemm_probe.py): force a tile width
+    static const char* force = getenv("DYT_GEMM_FORCE_BN");
+    if (force != nullptr && N % atoi(force) == 0 && K > 128 && dot_w == nullptr &&
+        (epi == EPI_BIAS || epi == EPI_BIAS_RESID))
+      bn = atoi(force);
+  }
   CUtensorMap ta, tb;
   int s = make_tmap_f16_sw128(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(K),
                               static_cast<uint64_t>(lda), 128);
