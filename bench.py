@@ -342,9 +342,14 @@ def run_ours(args, world, rank, local):
     cal = torch.randn(64, 3, 224, 224, generator=torch.Generator().manual_seed(0)).to(device)
     keep_cal = synthetic.calibrate_keep_rate(model, cal, RATE)
 
-    def forward(imgs):
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
-            return model(imgs)
+    # The call a user makes: dyt_b200.GraphedForward(model)(images) = model(images) under no_grad +
+    # fp16 autocast, captured once into a CUDA graph and replayed (the ~115 launches of one forward
+    # otherwise leave host-dependent gaps: 0.3-0.8 ms per step across boxes).
+    from dyt_b200 import GraphedForward
+    graphed = GraphedForward(model)
+
+    def forward(imgs, slot=0):
+        return graphed(imgs, slot=slot)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -378,7 +383,9 @@ def run_ours(args, world, rank, local):
     # the H2D copy of step i+1 runs on a copy stream while step i computes; every step's copy and
     # logits read-back are inside the timed region.
     host_logits = torch.empty(BATCH, NUM_CLASSES, dtype=torch.float16).pin_memory()
-    dev_in = [torch.empty_like(images), torch.empty_like(images)]
+    # two static input slots of the graphed forward: the H2D copy lands directly in the graph's input
+    dev_in = [graphed.input_buffer(images.shape, images.dtype, device, slot=1),
+              graphed.input_buffer(images.shape, images.dtype, device, slot=2)]
     copy_stream = torch.cuda.Stream()
     main_stream = torch.cuda.current_stream()
     copied = [torch.cuda.Event(), torch.cuda.Event()]
@@ -399,7 +406,7 @@ def run_ours(args, world, rank, local):
                     dev_in[nxt].copy_(host_images, non_blocking=True)
                     copied[nxt].record(copy_stream)
             main_stream.wait_event(copied[cur])
-            host_logits.copy_(forward(dev_in[cur]), non_blocking=True)
+            host_logits.copy_(forward(dev_in[cur], slot=cur + 1), non_blocking=True)
             consumed[cur].record(main_stream)
 
     e2e_loop(2)
@@ -428,6 +435,8 @@ def run_ours(args, world, rank, local):
                    "kept_tokens_per_image_layer": round(kept_tokens, 2),
                    "l2": "per-step working set ~1.1 GB of activations >> 126 MB L2 (no flush needed)",
                    "weights": "random init seed 0, selector bias calibrated on the GPU path",
+                   "launch": "dyt_b200.GraphedForward: model(images) captured once, replayed as one "
+                             "CUDA graph per step (both timed regions)",
                    "stem_head": "patch embed = own im2col + tcgen05 GEMM + assemble kernels; final LN "
                                 "(cls rows, own row-gather LayerNorm kernel) + 768x100 head (own "
                                 "tcgen05 GEMM, classes zero-padded to 104)"},

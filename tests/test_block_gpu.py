@@ -397,3 +397,25 @@ def test_forward_is_cuda_graph_capturable_and_replay_safe(dev, vitb_sd):
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(static_out, ref)
+
+
+def test_graphed_forward_public_wrapper(dev, vitb_sd):
+    """dyt_b200.GraphedForward: same logits as the eager call for new input contents, per shape and
+    per static-input slot; writing straight into a slot's input buffer + replay works (bench e2e)."""
+    from dyt_b200 import GraphedForward
+    g, sd, img = vitb_sd
+    m = _speed_model(sd, dev)
+    gm = GraphedForward(m)
+    xs = [torch.randn(3, 3, 224, 224, generator=torch.Generator().manual_seed(s)).to(dev) for s in (5, 6)]
+    for x in xs + [xs[0][:2].contiguous()]:
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            ref = m(x)
+        assert torch.equal(gm(x), ref)
+        assert torch.equal(gm(x, slot=1), ref)
+    buf = gm.input_buffer(xs[1].shape, xs[1].dtype, dev, slot=2)
+    buf.copy_(xs[1])
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        ref = m(xs[1])
+    assert torch.equal(gm.replay(xs[1].shape, xs[1].dtype, dev, slot=2), ref)
+    with pytest.raises(Exception):
+        gm(torch.zeros(1, 3, 224, 224))                      # CPU tensor: no fallback
