@@ -40,6 +40,18 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 print(f"finetune step bs{B}: {ms:.2f} ms  {B / ms * 1e3:.1f} img/s  loss {loss.item():.4f} "
       f"arena {arena.nbytes / 1e6:.2f} MB / {len(arena.params)} tensors")
+if os.environ.get("TRAIN_NCU", "0") == "1":
+    # one eager step inside a cudaProfilerStart/Stop window:
+    #   ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    #       --log-file gpurun_out/finetune_launches.csv python scripts/train_probe.py   (TRAIN_NCU=1)
+    eager = FinetuneStep(model, opt, arena)
+    eager(img, tgt)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    eager(img, tgt)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+    sys.exit(0)
 if os.environ.get("TRAIN_PROF", "1") == "1":
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
