@@ -142,3 +142,32 @@ def test_video_model_state_dict_keys_match_reference():
     import pytest, torch
     with pytest.raises(Exception):          # CPU tensors: no fallback
         m.eval()(torch.zeros(1, 3, 2, 32, 32))
+
+
+def test_finetune_loss_matches_reference_golden():
+    """dyt_b200.finetune.finetune_loss (host-side glue: AdaLoss + teacher CE + KL, engine_finetune.py:
+    52-65, models/losses.py:50-82) on the reference's own outputs reproduces the reference's loss."""
+    from dyt_b200.finetune import ada_loss, finetune_loss
+    g = load_golden("finetune_tiny.pt")
+    loss = finetune_loss(g["student_logits"], g["token_select"], g["teacher_logits"], g["targets"])
+    assert abs(loss.item() - g["loss"].item()) <= 1e-5
+    # AdaLoss alone: cross-entropy + 2 * ((mean keep - 0.5)^2 + sum(clamp(0.1 - sel, 0)))
+    sel = g["token_select"]
+    want = torch.nn.functional.cross_entropy(g["student_logits"], g["targets"]) + 2.0 * (
+        (sel.mean() - 0.5) ** 2 + (0.1 - sel.mean(-1)).clamp(min=0).sum())
+    assert abs(ada_loss(g["student_logits"], sel, g["targets"]).item() - want.item()) <= 1e-6
+
+
+def test_graphed_forward_and_accounting_refuse_cpu():
+    from dyt_b200 import DytError, GraphedForward, flops
+    from models.model_speed_test import VisionTransformer
+    tuning, select = _cfgs(16, 128)
+    m = VisionTransformer(img_size=32, patch_size=16, embed_dim=128, depth=1, num_heads=2,
+                          num_classes=10, tuning_config=tuning, select_config=select).eval()
+    with pytest.raises(DytError):
+        GraphedForward(m)(torch.zeros(1, 3, 32, 32))
+    with pytest.raises(DytError):
+        flops.batch_select_flops(1, torch.zeros(198), torch.zeros(1, 12, 196, 1))
+    t = flops.block_flops_table()
+    assert t.shape == (198,) and t[0] == 0 and bool((t[1:].diff() > 0).all())
+    assert abs(12 * t[197].item() + flops.base_flops() - 17.8) < 0.1      # GMACs of dense ViT-B/16 + DyT
