@@ -58,6 +58,7 @@ SIGNATURES = {
                             _f, _vp]),
     "dyt_linear_f16_aux": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "dyt_attn_varlen_fwd": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "dyt_attn_bias_fwd": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "dyt_layernorm_f16": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _f, _vp, _i, _vp]),
     "dyt_dispatch_workspace_bytes": (_sz, [_i]),
     "dyt_dispatch_fwd": (_i, [_vp, _i, _vp, _vp, _i, _f, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _f,

@@ -121,6 +121,26 @@ def attn_varlen(qkv: torch.Tensor, num_heads: int, cu_seqlens: Optional[torch.Te
     return out.reshape(*qkv.shape[:-1], Cdim)
 
 
+def attn_bias(qkv: torch.Tensor, num_heads: int, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Long-sequence attention with an additive per-head bias.  qkv fp16 [B, N, 3*C]; bias fp32
+    [num_heads, N, N] or None.  Returns fp16 [B, N, C]."""
+    _need_cuda(qkv, bias)
+    if qkv.dtype != torch.float16 or qkv.dim() != 3:
+        raise DytError("attn_bias expects fp16 qkv [B, N, 3C]")
+    B, N, C3 = qkv.shape
+    Cdim = C3 // 3
+    q2 = _rows2d(qkv)
+    if bias is not None:
+        bias = bias.to(torch.float32).contiguous()
+        if tuple(bias.shape) != (num_heads, N, N):
+            raise DytError(f"attn_bias: bias must be [heads, N, N] = [{num_heads}, {N}, {N}]")
+    out = torch.empty((B * N, Cdim), dtype=torch.float16, device=qkv.device)
+    check(_lib.lib().dyt_attn_bias_fwd(q2.data_ptr(), q2.stride(0), _ptr(bias), B, N, num_heads,
+                                       Cdim // num_heads, out.data_ptr(), Cdim, _stream()),
+          "dyt_attn_bias_fwd")
+    return out.reshape(B, N, Cdim)
+
+
 def layernorm_f16(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6,
                   row_idx: Optional[torch.Tensor] = None,
                   n_rows_dev: Optional[torch.Tensor] = None) -> torch.Tensor:

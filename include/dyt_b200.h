@@ -74,6 +74,17 @@ int dyt_attn_varlen_fwd(const void* qkv, int ld_qkv, const int* cu_seqlens, int 
                         int uniform_len, int max_seqlen, int total_tokens, int num_heads,
                         int head_dim, void* out, int ldo, void* stream);
 
+/* Attention over sequences of any length with an additive per-head bias:
+ *   out = softmax(f16(q * head_dim^-0.5) k^T + bias[h]) v.
+ * Replaces the eager attention path of the segmentation backbone with its relative-position bias
+ * (reference dense_tasks/Segmentation/backbone/segmentation_vision_transformer_IN21K.py:181-203;
+ * 1025 tokens at 512 x 512).  qkv fp16 [num_seqs * seq_len, 3, num_heads, 64] (row stride ld_qkv),
+ * uniform sequences; bias fp32 [num_heads, seq_len, seq_len] contiguous or NULL; out fp16
+ * [num_seqs * seq_len, num_heads * 64].  Rounding points of that path under fp16 autocast: q * scale
+ * and q k^T fp16, bias add and softmax fp32, probabilities fp16 for the PV product. */
+int dyt_attn_bias_fwd(const void* qkv, int ld_qkv, const float* bias, int num_seqs, int seq_len,
+                      int num_heads, int head_dim, void* out, int ldo, void* stream);
+
 /* LayerNorm(eps) over the last dim of fp32 rows, result rounded once to fp16 (the rounding the
  * consumer Linear applies under autocast).  Output row r reads input row row_idx[r] (or r when
  * row_idx is NULL); n_rows_dev optionally bounds the row count from device memory.

@@ -177,6 +177,40 @@ def attention_core(qkv: Tensor, num_heads: int, policy: str = "fp32") -> Tensor:
     return o.transpose(1, 2).reshape(bsz, n, c)
 
 
+def relative_position_bias(table: Tensor, index: Tensor) -> Tensor:
+    """[num_heads, N, N] bias of the segmentation backbone's attention (reference dense_tasks/
+    Segmentation/backbone/segmentation_vision_transformer_IN21K.py:192-197): table
+    [num_relative_distance, heads] gathered by relative_position_index [N, N]."""
+    n = index.shape[0]
+    return table[index.reshape(-1)].reshape(n, n, -1).permute(2, 0, 1).contiguous()
+
+
+def attention_bias_core(qkv: Tensor, num_heads: int, bias: Optional[Tensor] = None,
+                        policy: str = "fp32") -> Tensor:
+    """Eager attention with an additive bias (same file, :181-203): q * scale, q k^T, + bias,
+    softmax, @ v.  amp16: q * scale and the scores are fp16 tensors, the bias add and the softmax
+    run in fp32, the probabilities are cast to fp16 for the PV product (fp32 accumulate)."""
+    bsz, n, c3 = qkv.shape
+    c = c3 // 3
+    d = c // num_heads
+    qkv = qkv.reshape(bsz, n, 3, num_heads, d).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv.unbind(0)
+    q = q * d ** -0.5                                                   # :189
+    if policy == "amp16":
+        q = _r16(q)
+    s = q @ k.transpose(-2, -1)                                         # :190
+    if policy == "amp16":
+        s = _r16(s)
+    if bias is not None:
+        s = s + bias.unsqueeze(0)                                       # :197
+    pr = s.softmax(dim=-1)                                              # :199
+    if policy == "amp16":
+        o = _r16(_r16(pr) @ v)
+    else:
+        o = pr @ v                                                      # :202
+    return o.transpose(1, 2).reshape(bsz, n, c)
+
+
 def attention(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int,
               policy: str = "fp32") -> Tensor:
     qkv = linear(x, p[prefix + "qkv.weight"], p[prefix + "qkv.bias"], policy)

@@ -18,6 +18,8 @@ itself are the pins of the oracle (oracle/dyt_oracle.py):
                     parameter's gradient
   flops_accounting.pt  per-image GFLOPs of block_flops_dict.batch_select_flops and per-layer keep rates
                     for random masks / a random table
+  seg_attention.pt  the segmentation backbone's Attention module (relative-position bias, eager path):
+                    inputs, qkv, outputs, bias table / index for two window sizes
   vitb_b2.pt        ViT-B/16, synthetic seed-0 weights (regenerated from the seed, not stored),
                     calibrated selector biases, B=2: logits / masks / token logits of the speed model
                     and the train model (eval, complete_model on/off), config-1 imposed-mask logits
@@ -291,6 +293,62 @@ def flops_accounting():
     return out
 
 
+def seg_attention():
+    """Attention module of the segmentation backbone (reference dense_tasks/Segmentation/backbone/
+    segmentation_vision_transformer_IN21K.py:120-203) with its relative-position bias: eager path
+    (TIMM_FUSED_ATTN does not apply: the module always takes the bias branch).  The file imports
+    mmcv_custom / mmseg at the top (checkpoint loading, registry): stubbed, unused by Attention."""
+    import importlib.util
+    import types
+    ref_shim.install()
+
+    class _Reg:
+        def register_module(self, *a, **k):
+            return lambda cls: cls
+
+    for name, attrs in (("mmcv_custom", {"load_checkpoint": None}), ("mmseg", {}),
+                        ("mmseg.utils", {"get_root_logger": None}), ("mmseg.models", {}),
+                        ("mmseg.models.builder", {"BACKBONES": _Reg()})):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+    ref_shim.import_reference("models.dynamic_adapter")   # warms the shim; the backbone imports it
+    path = os.path.join(ref_shim.REFERENCE_ROOT, "dense_tasks", "Segmentation", "backbone",
+                        "segmentation_vision_transformer_IN21K.py")
+    sys.path.insert(0, ref_shim.REFERENCE_ROOT)
+    saved = {k: v for k, v in sys.modules.items() if k == "models" or k.startswith("models.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        spec = importlib.util.spec_from_file_location("_ref_seg_backbone", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove(ref_shim.REFERENCE_ROOT)
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+        for name in ("mmcv_custom", "mmseg", "mmseg.utils", "mmseg.models", "mmseg.models.builder"):
+            sys.modules.pop(name, None)
+    out = {}
+    for tag, (win, bsz) in (("w4", ((4, 4), 3)), ("w9x7", ((9, 7), 2))):
+        torch.manual_seed(17)
+        attn = mod.Attention(128, num_heads=2, qkv_bias=True, window_size=win).eval()
+        g = torch.Generator().manual_seed(23)
+        with torch.no_grad():
+            attn.relative_position_bias_table.copy_(
+                torch.randn(attn.relative_position_bias_table.shape, generator=g) * 0.5)
+            n = win[0] * win[1] + 1
+            x = torch.randn(bsz, n, 128, generator=g)
+            y = attn(x)
+            qkv = attn.qkv(x)
+        out[tag] = dict(x=x, y=y, qkv=qkv, table=attn.relative_position_bias_table.detach().clone(),
+                        index=attn.relative_position_index.clone(), window=win,
+                        qkv_w=attn.qkv.weight.detach().clone(), qkv_b=attn.qkv.bias.detach().clone(),
+                        proj_w=attn.proj.weight.detach().clone(), proj_b=attn.proj.bias.detach().clone())
+    return out
+
+
 def main():
     assert ref_shim.reference_available(), "needs the reference checkout at " + ref_shim.REFERENCE_ROOT
     torch.set_num_threads(os.cpu_count())
@@ -305,6 +363,7 @@ def main():
     ref_video = ref_shim.import_reference("video_models.video_vision_transformer_IN21K")
     torch.save(tiny_video(ref_video), os.path.join(OUT, "video_tiny.pt"))
     torch.save(flops_accounting(), os.path.join(OUT, "flops_accounting.pt"))
+    torch.save(seg_attention(), os.path.join(OUT, "seg_attention.pt"))
     ref_losses = ref_shim.import_reference("models.losses")
     torch.save(tiny_finetune(ref_train, ref_losses), os.path.join(OUT, "finetune_tiny.pt"))
     for f in sorted(os.listdir(OUT)):

@@ -380,3 +380,36 @@ def test_keep_stats_kernel_matches_reference_accounting():
     assert drop_in.get_block_flops().shape == (198,) and abs(drop_in.get_base_flops() - 0.1157) < 2e-3
     with pytest.raises(Exception):
         flops.batch_select_flops(1, g["table"], g["token_select"].float())      # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("B,N,H,with_bias", [(2, 1025, 12, True), (3, 197, 2, False), (1, 64, 1, True),
+                                              (2, 65, 3, True), (4, 5, 2, True)])
+def test_attention_with_bias_long_sequences(dev, B, N, H, with_bias):
+    """dyt_attn_bias_fwd (any sequence length, additive per-head bias) against the oracle's amp16
+    restatement of the segmentation backbone's eager attention; 1025 tokens = 512 x 512 images."""
+    from dyt_b200 import ops
+    g = _gen(B * N + H)
+    C = 64 * H
+    qkv = (torch.randn(B, N, 3 * C, generator=g) * 1.2).half()
+    bias = (torch.randn(H, N, N, generator=g) * 1.5) if with_bias else None
+    ref = O.attention_bias_core(qkv.float(), H, bias, "amp16")
+    got = ops.attn_bias(qkv.to(dev), H, None if bias is None else bias.to(dev))
+    assert got.shape == (B, N, C) and got.dtype == torch.float16
+    _close(got, ref, atol=2e-3, rtol=4e-3)
+    if not with_bias and N <= 256:      # same answer as the tcgen05 kernel on its own domain
+        _close(got, ops.attn_varlen(qkv.to(dev), H), atol=2e-3, rtol=4e-3)
+
+
+def test_segmentation_attention_module_golden(dev):
+    """The reference's segmentation Attention module (golden, fp32): qkv Linear -> attention with the
+    gathered relative-position bias -> proj, on the kernels."""
+    from conftest import load_golden
+    from dyt_b200 import ops
+    g = load_golden("seg_attention.pt")
+    for tag, d in g.items():
+        bias = O.relative_position_bias(d["table"], d["index"])
+        qkv, _ = ops.linear_f16(d["x"].half().to(dev), d["qkv_w"].half().to(dev), d["qkv_b"].half().to(dev))
+        o = ops.attn_bias(qkv, 2, bias.to(dev))
+        y, _ = ops.linear_f16(o, d["proj_w"].half().to(dev), d["proj_b"].half().to(dev))
+        ref = d["y"]
+        assert ((y.float().cpu() - ref).abs().max() / ref.abs().max()).item() <= 1e-2, tag
