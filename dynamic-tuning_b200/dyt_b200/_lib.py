@@ -39,7 +39,7 @@ class BlockOpts(C.Structure):
     _fields_ = [("eps", C.c_float), ("logit_fp16", C.c_int), ("min_kept", C.c_float),
                 ("noise1", C.c_void_p), ("noise2", C.c_void_p), ("tau", C.c_float),
                 ("forced_mask", C.c_void_p), ("gate_out", C.c_void_p), ("xn_ready", C.c_int),
-                ("next_ln_w", C.c_void_p), ("next_ln_b", C.c_void_p)]
+                ("next_ln_w", C.c_void_p), ("next_ln_b", C.c_void_p), ("attn_bias", C.c_void_p)]
 
 
 class BlockBuffers(C.Structure):

@@ -119,11 +119,13 @@ def _prepared(block: torch.nn.Module) -> PreparedBlock:
 def run_blocks(x: torch.Tensor, blocks: Sequence[torch.nn.Module], *, eps: float = 1e-6,
                logit_dtype: torch.dtype = torch.float16, forced_masks=None,
                noises=None, final_ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-               fuse_next_ln: bool = True, report_gate: bool = False):
+               fuse_next_ln: bool = True, report_gate: bool = False, attn_biases=None):
     """x [B, N, C] fp32 CUDA -> (x_out fp32 [B,N,C], masks [L,B,N] f32, logits [L,B,N-1] f32,
     final_ln_out f16 [B,N,C] or None).  report_gate=True returns the selectors' own decisions as
     `masks` even where a mask is forced (teacher pass, complete_model=True).  forced_masks[i] ([B,N] or [B,N,1]) imposes layer i's mask;
-    noises[i] = (g1, g2) switches layer i's gate to the train-mode Gumbel form."""
+    noises[i] = (g1, g2) switches layer i's gate to the train-mode Gumbel form.  attn_biases[i]
+    (fp32 [H, N, N] or None) adds a per-head bias to layer i's attention scores (segmentation
+    backbone); sequences longer than 256 tokens or a bias run the flash-style attention kernel."""
     if not x.is_cuda:
         raise DytError("dyt_b200.run_blocks needs a CUDA tensor: the sm_100a kernels are the only "
                        "implementation (no CPU fallback)")
@@ -162,6 +164,12 @@ def run_blocks(x: torch.Tensor, blocks: Sequence[torch.nn.Module], *, eps: float
             opts.forced_mask = fm.data_ptr()
         if gates is not None:
             opts.gate_out = gates[i].data_ptr()
+        if attn_biases is not None and attn_biases[i] is not None:
+            ab = attn_biases[i].to(device=dev, dtype=torch.float32).contiguous()
+            if tuple(ab.shape) != (shape.H, N, N):
+                raise DytError(f"attention bias must be [{shape.H}, {N}, {N}], got {tuple(ab.shape)}")
+            keep_alive.append(ab)
+            opts.attn_bias = ab.data_ptr()
         opts.xn_ready = xn_ready
         nxt = None
         if fuse_next_ln:

@@ -283,6 +283,9 @@ typedef struct dyt_block_opts {
   int xn_ready;            /* 1: workspace already holds LN1(x) (written by the previous call) */
   const float* next_ln_w;  /* optional: also emit LayerNorm(out) for the next block / final norm */
   const float* next_ln_b;
+  const float* attn_bias;  /* optional [H, N, N] additive attention bias (relative position bias of
+                              the segmentation backbone); sequences > 256 tokens or a bias use
+                              dyt_attn_bias_fwd instead of dyt_attn_varlen_fwd */
 } dyt_block_opts;
 
 typedef struct dyt_block_buffers { /* where dyt_block_fwd keeps its intermediates (for tests) */

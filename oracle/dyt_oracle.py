@@ -409,6 +409,66 @@ def vit_forward(img: Tensor, p: Dict[str, Tensor], depth: int, num_heads: int, s
 
 
 # ----------------------------------------------------------------------------------------------
+# segmentation backbone, eval mode (reference dense_tasks/Segmentation/backbone/
+# segmentation_vision_transformer_IN21K.py: Block.forward :275-298, forward_features :526-560)
+# ----------------------------------------------------------------------------------------------
+def block_seg(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int, scale: float,
+              policy: str = "fp32") -> Dict[str, Tensor]:
+    """Dense masked block whose attention is the eager path with an optional relative-position bias."""
+    bias = None
+    if prefix + "attn.relative_position_bias_table" in p:
+        bias = relative_position_bias(p[prefix + "attn.relative_position_bias_table"],
+                                      p[prefix + "attn.relative_position_index"])
+    xn = layer_norm(x, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"])
+    qkv = linear(xn, p[prefix + "attn.qkv.weight"], p[prefix + "attn.qkv.bias"], policy)
+    o = attention_bias_core(qkv, num_heads, bias, policy)
+    x1 = x + linear(o, p[prefix + "attn.proj.weight"], p[prefix + "attn.proj.bias"], policy)   # :276
+    mask, logits = token_select(x1, p[prefix + "mlp_token_select.mlp_head.weight"],
+                                p[prefix + "mlp_token_select.mlp_head.bias"], policy)          # :280-282
+    adapt_x = adapter(x1, p, prefix + "adaptmlp.", scale, policy)                              # :287
+    mlp_x = mlp(layer_norm(x1, p[prefix + "norm2.weight"], p[prefix + "norm2.bias"]), p,
+                prefix + "mlp.", policy)                                                       # :289
+    out = x1 + mask * mlp_x + adapt_x                                                          # :291-293
+    return dict(out=out, mask=mask, logits=logits)
+
+
+def seg_forward(img: Tensor, p: Dict[str, Tensor], depth: int, num_heads: int, scale: float,
+                out_indices, patch: int = 16, policy: str = "fp32", token_target_ratio: float = 0.5,
+                token_ratio: float = 2.0, token_minimal: float = 0.1,
+                token_minimal_weight: float = 1.0) -> Dict[str, Tensor]:
+    """forward_features of the segmentation backbone: tokens -> blocks -> maps after `out_indices`
+    -> FPN heads (fpn1: deconv-GELU-deconv, fpn2: deconv, fpn3: identity, fpn4: max-pool) + the
+    token-rate loss."""
+    bsz, _, h, w = img.shape
+    hp, wp = h // patch, w // patch
+    x = patch_embed(img, p, patch, policy)
+    x = torch.cat((p["cls_token"].expand(bsz, -1, -1), x), dim=1) + p["pos_embed"]
+    feats, sels, logs = [], [], []
+    for i in range(depth):
+        r = block_seg(x, p, f"blocks.{i}.", num_heads, scale, policy)
+        x = r["out"]
+        sels.append(r["mask"])
+        logs.append(r["logits"])
+        if i in out_indices:
+            feats.append(x[:, 1:, :].permute(0, 2, 1).reshape(bsz, -1, hp, wp).contiguous())   # :549-551
+    token_sel = torch.stack(sels, dim=1)[:, :, 1:, :]
+    heads = [
+        lambda f: F.conv_transpose2d(F.gelu(F.conv_transpose2d(f, p["fpn1.0.weight"], p["fpn1.0.bias"],
+                                                             stride=2)),
+                                     p["fpn1.2.weight"], p["fpn1.2.bias"], stride=2),
+        lambda f: F.conv_transpose2d(f, p["fpn2.0.weight"], p["fpn2.0.bias"], stride=2),
+        lambda f: f,
+        lambda f: F.max_pool2d(f, kernel_size=2, stride=2),
+    ]
+    feats = [heads[i](f) for i, f in enumerate(feats)]
+    loss = ((token_sel.mean() - token_target_ratio) ** 2).mean()
+    if token_minimal_weight > 0:
+        loss = loss + token_minimal_weight * (token_minimal - token_sel.mean(-1)).clamp(min=0.0).sum()
+    return dict(features=feats, token_select=token_sel, token_logits=torch.stack(logs, dim=1),
+                loss=token_ratio * loss)
+
+
+# ----------------------------------------------------------------------------------------------
 # evaluation analytics (reference block_flops_dict.py:57-83, engine_finetune.py:341-352)
 # ----------------------------------------------------------------------------------------------
 def batch_select_flops(flops_dict: Tensor, token_select: Tensor, block_num: int = 12,

@@ -20,6 +20,8 @@ itself are the pins of the oracle (oracle/dyt_oracle.py):
                     for random masks / a random table
   seg_attention.pt  the segmentation backbone's Attention module (relative-position bias, eager path):
                     inputs, qkv, outputs, bias table / index for two window sizes
+  seg_tiny.pt       a 4-layer dim-128 segmentation backbone with relative-position bias: state_dict,
+                    image, FPN feature maps, masks, logits, token loss
   vitb_b2.pt        ViT-B/16, synthetic seed-0 weights (regenerated from the seed, not stored),
                     calibrated selector biases, B=2: logits / masks / token logits of the speed model
                     and the train model (eval, complete_model on/off), config-1 imposed-mask logits
@@ -293,11 +295,9 @@ def flops_accounting():
     return out
 
 
-def seg_attention():
-    """Attention module of the segmentation backbone (reference dense_tasks/Segmentation/backbone/
-    segmentation_vision_transformer_IN21K.py:120-203) with its relative-position bias: eager path
-    (TIMM_FUSED_ATTN does not apply: the module always takes the bias branch).  The file imports
-    mmcv_custom / mmseg at the top (checkpoint loading, registry): stubbed, unused by Attention."""
+def _load_seg_module():
+    """Import the reference segmentation backbone file.  It imports mmcv_custom / mmseg at the top
+    (checkpoint loading, registry): stubbed, unused by the modules exercised here."""
     import importlib.util
     import types
     ref_shim.install()
@@ -330,6 +330,14 @@ def seg_attention():
         sys.modules.update(saved)
         for name in ("mmcv_custom", "mmseg", "mmseg.utils", "mmseg.models", "mmseg.models.builder"):
             sys.modules.pop(name, None)
+    return mod
+
+
+def seg_attention():
+    """Attention module of the segmentation backbone (reference dense_tasks/Segmentation/backbone/
+    segmentation_vision_transformer_IN21K.py:120-203) with its relative-position bias: eager path
+    (the module always takes the bias branch)."""
+    mod = _load_seg_module()
     out = {}
     for tag, (win, bsz) in (("w4", ((4, 4), 3)), ("w9x7", ((9, 7), 2))):
         torch.manual_seed(17)
@@ -349,6 +357,38 @@ def seg_attention():
     return out
 
 
+def seg_tiny():
+    """A 4-layer dim-128 segmentation backbone (reference VisionTransformer21K, use_rel_pos_bias=True,
+    64 x 64 input = 17 tokens, a feature map after every block): state_dict, image, the four FPN
+    feature maps, masks, logits and the token loss, eval mode, fp32."""
+    mod = _load_seg_module()
+    tuning, select = ref_shim.reference_configs(ffn_num=16, scalar="0.1", d_model=128)
+    select.update(layer_target_ratio=0.5, layer_loss_ratio=2.0, layer_diverse_ratio=0.0,
+                  layer_entropy_weight=0.0, layer_minimal_weight=0.0, layer_minimal=0.0,
+                  token_ratio=2.0, token_minimal=0.1, token_minimal_weight=1.0)
+    torch.manual_seed(29)
+    m = mod.VisionTransformer21K(img_size=64, patch_size=16, embed_dim=128, depth=4, num_heads=2,
+                                 num_classes=0, tuning_config=tuning, select_config=select,
+                                 out_indices=[0, 1, 2, 3], use_rel_pos_bias=True).eval()
+    g = torch.Generator().manual_seed(37)
+    with torch.no_grad():
+        for name, prm in m.named_parameters():      # non-degenerate adapters / selectors / bias tables
+            if name.endswith("up_proj.weight"):
+                prm.copy_(torch.randn(prm.shape, generator=g) * 0.02)
+            elif "mlp_token_select" in name and name.endswith("weight"):
+                prm.copy_(torch.randn(prm.shape, generator=g) * 0.5)
+            elif name.endswith("relative_position_bias_table"):
+                prm.copy_(torch.randn(prm.shape, generator=g) * 0.5)
+            elif name in ("cls_token",):
+                prm.copy_(torch.randn(prm.shape, generator=g) * 0.02)
+        img = torch.randn(3, 3, 64, 64, generator=g)
+        feats, d = m(img)
+    return dict(state_dict={k: v.clone() for k, v in m.state_dict().items()}, img=img,
+                features=[f.clone() for f in feats], token_select=d["token_select"].clone(),
+                token_logits=d["token_logits"].clone(), loss=d["loss"].clone(),
+                keys=sorted(m.state_dict().keys()))
+
+
 def main():
     assert ref_shim.reference_available(), "needs the reference checkout at " + ref_shim.REFERENCE_ROOT
     torch.set_num_threads(os.cpu_count())
@@ -364,6 +404,7 @@ def main():
     torch.save(tiny_video(ref_video), os.path.join(OUT, "video_tiny.pt"))
     torch.save(flops_accounting(), os.path.join(OUT, "flops_accounting.pt"))
     torch.save(seg_attention(), os.path.join(OUT, "seg_attention.pt"))
+    torch.save(seg_tiny(), os.path.join(OUT, "seg_tiny.pt"))
     ref_losses = ref_shim.import_reference("models.losses")
     torch.save(tiny_finetune(ref_train, ref_losses), os.path.join(OUT, "finetune_tiny.pt"))
     for f in sorted(os.listdir(OUT)):

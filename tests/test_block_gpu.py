@@ -419,3 +419,64 @@ def test_graphed_forward_public_wrapper(dev, vitb_sd):
     assert torch.equal(gm.replay(xs[1].shape, xs[1].dtype, dev, slot=2), ref)
     with pytest.raises(Exception):
         gm(torch.zeros(1, 3, 224, 224))                      # CPU tensor: no fallback
+
+
+def _seg_cfg(ffn_num=16, d_model=128):
+    tuning, select = configs(ffn_num=ffn_num, d_model=d_model)
+    select.update(token_ratio=2.0, token_minimal=0.1, token_minimal_weight=1.0)
+    return tuning, select
+
+
+def test_segmentation_backbone_vs_reference_golden(dev):
+    """The drop-in segmentation backbone (relative-position-bias attention through dyt_attn_bias_fwd,
+    DyT blocks, FPN heads) against the unmodified reference (fp32 golden) and the amp16 oracle."""
+    from dense_tasks.Segmentation.backbone.segmentation_vision_transformer_IN21K import VisionTransformer21K
+    g = load_golden("seg_tiny.pt")
+    tuning, select = _seg_cfg()
+    m = VisionTransformer21K(img_size=64, patch_size=16, embed_dim=128, depth=4, num_heads=2,
+                             num_classes=0, tuning_config=tuning, select_config=select,
+                             out_indices=[0, 1, 2, 3], use_rel_pos_bias=True)
+    m.load_state_dict(g["state_dict"], strict=True)
+    m = m.eval().to(dev)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        feats, d = m(g["img"].to(dev))
+    assert len(feats) == 4 and d["token_select"].shape == g["token_select"].shape
+    ref16 = O.seg_forward(g["img"], g["state_dict"], 4, 2, 0.1, [0, 1, 2, 3], policy="amp16")
+    same = (d["token_select"].float().cpu() > 0.5) == (ref16["token_select"] > 0.5)
+    assert same.float().mean() >= 0.98
+    if bool(same.all()):
+        for a, b, c in zip(feats, ref16["features"], g["features"]):
+            assert a.shape == c.shape
+            assert _rel(a, b) <= 1e-2 and _rel(a, c) <= 3e-2
+        assert abs(d["loss"].item() - ref16["loss"].item()) <= 1e-3 * abs(ref16["loss"].item())
+    with pytest.raises(NotImplementedError):
+        m.train()(g["img"].to(dev))
+
+
+def test_segmentation_backbone_512_tokens_1025(dev):
+    """ViT-B width at 512 x 512 (1025 tokens per image, no relative bias = the reference default
+    use_rel_pos_bias=False): two layers against the amp16 oracle."""
+    from dense_tasks.Segmentation.backbone.segmentation_vision_transformer_IN21K import VisionTransformer21K
+    tuning, select = _seg_cfg(ffn_num=64, d_model=768)
+    torch.manual_seed(3)
+    m = VisionTransformer21K(img_size=512, patch_size=16, embed_dim=768, depth=2, num_heads=12,
+                             num_classes=0, tuning_config=tuning, select_config=select,
+                             out_indices=[0, 1], use_rel_pos_bias=False)
+    gen = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith("up_proj.weight"):
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.02)
+            elif "mlp_token_select" in n and n.endswith("weight"):
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.5)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    img = torch.randn(2, 3, 512, 512, generator=gen)
+    m = m.eval().to(dev)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        feats, d = m(img.to(dev))
+    assert d["token_select"].shape == (2, 2, 1024, 1)
+    assert feats[0].shape == (2, 768, 128, 128) and feats[1].shape == (2, 768, 64, 64)
+    ref = O.seg_forward(img, sd, 2, 12, 0.1, [0, 1], policy="amp16")
+    agree = ((d["token_select"].float().cpu() > 0.5) == (ref["token_select"] > 0.5)).float().mean(dim=(0, 2, 3))
+    assert agree[0] >= 0.995 and agree[1] >= 0.98, agree
+    assert _rel(feats[0], ref["features"][0]) <= 2e-2

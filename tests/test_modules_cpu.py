@@ -171,3 +171,26 @@ def test_graphed_forward_and_accounting_refuse_cpu():
     t = flops.block_flops_table()
     assert t.shape == (198,) and t[0] == 0 and bool((t[1:].diff() > 0).all())
     assert abs(12 * t[197].item() + flops.base_flops() - 17.8) < 0.1      # GMACs of dense ViT-B/16 + DyT
+
+
+def test_segmentation_backbone_state_dict_keys_match_reference():
+    """dense_tasks.Segmentation.backbone drop-in: same parameter / buffer names as the reference
+    VisionTransformer21K (golden key list), strict load, relative-position index identical, pos-embed
+    resize hook for 224-pretrained checkpoints; no CPU fallback."""
+    from dense_tasks.Segmentation.backbone.segmentation_vision_transformer_IN21K import VisionTransformer21K
+    g = load_golden("seg_tiny.pt")
+    tuning, select = _cfgs(16, 128)
+    kw = dict(patch_size=16, embed_dim=128, depth=4, num_heads=2, num_classes=0, tuning_config=tuning,
+              select_config=select, out_indices=[0, 1, 2, 3], use_rel_pos_bias=True)
+    m = VisionTransformer21K(img_size=64, **kw)
+    assert sorted(m.state_dict().keys()) == g["keys"]
+    idx_before = m.blocks[0].attn.relative_position_index.clone()
+    res = m.load_state_dict(g["state_dict"], strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(idx_before, g["state_dict"]["blocks.0.attn.relative_position_index"])
+    big = VisionTransformer21K(img_size=96, **{**kw, "use_rel_pos_bias": False})
+    sd = {k: v for k, v in g["state_dict"].items() if "relative_position" not in k}
+    big.load_state_dict(sd, strict=True)          # 4x4 -> 6x6 position embedding, resized by the hook
+    assert big.pos_embed.shape == (1, 37, 128)
+    with pytest.raises(Exception):
+        m.eval()(torch.zeros(1, 3, 64, 64))
