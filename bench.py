@@ -486,6 +486,23 @@ def run_extra(args, world, rank, local):
         images = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(rank)).to(device)
         cal = images[:32]
         per_step = batch
+    elif args.workload == "seg_b16":
+        # segmentation backbone: ViT-B/16 DyT at 512 x 512 = 1025 tokens per
+        # image, reference default use_rel_pos_bias=False, feature maps after blocks 3 / 5 / 7 / 11 + FPN
+        from dense_tasks.Segmentation.backbone.segmentation_vision_transformer_IN21K import VisionTransformer21K
+        tuning, select = synthetic.reference_configs()
+        select.update(token_ratio=2.0, token_minimal=0.1, token_minimal_weight=1.0)
+        torch.manual_seed(0)
+        model = VisionTransformer21K(img_size=512, patch_size=16, embed_dim=768, depth=12, num_heads=12,
+                                     num_classes=0, tuning_config=tuning, select_config=select,
+                                     use_rel_pos_bias=False)
+        synthetic._randomise_dyt_parts(model, 0)
+        model = model.eval().to(device)
+        batch, rate, units = 16, 0.5, "images/s"
+        name = "segmentation backbone ViT-B/16 DyT, 16 images 512x512 (1025 tokens), r~0.5, incl. FPN heads"
+        images = torch.randn(batch, 3, 512, 512, generator=torch.Generator().manual_seed(rank)).to(device)
+        cal = None
+        per_step = batch
     else:
         model = synthetic.build_video_b16(device, seed=0)
         clips = 32 if world == 1 else 8   # BASELINE: 64 clips over 8 GPUs; one GPU alone takes 32
@@ -493,7 +510,23 @@ def run_extra(args, world, rank, local):
         images = torch.randn(clips, 3, 8, 224, 224, generator=torch.Generator().manual_seed(rank)).to(device)
         cal = images[:4].permute(0, 2, 1, 3, 4).reshape(-1, 3, 224, 224)
         per_step = clips
-    keep = synthetic.calibrate_keep_rate(model, cal, rate)
+    if cal is not None:
+        keep = synthetic.calibrate_keep_rate(model, cal, rate)
+    else:   # segmentation: calibrate the selector biases layer by layer on the bench images
+        from dyt_b200 import engine
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            pe = model.patch_embed
+            from dyt_b200 import ops as _ops
+            x = _ops.patch_embed(images[:4], pe.proj.weight, pe.proj.bias, model.cls_token,
+                                 model.pos_embed, pe.patch_size[0])
+            kept = []
+            for blk in model.blocks:
+                blk.mlp_token_select.mlp_head.bias.zero_()
+                _, _, lg, _ = engine.run_blocks(x, [blk], fuse_next_ln=False)
+                blk.mlp_token_select.mlp_head.bias.fill_(-float(torch.quantile(lg.flatten().float(), 1.0 - rate)))
+                x, mk, _, _ = engine.run_blocks(x, [blk], fuse_next_ln=False)
+                kept.append(mk[:, :, 1:].mean().item())
+        keep = sum(kept) / len(kept)
 
     from dyt_b200 import GraphedForward
     graphed = GraphedForward(model)
@@ -585,7 +618,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="vit_b16", choices=["vit_b16", "vit_l16", "video_b16", "finetune_b16"],
+    ap.add_argument("--workload", default="vit_b16", choices=["vit_b16", "vit_l16", "video_b16", "finetune_b16", "seg_b16"],
                     help="vit_b16 = the BASELINE metric (default); the others are extra lines")
     args = ap.parse_args()
     if args.impl == "reference":
