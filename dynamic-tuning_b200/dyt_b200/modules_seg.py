@@ -74,9 +74,16 @@ class SegAttention(nn.Module):
         """[heads, N, N] fp32 (reference :192-197), None without a table."""
         if self.relative_position_bias_table is None:
             return None
-        n = self.relative_position_index.shape[0]
-        t = self.relative_position_bias_table.detach().float()
-        return t[self.relative_position_index.reshape(-1)].reshape(n, n, -1).permute(2, 0, 1).contiguous()
+        tab = self.relative_position_bias_table
+        key = (tab.data_ptr(), tab._version, tab.device)
+        cached = self.__dict__.get("_dyt_bias")
+        if cached is None or cached[0] != key:     # gathered once per table version, not per forward
+            n = self.relative_position_index.shape[0]
+            t = tab.detach().float()
+            b = t[self.relative_position_index.reshape(-1)].reshape(n, n, -1).permute(2, 0, 1).contiguous()
+            cached = (key, b)
+            self.__dict__["_dyt_bias"] = cached
+        return cached[1]
 
     def forward(self, x):
         _no_backward("Attention", x, self.qkv.weight, self.proj.weight)
