@@ -558,6 +558,22 @@ def run_extra(args, world, rank, local):
                           "config": {"workload": name, "keep_rate_calibration": round(keep, 4)}}), flush=True)
 
 
+def finetune_flops_per_image(bottleneck: int = 16) -> float:
+    """Algorithmic FLOPs (2 x MAC) of one fine-tune step per image: two dense forward passes
+    (student, teacher) and their backward through the frozen backbone = data-gradient GEMMs of the
+    same size as the forward ones, attention backward = 5 contractions against the forward's 2,
+    adapter weight gradients; block 0 needs no gradient w.r.t. its input (stem frozen)."""
+    n, c, hid = N_TOK, C_DIM, HIDDEN
+    qkv, proj, mlp = 2.0 * n * c * 3 * c, 2.0 * n * c * c, 4.0 * n * c * hid
+    attn = 4.0 * n * n * c
+    adapter = 4.0 * n * c * bottleneck
+    fwd = qkv + proj + mlp + attn + adapter + 2.0 * (n - 1) * c
+    bwd = qkv + proj + mlp + 2.5 * attn + 2.0 * adapter
+    bwd_first = bwd - (qkv + proj + 2.5 * attn)       # block 0: no input gradient
+    per_pass = DEPTH * fwd + (DEPTH - 1) * bwd + bwd_first + 2.0 * (n - 1) * c * 3 * 256
+    return 2.0 * per_pass
+
+
 def run_finetune(args, world, rank, local):
     """BASELINE configs[2]: ViT-B/16 DyT fine-tune step on synthetic VTAB-shape data, 64 images per
     GPU (512 global at 8), ffn_num 16, adapter scale 1 (train_vtab.sh:8, main_vtab.py:351).  One step
@@ -608,6 +624,8 @@ def run_finetune(args, world, rank, local):
                        "cuda_graph": "forward + backward of the step replayed as one CUDA graph",
                        "allreduce_bytes_per_step": arena.nbytes if world > 1 else 0,
                        "trainable_tensors": len(arena.params)},
+            "model_flops_per_image": finetune_flops_per_image(16),
+            "model_tflops": batch * args.steps / sec * finetune_flops_per_image(16) / 1e12,
             "cpu_baseline": cpu}), flush=True)
 
 
