@@ -108,9 +108,10 @@ def dist_setup(n_gpus: int):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: keep NCCL's version banner off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly one JSON line: NCCL prints its version banner to stdout at the
+        # VERSION and WARN levels, so run those at NONE (INFO / TRACE are left to whoever asked)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG", None)
         if torch.cuda.is_available():
             torch.cuda.set_device(local)
             dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
