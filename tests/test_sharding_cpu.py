@@ -50,6 +50,10 @@ def test_flops_model_matches_survey():
     import bench
     assert bench.flops_per_image(197) / 1e9 == pytest.approx(35.60, abs=0.02)   # dense ViT-B
     assert bench.flops_per_image(99) / 1e9 == pytest.approx(24.50, abs=0.02)    # r = 0.5
+    # fine-tune step: two dense forwards + their backward (data gradients ~ forward GEMMs,
+    # attention backward 2.5x its forward): a little under 4x the dense forward
+    ft = bench.finetune_flops_per_image(16) / 1e9
+    assert 3.9 * 35.6 < ft < 4.1 * 35.6
 
 
 def _arena_worker(rank, world, port, q):
