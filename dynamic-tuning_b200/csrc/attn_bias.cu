@@ -8,7 +8,7 @@
 // for the PV product (fp32 accumulate, fp16 output).
 //
 // Flash-style: one CTA (4 warps) per (image, head, block of 64 queries); keys / values stream
-// through shared memory in blocks of 64; S and PV on HMMA through nvcuda::wmma; the online softmax
+// through two shared-memory buffers in blocks of 64 (cp.async, the next block in flight); S and PV on HMMA through nvcuda::wmma; the online softmax
 // works on the accumulator registers (m16n16k16 fp32 layout, verified at run time like
 // attn_bwd.cu).  The tcgen05 kernel (attn_varlen.cu) holds all keys of a sequence in one TMEM tile
 // and stops at 256 keys; this kernel has no such limit and is the base for SURVEY section 8f rank 5.
@@ -21,6 +21,21 @@
 namespace dyt {
 
 constexpr int FB_Q = 64, FB_K = 64, FB_LD = 72, FB_WARPS = 4;
+constexpr int FB_TILE = FB_K * FB_LD;                       // halves per 64-row tile
+// Q, 2 x K, 2 x V (double-buffered with cp.async), per-warp P tiles, per-warp fp32 staging
+constexpr size_t FB_SMEM = (5 * FB_TILE + FB_WARPS * 16 * FB_LD) * 2 + FB_WARPS * 16 * 20 * 4;
+
+// 16-byte asynchronous global -> shared copy; src_bytes = 0 writes zeros (rows past the sequence)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 using namespace nvcuda;
 typedef wmma::fragment<wmma::accumulator, 16, 16, 16, float> FbC;
@@ -31,11 +46,12 @@ typedef wmma::fragment<wmma::matrix_b, 16, 16, 16, __half, wmma::col_major> FbBt
 __global__ void __launch_bounds__(FB_WARPS * 32)
 attn_bias_fwd_kernel(const __half* __restrict__ qkv, int ld_qkv, const float* __restrict__ bias,
                      int N, int H, int C, float scale, __half* __restrict__ out, int ldo) {
-  __shared__ __align__(32) __half Qs[FB_Q * FB_LD];
-  __shared__ __align__(32) __half Ks[FB_K * FB_LD];
-  __shared__ __align__(32) __half Vs[FB_K * FB_LD];
-  __shared__ __align__(32) __half Ps[FB_WARPS][16 * FB_LD];
-  __shared__ __align__(32) float stg_all[FB_WARPS][16 * 20];
+  extern __shared__ __align__(128) unsigned char fb_smem[];
+  __half* Qs = reinterpret_cast<__half*>(fb_smem);
+  __half* Kbuf = Qs + FB_TILE;              // [2][FB_TILE]
+  __half* Vbuf = Kbuf + 2 * FB_TILE;        // [2][FB_TILE]
+  __half* Pall = Vbuf + 2 * FB_TILE;        // [FB_WARPS][16 * FB_LD]
+  float* stg_base = reinterpret_cast<float*>(Pall + FB_WARPS * 16 * FB_LD);
 
   const int qblocks = (N + FB_Q - 1) / FB_Q;
   const int qb = blockIdx.x % qblocks;
@@ -44,7 +60,8 @@ attn_bias_fwd_kernel(const __half* __restrict__ qkv, int ld_qkv, const float* __
   const int q0 = qb * FB_Q;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  float* stg = stg_all[warp];
+  float* stg = stg_base + warp * 16 * 20;
+  __half* Pw = Pall + warp * 16 * FB_LD;
   const size_t row_base = static_cast<size_t>(b) * N;
 
   // accumulator layout self-check (see attn_bwd.cu)
@@ -90,23 +107,34 @@ attn_bias_fwd_kernel(const __half* __restrict__ qkv, int ld_qkv, const float* __
   FbC acc[4];
 #pragma unroll
   for (int dn = 0; dn < 4; ++dn) wmma::fill_fragment(acc[dn], 0.f);
-  __half* pw0 = Ps[warp] + g * FB_LD + 2 * t4;
+  __half* pw0 = Pw + g * FB_LD + 2 * t4;
   __half* pw1 = pw0 + 8 * FB_LD;
 
-  for (int k0 = 0; k0 < N; k0 += FB_K) {
-    __syncthreads();  // the previous block's K / V are no longer read
+  // K / V blocks stream through two shared-memory buffers: block i+1 is in flight (cp.async) while
+  // block i is multiplied
+  auto load_block = [&](int k0, int buf) {
     for (int e = tid; e < FB_K * 8; e += FB_WARPS * 32) {
       const int r = e >> 3, c = e & 7;
-      uint4 k = make_uint4(0, 0, 0, 0), v = k;
-      if (k0 + r < N) {
-        const __half* row = qkv + (row_base + k0 + r) * ld_qkv + h * 64 + c * 8;
-        k = *reinterpret_cast<const uint4*>(row + C);
-        v = *reinterpret_cast<const uint4*>(row + 2 * C);
-      }
-      *reinterpret_cast<uint4*>(Ks + r * FB_LD + c * 8) = k;
-      *reinterpret_cast<uint4*>(Vs + r * FB_LD + c * 8) = v;
+      const bool ok = k0 + r < N;
+      const __half* row = qkv + (row_base + (ok ? k0 + r : 0)) * ld_qkv + h * 64 + c * 8;
+      cp_async16(Kbuf + buf * FB_TILE + r * FB_LD + c * 8, row + C, ok ? 16 : 0);
+      cp_async16(Vbuf + buf * FB_TILE + r * FB_LD + c * 8, row + 2 * C, ok ? 16 : 0);
     }
-    __syncthreads();
+    cp_async_commit();
+  };
+  load_block(0, 0);
+  int buf = 0;
+  for (int k0 = 0; k0 < N; k0 += FB_K, buf ^= 1) {
+    __syncthreads();  // every warp is done with the block that used the other buffer
+    if (k0 + FB_K < N) {
+      load_block(k0 + FB_K, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();  // this block has landed for every thread
+    const __half* Ks = Kbuf + buf * FB_TILE;
+    const __half* Vs = Vbuf + buf * FB_TILE;
 
     // scores of this warp's 16 rows against the 64 keys: fp16-rounded q k^T, then + bias in fp32
     float sv[4][8];
@@ -165,7 +193,7 @@ attn_bias_fwd_kernel(const __half* __restrict__ qkv, int ld_qkv, const float* __
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       FbA ap;
-      wmma::load_matrix_sync(ap, Ps[warp] + kk * 16, FB_LD);
+      wmma::load_matrix_sync(ap, Pw + kk * 16, FB_LD);
 #pragma unroll
       for (int dn = 0; dn < 4; ++dn) {
         FbB bv;
@@ -219,7 +247,13 @@ extern "C" int dyt_attn_bias_fwd(const void* qkv, int ld_qkv, const float* bias,
   if (num_seqs == 0) return DYT_OK;
   const long blocks = static_cast<long>(num_seqs) * num_heads * ((seq_len + FB_Q - 1) / FB_Q);
   DYT_CHECK_ARG(blocks < (1l << 31), "attn_bias: grid too large");
-  attn_bias_fwd_kernel<<<static_cast<unsigned>(blocks), FB_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  static bool configured = false;
+  if (!configured) {
+    DYT_CUDA(cudaFuncSetAttribute(attn_bias_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(FB_SMEM)));
+    configured = true;
+  }
+  attn_bias_fwd_kernel<<<static_cast<unsigned>(blocks), FB_WARPS * 32, FB_SMEM, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(qkv), ld_qkv, bias, seq_len, num_heads, C, 1.0f / 8.0f,
       static_cast<__half*>(out), ldo);
   return cuda_status(cudaGetLastError(), "attn_bias_fwd_kernel launch");
