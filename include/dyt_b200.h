@@ -1,4 +1,7 @@
-/* dyt_b200 — C ABI of the B200-native token-dispatched ViT block forward (Dynamic-Tuning / DyT).
+/* dyt_b200 — C ABI of the B200-native token-dispatched ViT block (Dynamic-Tuning / DyT): the
+ * inference forward (dyt_block_fwd and its parts), the backward of the block for parameter-efficient
+ * fine-tuning, and the kernels of the rows either side of it (stem, heads, video pooling head,
+ * long-sequence attention of the segmentation backbone, keep-rate / FLOPs accounting).
  *
  * The reference (NUS-HPC-AI-Lab/Dynamic-Tuning) has no FFI layer: its hot path is the timm-style
  * nn.Module surface of models/model_speed_test.py and models/vision_transformer_IN21K.py, which
