@@ -293,7 +293,8 @@ __global__ void __launch_bounds__(256)
 token_select_kernel(const float* __restrict__ x1, int ldx, const float* __restrict__ sel_w,
                     const float* __restrict__ sel_b, int logit_fp16, float min_kept,
                     const float* __restrict__ noise1, const float* __restrict__ noise2, float tau,
-                    int T, int N, float* __restrict__ mask, float* __restrict__ logits) {
+                    int T, int N, float* __restrict__ mask, float* __restrict__ logits,
+                    int* __restrict__ row_of) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   float bias = sel_b[0];
@@ -310,7 +311,10 @@ token_select_kernel(const float* __restrict__ x1, int ldx, const float* __restri
        t += gridDim.x * warps_per_block) {
     const int n = t % N;
     if (n == 0) {  // cls: always kept, no logit
-      if (lane == 0) mask[t] = 1.0f;
+      if (lane == 0) {
+        mask[t] = 1.0f;
+        if (row_of != nullptr) row_of[t] = t;
+      }
       continue;
     }
     float4 v[NV];
@@ -349,7 +353,9 @@ token_select_kernel(const float* __restrict__ x1, int ldx, const float* __restri
         }
       }
       logits[li] = logit;
-      mask[t] = g >= min_kept ? 1.0f : 0.0f;
+      const bool keep = g >= min_kept;
+      mask[t] = keep ? 1.0f : 0.0f;
+      if (row_of != nullptr) row_of[t] = keep ? t : -1;  // dense "token_pos" for dyt_scatter_merge_fwd
     }
   }
 }
@@ -359,7 +365,7 @@ token_select_kernel(const float* __restrict__ x1, int ldx, const float* __restri
 extern "C" int dyt_token_select_fwd(const float* x1, int ldx, const float* sel_w, const float* sel_b,
                                     int logit_fp16, float min_kept, const float* noise1,
                                     const float* noise2, float tau, int B, int N, int C, float* mask,
-                                    float* logits, void* stream) {
+                                    float* logits, int* row_of, void* stream) {
   using namespace dyt;
   DYT_CHECK_ARG(x1 && sel_w && sel_b && mask && logits, "token_select: null buffer");
   DYT_CHECK_ARG(B >= 0 && N >= 2 && ldx >= C && ldx % 4 == 0, "token_select: bad sizes");
@@ -373,7 +379,7 @@ extern "C" int dyt_token_select_fwd(const float* x1, int ldx, const float* sel_w
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define DYT_TS(NV)                                                                                 \
   token_select_kernel<NV><<<grid, 256, 0, st>>>(x1, ldx, sel_w, sel_b, logit_fp16, min_kept, noise1, \
-                                                noise2, tau, T, N, mask, logits)
+                                                noise2, tau, T, N, mask, logits, row_of)
   switch (C) {
     case 768: DYT_TS(6); break;
     case 1024: DYT_TS(8); break;

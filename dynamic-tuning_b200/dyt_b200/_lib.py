@@ -63,7 +63,8 @@ SIGNATURES = {
     "dyt_dispatch_workspace_bytes": (_sz, [_i]),
     "dyt_dispatch_fwd": (_i, [_vp, _i, _vp, _vp, _i, _f, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _f,
                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
-    "dyt_token_select_fwd": (_i, [_vp, _i, _vp, _vp, _i, _f, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp]),
+    "dyt_token_select_fwd": (_i, [_vp, _i, _vp, _vp, _i, _f, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp,
+                                  _vp]),
     "dyt_scatter_merge_fwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _f,
                                    _vp, _i, _vp]),
     "dyt_patch_embed_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),

@@ -220,8 +220,10 @@ def dispatch(x1: torch.Tensor, sel_w: torch.Tensor, sel_b: torch.Tensor, *,
 
 def token_select(x1: torch.Tensor, sel_w: torch.Tensor, sel_b: torch.Tensor, *,
                  logit_dtype: torch.dtype = torch.float16, threshold: float = 0.5,
-                 noise: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, tau: float = 5.0):
-    """Score + gate without compaction: (mask [B, N, 1] f32, logits [B, N-1, 1] f32)."""
+                 noise: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, tau: float = 5.0,
+                 want_row_of: bool = False):
+    """Score + gate without compaction: (mask [B, N, 1] f32, logits [B, N-1, 1] f32[, row_of i32
+    [B*N]: t for kept tokens, -1 for dropped ones])."""
     _need_cuda(x1, sel_w, sel_b)
     if x1.dtype != torch.float32 or x1.dim() != 3:
         raise DytError("token_select expects x1 [B, N, C] fp32")
@@ -235,11 +237,14 @@ def token_select(x1: torch.Tensor, sel_w: torch.Tensor, sel_b: torch.Tensor, *,
         n2 = noise[1].to(torch.float32).contiguous()
     sw = sel_w.reshape(-1).to(torch.float32).contiguous()
     sb = sel_b.reshape(-1).to(torch.float32).contiguous()
+    row_of = torch.empty(B * N, dtype=torch.int32, device=x1.device) if want_row_of else None
     check(_lib.lib().dyt_token_select_fwd(
         x1.data_ptr(), Cdim, sw.data_ptr(), sb.data_ptr(),
         1 if logit_dtype == torch.float16 else 0, float(min_kept_logit(logit_dtype, threshold)),
-        _ptr(n1), _ptr(n2), float(tau), B, N, Cdim, mask.data_ptr(), logits.data_ptr(), _stream()),
-        "dyt_token_select_fwd")
+        _ptr(n1), _ptr(n2), float(tau), B, N, Cdim, mask.data_ptr(), logits.data_ptr(),
+        _ptr(row_of), _stream()), "dyt_token_select_fwd")
+    if want_row_of:
+        return mask, logits, row_of
     return mask, logits
 
 

@@ -97,6 +97,18 @@ def _adapter_f16(block, down_w, down_b, up_w, up_b):
     return c[1]
 
 
+_arange_cache: Dict[Tuple, torch.Tensor] = {}
+
+
+def _arange_i32(n: int, device) -> torch.Tensor:
+    key = (n, device)
+    t = _arange_cache.get(key)
+    if t is None:
+        t = torch.arange(n, device=device, dtype=torch.int32)
+        _arange_cache[key] = t
+    return t
+
+
 def _scale_of(block) -> float:
     s = block.adaptmlp.scale
     if torch.is_tensor(s):
@@ -142,9 +154,9 @@ class DytBlockFn(torch.autograd.Function):
             mask, logits = d["mask"], d["logits"]
             compaction = (d["token_pos"], d["packed_idx"], d["n_kept"])
         else:
-            mask, logits = ops.token_select(x1.reshape(B, N, Cd), sel_w.detach(), sel_b.detach(),
-                                            logit_dtype=torch.float16, threshold=thr,
-                                            noise=noise if training_gate else None, tau=tau)
+            mask, logits, row_of = ops.token_select(
+                x1.reshape(B, N, Cd), sel_w.detach(), sel_b.detach(), logit_dtype=torch.float16,
+                threshold=thr, noise=noise if training_gate else None, tau=tau, want_row_of=True)
             empty = torch.empty(0, dtype=torch.int32, device=x.device)
             compaction = (empty, empty, empty)
         ln2 = ops.layernorm_f16(x1, fz["ln2_w"], fz["ln2_b"], eps)
@@ -158,11 +170,13 @@ class DytBlockFn(torch.autograd.Function):
         if drop_mult is not None:
             hd = ops.eltwise_f16(_lib.EW_MUL, hd, drop_mult.reshape(hd.shape))
         up, _ = ops.linear_f16(hd, uw16, ub16, epilogue=_lib.EPI_BIAS, scale=scale)
-        ar = torch.arange(T, device=x.device, dtype=torch.int32)
         if complete_model:
-            token_pos = ar
-        else:
+            token_pos = _arange_i32(T, x.device)
+        elif sparse_bwd:
+            ar = _arange_i32(T, x.device)
             token_pos = torch.where(mask.reshape(-1) > 0, ar, torch.full_like(ar, -1))
+        else:
+            token_pos = row_of          # written by the selector kernel: t if kept else -1
         out, _ = ops.scatter_merge(x1.reshape(B, N, Cd), up.reshape(B, N, Cd), mlp_x.reshape(T, Cd),
                                    token_pos)
         ctx.block = block

@@ -126,10 +126,13 @@ int dyt_dispatch_fwd(const float* x1, int ldx, const float* sel_w, const float* 
 /* TokenSelect.forward alone: score Linear(C -> 1) + gate, no compaction (reference
  * models/dynamic_adapter.py:70-77 / :25-54 forward value).  Same arithmetic, arguments and outputs
  * (mask [B, N] with cls = 1, logits [B, N-1]) as dyt_dispatch_fwd; one warp per token, so small
- * batches still fill the GPU.  Used by the train-mode forward, which needs no packed buffer. */
+ * batches still fill the GPU.  Used by the train-mode forward, which needs no packed buffer.
+ * row_of (optional, [B*N]): row_of[t] = t for kept tokens, -1 for dropped ones, i.e. the token_pos
+ * argument of dyt_scatter_merge_fwd for a DENSE (unpacked) MLP output. */
 int dyt_token_select_fwd(const float* x1, int ldx, const float* sel_w, const float* sel_b,
                          int logit_fp16, float min_kept, const float* noise1, const float* noise2,
-                         float tau, int B, int N, int C, float* mask, float* logits, void* stream);
+                         float tau, int B, int N, int C, float* mask, float* logits, int* row_of,
+                         void* stream);
 
 /* Vectorised scatter-merge: out[t] = adapt[t] + (x1[t] + (token_pos[t] >= 0 ? mlp[token_pos[t]] : 0)).
  * Replaces torch.zeros + index_put + the two adds (reference models/model_speed_test.py:302-308).
