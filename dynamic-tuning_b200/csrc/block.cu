@@ -7,6 +7,7 @@
 //   mlp_packed = fc2(gelu(fc1(LN2(x1[kept]))))            :297-304 (kept tokens only)
 //   x   = adapt + (x1 + scatter(mlp_packed))              :305-308
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/dyt_b200.h"
 #include "gemm_tn.cuh"
@@ -68,6 +69,31 @@ static BlockWorkspace carve(const dyt_block_shape* s, void* base) {
   w.n_kept = static_cast<int*>(take(256));
   w.total = off;
   return w;
+}
+
+// The adapter branch (down + ReLU, up * scale: two short, store-bound GEMMs) depends only on x1, like
+// the dispatcher -> fc1 -> fc2 chain: it runs on a side stream forked after the proj GEMM and joined
+// before the scatter-merge, so its HBM traffic overlaps the dispatcher's (fork / join by events:
+// capturable into a CUDA graph like everything else).  One stream + two events per host thread,
+// created on first use (no device memory).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+};
+static SideStream& side_stream() {
+  static thread_local SideStream s;
+  if (s.stream == nullptr) {
+    const char* off = getenv("DYT_NO_SIDE_STREAM");
+    if ((off == nullptr || off[0] == '0') &&
+        cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess)
+      s.ok = true;
+    else if (s.stream == nullptr)
+      s.stream = reinterpret_cast<cudaStream_t>(1);  // tried once; stay on the caller's stream
+  }
+  return s;
 }
 
 static int check_shape(const dyt_block_shape* s) {
@@ -145,6 +171,20 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   DYT_TRY(gemm_tn(w.attn_o, C, HP(wt->proj_w), C, T, C, C, nullptr, EPI_BIAS_RESID,
                   HP(wt->proj_b), w.x1h, C, w.x1, C, x, C, 1.0f, stream,
                   fuse_score ? wt->sel_w : nullptr, w.score_part, slices, opt->logit_fp16));
+  // adapter on every token (steps 8./9.), forked onto the side stream
+  SideStream& ss = side_stream();
+  cudaStream_t astream = stream;
+  if (ss.ok) {
+    DYT_CUDA(cudaEventRecord(ss.fork, stream));
+    DYT_CUDA(cudaStreamWaitEvent(ss.stream, ss.fork, 0));
+    astream = ss.stream;
+  }
+  DYT_TRY(gemm_tn(w.x1h, C, HP(wt->down_w), C, T, shape->bottleneck, C, nullptr, EPI_BIAS_RELU,
+                  HP(wt->down_b), w.down, shape->bottleneck, nullptr, 0, nullptr, 0, 1.0f, astream));
+  DYT_TRY(gemm_tn(w.down, shape->bottleneck, HP(wt->up_w), shape->bottleneck, T, C,
+                  shape->bottleneck, nullptr, EPI_BIAS, HP(wt->up_b), w.adapt, C, nullptr, 0,
+                  nullptr, 0, wt->adapter_scale, astream));
+  if (ss.ok) DYT_CUDA(cudaEventRecord(ss.join, ss.stream));
   // 5. dispatcher: score, gate, compaction, LN2 of kept rows
   DYT_TRY(dispatch_fwd(w.x1, C, wt->sel_w, wt->sel_b, opt->logit_fp16, opt->min_kept,
                        opt->noise1, opt->noise2, opt->tau, B, N, C, wt->ln2_w, wt->ln2_b,
@@ -156,12 +196,8 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
                   HP(wt->fc1_b), w.hidden, shape->hidden, nullptr, 0, nullptr, 0, 1.0f, stream));
   DYT_TRY(gemm_tn(w.hidden, shape->hidden, HP(wt->fc2_w), shape->hidden, T, C, shape->hidden,
                   w.n_kept, EPI_BIAS, HP(wt->fc2_b), w.mlp, C, nullptr, 0, nullptr, 0, 1.0f, stream));
-  // 8./9. adapter on every token
-  DYT_TRY(gemm_tn(w.x1h, C, HP(wt->down_w), C, T, shape->bottleneck, C, nullptr, EPI_BIAS_RELU,
-                  HP(wt->down_b), w.down, shape->bottleneck, nullptr, 0, nullptr, 0, 1.0f, stream));
-  DYT_TRY(gemm_tn(w.down, shape->bottleneck, HP(wt->up_w), shape->bottleneck, T, C,
-                  shape->bottleneck, nullptr, EPI_BIAS, HP(wt->up_b), w.adapt, C, nullptr, 0,
-                  nullptr, 0, wt->adapter_scale, stream));
+  // join the adapter branch
+  if (ss.ok) DYT_CUDA(cudaStreamWaitEvent(stream, ss.join, 0));
   // 10. scatter-merge back to [B, N, C] (in place into x), optionally with the next LayerNorm
   DYT_TRY(scatter_merge(w.x1, C, w.adapt, C, w.mlp, C, w.token_pos, T, C, x, C, opt->next_ln_w,
                         opt->next_ln_b, opt->eps, opt->next_ln_w ? w.xn : nullptr, C, stream));
