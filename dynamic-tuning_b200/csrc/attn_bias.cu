@@ -247,11 +247,10 @@ extern "C" int dyt_attn_bias_fwd(const void* qkv, int ld_qkv, const float* bias,
   if (num_seqs == 0) return DYT_OK;
   const long blocks = static_cast<long>(num_seqs) * num_heads * ((seq_len + FB_Q - 1) / FB_Q);
   DYT_CHECK_ARG(blocks < (1l << 31), "attn_bias: grid too large");
-  static bool configured = false;
-  if (!configured) {
-    DYT_CUDA(cudaFuncSetAttribute(attn_bias_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(FB_SMEM)));
-    configured = true;
+  static SmemAttrCache smem_cache;
+  {
+    const int st = ensure_dyn_smem(attn_bias_fwd_kernel, static_cast<int>(FB_SMEM), smem_cache);
+    if (st != DYT_OK) return st;
   }
   attn_bias_fwd_kernel<<<static_cast<unsigned>(blocks), FB_WARPS * 32, FB_SMEM, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(qkv), ld_qkv, bias, seq_len, num_heads, C, 1.0f / 8.0f,

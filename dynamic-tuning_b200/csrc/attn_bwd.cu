@@ -329,11 +329,10 @@ extern "C" int dyt_attn_varlen_bwd(const void* qkv, int ld_qkv, const void* out,
                   reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(d_qkv)) & 15) == 0,
                 "attn_bwd: buffers must be 16-byte aligned");
   if (num_seqs == 0) return DYT_OK;
-  static bool configured = false;
-  if (!configured) {
-    DYT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(AB_SMEM)));
-    configured = true;
+  static SmemAttrCache smem_cache;
+  {
+    const int st = ensure_dyn_smem(attn_bwd_kernel, static_cast<int>(AB_SMEM), smem_cache);
+    if (st != DYT_OK) return st;
   }
   const float scale = 0.125f;  // head_dim^-0.5
   attn_bwd_kernel<<<num_seqs * num_heads, AB_WARPS * 32, AB_SMEM, static_cast<cudaStream_t>(stream)>>>(

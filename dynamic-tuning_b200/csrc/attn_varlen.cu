@@ -49,7 +49,6 @@ struct AttnParams {
   int s_col[2];       // TMEM column of S for tile A / B
   int o_col[2];       // TMEM column of O for tile A / B
   int o_alias[2];     // 1: O lives inside the tile's own S region
-  long long* trace;   // debug only (DYT_ATTN_TRACE=1): clock64 timeline of CTA 0, else nullptr
 };
 
 constexpr int ATT_BM = 128;
@@ -60,12 +59,6 @@ constexpr int ATT_Q_BYTES = 2 * ATT_BM * 128;  // both query tiles of a unit
 constexpr int ATT_OSTAGE_BYTES = 4 * 32 * 128;  // per-output-warp transpose slabs
 constexpr int ATT_INV_BYTES = 2 * 2 * ATT_BM * 4;  // 1/rowsum: [unit parity][tile][row]
 constexpr int ATT_SPLIT_KEYS = 128;  // keys covered by the early first part of the PV product
-constexpr int ATT_TRACE_ITERS = 24, ATT_TRACE_EVENTS = 8, ATT_TRACE_ROLES = 6;
-
-__device__ __forceinline__ void trace_ev(const AttnParams& p, int role, uint32_t iter, int ev) {
-  if (p.trace != nullptr && blockIdx.x == 0 && iter < ATT_TRACE_ITERS)
-    p.trace[(role * ATT_TRACE_ITERS + iter) * ATT_TRACE_EVENTS + ev] = clock64();
-}
 
 __device__ __forceinline__ void unit_span(const AttnParams& p, int unit, int& b, int& h,
                                           int& seq_start, int& seq_len) {
@@ -194,7 +187,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (seq_len == 0) continue;
         const int s = it & 1;
         mbar_wait(&qk_empty[s], ((it >> 1) & 1) ^ 1);
-        trace_ev(p, 4, it, 0);
         uint8_t* sQ = smem + s * stage_bytes;
         uint8_t* sK = sQ + ATT_Q_BYTES;
         uint8_t* sV = sK + kv_bytes;
@@ -270,11 +262,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
           }
           __syncwarp();
         }
-        if (lane == 0) trace_ev(p, 2 + tile, k, 0);
         // ---- O = P V ----  (16 keys per MMA: 8 TMEM columns of packed fp16 P; 16 V rows = +128)
         const uint64_t v_desc = umma_desc_sw128(stage_addr + ATT_Q_BYTES + kv_bytes);
         mbar_wait(&p_half[tile], k & 1);
-        if (lane == 0) trace_ev(p, 2 + tile, k, 1);
         mbar_wait(&full_v[s], ring_par);
         if (!alias) mbar_wait(&o_free[tile], (k & 1) ^ 1);  // O(k-1) read out
         tc_fence_after();
@@ -283,10 +273,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
             umma_ts_f16(d_tmem, a_tmem + kk * 8, v_desc + kk * 128, idesc_o, kk != 0 ? 1u : 0u);
         }
         __syncwarp();
-        if (lane == 0) trace_ev(p, 2 + tile, k, 2);
         mbar_wait(&p_full[tile], k & 1);
         tc_fence_after();
-        if (lane == 0) trace_ev(p, 2 + tile, k, 3);
         if (elect_one()) {
           for (int kk = early; kk < steps; ++kk)
             umma_ts_f16(d_tmem, a_tmem + kk * 8, v_desc + kk * 128, idesc_o, kk != 0 ? 1u : 0u);
@@ -294,7 +282,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
           umma_commit(&v_empty[s]);  // V of this stage is free once both tiles' PV retire
         }
         __syncwarp();
-        if (lane == 0) trace_ev(p, 2 + tile, k, 4);
         ++k;
       }
     }
@@ -320,7 +307,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
       mbar_wait(&s_full[tile], cnt & 1);
       tc_fence_after();
-      if (q == 0 && lane == 0) trace_ev(p, tile, cnt, 0);
       bool half_sent = false;
       if (active) {
         float mx;
@@ -360,7 +346,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
           }
           mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         }
-        if (q == 0 && lane == 0) trace_ev(p, tile, cnt, 1);
         // ---- pass 2: exponentials, row sum, P -> TMEM (aliasing the consumed part of S) ----
         uint32_t ra[32], rb[32];
         const float mb = mx * sl2;
@@ -405,7 +390,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (!half_sent) mbar_arrive(&p_half[tile]);
         mbar_arrive(&p_full[tile]);
       }
-      if (q == 0 && lane == 0) trace_ev(p, tile, cnt, 2);
       ++cnt;
     }
   } else {
@@ -425,7 +409,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const bool active = tile * ATT_BM + q * 32 < seq_len;  // warp-uniform
         mbar_wait(&o_full[tile], cnt & 1);
         tc_fence_after();
-        if (q == 0 && lane == 0) trace_ev(p, 5, cnt, tile * 4 + 0);
         uint32_t o0[32], o1[32];
         if (active) {
           const uint32_t o_addr = tmem_base + lane_off + o_col(tile);
@@ -436,7 +419,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_free[tile]);
-        if (q == 0 && lane == 0) trace_ev(p, 5, cnt, tile * 4 + 1);
         if (active) {
           // normalise, round once to fp16, transpose through the warp's smem slab (16-byte chunks
           // XOR-swizzled by row: conflict-free both ways) so that every global store instruction
@@ -476,7 +458,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
           }
           __syncwarp();  // the slab is rewritten by the next tile
         }
-        if (q == 0 && lane == 0) trace_ev(p, 5, cnt, tile * 4 + 2);
         if (tile) ++cnt_b; else ++cnt_a;
       }
     }
@@ -542,40 +523,12 @@ int attn_varlen_fwd(const __half* qkv, int ld_qkv, const int* cu_seqlens, int nu
     p.o_alias[0] = 1; p.o_alias[1] = 1;
   }
   const int smem_bytes = 1024 + 2 * (ATT_Q_BYTES + 2 * nk_box * 128) + ATT_OSTAGE_BYTES + ATT_INV_BYTES + 256;
-  static int configured_smem = 0;
-  if (smem_bytes > configured_smem) {
-    DYT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  smem_bytes));
-    configured_smem = smem_bytes;
+  static SmemAttrCache smem_cache;  // per device; always the kernel's maximum (227 KB)
+  {
+    const int st = ensure_dyn_smem(attn_fwd_kernel, 232448, smem_cache);
+    if (st != DYT_OK) return st;
   }
   const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
-  p.trace = nullptr;
-  static const bool want_trace = getenv("DYT_ATTN_TRACE") != nullptr;
-  if (want_trace) {
-    // debug: per-event clock64 timeline of CTA 0 (synchronises; never enabled in production)
-    const size_t n = ATT_TRACE_ROLES * ATT_TRACE_ITERS * ATT_TRACE_EVENTS;
-    long long* d = nullptr;
-    cudaMalloc(&d, n * sizeof(long long));
-    cudaMemsetAsync(d, 0, n * sizeof(long long), stream);
-    p.trace = d;
-    attn_fwd_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tq, tkv, p);
-    cudaStreamSynchronize(stream);
-    static long long h[ATT_TRACE_ROLES * ATT_TRACE_ITERS * ATT_TRACE_EVENTS];
-    cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
-    cudaFree(d);
-    long long t0 = h[(2 * ATT_TRACE_ITERS) * ATT_TRACE_EVENTS];  // first S issue of tile A
-    const char* names[6] = {"wgA", "wgB", "mmA", "mmB", "tma", "out"};
-    for (int r = 0; r < ATT_TRACE_ROLES; ++r)
-      for (int i = 0; i < ATT_TRACE_ITERS; ++i) {
-        fprintf(stderr, "trace %s it=%2d:", names[r], i);
-        for (int e = 0; e < ATT_TRACE_EVENTS; ++e) {
-          long long v = h[(r * ATT_TRACE_ITERS + i) * ATT_TRACE_EVENTS + e];
-          fprintf(stderr, " %8lld", v ? v - t0 : -1);
-        }
-        fprintf(stderr, "\n");
-      }
-    return cuda_status(cudaGetLastError(), "attn_fwd_kernel launch");
-  }
   attn_fwd_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tq, tkv, p);
   return cuda_status(cudaGetLastError(), "attn_fwd_kernel launch");
 }

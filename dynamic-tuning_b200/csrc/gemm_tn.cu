@@ -13,11 +13,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN, EW>;
   auto kern = gemm_tn_kernel<BN, EPI, EW>;
-  static bool configured = false;
-  if (!configured) {
-    DYT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::SMEM_BYTES));
-    configured = true;
+  static SmemAttrCache smem_cache;   // one per kernel instantiation, per device inside
+  {
+    const int st = ensure_dyn_smem(kern, Cfg::SMEM_BYTES, smem_cache);
+    if (st != DYT_OK) return st;
   }
   const int m_tiles = (p.M + Cfg::BM - 1) / Cfg::BM;
   const int n_tiles = (p.N + BN - 1) / BN;
@@ -110,12 +109,6 @@ int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, in
     if (r192 * 192 * 10 <= r256 * 256 * 9) bn = 192;  // only for a clear (>= 10 %) saving
   }
 
-  {  // experiment hook (scripts/gemm_probe.py): force a tile width
-    static const char* force = getenv("DYT_GEMM_FORCE_BN");
-    if (force != nullptr && N % atoi(force) == 0 && K > 128 && dot_w == nullptr &&
-        (epi == EPI_BIAS || epi == EPI_BIAS_RESID))
-      bn = atoi(force);
-  }
   CUtensorMap ta, tb;
   int s = make_tmap_f16_sw128(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(K),
                               static_cast<uint64_t>(lda), 128);

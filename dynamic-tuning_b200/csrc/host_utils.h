@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 namespace dyt {
 
 // Status convention of include/dyt_b200.h: 0 ok, <0 argument error, >0 cudaError_t.
@@ -82,15 +84,40 @@ inline int make_tmap_f16_sw128(CUtensorMap* map, const void* ptr, uint64_t rows,
   return DYT_OK;
 }
 
+// Host-side caches are per device and lock-free: one process may drive several GPUs from several
+// threads (the C ABI is a plain stream-based API with no such restriction).
+constexpr int kMaxDevices = 64;
+
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 inline int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = current_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (kernel, device): set it once per device to
+// the kernel's fixed maximum (racing threads write the same value, so the race is benign).
+struct SmemAttrCache {
+  std::atomic<int> done[kMaxDevices];
+};
+template <typename Kernel>
+inline int ensure_dyn_smem(Kernel kern, int max_bytes, SmemAttrCache& cache) {
+  const int dev = current_device();
+  if (cache.done[dev].load(std::memory_order_acquire) == max_bytes) return DYT_OK;
+  DYT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
+  cache.done[dev].store(max_bytes, std::memory_order_release);
+  return DYT_OK;
 }
 
 }  // namespace dyt

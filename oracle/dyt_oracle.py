@@ -279,6 +279,24 @@ def block_dense(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int, sc
 
 
 # ----------------------------------------------------------------------------------------------
+# a11: Block.forward_count_flops, the FLOP probe block_flops_dict.get_block_flops traces
+#      (reference models/vision_transformer_IN21K.py:167-185): MLP on the FIRST token_select_num
+#      tokens whatever the selector says
+# ----------------------------------------------------------------------------------------------
+def block_count_flops(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int, scale: float,
+                      token_select_num: int, policy: str = "fp32") -> Tensor:
+    x1 = x + attention(layer_norm(x, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"]), p,
+                       prefix + "attn.", num_heads, policy)                       # :168
+    adapt_x = adapter(x1, p, prefix + "adaptmlp.", scale, policy)                 # :177
+    t = token_select_num
+    mlp_x = mlp(layer_norm(x1[:, :t, :], p[prefix + "norm2.weight"], p[prefix + "norm2.bias"]), p,
+                prefix + "mlp.", policy)                                          # :180
+    out = x1 + adapt_x                                                            # :182
+    out[:, :t, :] = out[:, :t, :] + mlp_x                                         # :183
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # a2 / a4 / a5 in train mode, differentiable (fp32): the dense masked block with the hard
 # straight-through Gumbel gate and adapter dropout (reference models/vision_transformer_IN21K.py:
 # 144-165, models/dynamic_adapter.py:25-54, :127-130).  Gradients come from torch.autograd on this
@@ -413,7 +431,7 @@ def vit_forward(img: Tensor, p: Dict[str, Tensor], depth: int, num_heads: int, s
 # segmentation_vision_transformer_IN21K.py: Block.forward :275-298, forward_features :526-560)
 # ----------------------------------------------------------------------------------------------
 def block_seg(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int, scale: float,
-              policy: str = "fp32") -> Dict[str, Tensor]:
+              policy: str = "fp32", forced_mask: Optional[Tensor] = None) -> Dict[str, Tensor]:
     """Dense masked block whose attention is the eager path with an optional relative-position bias."""
     bias = None
     if prefix + "attn.relative_position_bias_table" in p:
@@ -425,6 +443,8 @@ def block_seg(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int, scal
     x1 = x + linear(o, p[prefix + "attn.proj.weight"], p[prefix + "attn.proj.bias"], policy)   # :276
     mask, logits = token_select(x1, p[prefix + "mlp_token_select.mlp_head.weight"],
                                 p[prefix + "mlp_token_select.mlp_head.bias"], policy)          # :280-282
+    if forced_mask is not None:      # test aid: continue with an imposed decision
+        mask = forced_mask.float()
     adapt_x = adapter(x1, p, prefix + "adaptmlp.", scale, policy)                              # :287
     mlp_x = mlp(layer_norm(x1, p[prefix + "norm2.weight"], p[prefix + "norm2.bias"]), p,
                 prefix + "mlp.", policy)                                                       # :289
@@ -435,7 +455,7 @@ def block_seg(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int, scal
 def seg_forward(img: Tensor, p: Dict[str, Tensor], depth: int, num_heads: int, scale: float,
                 out_indices, patch: int = 16, policy: str = "fp32", token_target_ratio: float = 0.5,
                 token_ratio: float = 2.0, token_minimal: float = 0.1,
-                token_minimal_weight: float = 1.0) -> Dict[str, Tensor]:
+                token_minimal_weight: float = 1.0, forced_masks=None) -> Dict[str, Tensor]:
     """forward_features of the segmentation backbone: tokens -> blocks -> maps after `out_indices`
     -> FPN heads (fpn1: deconv-GELU-deconv, fpn2: deconv, fpn3: identity, fpn4: max-pool) + the
     token-rate loss."""
@@ -445,7 +465,8 @@ def seg_forward(img: Tensor, p: Dict[str, Tensor], depth: int, num_heads: int, s
     x = torch.cat((p["cls_token"].expand(bsz, -1, -1), x), dim=1) + p["pos_embed"]
     feats, sels, logs = [], [], []
     for i in range(depth):
-        r = block_seg(x, p, f"blocks.{i}.", num_heads, scale, policy)
+        r = block_seg(x, p, f"blocks.{i}.", num_heads, scale, policy,
+                      forced_mask=None if forced_masks is None else forced_masks[i])
         x = r["out"]
         sels.append(r["mask"])
         logs.append(r["logits"])
@@ -528,13 +549,14 @@ def attentive_pool(tokens: Tensor, p: Dict[str, Tensor], num_heads: int,
 
 
 def video_forward(clip: Tensor, p: Dict[str, Tensor], depth: int, num_heads: int, scale: float,
-                  policy: str = "fp32", patch: int = 16) -> Dict[str, Tensor]:
+                  policy: str = "fp32", patch: int = 16, forced_masks=None) -> Dict[str, Tensor]:
     """Video model, eval mode (reference video_models/video_vision_transformer_IN21K.py:435-483):
     every frame goes through the image blocks independently (dense masked block == the sparse
     block in eval), then norm -> [b, t*N, C] -> attentive pooling -> head."""
     b, ch, t, h, w = clip.shape
     frames = clip.permute(0, 2, 1, 3, 4).reshape(b * t, ch, h, w)
-    r = vit_forward(frames, p, depth, num_heads, scale, policy=policy, sparse=True, patch=patch)
+    r = vit_forward(frames, p, depth, num_heads, scale, policy=policy, sparse=True, patch=patch,
+                    forced_masks=forced_masks)
     xn = layer_norm(r["x_final"], p["norm.weight"], p["norm.bias"])
     tokens = xn.reshape(b, t * xn.shape[1], xn.shape[2])
     pooled = attentive_pool(tokens, p, num_heads, policy)

@@ -22,6 +22,8 @@ itself are the pins of the oracle (oracle/dyt_oracle.py):
                     inputs, qkv, outputs, bias table / index for two window sizes
   seg_tiny.pt       a 4-layer dim-128 segmentation backbone with relative-position bias: state_dict,
                     image, FPN feature maps, masks, logits, token loss
+  count_flops_tiny.pt  Block.forward_count_flops (FLOP probe) of the reference train Block on the tiny
+                    ViT for token_select_num = 1, 3, 5
   vitb_b2.pt        ViT-B/16, synthetic seed-0 weights (regenerated from the seed, not stored),
                     calibrated selector biases, B=2: logits / masks / token logits of the speed model
                     and the train model (eval, complete_model on/off), config-1 imposed-mask logits
@@ -113,6 +115,26 @@ def tiny_vit(ref_speed, ref_train):
         out["blk0_out"] = blk(x)
         out["blk0_out_b1"] = blk(x[:1])          # single_forward path (B == 1)
         out["blk0_train_out"] = mt.blocks[0](x)[0]
+    return out
+
+
+def count_flops_tiny(ref_train):
+    """Block.forward_count_flops of the reference train Block (the FLOP probe of
+    block_flops_dict.get_block_flops, vision_transformer_IN21K.py:167-185) on the tiny ViT's block 0
+    for several token_select_num."""
+    dims = dict(embed_dim=128, depth=2, num_heads=2, bottleneck=16, num_classes=10, img_size=32)
+    sd = O.synthetic_state_dict(seed=3, **dims)
+    mt = _build(ref_train, sd, 10, 128, 2, 2, 32, 16, "0.1", True)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 5, 128, generator=g)
+    blk = mt.blocks[0]
+    out = dict(dims=dims, scale=0.1, seed=3, x=x, outs={})   # weights: O.synthetic_state_dict(seed, **dims)
+    blk.count_flops = True
+    with torch.no_grad():
+        for t in (1, 3, 5):
+            blk.token_select_num = t
+            out["outs"][t] = blk(x).clone()
+    blk.count_flops = None
     return out
 
 
@@ -390,6 +412,13 @@ def seg_tiny():
 
 
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--only":      # regenerate a single fixture
+        assert ref_shim.reference_available()
+        if sys.argv[2] == "count_flops_tiny":
+            ref_train = ref_shim.import_reference("models.vision_transformer_IN21K")
+            torch.save(count_flops_tiny(ref_train), os.path.join(OUT, "count_flops_tiny.pt"))
+            return
+        raise SystemExit("unknown fixture " + sys.argv[2])
     assert ref_shim.reference_available(), "needs the reference checkout at " + ref_shim.REFERENCE_ROOT
     torch.set_num_threads(os.cpu_count())
     ref_dyn = ref_shim.import_reference("models.dynamic_adapter")
@@ -400,6 +429,7 @@ def main():
     torch.save(gumbel_train(ref_dyn), os.path.join(OUT, "gumbel_train.pt"))
     torch.save(tiny_vit(ref_speed, ref_train), os.path.join(OUT, "tiny_vit.pt"))
     torch.save(vitb_b2(ref_speed, ref_train), os.path.join(OUT, "vitb_b2.pt"))
+    torch.save(count_flops_tiny(ref_train), os.path.join(OUT, "count_flops_tiny.pt"))
     ref_video = ref_shim.import_reference("video_models.video_vision_transformer_IN21K")
     torch.save(tiny_video(ref_video), os.path.join(OUT, "video_tiny.pt"))
     torch.save(flops_accounting(), os.path.join(OUT, "flops_accounting.pt"))

@@ -22,4 +22,5 @@ def golden_dir():
 
 def load_golden(name):
     import torch
-    return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=False)
+    # the fixtures are plain containers of tensors / numbers / strings: no pickled code is executed
+    return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=True)

@@ -72,13 +72,25 @@ def _train_model(sd, dev, num_classes=100):
     return m.eval().to(dev)
 
 
-def _check_masks(mask, mask_ref, logit_ref, max_flips):
+def _rel_rows(got, ref, rows):
+    """max|err| over the selected token rows [B, N] relative to max|ref| of the whole tensor: a token
+    whose gate decision sits on the threshold tie changes its own row by a full MLP output, every
+    other row of the block is still compared."""
+    got, ref = got.float().cpu(), ref.float().cpu()
+    assert bool(rows.any())
+    return ((got - ref)[rows].abs().max() / ref.abs().max()).item()
+
+
+def _check_masks(mask, mask_ref, logit_ref, max_flips, near_tol=1.2e-5):
+    """Gate decisions must be bit-equal; a mismatch is tolerated (and counted) only for a token whose
+    reference logit lies within near_tol of the gate threshold: the 768-term fp32 dot product of the
+    logit (|logit| ~ 10) carries ~1e-6 relative accumulation-order noise."""
     mism = mask != mask_ref
     n = int(mism.sum())
     if n:
         thr = O.min_kept_logit(torch.float16)
-        near = (logit_ref[mism[:, 1:]] - thr).abs() <= 1.2e-5
-        assert bool(near.all()), "mask mismatch away from the gate threshold"
+        dist = (logit_ref[mism[:, 1:]] - thr).abs()
+        assert bool((dist <= near_tol).all()), f"mask mismatch away from the gate threshold: {dist}"
     assert n <= max_flips
     return n
 
@@ -99,9 +111,9 @@ def test_block_matches_oracle(dev, vitb_sd, B):
         from dyt_b200 import engine
         out2, masks, logits, _ = engine.run_blocks(x.to(dev), [m.blocks[layer]], fuse_next_ln=False)
         assert torch.equal(out, out2)
-        flips = _check_masks(masks[0].unsqueeze(-1).cpu(), ref["mask"], ref["logits"], max_flips=1)
-        if flips == 0:
-            assert _rel(out, ref["out"]) <= 1e-3
+        _check_masks(masks[0].unsqueeze(-1).cpu(), ref["mask"], ref["logits"], max_flips=1)
+        same = masks[0].cpu() == ref["mask"][..., 0]            # [B, N]: rows with the oracle's decision
+        assert _rel_rows(out, ref["out"], same) <= 1e-3
         assert _rel(logits[0].unsqueeze(-1), ref["logits"]) <= 2e-3
 
 
@@ -232,9 +244,9 @@ def test_vit_large_block_matches_oracle(dev):
     x = torch.randn(2, 197, 1024, generator=torch.Generator().manual_seed(5)) * 0.7
     ref = O.block_sparse(x, sd, "blocks.1.", 16, 0.1, "amp16")
     out, masks, logits, _ = engine.run_blocks(x.to(dev), [m.blocks[1]], fuse_next_ln=False)
-    flips = _check_masks(masks[0].unsqueeze(-1).cpu(), ref["mask"], ref["logits"], max_flips=1)
-    if flips == 0:
-        assert _rel(out, ref["out"]) <= 1e-3
+    _check_masks(masks[0].unsqueeze(-1).cpu(), ref["mask"], ref["logits"], max_flips=1)
+    same = masks[0].cpu() == ref["mask"][..., 0]
+    assert _rel_rows(out, ref["out"], same) <= 1e-3
     keep = float(masks[0][:, 1:].mean())
     assert 0.4 < keep < 0.95
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
@@ -313,6 +325,60 @@ def test_full_batch_properties(dev, vitb_sd):
     assert torch.equal(o0[:, 0], o1[:, 0])          # cls rows are kept in both
 
 
+def test_full_batch_matches_oracle(dev, vitb_sd):
+    """BASELINE batch size (256 images, T = 50 432 tokens): two layers against the amp16 oracle on
+    identical inputs.  Exercises what the small batches do not: several rounds of the persistent
+    GEMM tile loops, the device-side row count of the MLP GEMMs, the 256-image look-back of the
+    dispatcher.  Layer by layer the oracle continues with the kernels' own gate decisions (after
+    they were checked against its own: bit-equal except threshold ties), so every row is compared."""
+    g, sd, img = vitb_sd
+    m = _speed_model(sd, dev)
+    from dyt_b200 import engine
+    B = 256
+    x = torch.randn(B, 197, 768, generator=torch.Generator().manual_seed(77)) * 0.7
+    torch.set_num_threads(max(1, (torch.get_num_threads())))
+    xg = x.to(dev)
+    xo = x
+    total_flips = 0
+    for layer in (0, 1):
+        outg, masks, logits, _ = engine.run_blocks(xg, [m.blocks[layer]], fuse_next_ln=False)
+        free = O.block_sparse(xo, sd, f"blocks.{layer}.", 12, g["scale"], "amp16")
+        # 50 432 tokens per layer with logits ~ N(0, 10^2): about a dozen lie within 5e-3 of the
+        # threshold, and the logit inherits the (equally valid) fp16 rounding differences of x1
+        # between two fp32-accumulating implementations: ~2e-4 per element x sqrt(768) x |w| ~ 3e-3
+        total_flips += _check_masks(masks[0].unsqueeze(-1).cpu(), free["mask"], free["logits"],
+                                    max_flips=12, near_tol=5e-3)
+        assert _rel(logits[0].unsqueeze(-1), free["logits"]) <= 2e-3
+        ref = O.block_sparse(xo, sd, f"blocks.{layer}.", 12, g["scale"], "amp16",
+                             forced_mask=masks[0].unsqueeze(-1).cpu())
+        assert _rel(outg, ref["out"]) <= 1e-3, layer
+        assert int(masks[0].sum()) == int(ref["cu_seqlens"][-1])
+        xg, xo = outg, ref["out"]                      # each side continues with its own stream
+    assert total_flips <= 16
+
+
+def test_forward_count_flops_matches_oracle(dev, vitb_sd):
+    """a11: Block.forward_count_flops (block_flops_dict.get_block_flops' probe): MLP on the FIRST
+    token_select_num tokens (vision_transformer_IN21K.py:167-185); oracle pinned to the reference by
+    tests/golden/count_flops_tiny.pt."""
+    g, sd, img = vitb_sd
+    m = _train_model(sd, dev)
+    x = torch.randn(2, 197, 768, generator=torch.Generator().manual_seed(8)) * 0.7
+    blk = m.blocks[2]
+    blk.count_flops = True
+    try:
+        for t in (1, 64, 197):
+            blk.token_select_num = t
+            with torch.no_grad():
+                out = blk(x.to(dev))
+            ref = O.block_count_flops(x, sd, "blocks.2.", 12, g["scale"], t, "amp16")
+            assert out.shape == x.shape
+            assert _rel(out, ref) <= 1e-3, t
+    finally:
+        blk.count_flops = None
+        blk.token_select_num = None
+
+
 # ---------------------------------------------------------------------------------------------
 # video model: per-frame DyT blocks + attentive pooling head (SURVEY section 8f rank 3)
 # ---------------------------------------------------------------------------------------------
@@ -362,10 +428,16 @@ def test_tiny_video_model_vs_reference_golden(dev):
     assert ts["token_select"].shape == g["token_select"].shape
     ref16 = O.video_forward(g["clip"], g["state_dict"], d["depth"], d["num_heads"], g["scale"],
                             policy="amp16")
-    mism = int((ts["token_select"].float().cpu() != ref16["token_select"].float()).sum())
+    got_sel = ts["token_select"].float().cpu()                    # [b*t, depth, N-1, 1]
+    mism = int((got_sel != ref16["token_select"].float()).sum())
     assert mism <= 1
-    if mism == 0:
-        assert _rel(logits.float(), ref16["logits"]) <= 1e-2
+    # the oracle continued with the kernels' own gate decisions: compared whatever the flip count
+    forced = [torch.cat([torch.ones(got_sel.shape[0], 1, 1), got_sel[:, i]], dim=1)
+              for i in range(d["depth"])]
+    ref_f = O.video_forward(g["clip"], g["state_dict"], d["depth"], d["num_heads"], g["scale"],
+                            policy="amp16", forced_masks=forced)
+    assert _rel(logits.float(), ref_f["logits"]) <= 1e-2
+    if bool((got_sel == g["token_select"].float()).all()):        # same decisions as the fp32 reference
         assert _rel(logits.float(), g["logits"]) <= 3e-2
 
 
@@ -442,13 +514,20 @@ def test_segmentation_backbone_vs_reference_golden(dev):
         feats, d = m(g["img"].to(dev))
     assert len(feats) == 4 and d["token_select"].shape == g["token_select"].shape
     ref16 = O.seg_forward(g["img"], g["state_dict"], 4, 2, 0.1, [0, 1, 2, 3], policy="amp16")
-    same = (d["token_select"].float().cpu() > 0.5) == (ref16["token_select"] > 0.5)
+    got_sel = (d["token_select"].float().cpu() > 0.5).float()     # [B, depth, N-1, 1]
+    same = (got_sel > 0.5) == (ref16["token_select"] > 0.5)
     assert same.float().mean() >= 0.98
-    if bool(same.all()):
-        for a, b, c in zip(feats, ref16["features"], g["features"]):
-            assert a.shape == c.shape
-            assert _rel(a, b) <= 1e-2 and _rel(a, c) <= 3e-2
-        assert abs(d["loss"].item() - ref16["loss"].item()) <= 1e-3 * abs(ref16["loss"].item())
+    # the oracle continued with the kernels' own gate decisions: compared whatever the flip count
+    forced = [torch.cat([torch.ones(got_sel.shape[0], 1, 1), got_sel[:, i]], dim=1) for i in range(4)]
+    ref_f = O.seg_forward(g["img"], g["state_dict"], 4, 2, 0.1, [0, 1, 2, 3], policy="amp16",
+                          forced_masks=forced)
+    for a, b, c in zip(feats, ref_f["features"], g["features"]):
+        assert a.shape == c.shape
+        assert _rel(a, b) <= 1e-2
+    assert abs(d["loss"].item() - ref_f["loss"].item()) <= 1e-3 * abs(ref_f["loss"].item())
+    if bool(same.all()) and bool(((g["token_select"] > 0.5) == (got_sel > 0.5)).all()):
+        for a, c in zip(feats, g["features"]):
+            assert _rel(a, c) <= 3e-2
     with pytest.raises(NotImplementedError):
         m.train()(g["img"].to(dev))
 
