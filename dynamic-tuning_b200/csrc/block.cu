@@ -74,24 +74,22 @@ static BlockWorkspace carve(const dyt_block_shape* s, void* base) {
 // The adapter branch (down + ReLU, up * scale: two short, store-bound GEMMs) depends only on x1, like
 // the dispatcher -> fc1 -> fc2 chain: it runs on a side stream forked after the proj GEMM and joined
 // before the scatter-merge, so its HBM traffic overlaps the dispatcher's (fork / join by events:
-// capturable into a CUDA graph like everything else).  One stream + two events per host thread,
-// created on first use (no device memory).
+// capturable into a CUDA graph like everything else).  One stream + two events per host thread and
+// device, created on first use (no device memory).
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
-  bool ok = false;
+  bool tried = false, ok = false;
 };
 static SideStream& side_stream() {
-  static thread_local SideStream s;
-  if (s.stream == nullptr) {
-    const char* off = getenv("DYT_NO_SIDE_STREAM");
-    if ((off == nullptr || off[0] == '0') &&
-        cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
-        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
-        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess)
-      s.ok = true;
-    else if (s.stream == nullptr)
-      s.stream = reinterpret_cast<cudaStream_t>(1);  // tried once; stay on the caller's stream
+  static thread_local SideStream per_device[kMaxDevices];   // streams / events belong to a device
+  SideStream& s = per_device[current_device()];
+  if (!s.tried) {
+    s.tried = true;
+    s.ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+    // on failure the adapter branch simply stays on the caller's stream
   }
   return s;
 }
@@ -134,6 +132,10 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   int st = check_shape(shape);
   if (st != 0) return st;
   DYT_CHECK_ARG(wt && opt && x && mask_out && logits_out && workspace, "block: null argument");
+  DYT_CHECK_ARG(opt->struct_size == sizeof(dyt_block_opts),
+                "block: dyt_block_opts.struct_size is %zu, this library expects %zu (ABI version %d): "
+                "the caller's binding does not match include/dyt_b200.h",
+                opt->struct_size, sizeof(dyt_block_opts), DYT_ABI_VERSION);
   DYT_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
                 "block: workspace must be 256-byte aligned");
   BlockWorkspace w = carve(shape, workspace);

@@ -7,3 +7,4 @@ merge) reached through the C ABI declared in include/dyt_b200.h.  There is no CP
 from ._lib import ABI_VERSION, DytError, LIB_PATH, lib  # noqa: F401
 from .gate import min_kept_logit  # noqa: F401
 from .graph import GraphedForward  # noqa: F401,E402
+from .engine import invalidate_caches  # noqa: F401,E402

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdyt_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_BIAS_RESID = 0, 1, 2, 3
 EPI_BIAS_GELU_KEEP, EPI_DGELU = 4, 5
@@ -36,7 +36,8 @@ class BlockWeights(C.Structure):
 
 
 class BlockOpts(C.Structure):
-    _fields_ = [("eps", C.c_float), ("logit_fp16", C.c_int), ("min_kept", C.c_float),
+    _fields_ = [("struct_size", C.c_size_t),
+                ("eps", C.c_float), ("logit_fp16", C.c_int), ("min_kept", C.c_float),
                 ("noise1", C.c_void_p), ("noise2", C.c_void_p), ("tau", C.c_float),
                 ("forced_mask", C.c_void_p), ("gate_out", C.c_void_p), ("xn_ready", C.c_int),
                 ("next_ln_w", C.c_void_p), ("next_ln_b", C.c_void_p), ("attn_bias", C.c_void_p)]

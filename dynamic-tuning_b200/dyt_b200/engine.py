@@ -116,6 +116,18 @@ def _prepared(block: torch.nn.Module) -> PreparedBlock:
     return prep
 
 
+def invalidate_caches(module: torch.nn.Module) -> None:
+    """Forget every cached fp16 / fp32 working copy of `module`'s parameters (block weights, head,
+    stem).  The caches notice a parameter that was replaced or modified in place through autograd-
+    visible ops (`_version`), i.e. optimizer steps and load_state_dict; a write through `.data`
+    (`p.data.copy_(...)`, `p.data.mul_(...)`) bumps no version counter: call this after such writes."""
+    from . import ops
+    for m in module.modules():
+        for key in [k for k in m.__dict__ if k.startswith("_dyt_")]:
+            m.__dict__.pop(key, None)
+    ops.invalidate_stem_cache()
+
+
 def run_blocks(x: torch.Tensor, blocks: Sequence[torch.nn.Module], *, eps: float = 1e-6,
                logit_dtype: torch.dtype = torch.float16, forced_masks=None,
                noises=None, final_ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
@@ -148,6 +160,7 @@ def run_blocks(x: torch.Tensor, blocks: Sequence[torch.nn.Module], *, eps: float
         ws = _workspace(shape, dev)
         wt = _prepared(blk).get()
         opts = BlockOpts()
+        opts.struct_size = C.sizeof(BlockOpts)
         opts.eps = eps
         opts.logit_fp16 = 1 if logit_dtype == torch.float16 else 0
         thr = float(getattr(blk.mlp_token_select, "threshold", 0.5))

@@ -17,12 +17,17 @@ from .ddp import GradArena
 
 
 def ada_loss(student_logits, token_select, targets, token_target_ratio=0.5, token_loss_ratio=2.0,
-             token_minimal=0.1, token_minimal_weight=1.0):
-    """models/losses.py:50-82 with a cross-entropy base criterion."""
+             token_minimal=0.0, token_minimal_weight=0.0):
+    """models/losses.py:50-82 with a cross-entropy base criterion.  The defaults are the recipe of
+    the reference's entry scripts, NOT the AdaLoss class defaults: every main_*.py passes
+    token_ratio 2, token_minimal 0, token_minimal_weight 0 (main_image.py:206-209,
+    main_vtab.py:200-203, main_video.py:234-237), i.e. the per-token minimal-keep term is off."""
     base = F.cross_entropy(student_logits, targets)
-    flops = ((token_select.mean() - token_target_ratio) ** 2).mean()
-    minimal = (token_minimal - token_select.mean(-1)).clamp(min=0.0).sum()
-    return base + token_loss_ratio * (flops + token_minimal_weight * minimal)
+    token_loss = ((token_select.mean() - token_target_ratio) ** 2).mean()
+    if token_minimal_weight > 0:                                   # losses.py:76-80
+        token_loss = token_loss + token_minimal_weight * (
+            token_minimal - token_select.mean(-1)).clamp(min=0.0).sum()
+    return base + token_loss_ratio * token_loss
 
 
 def finetune_loss(student_logits, token_select, teacher_logits, targets, **kw):

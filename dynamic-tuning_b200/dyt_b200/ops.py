@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -272,7 +273,10 @@ def scatter_merge(x1: torch.Tensor, adapt: torch.Tensor, mlp_packed: torch.Tenso
 
 
 _stem_ws = {}
-_stem_params = {}
+# fp16 / fp32 working copies of the stem parameters, keyed by the PARAMETER OBJECT (weak): an entry
+# dies with its model, so a new model whose tensors land on recycled addresses can never pick up
+# another model's copies (a cache keyed by data_ptr could), and nothing accumulates.
+_stem_params = weakref.WeakKeyDictionary()
 
 
 def patch_embed(img: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torch.Tensor],
@@ -287,13 +291,13 @@ def patch_embed(img: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torch.
     # fp16 copies of the (frozen) stem parameters, rebuilt only when a parameter changes
     key = (conv_w.data_ptr(), conv_w._version, None if conv_b is None else conv_b._version,
            cls_token.data_ptr(), cls_token._version, pos_embed.data_ptr(), pos_embed._version)
-    cached = _stem_params.get(conv_w.data_ptr())
+    cached = _stem_params.get(conv_w)
     if cached is None or cached[0] != key:
         w16 = conv_w.detach().reshape(Cdim, -1).to(torch.float16).contiguous()
         b16 = None if conv_b is None else conv_b.detach().to(torch.float16).contiguous()
         cls = cls_token.detach().reshape(-1).to(torch.float32).contiguous()
         pos = pos_embed.detach().reshape(L + 1, Cdim).to(torch.float32).contiguous()
-        _stem_params[conv_w.data_ptr()] = cached = (key, w16, b16, cls, pos)
+        _stem_params[conv_w] = cached = (key, w16, b16, cls, pos)
     _, w16, b16, cls, pos = cached
     need = int(_lib.lib().dyt_patch_embed_workspace_bytes(B, H, W, patch, Cin, Cdim))
     if need == 0:
@@ -309,6 +313,11 @@ def patch_embed(img: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torch.
         pos.data_ptr(), Cdim, x.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
         "dyt_patch_embed_fwd")
     return x
+
+
+def invalidate_stem_cache() -> None:
+    """Drop the cached stem parameter copies (see engine.invalidate_caches)."""
+    _stem_params.clear()
 
 
 def pool_layernorm_f16(x: torch.Tensor, norm0, norm_k, norm_v, eps: float = 1e-6):

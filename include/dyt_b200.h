@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DYT_ABI_VERSION 1
+#define DYT_ABI_VERSION 2
 
 /* epilogues of dyt_linear_f16 */
 #define DYT_EPI_BIAS 0       /* y = f16(x W^T + b)                                            */
@@ -278,6 +278,9 @@ typedef struct dyt_block_weights { /* device pointers; *_w of Linears are fp16 [
 } dyt_block_weights;
 
 typedef struct dyt_block_opts {
+  size_t struct_size;      /* = sizeof(dyt_block_opts) of the header the caller was built against;
+                              dyt_block_fwd rejects any other value (a binding whose field list has
+                              gone stale fails loudly instead of being read past its end) */
   float eps;               /* LayerNorm eps (1e-6) */
   int logit_fp16;          /* see dyt_dispatch_fwd */
   float min_kept;

@@ -50,6 +50,47 @@ def test_struct_layouts_match_header_field_order():
         assert fields == [f[0] for f in cls._fields_], cname
 
 
+def _header_fields(cname):
+    src = open(HEADER).read()
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            fields.append(re.sub(r"[\*\s]", " ", decl).split()[-1])
+    return fields
+
+
+def test_integration_doc_stub_matches_the_header():
+    """INTEGRATION.md shows the ctypes stub a reference maintainer would add; its structure field
+    lists must be the header's, field for field (the round-1 stub had lost `attn_bias`: the library
+    would have read past the end of the caller's struct)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for cls, cname in (("Shape", "dyt_block_shape"), ("Weights", "dyt_block_weights"),
+                       ("Opts", "dyt_block_opts")):
+        block = re.search(r"class %s\(ctypes\.Structure\):(.*?)\n(?=class |\n|_lib)" % cls, doc, flags=re.S)
+        assert block is not None, cls
+        names = re.findall(r'"([A-Za-z_0-9]+)"', block.group(1))
+        assert names == _header_fields(cname), (cls, names)
+    assert "struct_size=ctypes.sizeof(Opts)" in doc
+    assert re.search(r"dyt_version\(\) == (\d+)", doc).group(1) == re.search(
+        r"#define DYT_ABI_VERSION (\d+)", open(HEADER).read()).group(1)
+
+
+def test_block_opts_struct_size_is_enforced():
+    """dyt_block_fwd validates opts.struct_size before anything touches the GPU."""
+    from dyt_b200 import _lib
+    lib = _lib.lib()
+    shape = _lib.BlockShape(2, 197, 768, 12, 3072, 64)
+    wt, opts = _lib.BlockWeights(), _lib.BlockOpts()
+    opts.struct_size = ctypes.sizeof(_lib.BlockOpts) - 8          # a binding without the last field
+    st = lib.dyt_block_fwd(ctypes.byref(shape), ctypes.byref(wt), ctypes.byref(opts), 256, 256, 256,
+                           256, 1 << 40, None)
+    assert st < 0 and b"struct_size" in lib.dyt_last_error()
+    assert ctypes.sizeof(_lib.BlockOpts) == 96                    # 64-bit layout of the header struct
+
+
 def test_argument_errors_are_reported_not_raised_across_the_abi():
     from dyt_b200 import _lib
     lib = _lib.lib()

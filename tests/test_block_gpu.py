@@ -559,3 +559,39 @@ def test_segmentation_backbone_512_tokens_1025(dev):
     agree = ((d["token_select"].float().cpu() > 0.5) == (ref["token_select"] > 0.5)).float().mean(dim=(0, 2, 3))
     assert agree[0] >= 0.995 and agree[1] >= 0.98, agree
     assert _rel(feats[0], ref["features"][0]) <= 2e-2
+
+
+def test_parameter_caches_are_per_model_and_can_be_invalidated(dev):
+    """The fp16 working copies of the stem / block / head parameters belong to their model: a second
+    model built after the first was freed (its tensors typically land on the recycled addresses,
+    with identical version counters) must not see the first one's copies; a write through `.data`
+    (no version bump) is picked up after dyt_b200.invalidate_caches()."""
+    import dyt_b200
+    from models.model_speed_test import VisionTransformer
+
+    def stem_ref(m, img):
+        w = m.patch_embed.proj.weight.detach().half().float()
+        b = m.patch_embed.proj.bias.detach().half().float()
+        t = torch.nn.functional.conv2d(img.half().float(), w, b, stride=16).flatten(2).transpose(1, 2)
+        t = torch.cat((m.cls_token.detach().expand(img.shape[0], -1, -1), t), dim=1)
+        return t + m.pos_embed.detach()
+
+    img = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(0)).to(dev)
+    tuning, select = configs(ffn_num=16, d_model=128)
+    for seed in (1, 2, 3):
+        torch.manual_seed(seed)
+        m = VisionTransformer(img_size=32, patch_size=16, embed_dim=128, depth=1, num_heads=2,
+                              num_classes=10, tuning_config=tuning, select_config=select).eval().to(dev)
+        with torch.no_grad():
+            torch.nn.init.normal_(m.patch_embed.proj.weight, std=0.05 * seed)
+            torch.nn.init.normal_(m.cls_token, std=0.1 * seed)
+            got = m._embed(img)
+            assert _rel(got, stem_ref(m, img)) <= 2e-3, seed
+            logits0 = m(img)
+            # a write that bumps no version counter ...
+            m.patch_embed.proj.weight.data.mul_(2.0)
+            m.head.weight.data.mul_(0.5)
+            dyt_b200.invalidate_caches(m)
+            assert _rel(m._embed(img), stem_ref(m, img)) <= 2e-3, seed
+            assert not torch.equal(m(img), logits0)
+        del m

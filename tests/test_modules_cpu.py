@@ -149,13 +149,27 @@ def test_finetune_loss_matches_reference_golden():
     52-65, models/losses.py:50-82) on the reference's own outputs reproduces the reference's loss."""
     from dyt_b200.finetune import ada_loss, finetune_loss
     g = load_golden("finetune_tiny.pt")
-    loss = finetune_loss(g["student_logits"], g["token_select"], g["teacher_logits"], g["targets"])
+    # the fixture was made with the AdaLoss class defaults (token_minimal 0.1, weight 1.0)
+    cls = dict(token_minimal=0.1, token_minimal_weight=1.0)
+    loss = finetune_loss(g["student_logits"], g["token_select"], g["teacher_logits"], g["targets"], **cls)
     assert abs(loss.item() - g["loss"].item()) <= 1e-5
     # AdaLoss alone: cross-entropy + 2 * ((mean keep - 0.5)^2 + sum(clamp(0.1 - sel, 0)))
     sel = g["token_select"]
     want = torch.nn.functional.cross_entropy(g["student_logits"], g["targets"]) + 2.0 * (
         (sel.mean() - 0.5) ** 2 + (0.1 - sel.mean(-1)).clamp(min=0).sum())
-    assert abs(ada_loss(g["student_logits"], sel, g["targets"]).item() - want.item()) <= 1e-6
+    assert abs(ada_loss(g["student_logits"], sel, g["targets"], **cls).item() - want.item()) <= 1e-6
+    # the recipe of the entry scripts (main_image.py:206-209): no minimal-keep term
+    want0 = torch.nn.functional.cross_entropy(g["student_logits"], g["targets"]) + 2.0 * (sel.mean() - 0.5) ** 2
+    assert abs(ada_loss(g["student_logits"], sel, g["targets"]).item() - want0.item()) <= 1e-6
+    # drop-in models.losses.AdaLoss: the reference's class (same ctor keywords, same return)
+    from models.losses import AdaLoss
+    crit = AdaLoss(torch.nn.CrossEntropyLoss(), token_target_ratio=0.5, token_loss_ratio=2.0,
+                   token_minimal=0.1, token_minimal_weight=1.0)
+    l, parts = crit(dict(prediction=g["student_logits"], token_select=sel, token_logits=None), g["targets"])
+    assert abs(l.item() - want.item()) <= 1e-6 and set(parts) == {"base_loss", "token_loss"}
+    l0, _ = AdaLoss(torch.nn.CrossEntropyLoss(), token_minimal=0.0, token_minimal_weight=0.0)(
+        dict(prediction=g["student_logits"], token_select=sel, token_logits=None), g["targets"])
+    assert abs(l0.item() - want0.item()) <= 1e-6
 
 
 def test_graphed_forward_and_accounting_refuse_cpu():
