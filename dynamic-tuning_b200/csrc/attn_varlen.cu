@@ -141,6 +141,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   // kernel parameters are not indexed dynamically (would force a local-memory copy)
   auto s_col = [&](int tile) { return static_cast<uint32_t>(tile ? p.s_col[1] : p.s_col[0]); };
   auto o_col = [&](int tile) { return static_cast<uint32_t>(tile ? p.o_col[1] : p.o_col[0]); };
@@ -172,6 +173,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // qkv (and cu_seqlens) of the previous kernel are read from here on
 
   // register budget per warpgroup (512 threads start at 128 each): control 56, softmax 168,
   // output 96 -> 128 * (56 + 2 * 168 + 96) = 62464 <= 65536
@@ -529,8 +531,9 @@ int attn_varlen_fwd(const __half* qkv, int ld_qkv, const int* cu_seqlens, int nu
     if (st != DYT_OK) return st;
   }
   const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
-  attn_fwd_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tq, tkv, p);
-  return cuda_status(cudaGetLastError(), "attn_fwd_kernel launch");
+  return cuda_status(launch_pdl(attn_fwd_kernel, dim3(grid), dim3(ATT_THREADS), smem_bytes, stream,
+                                tq, tkv, p),
+                     "attn_fwd_kernel launch");
 }
 
 }  // namespace dyt

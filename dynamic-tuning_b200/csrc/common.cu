@@ -6,3 +6,13 @@
 
 extern "C" int dyt_version(void) { return DYT_ABI_VERSION; }
 extern "C" const char* dyt_last_error(void) { return dyt::last_error_buf(); }
+
+extern "C" int dyt_configure(int option, int value) {
+  switch (option) {
+    case DYT_OPT_PDL:
+      dyt::pdl_option().store(value != 0 ? 1 : 0);
+      return dyt::DYT_OK;
+    default:
+      return dyt::fail(dyt::DYT_EINVAL, "dyt_configure: unknown option %d", option);
+  }
+}

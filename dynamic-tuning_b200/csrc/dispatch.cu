@@ -23,6 +23,7 @@
 
 #include "../../include/dyt_b200.h"
 #include "host_utils.h"
+#include "ptx.cuh"
 #include "rowwise.cuh"
 
 namespace dyt {
@@ -96,6 +97,8 @@ dispatch_kernel(const DispatchParams p) {
   __shared__ unsigned char s_keep[DISPATCH_MAX_N];
   __shared__ int s_wsum[8];
 
+  pdl_launch_dependents();
+  pdl_wait();  // x1 / the score partials of the preceding GEMM
   if (threadIdx.x == 0) {
     s_b = static_cast<int>(atomicAdd(&p.ctl[0], 1u));   // ticket order: predecessors are running
     s_tag = *reinterpret_cast<volatile unsigned int*>(&p.ctl[2]) + 1u;
@@ -275,8 +278,9 @@ dispatch_kernel(const DispatchParams p) {
 
 template <int NV>
 static int launch_dispatch(const DispatchParams& p, cudaStream_t stream) {
-  dispatch_kernel<NV><<<p.B, 256, 0, stream>>>(p);   // one CTA per image, taken in ticket order
-  return cuda_status(cudaGetLastError(), "dispatch_kernel launch");
+  // one CTA per image, taken in ticket order
+  return cuda_status(launch_pdl(dispatch_kernel<NV>, dim3(p.B), dim3(256), 0, stream, p),
+                     "dispatch_kernel launch");
 }
 
 }  // namespace dyt

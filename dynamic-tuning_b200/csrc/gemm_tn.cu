@@ -29,13 +29,15 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // the kernel calls pdl_wait()
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_option().load(std::memory_order_relaxed) ? 2 : 1;
   return cuda_status(cudaLaunchKernelEx(&cfg, kern, ta, tb, p), "gemm_tn_kernel launch");
 }
 

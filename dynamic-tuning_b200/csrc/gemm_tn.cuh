@@ -110,18 +110,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  int m_eff = p.M;
-  if (p.m_dev != nullptr) {
-    int md = *p.m_dev;
-    m_eff = md < p.M ? md : p.M;
-  }
-  const int m_tiles = (m_eff + BM - 1) / BM;
-  const int n_tiles = (p.N + BN - 1) / BN;
-  // work item = a pair of vertically adjacent tiles, one per CTA of the cluster (the odd last tile
-  // row pairs with an all-masked dummy: its TMA boxes are out of bounds and read as zeros)
-  const int total_tiles = ((m_tiles + 1) / 2) * n_tiles;
-  const int k_blocks = (p.K + BK - 1) / BK;
+  pdl_launch_dependents();
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -147,6 +136,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // everything above overlapped the previous kernel's tail; its results (A, the residual, the
+  // device-side row count) are read from here on
+  pdl_wait();
+  int m_eff = p.M;
+  if (p.m_dev != nullptr) {
+    int md = *p.m_dev;
+    m_eff = md < p.M ? md : p.M;
+  }
+  const int m_tiles = (m_eff + BM - 1) / BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  // work item = a pair of vertically adjacent tiles, one per CTA of the cluster (the odd last tile
+  // row pairs with an all-masked dummy: its TMA boxes are out of bounds and read as zeros)
+  const int total_tiles = ((m_tiles + 1) / 2) * n_tiles;
+  const int k_blocks = (p.K + BK - 1) / BK;
   const int cta_rank = static_cast<int>(cluster_ctarank());
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;

@@ -29,6 +29,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch (PDL).  launch_dependents: the next kernel of the stream may be
+// scheduled once every CTA of this grid has got here (its CTAs then take over SM resources as ours
+// exit and run their prologue -- barrier init, TMEM allocation, descriptor prefetch -- under our
+// tail).  wait: returns when the preceding grid has completed and its memory is visible; nothing
+// that a predecessor produces may be read, and nothing global written, before it.  Both are no-ops
+// for a kernel launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Explicit shared-space accesses.  The dynamic-smem base pointer goes through an integer round-up
 // to 1024 B, after which the compiler no longer knows the address space and would emit generic
 // LD/ST (slower issue, tracked on the long scoreboard) instead of LDS/STS.

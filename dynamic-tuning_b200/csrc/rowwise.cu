@@ -5,6 +5,7 @@
 
 #include "../../include/dyt_b200.h"
 #include "host_utils.h"
+#include "ptx.cuh"
 #include "rowwise.cuh"
 
 namespace dyt {
@@ -21,6 +22,8 @@ layernorm_f16_kernel(const float* __restrict__ x, int ldx, const int* __restrict
                      const float* __restrict__ beta, float eps, __half* __restrict__ out, int ldo) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
   int rows = n_rows;
   if (n_rows_dev != nullptr) {
     const int nd = *n_rows_dev;
@@ -46,27 +49,28 @@ int layernorm_f16(const float* x, int ldx, const int* row_idx, const int* n_rows
   int grid = (n_rows + 7) / 8;
   const int cap = sm_count() * 16;
   if (grid > cap) grid = cap;
+  cudaError_t err = cudaSuccess;
   switch (C) {
     case 768:
-      layernorm_f16_kernel<6><<<grid, 256, 0, stream>>>(x, ldx, row_idx, n_rows_dev, n_rows, gamma,
-                                                        beta, eps, out, ldo);
+      err = launch_pdl(layernorm_f16_kernel<6>, dim3(grid), dim3(256), 0, stream, x, ldx, row_idx,
+                       n_rows_dev, n_rows, gamma, beta, eps, out, ldo);
       break;
     case 1024:
-      layernorm_f16_kernel<8><<<grid, 256, 0, stream>>>(x, ldx, row_idx, n_rows_dev, n_rows, gamma,
-                                                        beta, eps, out, ldo);
+      err = launch_pdl(layernorm_f16_kernel<8>, dim3(grid), dim3(256), 0, stream, x, ldx, row_idx,
+                       n_rows_dev, n_rows, gamma, beta, eps, out, ldo);
       break;
     case 384:
-      layernorm_f16_kernel<3><<<grid, 256, 0, stream>>>(x, ldx, row_idx, n_rows_dev, n_rows, gamma,
-                                                        beta, eps, out, ldo);
+      err = launch_pdl(layernorm_f16_kernel<3>, dim3(grid), dim3(256), 0, stream, x, ldx, row_idx,
+                       n_rows_dev, n_rows, gamma, beta, eps, out, ldo);
       break;
     case 128:
-      layernorm_f16_kernel<1><<<grid, 256, 0, stream>>>(x, ldx, row_idx, n_rows_dev, n_rows, gamma,
-                                                        beta, eps, out, ldo);
+      err = launch_pdl(layernorm_f16_kernel<1>, dim3(grid), dim3(256), 0, stream, x, ldx, row_idx,
+                       n_rows_dev, n_rows, gamma, beta, eps, out, ldo);
       break;
     default:
       return fail(DYT_EUNSUPPORTED, "layernorm: embed dim %d not instantiated (128/384/768/1024)", C);
   }
-  return cuda_status(cudaGetLastError(), "layernorm_f16_kernel launch");
+  return cuda_status(err, "layernorm_f16_kernel launch");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -139,6 +143,8 @@ scatter_merge_kernel(const float* __restrict__ x1, int ldx, const __half* __rest
                      int ldn) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n_rows;
        r += gridDim.x * warps_per_block) {
     float4 v[NV];
@@ -185,9 +191,10 @@ int scatter_merge(const float* x1, int ldx, const __half* adapt, int lda, const 
   int grid = (n_rows + 7) / 8;
   const int cap = sm_count() * 16;
   if (grid > cap) grid = cap;
-#define DYT_LAUNCH_MERGE(NV)                                                                      \
-  scatter_merge_kernel<NV><<<grid, 256, 0, stream>>>(x1, ldx, adapt, lda, mlp_packed, ldm, token_pos, \
-                                                     n_rows, out, ldo, nln_w, nln_b, eps, nln_out, ldn)
+  cudaError_t err = cudaSuccess;
+#define DYT_LAUNCH_MERGE(NV)                                                                       \
+  err = launch_pdl(scatter_merge_kernel<NV>, dim3(grid), dim3(256), 0, stream, x1, ldx, adapt, lda, \
+                   mlp_packed, ldm, token_pos, n_rows, out, ldo, nln_w, nln_b, eps, nln_out, ldn)
   switch (C) {
     case 768: DYT_LAUNCH_MERGE(6); break;
     case 1024: DYT_LAUNCH_MERGE(8); break;
@@ -197,7 +204,7 @@ int scatter_merge(const float* x1, int ldx, const __half* adapt, int lda, const 
       return fail(DYT_EUNSUPPORTED, "scatter_merge: embed dim %d not instantiated", C);
   }
 #undef DYT_LAUNCH_MERGE
-  return cuda_status(cudaGetLastError(), "scatter_merge_kernel launch");
+  return cuda_status(err, "scatter_merge_kernel launch");
 }
 
 }  // namespace dyt

@@ -16,6 +16,7 @@ ABI_VERSION = 2
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_BIAS_RESID = 0, 1, 2, 3
 EPI_BIAS_GELU_KEEP, EPI_DGELU = 4, 5
+OPT_PDL = 1
 EW_GELU_FWD, EW_GELU_BWD, EW_RELU_DROP_BWD, EW_MUL = 0, 1, 2, 3
 
 
@@ -55,6 +56,7 @@ _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 SIGNATURES = {
     "dyt_version": (_i, []),
     "dyt_last_error": (C.c_char_p, []),
+    "dyt_configure": (_i, [_i, _i]),
     "dyt_linear_f16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i,
                             _f, _vp]),
     "dyt_linear_f16_aux": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp]),

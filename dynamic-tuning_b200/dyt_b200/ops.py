@@ -273,10 +273,21 @@ def scatter_merge(x1: torch.Tensor, adapt: torch.Tensor, mlp_packed: torch.Tenso
 
 
 _stem_ws = {}
-# fp16 / fp32 working copies of the stem parameters, keyed by the PARAMETER OBJECT (weak): an entry
-# dies with its model, so a new model whose tensors land on recycled addresses can never pick up
-# another model's copies (a cache keyed by data_ptr could), and nothing accumulates.
-_stem_params = weakref.WeakKeyDictionary()
+# fp16 / fp32 working copies of the stem parameters, keyed by the identity of the PARAMETER OBJECT
+# (held weakly: the entry is dropped when the parameter dies), so a new model whose tensors land on
+# recycled device addresses can never pick up another model's copies (a cache keyed by data_ptr
+# could), and nothing accumulates.
+_stem_params = {}
+
+
+def _stem_get(param):
+    ent = _stem_params.get(id(param))
+    return ent[1] if ent is not None and ent[0]() is param else None
+
+
+def _stem_put(param, value):
+    pid = id(param)
+    _stem_params[pid] = (weakref.ref(param, lambda _r, pid=pid: _stem_params.pop(pid, None)), value)
 
 
 def patch_embed(img: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torch.Tensor],
@@ -291,13 +302,14 @@ def patch_embed(img: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torch.
     # fp16 copies of the (frozen) stem parameters, rebuilt only when a parameter changes
     key = (conv_w.data_ptr(), conv_w._version, None if conv_b is None else conv_b._version,
            cls_token.data_ptr(), cls_token._version, pos_embed.data_ptr(), pos_embed._version)
-    cached = _stem_params.get(conv_w)
+    cached = _stem_get(conv_w)
     if cached is None or cached[0] != key:
         w16 = conv_w.detach().reshape(Cdim, -1).to(torch.float16).contiguous()
         b16 = None if conv_b is None else conv_b.detach().to(torch.float16).contiguous()
         cls = cls_token.detach().reshape(-1).to(torch.float32).contiguous()
         pos = pos_embed.detach().reshape(L + 1, Cdim).to(torch.float32).contiguous()
-        _stem_params[conv_w] = cached = (key, w16, b16, cls, pos)
+        cached = (key, w16, b16, cls, pos)
+        _stem_put(conv_w, cached)
     _, w16, b16, cls, pos = cached
     need = int(_lib.lib().dyt_patch_embed_workspace_bytes(B, H, W, patch, Cin, Cdim))
     if need == 0:

@@ -41,6 +41,15 @@ extern "C" {
 int dyt_version(void);
 const char* dyt_last_error(void);
 
+/* Process-wide library options (thread-safe; take effect for subsequent launches).
+ *   DYT_OPT_PDL (default 0): launch the forward-path kernels with programmatic stream serialization
+ *   (cudaLaunchAttributeProgrammaticStreamSerialization): every kernel signals launch_dependents at
+ *   its start and executes griddepcontrol.wait after its prologue (barrier init, TMEM allocation,
+ *   tensor-map prefetch), so that prologue overlaps the previous kernel's tail.  CUDA-graph
+ *   capturable.  0 = plain stream order (the default: no gain was measured on B200). */
+#define DYT_OPT_PDL 1
+int dyt_configure(int option, int value);
+
 /* y = epilogue(x[M,K] * w[N,K]^T): the nn.Linear forward under fp16 autocast.
  * Replaces: attn.qkv / attn.proj (reference models/model_speed_test.py:147, :164),
  *           timm Mlp fc1/fc2 (models/model_speed_test.py:303 via timm.layers.Mlp),
