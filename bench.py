@@ -81,7 +81,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, pw, mx, reasons = [], [], None, set()
         try:
             for line in open(self.path):
                 f = [t.strip() for t in line.split(",")]
@@ -89,6 +89,10 @@ class ClockSampler:
                     continue
                 sm.append(float(f[1]))
                 mx = float(f[2])
+                try:
+                    pw.append(float(f[3]))
+                except ValueError:
+                    pass
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                                     "sw_power_cap"), f[5:9]):
                     if v.lower().startswith("active"):
@@ -97,8 +101,13 @@ class ClockSampler:
         except Exception:
             pass
         sm.sort()
+        pw.sort()
         return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm),
+                    # board power under load: the samples cover idle set-up phases too, so report the
+                    # upper quartile and the maximum (cap: 1000 W)
+                    power_w=(pw[(3 * len(pw)) // 4] if pw else None),
+                    power_w_max=(pw[-1] if pw else None))
 
 
 def dist_setup(n_gpus: int):
@@ -148,23 +157,43 @@ def barrier(world: int):
 # reference's own outputs by tests/test_oracle_golden.py) on the host cores
 # ---------------------------------------------------------------------------------------------
 def cpu_reference_run(state_dict, steps: int, warmup: int, sample_batch: int, seed: int = 0):
+    """The reference's own CPU forward of the path on a bounded sample: models/model_speed_test.py
+    UNMODIFIED (oracle/_ref/, made by oracle/build_ref.py from the read-only checkout, imported
+    through oracle/ref_shim.py's timm / easydict stand-ins) -> kind "reference"; the oracle port
+    only if those files are not there -> kind "port".  fp32, eval, no_grad, all host threads."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import dyt_oracle as O
+    import ref_shim
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     img = torch.randn(sample_batch, 3, 224, 224, generator=torch.Generator().manual_seed(seed))
     sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
+    kind = "port"
+    fwd = lambda: O.vit_forward(img, sd, DEPTH, HEADS, 0.1, policy="fp32", sparse=True)["logits"]
+    if ref_shim.reference_available():
+        ref = ref_shim.import_reference("models.model_speed_test")
+        tuning, select = ref_shim.reference_configs(ffn_num=BOTTLENECK, scalar="0.1", d_model=C_DIM,
+                                                    ratio=RATE)
+        model = ref.vit_base_patch16_224_in21k(num_classes=NUM_CLASSES, drop_path_rate=0.0,
+                                               tuning_config=tuning, select_config=select)
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        fwd = lambda: model(img)
+        kind = "reference"
     with torch.no_grad():
         for _ in range(warmup):
-            O.vit_forward(img, sd, DEPTH, HEADS, 0.1, policy="fp32", sparse=True)
+            fwd()
         t0 = time.perf_counter()
         for _ in range(steps):
-            r = O.vit_forward(img, sd, DEPTH, HEADS, 0.1, policy="fp32", sparse=True)
+            fwd()
         dt = time.perf_counter() - t0
-    keep = r["token_select"].float().mean().item()
+        keep = O.vit_forward(img[:4], sd, DEPTH, HEADS, 0.1, policy="fp32",
+                             sparse=True)["token_select"].float().mean().item()
+    what = ("reference models/model_speed_test.py (unmodified, oracle/_ref)" if kind == "reference"
+            else "oracle port of the reference forward")
     return dict(value=sample_batch * steps / dt, ms_per_step=dt / steps * 1e3, cores=cores,
-                keep_rate=keep,
-                sample=f"{steps} forward(s) of {sample_batch} seed-{seed} images, fp32, "
+                keep_rate=keep, kind=kind,
+                sample=f"{steps} forward(s) of {sample_batch} seed-{seed} images, {what}, fp32, "
                        f"torch {torch.__version__} CPU, {cores} threads")
 
 
@@ -224,7 +253,7 @@ def synthetic_cpu_state_dict(seed: int = 0):
 def run_reference(args, world, rank):
     if rank != 0:
         return
-    sample = 16
+    sample = 32
     sd = synthetic_cpu_state_dict(0)
     r = cpu_reference_run(sd, max(1, args.steps), max(1, min(args.warmup, 2)), sample)
     line = {
@@ -235,7 +264,7 @@ def run_reference(args, world, rank):
         "config": {"workload": "ViT-B/16 DyT inference 224x224 r~0.5 (speed.py path), CPU sample "
                                f"of {sample} images per step", "keep_rate": r["keep_rate"]},
         "cpu_baseline": {"value": r["value"], "unit": "images/s", "cores": r["cores"],
-                         "kind": "port", "sample": r["sample"]},
+                         "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -432,6 +461,16 @@ def run_ours(args, world, rank, local):
     sec_e2e = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, world, device)
     e2e_value = BATCH * world * args.steps / sec_e2e
 
+    # ---- extras that involve every rank (fine-tune step with its gradient all-reduce), measured
+    # after and outside the headline's timed regions ----
+    del graphed, dev_in, static_images
+    torch.cuda.empty_cache()
+    extras = {}
+    if not args.no_extras:
+        try:
+            extras = gather_extras_after(args, world, rank, local)
+        except Exception as e:       # an extra must never take the headline down
+            extras = {"error": repr(e)[:300]}
     if rank != 0:
         return
     fl_img = flops_per_image(kept_tokens)
@@ -466,30 +505,61 @@ def run_ours(args, world, rank, local):
     if world == 1:
         rows = kernel_table(model, x0, kept_tokens * BATCH, peaks, device)
         top = max((r for r in rows if r["bound"] == "tensor"), key=lambda r: r["us"])
-        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed
-        # ncu --set full capture (profiles/r1e_ncu_full_one_layer.md), per launch
-        traffic = {"gemm qkv [T,768]x[2304,768]": 261.9e6, "gemm fc1 + GELU (kept rows)": 147.9e6,
-                   "gemm fc2 (kept rows)": 189.9e6}.get(top["kernel"])
         line["roofline"] = {"kernel": top["kernel"], "bound": "tensor", "achieved": top["achieved"],
                             "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": top["frac"],
-                            "traffic": traffic, "us_per_launch": top["us"],
-                            "peak_source": peaks["source"] + " bf16 burst (kernel timed alone)"}
+                            "traffic": ncu_traffic(top["kernel"]), "us_per_launch": top["us"],
+                            "peak_source": peaks["source"] + " bf16 burst (kernel timed alone)",
+                            # the whole step against the r-scaled compute roofline (the north-star
+                            # figure): model FLOPs / step time / sustained tensor peak
+                            "frac_model": line["frac_of_r_scaled_compute_roofline"],
+                            "frac_model_peak": peaks["tf_sust"],
+                            "frac_model_note": "whole forward: algorithmic FLOPs per image x images/s / "
+                                               "measured sustained bf16 peak (kernel inside a long step)"}
         line["kernels"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()}
                            for r in rows]
         if not args.no_cpu_baseline:
             sd = model.state_dict()
-            r = cpu_reference_run(sd, steps=10, warmup=1, sample_batch=16)
+            r = cpu_reference_run(sd, steps=8, warmup=1, sample_batch=32)
             line["cpu_baseline"] = {"value": r["value"], "unit": "images/s", "cores": r["cores"],
-                                    "kind": "port", "sample": r["sample"]}
+                                    "kind": r["kind"], "sample": r["sample"]}
+    if not args.no_extras and world == 1:
+        try:
+            extras["torch_eager_b200"] = torch_eager_b200(model, images)
+        except Exception as e:
+            extras["torch_eager_b200"] = {"error": repr(e)[:200]}
+    line["extras"] = extras or None
     print(json.dumps(line), flush=True)
 
 
-def run_extra(args, world, rank, local):
+def gather_extras_after(args, world, rank, local):
+    """Other BASELINE configs as one-liners inside the headline JSON: the fine-tune step at the same
+    N ranks (BASELINE configs[2]; the only path with a collective: flat-arena gradient all-reduce,
+    reported with its bytes and its own device time), and at N = 1 ViT-L/16 (configs[3] without the
+    MoE-adapter) and the video model (configs[4])."""
+    ex = {}
+    ft = measure_finetune(8, 6, world, rank, local, cpu_baseline=False)
+    if ft is not None:
+        ex["finetune_b16"] = {k: ft[k] for k in ("value", "unit", "ms_per_step", "n_gpus", "model_tflops")}
+        ex["finetune_b16"].update(allreduce_bytes_per_step=ft["config"]["allreduce_bytes_per_step"],
+                                  allreduce_us=ft["config"]["allreduce_us"], loss=ft["config"]["loss"],
+                                  images_per_gpu=64, workload=ft["config"]["workload"])
+    if world == 1:
+        for wl in ("vit_l16", "video_b16"):
+            r = measure_extra(wl, 8, 4, world, rank, local)
+            if r is not None:
+                ex[wl] = {"value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"],
+                          "workload": r["config"]["workload"]}
+    return ex
+
+
+def measure_extra(workload, steps, warmup, world, rank, local):
     """Extra workloads (not the headline line): the other single-GPU BASELINE configs, same timing
-    rules (CUDA events, >= 3 warm-up steps, inputs in HBM, working set >> L2)."""
+    rules (CUDA events, >= 3 warm-up steps, inputs in HBM, working set >> L2).  Returns the JSON
+    object (rank 0) or None."""
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     from dyt_b200 import synthetic
+    args = argparse.Namespace(workload=workload, steps=steps, warmup=warmup)
     if args.workload == "vit_l16":
         model = synthetic.build_vit_l16(device, seed=0)
         batch, rate, units, name = 128, 0.7, "images/s", "ViT-L/16 DyT inference bs128 224x224 r~0.7 (no MoE-adapter: not in the reference)"
@@ -560,12 +630,21 @@ def run_extra(args, world, rank, local):
     torch.cuda.synchronize()
     barrier(world)
     sec = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, world, device)
-    if rank == 0:
-        print(json.dumps({"metric": f"extra workload {args.workload}", "value": per_step * world * args.steps / sec,
-                          "unit": units, "n_gpus": world, "steps": args.steps, "warmup": warm,
-                          "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-                          "config": {"workload": name, "keep_rate_calibration": round(keep, 4)}}), flush=True)
+    del graphed, model
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {"metric": f"extra workload {args.workload}", "value": per_step * world * args.steps / sec,
+            "unit": units, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": name, "keep_rate_calibration": round(keep, 4)}}
+
+
+def run_extra(args, world, rank, local):
+    line = measure_extra(args.workload, args.steps, args.warmup, world, rank, local)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 def finetune_flops_per_image(bottleneck: int = 16) -> float:
@@ -584,7 +663,7 @@ def finetune_flops_per_image(bottleneck: int = 16) -> float:
     return 2.0 * per_pass
 
 
-def run_finetune(args, world, rank, local):
+def measure_finetune(steps, warmup, world, rank, local, cpu_baseline=False):
     """BASELINE configs[2]: ViT-B/16 DyT fine-tune step on synthetic VTAB-shape data, 64 images per
     GPU (512 global at 8), ffn_num 16, adapter scale 1 (train_vtab.sh:8, main_vtab.py:351).  One step
     = student pass + teacher pass + loss + backward + ONE gradient all-reduce (NCCL, flat 74-tensor
@@ -605,6 +684,7 @@ def run_finetune(args, world, rank, local):
     arena = GradArena(params)
     step = FinetuneStep(model, torch.optim.AdamW(params, lr=1e-3, weight_decay=0.05), arena,
                         cuda_graph=True)
+    args = argparse.Namespace(steps=steps, warmup=warmup)
     warm = max(6, args.warmup)          # the dynamic loss scale settles within the first steps
     for _ in range(warm):
         loss = step(images, targets)
@@ -618,25 +698,114 @@ def run_finetune(args, world, rank, local):
     torch.cuda.synchronize()
     barrier(world)
     sec = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, world, device)
+    # the step's only collective on its own: the flat gradient arena all-reduce (NCCL over NVLink),
+    # timed on the device, max over ranks
+    ar_us = None
+    if world > 1:
+        for _ in range(5):
+            arena.all_reduce_mean()
+        barrier(world)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(20):
+            arena.all_reduce_mean()
+        ev1.record()
+        torch.cuda.synchronize()
+        ar_us = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, world, device) / 20 * 1e6
+    loss_val, scale_val, nbytes, ntens = float(loss), float(step.scaler.get_scale()), arena.nbytes, len(arena.params)
+    sd_cpu = {k: v.detach().float().cpu() for k, v in model.state_dict().items()} if (cpu_baseline and rank == 0) else None
+    del step, arena, model
+    torch.cuda.empty_cache()
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline and world == 1:
-            cpu = cpu_finetune_run(model.state_dict())
-        print(json.dumps({
+        if cpu_baseline and world == 1:
+            cpu = cpu_finetune_run(sd_cpu)
+        return ({
             "metric": "extra workload finetune_b16", "value": batch * world * args.steps / sec,
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": "ViT-B/16 DyT fine-tune step (student + teacher forward, backward, "
                                    "grad all-reduce, AdamW), 64 images per GPU, ffn_num 16, scale 1",
-                       "keep_rate_calibration": round(keep, 4), "loss": float(loss),
-                       "loss_scale": float(step.scaler.get_scale()),
+                       "keep_rate_calibration": round(keep, 4), "loss": loss_val,
+                       "loss_scale": scale_val,
+                       "loss_recipe": "AdaLoss(token_loss_ratio 2, token_minimal 0, token_minimal_weight 0) "
+                                      "+ teacher CE + KL (main_image.py:206-209, engine_finetune.py:47-65)",
                        "cuda_graph": "forward + backward of the step replayed as one CUDA graph",
-                       "allreduce_bytes_per_step": arena.nbytes if world > 1 else 0,
-                       "trainable_tensors": len(arena.params)},
+                       "allreduce_bytes_per_step": nbytes if world > 1 else 0,
+                       "allreduce_us": ar_us,
+                       "trainable_tensors": ntens},
             "model_flops_per_image": finetune_flops_per_image(16),
             "model_tflops": batch * args.steps / sec * finetune_flops_per_image(16) / 1e12,
-            "cpu_baseline": cpu}), flush=True)
+            "cpu_baseline": cpu})
+    return None
+
+
+def run_finetune(args, world, rank, local):
+    line = measure_finetune(args.steps, args.warmup, world, rank, local,
+                            cpu_baseline=not args.no_cpu_baseline)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def torch_eager_b200(model, images, steps=5, warm=3):
+    """The 'existing Blackwell kernels' bar: the reference's op sequence as plain PyTorch
+    on this GPU -- the oracle restatement under REAL torch.autocast(fp16): cuBLAS, flash-SDPA, ATen
+    nonzero / index gather-scatter with their host syncs -- timed with CUDA events.  A reported
+    baseline (kind "port"), not part of the product path."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dyt_oracle as O
+    import torch.nn.functional as F
+
+    def attention_sdpa(x, p, prefix, num_heads, policy="fp32"):   # vision_transformer_IN21K.py:54-65
+        B, N, C = x.shape
+        qkv = F.linear(x, p[prefix + "qkv.weight"], p[prefix + "qkv.bias"])
+        q, k, v = qkv.reshape(B, N, 3, num_heads, C // num_heads).permute(2, 0, 3, 1, 4).unbind(0)
+        o = F.scaled_dot_product_attention(q, k, v)
+        return F.linear(o.transpose(1, 2).reshape(B, N, C), p[prefix + "proj.weight"], p[prefix + "proj.bias"])
+
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    saved = O.attention
+    O.attention = attention_sdpa
+    try:
+        def fwd():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+                return O.vit_forward(images, sd, DEPTH, HEADS, 0.1, policy="fp32", sparse=True)
+        for _ in range(warm):
+            fwd()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            fwd()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        O.attention = saved
+    return {"value": images.shape[0] / ms * 1e3, "unit": "images/s", "ms_per_step": ms, "kind": "port",
+            "what": "oracle restatement of the reference forward under torch.autocast(fp16) on this GPU "
+                    "(cuBLAS + flash SDPA + ATen nonzero/index), bs %d" % images.shape[0]}
+
+
+def ncu_traffic(kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the
+    committed ncu --set full summary of THIS build's kernel sources (profiles/r2_ncu_traffic.json;
+    null when the kernel source changed since the capture)."""
+    import hashlib
+    path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        rec = json.load(open(path))
+        h = hashlib.sha256()
+        for f in rec["source_files"]:
+            h.update(open(os.path.join(ROOT, f), "rb").read())
+        if h.hexdigest() != rec["source_sha256"]:
+            return None
+        return rec["dram_bytes_per_launch"].get(kernel_name)
+    except Exception:
+        return None
 
 
 def main():
@@ -646,6 +815,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extras block (fine-tune step, ViT-L, video, torch-eager bar)")
     ap.add_argument("--workload", default="vit_b16", choices=["vit_b16", "vit_l16", "video_b16", "finetune_b16", "seg_b16"],
                     help="vit_b16 = the BASELINE metric (default); the others are extra lines")
     args = ap.parse_args()

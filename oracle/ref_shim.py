@@ -20,7 +20,17 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REFERENCE_ROOT = os.environ.get("DYT_REFERENCE_ROOT", "/root/reference")
+def _reference_root() -> str:
+    """The reference checkout when it is there (this container), else the travelling copy of the
+    hot-path modules made by oracle/build_ref.py (GPU box: baseline timing only)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    for cand in (os.environ.get("DYT_REFERENCE_ROOT"), "/root/reference", os.path.join(here, "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "models", "model_speed_test.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 class _Mlp(nn.Module):
