@@ -82,7 +82,7 @@ SIGNATURES = {
     "dyt_rowscale_colsum": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "dyt_eltwise_f16": (_i, [_i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dyt_wgrad_f16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _i, _vp, _vp]),
-    "dyt_attn_varlen_bwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "dyt_attn_varlen_bwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "dyt_keep_stats": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp]),
     "dyt_block_workspace_bytes": (_sz, [C.POINTER(BlockShape)]),
     "dyt_block_workspace_layout": (_i, [C.POINTER(BlockShape), _vp, C.POINTER(BlockBuffers)]),

@@ -538,6 +538,6 @@ def attn_varlen_bwd(qkv: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, n
     dqkv = torch.empty_like(q2)
     check(_lib.lib().dyt_attn_varlen_bwd(
         q2.data_ptr(), q2.stride(0), o2.data_ptr(), o2.stride(0), g2.data_ptr(), g2.stride(0),
-        _ptr(cu_seqlens), nseq, uni, mx, num_heads, Cdim // num_heads, dqkv.data_ptr(),
+        _ptr(cu_seqlens), nseq, uni, mx, q2.shape[0], num_heads, Cdim // num_heads, dqkv.data_ptr(),
         dqkv.stride(0), _stream()), "dyt_attn_varlen_bwd")
     return dqkv.reshape(qkv.shape)

@@ -244,12 +244,13 @@ int dyt_wgrad_f16(const void* g_f16, int ldg, const void* x_f16, int ldx, int T,
                   float alpha, float* dW, int ldw, float* db, void* stream);
 
 /* Backward of dyt_attn_varlen_fwd: d_qkv [total_tokens, 3, H, 64] fp16 from qkv, the forward output
- * `out` and its gradient d_out ([total_tokens, H*64] fp16).  Probabilities are recomputed.
- * Sequences up to 208 tokens. */
+ * `out` and its gradient d_out ([total_tokens, H*64] fp16).  Probabilities are recomputed (no
+ * saved softmax statistics).  tcgen05 kernel: TMA-staged Q / K / V / dO, all five contractions on
+ * tcgen05.mma with TMEM accumulators.  Sequences up to 256 tokens, head_dim 64. */
 int dyt_attn_varlen_bwd(const void* qkv, int ld_qkv, const void* out, int ldo, const void* d_out,
                         int ld_do, const int* cu_seqlens, int num_seqs, int uniform_len,
-                        int max_seqlen, int num_heads, int head_dim, void* d_qkv, int ld_dqkv,
-                        void* stream);
+                        int max_seqlen, int total_tokens, int num_heads, int head_dim, void* d_qkv,
+                        int ld_dqkv, void* stream);
 
 /* ---- evaluation analytics ----------------------------------------
  * Per-image FLOPs and per-layer kept-token counters of one batch, on the device.
