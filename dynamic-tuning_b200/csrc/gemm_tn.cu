@@ -9,7 +9,7 @@
 namespace dyt {
 
 template <int BN, int EPI, int EW>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap (&tb)[3], const GemmParams& p,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN, EW>;
   auto kern = gemm_tn_kernel<BN, EPI, EW>;
@@ -38,11 +38,11 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_option().load(std::memory_order_relaxed) ? 2 : 1;
-  return cuda_status(cudaLaunchKernelEx(&cfg, kern, ta, tb, p), "gemm_tn_kernel launch");
+  return cuda_status(cudaLaunchKernelEx(&cfg, kern, ta, tb[0], tb[1], tb[2], p), "gemm_tn_kernel launch");
 }
 
 template <int BN>
-static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb,
+static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap (&tb)[3],
                         const GemmParams& p, cudaStream_t s) {
   // sixteen epilogue warps where the epilogue, not the main loop, sets the pace
   if constexpr (BN == 128 || BN == 256) {
@@ -111,14 +111,19 @@ int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, in
     if (r192 * 192 * 10 <= r256 * 256 * 9) bn = 192;  // only for a clear (>= 10 %) saving
   }
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb[3];
   int s = make_tmap_f16_sw128(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(K),
                               static_cast<uint64_t>(lda), 128);
   if (s != DYT_OK) return s;
-  // B box = half a tile: each CTA of a cluster fetches one half and multicasts it to both
-  s = make_tmap_f16_sw128(&tb, w, static_cast<uint64_t>(N), static_cast<uint64_t>(K),
-                          static_cast<uint64_t>(ldw), static_cast<uint32_t>(bn / 2));
-  if (s != DYT_OK) return s;
+  // B box = half a tile per CTA of the pair; the 256-wide kernel also gets boxes for the half- and
+  // quarter-width sub-tiles of its last round
+  const bool tail_split = bn == 256 && dot_w == nullptr && tail_split_option().load(std::memory_order_relaxed) != 0;
+  for (int i = 0; i < 3; ++i) {
+    const int rows = (tail_split ? bn >> i : bn) / 2;
+    s = make_tmap_f16_sw128(&tb[i], w, static_cast<uint64_t>(N), static_cast<uint64_t>(K),
+                            static_cast<uint64_t>(ldw), static_cast<uint32_t>(rows));
+    if (s != DYT_OK) return s;
+  }
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
@@ -129,6 +134,7 @@ int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, in
   p.scale = scale;
   p.dot_w = dot_w; p.dot_out = dot_out; p.dot_ld = dot_ld; p.dot_f16 = dot_f16;
   p.aux = aux; p.ld_aux = ld_aux;
+  p.tail_split = tail_split ? 1 : 0;
   if (epi == EPI_BIAS_GELU_KEEP || epi == EPI_DGELU) {
     DYT_CHECK_ARG(aux != nullptr && ld_aux >= N && ld_aux % 8 == 0 && N % 8 == 0 &&
                       (reinterpret_cast<uintptr_t>(aux) & 15) == 0 && ldo_h % 8 == 0 &&

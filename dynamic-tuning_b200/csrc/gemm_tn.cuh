@@ -62,6 +62,40 @@ struct GemmParams {
   int dot_f16;
   __half* aux;   // EPI_BIAS_GELU_KEEP: written; EPI_DGELU: read ([M, N] fp16, row stride ld_aux)
   int ld_aux;
+  int tail_split;  // 1 (BN = 256 only): tiles of the last, partial round are cut into 2 or 4 column
+                   // sub-tiles when that lets every cluster take one (wave quantisation)
+};
+
+// One work item of the persistent tile loop: a full BM x BN tile pair, or -- in the last round,
+// when the leftover tiles number at most half / a quarter of the clusters -- a column sub-tile of
+// width BN / 2 or BN / 4 (own TMA box for B, narrower MMA, fewer epilogue chunks).  With e.g. 297
+// tile pairs on 74 clusters the fifth round held ONE tile and cost a whole round; cut in four it
+// costs the A-bound time of a 64-wide tile.
+struct GemmItems {
+  int n_tiles, full, split, total;
+  __device__ __forceinline__ void init(int total_tiles, int n_tiles_, int clusters, int allow) {
+    n_tiles = n_tiles_;
+    full = (total_tiles / clusters) * clusters;
+    const int rem = total_tiles - full;
+    split = 1;
+    if (allow && rem > 0) {
+      if (rem * 4 <= clusters) split = 4;
+      else if (rem * 2 <= clusters) split = 2;
+    }
+    total = full + rem * split;
+  }
+  // item -> row pair index, first column, width
+  __device__ __forceinline__ void decode(int item, int bn_full, int& m_pair, int& n0, int& bn) const {
+    int tile = item, sub = 0;
+    bn = bn_full;
+    if (item >= full && split > 1) {
+      tile = full + (item - full) / split;
+      sub = (item - full) % split;
+      bn = bn_full / split;
+    }
+    m_pair = tile / n_tiles;
+    n0 = (tile % n_tiles) * bn_full + sub * bn;
+  }
 };
 
 // EW = epilogue warps: 8 (two per TMEM lane quarter) or 16 (four per quarter, for epilogue-bound
@@ -93,7 +127,10 @@ struct GemmCfg {
 template <int BN, int EPI, int EW>
 __global__ void __launch_bounds__(GemmCfg<BN, EW>::THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
-               const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmap_b,    // box = BN / 2 rows of W per CTA
+               const __grid_constant__ CUtensorMap tmap_b2,   // box = BN / 4 rows (half-width sub-tiles)
+               const __grid_constant__ CUtensorMap tmap_b4,   // box = BN / 8 rows (quarter-width)
+               const GemmParams p) {
   using Cfg = GemmCfg<BN, EW>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
 
@@ -154,24 +191,29 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int cta_rank = static_cast<int>(cluster_ctarank());
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
+  GemmItems items;
+  items.init(total_tiles, n_tiles, num_clusters, BN == 256 ? p.tail_split : 0);
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        const int m0 = ((tile / n_tiles) * 2 + cta_rank) * BM;
-        const int n0 = (tile % n_tiles) * BN;
+      for (int item = cluster_id; item < items.total; item += num_clusters) {
+        int m_pair, n0, bn;
+        items.decode(item, BN, m_pair, n0, bn);
+        const int m0 = (m_pair * 2 + cta_rank) * BM;
+        const CUtensorMap* tb = bn == BN ? &tmap_b : (bn * 2 == BN ? &tmap_b2 : &tmap_b4);
+        const uint32_t tx_bytes = 2u * (Cfg::A_BYTES + (bn / 2) * BK * 2);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           // all four boxes of the pair (2 x A, 2 x B half) complete on the leader's barrier
-          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
           tma_load_2d_cg2(sa, &tmap_a, lead_bar, kb * BK, m0);
-          tma_load_2d_cg2(sb, &tmap_b, lead_bar, kb * BK, n0 + cta_rank * (BN / 2));
+          tma_load_2d_cg2(sb, tb, lead_bar, kb * BK, n0 + cta_rank * (bn / 2));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -184,15 +226,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // The whole warp walks the pipeline with warp-uniform state (descriptors in uniform registers)
     // and one elected lane issues; issuing from inside an `if (lane == 0)` region makes the
     // compiler wrap every tcgen05.mma in a lane-serialising loop (~100 clk of scalar code each).
-    constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN, 0, 0);  // M = 256 over the CTA pair
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
-    const int tiles_u = __shfl_sync(0xffffffffu, total_tiles, 0);
+    const int items_u = __shfl_sync(0xffffffffu, items.total, 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cluster_id; cta_rank == 0 && tile < tiles_u; tile += num_clusters) {
+    for (int item = cluster_id; cta_rank == 0 && item < items_u; item += num_clusters) {
+      int m_pair, n0, bn;
+      items.decode(item, BN, m_pair, n0, bn);
+      const uint32_t idesc = umma_idesc_f16(2 * BM, bn, 0, 0);  // M = 256 over the CTA pair
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(acc * BN);
@@ -234,13 +278,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int swz_w = (lane >> 1) & 3;  // chunk swizzle of the row this lane writes
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-      const int m0 = ((tile / n_tiles) * 2 + cta_rank) * BM;
-      const int n0 = (tile % n_tiles) * BN + half * HALF;
+    for (int item = cluster_id; item < items.total; item += num_clusters) {
+      int m_pair, n_tile0, bn;
+      items.decode(item, BN, m_pair, n_tile0, bn);
+      const int m0 = (m_pair * 2 + cta_rank) * BM;
+      // this warp's 32-column chunks of the item: NCH of a full tile, fewer (or none) of a sub-tile
+      const int chunks_total = bn >> 5;
+      int cpp = chunks_total / Cfg::PARTS;
+      if (cpp == 0) cpp = 1;
+      const int c_first = half * cpp;
+      const int my_n = c_first < chunks_total ? cpp : 0;
+      const int n0 = n_tile0 + c_first * 32;
 
       // fp32 bias of this warp's columns -> smem (read back as warp-wide broadcasts); in flight
       // while the main loop of this tile finishes
-      for (int i = lane; i < HALF / 4; i += 32) {
+      for (int i = lane; i < my_n * 8; i += 32) {
         const int col = n0 + i * 4;
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias != nullptr && col < p.N) {
@@ -257,10 +309,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                             static_cast<uint32_t>(acc * BN + half * HALF);
+                             static_cast<uint32_t>(acc * BN + c_first * 32);
       float dot_acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // RESID row-dot partials
+      if (my_n == 0) {  // sub-tile narrower than the warps' column split: only the hand-back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
+      }
 #pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
+      for (int c = 0; c < my_n; ++c) {
         uint32_t r[32];
         tmem_ld32(t_row + c * 32, r);
         // residual rows of this chunk (coalesced layout, see below): in flight during the math
@@ -294,7 +351,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
         tmem_ld_wait();
-        if (c == NCH - 1) {
+        if (c == my_n - 1) {
           // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -411,7 +468,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if constexpr (EPI == EPI_BIAS_RESID) {
         if (p.dot_w != nullptr) {
           // the eight lanes that share a row add up their column partials, lane%8 == 0 stores
-          const int slice = (tile % n_tiles) * Cfg::PARTS + half;
+          const int slice = (n_tile0 / BN) * Cfg::PARTS + half;  // (full tiles only: no split with dot_w)
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             float v = dot_acc[it];

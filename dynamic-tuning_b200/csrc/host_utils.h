@@ -116,6 +116,13 @@ inline std::atomic<int>& pdl_option() {
   return v;
 }
 
+// Library option (dyt_configure): cut the tiles of a GEMM's last, partial round into column
+// sub-tiles (gemm_tn.cuh GemmItems).  On by default.
+inline std::atomic<int>& tail_split_option() {
+  static std::atomic<int> v{1};
+  return v;
+}
+
 // <<<grid, block, smem, stream>>> with the PDL attribute (the kernel must call pdl_wait() before
 // its first dependent global access)
 template <typename... KArgs, typename... Args>

@@ -17,6 +17,7 @@ ABI_VERSION = 2
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_BIAS_RESID = 0, 1, 2, 3
 EPI_BIAS_GELU_KEEP, EPI_DGELU = 4, 5
 OPT_PDL = 1
+OPT_GEMM_TAIL_SPLIT = 2
 EW_GELU_FWD, EW_GELU_BWD, EW_RELU_DROP_BWD, EW_MUL = 0, 1, 2, 3
 
 

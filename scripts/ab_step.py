@@ -14,13 +14,14 @@ synthetic.calibrate_keep_rate(model, cal, 0.5)
 images = torch.randn(256, 3, 224, 224, generator=torch.Generator().manual_seed(0)).to(dev)
 
 arms = {}
-for name, pdl in (("pdl_off", 0), ("pdl_on", 1)):
-    assert lib.dyt_configure(_lib.OPT_PDL, pdl) == 0
+OPT = getattr(_lib, os.environ.get("AB_OPT", "OPT_GEMM_TAIL_SPLIT"))
+for name, pdl in (("opt_off", 0), ("opt_on", 1)):
+    assert lib.dyt_configure(OPT, pdl) == 0
     g = GraphedForward(model)
     buf = g.input_buffer(images.shape, images.dtype, dev)
     buf.copy_(images)
     arms[name] = (g, buf)
-lib.dyt_configure(_lib.OPT_PDL, 0)
+lib.dyt_configure(OPT, 1 if OPT == _lib.OPT_GEMM_TAIL_SPLIT else 0)
 
 ref = None
 for name, (g, buf) in arms.items():
