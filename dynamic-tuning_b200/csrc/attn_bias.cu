@@ -1,232 +1,470 @@
-// Long-sequence attention with an additive per-head bias (first, correctness-first version):
+// Long-sequence attention with an optional additive per-head bias on tcgen05 (sm_100a):
 //   out = softmax(f16(q * scale) k^T + bias[h]) v      per (image, head), any sequence length
 // for the segmentation backbone's eager attention path with a relative-position bias
 // (reference dense_tasks/Segmentation/backbone/segmentation_vision_transformer_IN21K.py:181-203:
 // 1025 tokens at 512 x 512, bias [num_heads, N, N] gathered from relative_position_bias_table).
 // Rounding points of that path under fp16 autocast: q * scale and the scores q k^T are fp16
-// tensors, the bias add promotes to fp32, softmax runs in fp32, the probabilities are cast to fp16
-// for the PV product (fp32 accumulate, fp16 output).
+// tensors (scale = 2^-3 commutes with the fp32 accumulation, so the score is f16(acc * scale)), the
+// bias add promotes to fp32, softmax runs in fp32, the probabilities are cast to fp16 for the PV
+// product (fp32 accumulate, fp16 output).
 //
-// Flash-style: one CTA (4 warps) per (image, head, block of 64 queries); keys / values stream
-// through two shared-memory buffers in blocks of 64 (cp.async, the next block in flight); S and PV on HMMA through nvcuda::wmma; the online softmax
-// works on the accumulator registers (m16n16k16 fp32 layout, verified at run time like
-// attn_bwd.cu).  The tcgen05 kernel (attn_varlen.cu) holds all keys of a sequence in one TMEM tile
-// and stops at 256 keys; this kernel has no such limit and is the base for SURVEY section 8f rank 5.
-#include <mma.h>
+// Flash-style over key tiles of 128, persistent CTAs, unit = (image, head, 128-query tile):
+//   warp 0       TMA producer: the unit's Q tile, then K_j / V_j tiles through a 3-stage ring
+//   warp 1       tcgen05.mma issuer: S_j = Q K_j^T into one of two TMEM score buffers (S_{j+2} is
+//                issued right behind PV_j, so the next scores are ready before the softmax asks),
+//                O_part += P_j[:, part] V_j[part] with P read from TMEM (fp16, written over the
+//                consumed scores)
+//   warp 2       TMEM allocator
+//   warps 4-11   softmax: thread = (query row, half of the tile's keys): 64 scores in registers.
+//                The two halves of a row are INDEPENDENT flash-decoding streams: own running max
+//                and sum, own accumulator in TMEM (2 x 64 columns), own PV MMAs, own barriers -- no
+//                exchange between warps inside the key loop, so the two softmax warps of a
+//                sub-partition drift apart and one's exponentials cover the other's TMEM reads.
+//                When a row's max grows the thread rescales its accumulator in TMEM first (skipped
+//                warp-wide when no row of the warp changed, the common case after the first key
+//                tiles).  The bias values of the next tile are requested one tile ahead.  At the end
+//                of the unit the halves are combined exactly (out = (O_0 e^{m_0-m} + O_1 e^{m_1-m}) /
+//                (l_0 e^{m_0-m} + l_1 e^{m_1-m})), rounded once to fp16, staged through shared
+//                memory and stored as full 128-byte rows.
+// Measured on B200 at 16 x 12 x 1025: 159 us without bias (round-1 kernel: HMMA through
+// nvcuda::wmma + cp.async, 343 us), 302 us with an fp32 bias (470 us); design notes and the
+// variants that were slower (16 softmax warps with a per-tile max exchange: 208 us) are in
+// profiles/r2_attention_long.md.  Also serves sequences beyond the 256 tokens of
+// dyt_attn_varlen_fwd.
 #include <stdarg.h>
 
 #include "../../include/dyt_b200.h"
 #include "host_utils.h"
+#include "ptx.cuh"
 
 namespace dyt {
 
-constexpr int FB_Q = 64, FB_K = 64, FB_LD = 72, FB_WARPS = 4;
-constexpr int FB_TILE = FB_K * FB_LD;                       // halves per 64-row tile
-// Q, 2 x K, 2 x V (double-buffered with cp.async), per-warp P tiles, per-warp fp32 staging
-constexpr size_t FB_SMEM = (5 * FB_TILE + FB_WARPS * 16 * FB_LD) * 2 + FB_WARPS * 16 * 20 * 4;
+struct LongAttnParams {
+  int N;          // tokens per sequence (uniform)
+  int C;          // H * 64
+  int H;
+  int q_tiles;    // ceil(N / 128)
+  int kv_tiles;   // ceil(N / 128)
+  int num_units;  // num_seqs * H * q_tiles
+  const float* bias;  // [H, N, N] fp32 or nullptr
+  __half* out;
+  int ldo;
+};
 
-// 16-byte asynchronous global -> shared copy; src_bytes = 0 writes zeros (rows past the sequence)
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
-  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes)
-               : "memory");
+constexpr int LA_NP = 2;                       // key parts per row = softmax warps per lane quarter
+constexpr int LA_PK = 128 / LA_NP;             // keys of a tile per thread
+static_assert(LA_NP == 2, "the softmax code loads 2 x 32 scores and owns 32 columns of O per thread");
+constexpr int LA_THREADS = 128 + LA_NP * 128;
+constexpr int LA_STAGES = 3;                   // K / V ring
+constexpr int LA_TILE = 128 * 128;             // bytes of a [128 x 64] fp16 tile
+constexpr int LA_TMEM_COLS = 512;
+constexpr int LA_S0 = 0, LA_O = 256;           // two score buffers of 128 columns, one accumulator of 64 per part
+constexpr int LA_XCH = 2 * LA_NP * 128 * 4;    // row max and row sum per part and row (unit end)
+constexpr int LA_SMEM = 1024 + LA_TILE * (1 + 2 * LA_STAGES + 1) + LA_XCH + 256;
+constexpr float LA_LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ void la_named_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+        "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+        "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
 }
 
-using namespace nvcuda;
-typedef wmma::fragment<wmma::accumulator, 16, 16, 16, float> FbC;
-typedef wmma::fragment<wmma::matrix_a, 16, 16, 16, __half, wmma::row_major> FbA;
-typedef wmma::fragment<wmma::matrix_b, 16, 16, 16, __half, wmma::row_major> FbB;
-typedef wmma::fragment<wmma::matrix_b, 16, 16, 16, __half, wmma::col_major> FbBt;
+__device__ __forceinline__ void prefetch_l1(const void* ptr) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+}
 
-__global__ void __launch_bounds__(FB_WARPS * 32)
-attn_bias_fwd_kernel(const __half* __restrict__ qkv, int ld_qkv, const float* __restrict__ bias,
-                     int N, int H, int C, float scale, __half* __restrict__ out, int ldo) {
-  extern __shared__ __align__(128) unsigned char fb_smem[];
-  __half* Qs = reinterpret_cast<__half*>(fb_smem);
-  __half* Kbuf = Qs + FB_TILE;              // [2][FB_TILE]
-  __half* Vbuf = Kbuf + 2 * FB_TILE;        // [2][FB_TILE]
-  __half* Pall = Vbuf + 2 * FB_TILE;        // [FB_WARPS][16 * FB_LD]
-  float* stg_base = reinterpret_cast<float*>(Pall + FB_WARPS * 16 * FB_LD);
-
-  const int qblocks = (N + FB_Q - 1) / FB_Q;
-  const int qb = blockIdx.x % qblocks;
-  const int h = (blockIdx.x / qblocks) % H;
-  const int b = blockIdx.x / (qblocks * H);
-  const int q0 = qb * FB_Q;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t4 = lane & 3;
-  float* stg = stg_base + warp * 16 * 20;
-  __half* Pw = Pall + warp * 16 * FB_LD;
-  const size_t row_base = static_cast<size_t>(b) * N;
-
-  // accumulator layout self-check (see attn_bwd.cu)
-  if (warp == 0) {
-    const int rr = lane >> 1, cb = (lane & 1) * 8;
+// The 32 bias values of (my row, my keys of the tile at column `col`).
+__device__ __forceinline__ void la_load_bias(float4 (&bv)[8], const float* __restrict__ brow, int col,
+                                             int nvalid) {
+  const float* bp = brow + col;
+  if (brow == nullptr) {   // a row past the sequence inside a live warp
 #pragma unroll
-    for (int c = 0; c < 8; ++c) stg[rr * 20 + cb + c] = static_cast<float>(rr * 16 + cb + c);
-    __syncwarp();
-    FbC chk;
-    wmma::load_matrix_sync(chk, stg, 20, wmma::mem_row_major);
-    bool ok = true;
+    for (int i = 0; i < 8; ++i) bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else if (nvalid >= 32 && (reinterpret_cast<uintptr_t>(bp) & 15) == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      ok = ok && chk.x[i] == static_cast<float>((g + 8 * ((i >> 1) & 1)) * 16 + 2 * t4 + (i & 1) + 8 * (i >> 2));
-    if (!ok) __trap();
-    __syncwarp();
-  }
-
-  // Q block, scaled: q * scale is an fp16 tensor in the reference (:190)
-  for (int e = tid; e < FB_Q * 8; e += FB_WARPS * 32) {
-    const int r = e >> 3, c = e & 7;
-    uint4 q = make_uint4(0, 0, 0, 0);
-    if (q0 + r < N) {
-      q = *reinterpret_cast<const uint4*>(qkv + (row_base + q0 + r) * ld_qkv + h * 64 + c * 8);
-      __half2* hq = reinterpret_cast<__half2*>(&q);
+    for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bp) + i);
+  } else {   // ragged tail; rows of an odd N are only 4-byte aligned
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(hq[j]);
-        hq[j] = __floats2half2_rn(f.x * scale, f.y * scale);
-      }
+    for (int i = 0; i < 8; ++i) {
+      bv[i].x = 4 * i + 0 < nvalid ? __ldg(bp + 4 * i + 0) : 0.f;
+      bv[i].y = 4 * i + 1 < nvalid ? __ldg(bp + 4 * i + 1) : 0.f;
+      bv[i].z = 4 * i + 2 < nvalid ? __ldg(bp + 4 * i + 2) : 0.f;
+      bv[i].w = 4 * i + 3 < nvalid ? __ldg(bp + 4 * i + 3) : 0.f;
     }
-    *reinterpret_cast<uint4*>(Qs + r * FB_LD + c * 8) = q;
   }
+}
+
+// fp32 accumulators of q k^T -> scores as the reference's fp16 autocast produces them, in place, and
+// their maximum.  With a bias: score = f16(acc) / 8 + bias (fp32).  Without: the function leaves
+// f16(acc) and the caller carries the factor 1/8 in its constants.  f16(acc / 8) == f16(acc) / 8 for
+// every accumulator whose score is a normal fp16 number (a power-of-two scale commutes with the
+// rounding); below 6.1e-5 the two differ by < 2^-25.
+template <bool BIAS, bool MASK>
+__device__ __forceinline__ float la_scores(uint32_t (&r)[32], const float4 (&bv)[8], int nvalid) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 x = __half22float2(__floats2half2_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])));
+    float s0 = x.x, s1 = x.y;
+    if (BIAS) {
+      const float4 b4 = bv[i >> 1];
+      s0 = fmaf(s0, 0.125f, (i & 1) ? b4.z : b4.x);
+      s1 = fmaf(s1, 0.125f, (i & 1) ? b4.w : b4.y);
+    }
+    if (MASK) {   // keys past the sequence
+      if (2 * i >= nvalid) s0 = -INFINITY;
+      if (2 * i + 1 >= nvalid) s1 = -INFINITY;
+    }
+    r[2 * i] = __float_as_uint(s0);
+    r[2 * i + 1] = __float_as_uint(s1);
+    mx = fmaxf(mx, fmaxf(s0, s1));
+  }
+  return mx;
+}
+
+// p = exp(score - m), packed to fp16 pairs and written to TMEM columns [t_p, t_p + 16) eight at a
+// time (keeps the packed values out of the register peak); returns the fp32 sum of the part
+template <bool BIAS>
+__device__ __forceinline__ float la_exps(const uint32_t (&r)[32], uint32_t t_p, float m) {
+  const float c = BIAS ? LA_LOG2E : 0.125f * LA_LOG2E;
+  const float mb = m * LA_LOG2E;
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float e0 = ex2_approx(fmaf(__uint_as_float(r[16 * hf + 2 * i]), c, -mb));
+      const float e1 = ex2_approx(fmaf(__uint_as_float(r[16 * hf + 2 * i + 1]), c, -mb));
+      s0 += e0;
+      s1 += e1;
+      pk[i] = pack_half2(e0, e1);
+    }
+    tmem_st8(t_p + 8 * hf, pk);
+  }
+  return s0 + s1;
+}
+
+__global__ void __launch_bounds__(LA_THREADS, 1)
+attn_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const LongAttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sKV = sQ + LA_TILE;                        // stage s: K at +2s tiles, V at +2s+1
+  const uint32_t sOut = sKV + 2 * LA_STAGES * LA_TILE;      // output staging tile
+  const uint32_t xch = sOut + LA_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LA_TILE * (2 + 2 * LA_STAGES) + LA_XCH);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_free = bars + 1;     // MMA commit: every S of the unit has read Q
+  uint64_t* kv_full = bars + 2;    // [3]
+  uint64_t* kv_free = bars + 5;    // [3] MMA commit after PV_j
+  uint64_t* s_full = bars + 8;     // [2]
+  uint64_t* p_ready = bars + 10;   // [2 buffers][2 parts] softmax -> MMA (count 4: the part's warps)
+  uint64_t* pv_done = bars + 14;   // [2 parts] MMA commit after the part's PV_j
+  uint64_t* o_read = bars + 16;    // softmax -> MMA: both O of the unit read out (count 8)
+  uint64_t* o_full = bars + 17;    // MMA commit after the unit's last PV
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(q_free, 1);
+    for (int i = 0; i < LA_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_free[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&pv_done[i], 1);
+    }
+    for (int i = 0; i < 2 * LA_NP; ++i) mbar_init(&p_ready[i], 4);
+    mbar_init(o_read, 4 * LA_NP);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp_idx == 0 && lane == 0) tma_prefetch_desc(&tmap_qkv);
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_ptr_smem, LA_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
   __syncthreads();
-  FbA aq[4];
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) wmma::load_matrix_sync(aq[kk], Qs + warp * 16 * FB_LD + kk * 16, FB_LD);
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int T = p.kv_tiles;
 
-  const int row0 = q0 + warp * 16 + g, row1 = row0 + 8;  // the two query rows of this lane
-  const float* bias0 = bias != nullptr ? bias + (static_cast<size_t>(h) * N + min(row0, N - 1)) * N : nullptr;
-  const float* bias1 = bias != nullptr ? bias + (static_cast<size_t>(h) * N + min(row1, N - 1)) * N : nullptr;
-  float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
-  FbC acc[4];
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    reg_dealloc<56>();
+    if (lane == 0) {
+      uint32_t uc = 0, g = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++uc) {
+        const int qt = unit % p.q_tiles;
+        const int bh = unit / p.q_tiles;
+        const int h = bh % p.H, b = bh / p.H;
+        const int row0 = b * p.N;
+        mbar_wait(q_free, (uc & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, LA_TILE);
+        tma_load_2d(smem, &tmap_qkv, q_full, h * 64, row0 + qt * 128);
+        for (int j = 0; j < T; ++j, ++g) {
+          const uint32_t st = g % LA_STAGES;
+          mbar_wait(&kv_free[st], ((g / LA_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&kv_full[st], 2 * LA_TILE);
+          uint8_t* dst = smem + LA_TILE * (1 + 2 * st);
+          tma_load_2d(dst, &tmap_qkv, &kv_full[st], p.C + h * 64, row0 + j * 128);
+          tma_load_2d(dst + LA_TILE, &tmap_qkv, &kv_full[st], 2 * p.C + h * 64, row0 + j * 128);
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    reg_dealloc<56>();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
+    const uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 1);  // B = V is MN-major
+    uint32_t uc = 0, g = 0;   // g = key tiles processed so far by this CTA (ring / buffer parities)
+    auto issue_s = [&](uint32_t gt) {   // S of global key tile gt into score buffer gt & 1
+      const uint32_t st = gt % LA_STAGES;
+      mbar_wait(&kv_full[st], (gt / LA_STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t a = umma_desc_sw128(sQ);
+        const uint64_t b = umma_desc_sw128(sKV + 2 * st * LA_TILE);
 #pragma unroll
-  for (int dn = 0; dn < 4; ++dn) wmma::fill_fragment(acc[dn], 0.f);
-  __half* pw0 = Pw + g * FB_LD + 2 * t4;
-  __half* pw1 = pw0 + 8 * FB_LD;
+        for (int k16 = 0; k16 < 4; ++k16)
+          umma_ss_f16(tmem_u + LA_S0 + (gt & 1) * 128, a + 2 * k16, b + 2 * k16, idesc_s,
+                      k16 != 0 ? 1u : 0u);
+        umma_commit(&s_full[gt & 1]);
+      }
+      __syncwarp();
+    };
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++uc) {
+      mbar_wait(q_full, uc & 1);
+      issue_s(g);
+      if (T > 1) issue_s(g + 1);
+      if (T <= 2) {
+        if (elect_one()) umma_commit(q_free);
+        __syncwarp();
+      }
+      for (int j = 0; j < T; ++j, ++g) {
+        // ---- O_pt (+)= P_j[:, part keys] V_j[part keys]  (each part: own P, own accumulator) ----
+        const uint32_t st = g % LA_STAGES;
+        const uint64_t v = umma_desc_sw128(sKV + (2 * st + 1) * LA_TILE);
+#pragma unroll
+        for (int pt = 0; pt < LA_NP; ++pt) {
+          mbar_wait(&p_ready[(g & 1) * LA_NP + pt], (g >> 1) & 1);
+          if (j == 0 && pt == 0) mbar_wait(o_read, (uc & 1) ^ 1);   // O of the previous unit read out
+          tc_fence_after();
+          if (elect_one()) {
+            // P of the part: 32 columns of packed fp16 at the start of its own score columns
+            const uint32_t a_tmem = tmem_u + LA_S0 + (g & 1) * 128 + pt * LA_PK;
+#pragma unroll
+            for (int kk = 0; kk < LA_PK / 16; ++kk)   // 16 keys per MMA: 8 P columns, 16 V rows = +2048 B
+              umma_ts_f16(tmem_u + LA_O + pt * 64, a_tmem + kk * 8, v + (pt * (LA_PK / 16) + kk) * 128,
+                          idesc_o, (j | kk) != 0 ? 1u : 0u);
+            umma_commit(&pv_done[pt]);
+            if (pt == LA_NP - 1) {
+              umma_commit(&kv_free[st]);
+              if (j == T - 1) umma_commit(o_full);
+            }
+          }
+          __syncwarp();
+        }
+        // ---- S_{j+2} into the score buffer PV_j has just been issued on (executes after it) ----
+        if (j + 2 < T) {
+          issue_s(g + 2);
+          if (j + 3 == T) {   // last S of the unit: Q is free once it retires
+            if (elect_one()) umma_commit(q_free);
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 2 || warp_idx == 3) {
+    reg_dealloc<56>();
+  } else {
+    // ===================== softmax / correction / output =====================
+    reg_alloc<208>();   // 8 x 32 x 208 + 4 x 32 x 56 = 60416 <= 384 x 168
+    const int q = warp_idx & 3;             // TMEM lane quarter
+    const int pt = (warp_idx - 4) >> 2;     // key part: keys [64 pt, 64 pt + 64) of every tile
+    const int rit = q * 32 + lane;          // row inside the query tile = TMEM lane
+    const bool has_bias = p.bias != nullptr;
+    const float m_unit = has_bias ? 1.0f : 0.125f;   // la_scores leaves raw (unscaled) scores without bias
+    const uint32_t row_slot = xch + rit * 4;         // [m | l][part][row]
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t_acc = t_row + LA_O + pt * 64;   // my part's accumulator
+    uint64_t* const my_pv_done = &pv_done[pt];
+    uint32_t uc = 0, g = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++uc) {
+      const int qt = unit % p.q_tiles;
+      const int bh = unit / p.q_tiles;
+      const int h = bh % p.H, b = bh / p.H;
+      const int row = qt * 128 + rit;       // token of the sequence
+      // warp-uniform: a warp whose 32 rows all lie past the sequence (last query tile) only keeps
+      // the barrier protocol going; rows past N inside a live warp compute on whatever the TMA
+      // delivered (the next image's tokens or zero fill) and are not stored
+      const bool rows_live = qt * 128 + q * 32 < p.N;
+      const float* brow = has_bias && row < p.N
+                              ? p.bias + (static_cast<size_t>(h) * p.N + row) * p.N + pt * LA_PK
+                              : nullptr;
+      float m_run = -INFINITY, l_run = 0.f;   // of my part of the keys
+      // bias of (my row, my 64 keys) of the coming tile: requested one tile ahead, right after the
+      // previous tile's values have been consumed, so the L2 latency sits behind the exponentials
+      float4 bv0[8], bv1[8];
+      if (has_bias && rows_live && pt * LA_PK < p.N) {
+        la_load_bias(bv0, brow, 0, p.N - pt * LA_PK);
+        la_load_bias(bv1, brow, 32, p.N - pt * LA_PK - 32);
+      }
+      for (int j = 0; j < T; ++j, ++g) {
+        const int key0 = j * 128 + pt * LA_PK;       // first key of my part
+        const bool live = rows_live && key0 < p.N;   // warp-uniform
+        const int nvalid = p.N - key0;
+        const uint32_t t_s = t_row + LA_S0 + (g & 1) * 128 + pt * LA_PK;   // my 64 score columns
+        if (live) {
+          uint32_t r0[32], r1[32];
+          mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+          tc_fence_after();
+          tmem_ld32(t_s, r0);
+          tmem_ld32(t_s + 32, r1);
+          tmem_ld_wait();
+          float mx;
+          if (has_bias) {
+            if (nvalid >= 64) {
+              mx = fmaxf(la_scores<true, false>(r0, bv0, 32), la_scores<true, false>(r1, bv1, 32));
+            } else {
+              mx = fmaxf(la_scores<true, true>(r0, bv0, nvalid), la_scores<true, true>(r1, bv1, nvalid - 32));
+            }
+          } else {
+            if (nvalid >= 64) {
+              mx = fmaxf(la_scores<false, false>(r0, bv0, 32), la_scores<false, false>(r1, bv1, 32));
+            } else {
+              mx = fmaxf(la_scores<false, true>(r0, bv0, nvalid), la_scores<false, true>(r1, bv1, nvalid - 32));
+            }
+          }
+          if (has_bias && nvalid > 128) {   // my keys of the next tile exist
+            la_load_bias(bv0, brow, (j + 1) * 128, nvalid - 128);
+            la_load_bias(bv1, brow, (j + 1) * 128 + 32, nvalid - 160);
+          }
+          const float m_new = fmaxf(m_run, mx * m_unit);
+          const float alpha = ex2_approx((m_run - m_new) * LA_LOG2E);   // 0 on the first tile (m_run = -inf)
+          // P over the first half of my own (consumed) score columns
+          float sum;
+          if (has_bias) {
+            sum = la_exps<true>(r0, t_s, m_new) + la_exps<true>(r1, t_s + 16, m_new);
+          } else {
+            sum = la_exps<false>(r0, t_s, m_new) + la_exps<false>(r1, t_s + 16, m_new);
+          }
+          l_run = l_run * alpha + sum;
+          // rescale my accumulator when a row's max grew (not on the first tile: PV_0 overwrites it).
+          // PV_{j-2} is complete (S_j was issued behind it), so the parity wait cannot alias.
+          if (j > 0 && __any_sync(0xffffffffu, m_new > m_run)) {
+            mbar_wait(my_pv_done, (g - 1) & 1);   // PV_{j-1} of my part has accumulated
+            tc_fence_after();
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              uint32_t o[32];
+              tmem_ld32(t_acc + 32 * hf, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(t_acc + 32 * hf, o);
+            }
+          }
+          m_run = m_new;
+          tmem_st_wait();
+        } else {
+          mbar_wait(&s_full[g & 1], (g >> 1) & 1);   // S_j has been written: P may go over it
+          tc_fence_after();
+          if (rows_live) {   // my keys lie past the sequence: P = 0 (V there is another image's)
+            uint32_t z[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[i] = 0u;
+#pragma unroll
+            for (int i = 0; i < LA_PK / 16; ++i) tmem_st8(t_s + 8 * i, z);
+            tmem_st_wait();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[(g & 1) * LA_NP + pt]);
+      }
 
-  // K / V blocks stream through two shared-memory buffers: block i+1 is in flight (cp.async) while
-  // block i is multiplied
-  auto load_block = [&](int k0, int buf) {
-    for (int e = tid; e < FB_K * 8; e += FB_WARPS * 32) {
-      const int r = e >> 3, c = e & 7;
-      const bool ok = k0 + r < N;
-      const __half* row = qkv + (row_base + (ok ? k0 + r : 0)) * ld_qkv + h * 64 + c * 8;
-      cp_async16(Kbuf + buf * FB_TILE + r * FB_LD + c * 8, row + C, ok ? 16 : 0);
-      cp_async16(Vbuf + buf * FB_TILE + r * FB_LD + c * 8, row + 2 * C, ok ? 16 : 0);
-    }
-    cp_async_commit();
-  };
-  load_block(0, 0);
-  int buf = 0;
-  for (int k0 = 0; k0 < N; k0 += FB_K, buf ^= 1) {
-    __syncthreads();  // every warp is done with the block that used the other buffer
-    if (k0 + FB_K < N) {
-      load_block(k0 + FB_K, buf ^ 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();  // this block has landed for every thread
-    const __half* Ks = Kbuf + buf * FB_TILE;
-    const __half* Vs = Vbuf + buf * FB_TILE;
-
-    // scores of this warp's 16 rows against the 64 keys: fp16-rounded q k^T, then + bias in fp32
-    float sv[4][8];
-    float mx0 = -1e30f, mx1 = -1e30f;
+      // ---- unit end: combine the parts, O / l -> fp16 -> staging tile -> full rows ----
+      mbar_wait(o_full, uc & 1);   // the unit's last PV (own barrier: pv_done's parity could alias here)
+      tc_fence_after();
+      sts32(row_slot + pt * 512, __float_as_uint(m_run));
+      sts32(row_slot + 1024 + pt * 512, __float_as_uint(l_run));
+      la_named_sync(1 + q, LA_NP * 32);
+      if (rows_live) {
+        const float m0 = __uint_as_float(lds32(row_slot)), m1 = __uint_as_float(lds32(row_slot + 512));
+        const float l0 = __uint_as_float(lds32(row_slot + 1024)), l1 = __uint_as_float(lds32(row_slot + 1536));
+        const float m = fmaxf(m0, m1);
+        float f0 = ex2_approx((m0 - m) * LA_LOG2E), f1 = ex2_approx((m1 - m) * LA_LOG2E);   // 0 for a part without keys
+        const float inv = 1.0f / (l0 * f0 + l1 * f1);
+        f0 *= inv;
+        f1 *= inv;
+        // my 32 output columns of both accumulators
+        uint32_t o0[32], o1[32];
+        tmem_ld32(t_row + LA_O + pt * 32, o0);
+        tmem_ld32(t_row + LA_O + 64 + pt * 32, o1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_read);
 #pragma unroll
-    for (int jn = 0; jn < 4; ++jn) {
-      FbC s;
-      wmma::fill_fragment(s, 0.f);
+        for (int c = 0; c < 4; ++c) {
+          float y[8];
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        FbBt bk;
-        wmma::load_matrix_sync(bk, Ks + jn * 16 * FB_LD + kk * 16, FB_LD);
-        wmma::mma_sync(s, aq[kk], bk, s);
+          for (int i = 0; i < 8; ++i)
+            y[i] = fmaf(__uint_as_float(o0[8 * c + i]), f0, __uint_as_float(o1[8 * c + i]) * f1);
+          uint4 v;
+          v.x = pack_half2(y[0], y[1]);
+          v.y = pack_half2(y[2], y[3]);
+          v.z = pack_half2(y[4], y[5]);
+          v.w = pack_half2(y[6], y[7]);
+          sts128(sOut + rit * 128 + (((pt * 4 + c) ^ (rit & 7)) << 4), v);
+        }
+      } else {
+        if (lane == 0) mbar_arrive(o_read);
       }
+      la_named_sync(5, LA_NP * 128);
+      {
+        const int mw = warp_idx - 4;
+        __half* dst = p.out + static_cast<size_t>(b * p.N) * p.ldo + h * 64;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int j = k0 + jn * 16 + 8 * (i >> 2) + 2 * t4 + (i & 1);
-        float v = __half2float(__float2half_rn(s.x[i]));
-        if (bias != nullptr && j < N) v += ((i >> 1) & 1) ? bias1[j] : bias0[j];
-        v = j < N ? v : -1e30f;
-        sv[jn][i] = v;
-        if ((i >> 1) & 1) mx1 = fmaxf(mx1, v); else mx0 = fmaxf(mx0, v);
+        for (int it = 0; it < 8 / LA_NP; ++it) {
+          const int rr = mw * (32 / LA_NP) + it * 4 + (lane >> 3);
+          const int ch = lane & 7;
+          if (qt * 128 + rr < p.N) {
+            const uint4 v = lds128(sOut + rr * 128 + ((ch ^ (rr & 7)) << 4));
+            *reinterpret_cast<uint4*>(dst + static_cast<size_t>(qt * 128 + rr) * p.ldo + ch * 8) = v;
+          }
+        }
       }
+      la_named_sync(5, LA_NP * 128);   // the staging tile and the slots are rewritten by the next unit
     }
-#pragma unroll
-    for (int off = 1; off <= 2; off <<= 1) {
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, off));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, off));
-    }
-    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-    const float a0 = __expf(m0 - mn0), a1 = __expf(m1 - mn1);
-    m0 = mn0;
-    m1 = mn1;
-    l0 *= a0;
-    l1 *= a1;
-#pragma unroll
-    for (int dn = 0; dn < 4; ++dn)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[dn].x[i] *= ((i >> 1) & 1) ? a1 : a0;
-    // P = exp(s - m) -> fp16 into this warp's tile (the operand of the PV product)
-#pragma unroll
-    for (int jn = 0; jn < 4; ++jn) {
-      float pv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const bool r1 = (i >> 1) & 1;
-        pv[i] = __expf(sv[jn][i] - (r1 ? m1 : m0));
-        if (r1) l1 += pv[i]; else l0 += pv[i];   // fp32 softmax denominator (:199)
-      }
-      *reinterpret_cast<__half2*>(pw0 + jn * 16) = __floats2half2_rn(pv[0], pv[1]);
-      *reinterpret_cast<__half2*>(pw0 + jn * 16 + 8) = __floats2half2_rn(pv[4], pv[5]);
-      *reinterpret_cast<__half2*>(pw1 + jn * 16) = __floats2half2_rn(pv[2], pv[3]);
-      *reinterpret_cast<__half2*>(pw1 + jn * 16 + 8) = __floats2half2_rn(pv[6], pv[7]);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      FbA ap;
-      wmma::load_matrix_sync(ap, Pw + kk * 16, FB_LD);
-#pragma unroll
-      for (int dn = 0; dn < 4; ++dn) {
-        FbB bv;
-        wmma::load_matrix_sync(bv, Vs + kk * 16 * FB_LD + dn * 16, FB_LD);
-        wmma::mma_sync(acc[dn], ap, bv, acc[dn]);
-      }
-    }
-    __syncwarp();  // Ps is rewritten by the next block
   }
 
-#pragma unroll
-  for (int off = 1; off <= 2; off <<= 1) {
-    l0 += __shfl_xor_sync(0xffffffffu, l0, off);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, off);
-  }
-  const float i0 = 1.f / l0, i1 = 1.f / l1;
-  const int rr = lane >> 1, cb = (lane & 1) * 8;
-  __half* orow = out + (row_base + q0 + warp * 16) * ldo + h * 64;
-#pragma unroll
-  for (int dn = 0; dn < 4; ++dn) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[dn].x[i] *= ((i >> 1) & 1) ? i1 : i0;
-    wmma::store_matrix_sync(stg, acc[dn], 20, wmma::mem_row_major);
-    __syncwarp();
-    if (q0 + warp * 16 + rr < N) {
-      uint4 u;
-      __half2* hh = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        hh[c] = __floats2half2_rn(stg[rr * 20 + cb + 2 * c], stg[rr * 20 + cb + 2 * c + 1]);
-      *reinterpret_cast<uint4*>(orow + static_cast<size_t>(rr) * ldo + dn * 16 + cb) = u;
-    }
-    __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, LA_TMEM_COLS);
   }
 }
 
@@ -236,24 +474,39 @@ extern "C" int dyt_attn_bias_fwd(const void* qkv, int ld_qkv, const float* bias,
                                  int seq_len, int num_heads, int head_dim, void* out, int ldo,
                                  void* stream) {
   using namespace dyt;
-  DYT_CHECK_ARG(qkv && out, "attn_bias: null buffer");
+  DYT_CHECK_ARG(qkv != nullptr && out != nullptr, "attn_bias: null buffer");
   DYT_CHECK_ARG(head_dim == 64, "attn_bias: head_dim must be 64 (got %d)", head_dim);
-  DYT_CHECK_ARG(num_seqs >= 0 && seq_len >= 1 && num_heads > 0, "attn_bias: bad sizes");
+  DYT_CHECK_ARG(num_seqs >= 0 && seq_len >= 1 && num_heads >= 1, "attn_bias: bad sizes");
   const int C = num_heads * head_dim;
   DYT_CHECK_ARG(ld_qkv >= 3 * C && ldo >= C && ld_qkv % 8 == 0 && ldo % 8 == 0,
                 "attn_bias: strides must cover the row and be multiples of 8");
   DYT_CHECK_ARG(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
                 "attn_bias: buffers must be 16-byte aligned");
+  DYT_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 3) == 0,
+                "attn_bias: bias must be 4-byte aligned");
   if (num_seqs == 0) return DYT_OK;
-  const long blocks = static_cast<long>(num_seqs) * num_heads * ((seq_len + FB_Q - 1) / FB_Q);
-  DYT_CHECK_ARG(blocks < (1l << 31), "attn_bias: grid too large");
+  const long total = static_cast<long>(num_seqs) * seq_len;
+  DYT_CHECK_ARG(total < (1l << 31), "attn_bias: too many tokens");
+  CUtensorMap tq;
+  int s = make_tmap_f16_sw128(&tq, qkv, static_cast<uint64_t>(total), static_cast<uint64_t>(3 * C),
+                              static_cast<uint64_t>(ld_qkv), 128);
+  if (s != DYT_OK) return s;
+  LongAttnParams p;
+  p.N = seq_len;
+  p.C = C;
+  p.H = num_heads;
+  p.q_tiles = (seq_len + 127) / 128;
+  p.kv_tiles = p.q_tiles;
+  const long units = static_cast<long>(num_seqs) * num_heads * p.q_tiles;
+  DYT_CHECK_ARG(units < (1l << 31), "attn_bias: grid too large");
+  p.num_units = static_cast<int>(units);
+  p.bias = bias;
+  p.out = static_cast<__half*>(out);
+  p.ldo = ldo;
   static SmemAttrCache smem_cache;
-  {
-    const int st = ensure_dyn_smem(attn_bias_fwd_kernel, static_cast<int>(FB_SMEM), smem_cache);
-    if (st != DYT_OK) return st;
-  }
-  attn_bias_fwd_kernel<<<static_cast<unsigned>(blocks), FB_WARPS * 32, FB_SMEM, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(qkv), ld_qkv, bias, seq_len, num_heads, C, 1.0f / 8.0f,
-      static_cast<__half*>(out), ldo);
-  return cuda_status(cudaGetLastError(), "attn_bias_fwd_kernel launch");
+  s = ensure_dyn_smem(attn_long_kernel, LA_SMEM, smem_cache);
+  if (s != DYT_OK) return s;
+  const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
+  attn_long_kernel<<<grid, LA_THREADS, LA_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, p);
+  return cuda_status(cudaGetLastError(), "attn_long_kernel launch");
 }

@@ -383,7 +383,9 @@ def test_keep_stats_kernel_matches_reference_accounting():
 
 
 @pytest.mark.parametrize("B,N,H,with_bias", [(2, 1025, 12, True), (3, 197, 2, False), (1, 64, 1, True),
-                                              (2, 65, 3, True), (4, 5, 2, True)])
+                                              (2, 65, 3, True), (4, 5, 2, True), (2, 257, 2, True),
+                                              (1, 384, 1, False), (2, 513, 2, True), (1, 128, 1, True),
+                                              (1, 129, 2, False), (20, 300, 4, True), (9, 1025, 12, False)])
 def test_attention_with_bias_long_sequences(dev, B, N, H, with_bias):
     """dyt_attn_bias_fwd (any sequence length, additive per-head bias) against the oracle's amp16
     restatement of the segmentation backbone's eager attention; 1025 tokens = 512 x 512 images."""
