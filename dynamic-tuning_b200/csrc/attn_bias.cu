@@ -46,7 +46,8 @@ struct LongAttnParams {
   int q_tiles;    // ceil(N / 128)
   int kv_tiles;   // ceil(N / 128)
   int num_units;  // num_seqs * H * q_tiles
-  const float* bias;  // [H, N, N] fp32 or nullptr
+  const float* bias;  // [H, N, ld_bias] fp32 or nullptr
+  int ld_bias;        // floats between consecutive rows of the bias (>= N)
   __half* out;
   int ldo;
 };
@@ -85,7 +86,8 @@ __device__ __forceinline__ void prefetch_l1(const void* ptr) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
 }
 
-// The 32 bias values of (my row, my keys of the tile at column `col`).
+// The 32 bias values of (my row, my keys of the tile at column `col`): 16-byte loads when the
+// address allows (always, with a bias pitch that is a multiple of 4 floats), scalar ones otherwise.
 __device__ __forceinline__ void la_load_bias(float4 (&bv)[8], const float* __restrict__ brow, int col,
                                              int nvalid) {
   const float* bp = brow + col;
@@ -320,7 +322,7 @@ attn_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const LongAttnPar
       // delivered (the next image's tokens or zero fill) and are not stored
       const bool rows_live = qt * 128 + q * 32 < p.N;
       const float* brow = has_bias && row < p.N
-                              ? p.bias + (static_cast<size_t>(h) * p.N + row) * p.N + pt * LA_PK
+                              ? p.bias + (static_cast<size_t>(h) * p.N + row) * p.ld_bias + pt * LA_PK
                               : nullptr;
       float m_run = -INFINITY, l_run = 0.f;   // of my part of the keys
       // bias of (my row, my 64 keys) of the coming tile: requested one tile ahead, right after the
@@ -470,9 +472,9 @@ attn_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const LongAttnPar
 
 }  // namespace dyt
 
-extern "C" int dyt_attn_bias_fwd(const void* qkv, int ld_qkv, const float* bias, int num_seqs,
-                                 int seq_len, int num_heads, int head_dim, void* out, int ldo,
-                                 void* stream) {
+extern "C" int dyt_attn_bias_fwd(const void* qkv, int ld_qkv, const float* bias, int ld_bias,
+                                 int num_seqs, int seq_len, int num_heads, int head_dim, void* out,
+                                 int ldo, void* stream) {
   using namespace dyt;
   DYT_CHECK_ARG(qkv != nullptr && out != nullptr, "attn_bias: null buffer");
   DYT_CHECK_ARG(head_dim == 64, "attn_bias: head_dim must be 64 (got %d)", head_dim);
@@ -484,6 +486,9 @@ extern "C" int dyt_attn_bias_fwd(const void* qkv, int ld_qkv, const float* bias,
                 "attn_bias: buffers must be 16-byte aligned");
   DYT_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 3) == 0,
                 "attn_bias: bias must be 4-byte aligned");
+  if (ld_bias == 0) ld_bias = seq_len;
+  DYT_CHECK_ARG(bias == nullptr || ld_bias >= seq_len, "attn_bias: ld_bias (%d) < seq_len (%d)", ld_bias,
+                seq_len);
   if (num_seqs == 0) return DYT_OK;
   const long total = static_cast<long>(num_seqs) * seq_len;
   DYT_CHECK_ARG(total < (1l << 31), "attn_bias: too many tokens");
@@ -501,6 +506,7 @@ extern "C" int dyt_attn_bias_fwd(const void* qkv, int ld_qkv, const float* bias,
   DYT_CHECK_ARG(units < (1l << 31), "attn_bias: grid too large");
   p.num_units = static_cast<int>(units);
   p.bias = bias;
+  p.ld_bias = ld_bias;
   p.out = static_cast<__half*>(out);
   p.ldo = ldo;
   static SmemAttrCache smem_cache;

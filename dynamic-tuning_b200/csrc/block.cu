@@ -163,7 +163,8 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   // 3. attention (uniform sequences of N tokens): the tcgen05 kernel up to 256 tokens; longer
   //    sequences or an additive bias (segmentation backbone, 1025 tokens) take the flash-style kernel
   if (N > 256 || opt->attn_bias != nullptr)
-    DYT_TRY(dyt_attn_bias_fwd(w.qkv, 3 * C, opt->attn_bias, B, N, H, 64, w.attn_o, C, stream_));
+    DYT_TRY(dyt_attn_bias_fwd(w.qkv, 3 * C, opt->attn_bias, opt->attn_bias_ld, B, N, H, 64, w.attn_o, C,
+                              stream_));
   else
     DYT_TRY(attn_varlen_fwd(w.qkv, 3 * C, nullptr, B, N, N, T, H, 64, w.attn_o, C, stream));
   // 4. proj + residual -> x1 (fp32) and its fp16 copy

@@ -42,7 +42,8 @@ class BlockOpts(C.Structure):
                 ("eps", C.c_float), ("logit_fp16", C.c_int), ("min_kept", C.c_float),
                 ("noise1", C.c_void_p), ("noise2", C.c_void_p), ("tau", C.c_float),
                 ("forced_mask", C.c_void_p), ("gate_out", C.c_void_p), ("xn_ready", C.c_int),
-                ("next_ln_w", C.c_void_p), ("next_ln_b", C.c_void_p), ("attn_bias", C.c_void_p)]
+                ("next_ln_w", C.c_void_p), ("next_ln_b", C.c_void_p), ("attn_bias", C.c_void_p),
+                ("attn_bias_ld", C.c_int)]
 
 
 class BlockBuffers(C.Structure):
@@ -62,7 +63,7 @@ SIGNATURES = {
                             _f, _vp]),
     "dyt_linear_f16_aux": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "dyt_attn_varlen_fwd": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
-    "dyt_attn_bias_fwd": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "dyt_attn_bias_fwd": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "dyt_layernorm_f16": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _f, _vp, _i, _vp]),
     "dyt_dispatch_workspace_bytes": (_sz, [_i]),
     "dyt_dispatch_fwd": (_i, [_vp, _i, _vp, _vp, _i, _f, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _f,

@@ -178,11 +178,11 @@ def run_blocks(x: torch.Tensor, blocks: Sequence[torch.nn.Module], *, eps: float
         if gates is not None:
             opts.gate_out = gates[i].data_ptr()
         if attn_biases is not None and attn_biases[i] is not None:
-            ab = attn_biases[i].to(device=dev, dtype=torch.float32).contiguous()
-            if tuple(ab.shape) != (shape.H, N, N):
-                raise DytError(f"attention bias must be [{shape.H}, {N}, {N}], got {tuple(ab.shape)}")
+            from . import ops
+            ab, ab_ld = ops._bias_pitch(attn_biases[i].to(device=dev), shape.H, N)
             keep_alive.append(ab)
             opts.attn_bias = ab.data_ptr()
+            opts.attn_bias_ld = ab_ld
         opts.xn_ready = xn_ready
         nxt = None
         if fuse_next_ln:

@@ -71,7 +71,8 @@ class SegAttention(nn.Module):
             self.relative_position_index = None
 
     def bias(self) -> Optional[torch.Tensor]:
-        """[heads, N, N] fp32 (reference :192-197), None without a table."""
+        """[heads, N, N] fp32 (reference :192-197), None without a table.  The values live in a
+        buffer whose rows are padded to a multiple of 4 floats (ops.pad_attn_bias)."""
         if self.relative_position_bias_table is None:
             return None
         tab = self.relative_position_bias_table
@@ -80,7 +81,7 @@ class SegAttention(nn.Module):
         if cached is None or cached[0] != key:     # gathered once per table version, not per forward
             n = self.relative_position_index.shape[0]
             t = tab.detach().float()
-            b = t[self.relative_position_index.reshape(-1)].reshape(n, n, -1).permute(2, 0, 1).contiguous()
+            b = ops.pad_attn_bias(t[self.relative_position_index.reshape(-1)].reshape(n, n, -1).permute(2, 0, 1))
             cached = (key, b)
             self.__dict__["_dyt_bias"] = cached
         return cached[1]

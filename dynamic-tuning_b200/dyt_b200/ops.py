@@ -122,21 +122,45 @@ def attn_varlen(qkv: torch.Tensor, num_heads: int, cu_seqlens: Optional[torch.Te
     return out.reshape(*qkv.shape[:-1], Cdim)
 
 
+def pad_attn_bias(bias: torch.Tensor) -> torch.Tensor:
+    """[heads, N, N] fp32 view of a buffer whose rows are padded to a multiple of 4 floats, the
+    layout dyt_attn_bias_fwd reads in 16-byte vectors (N = 1025 -> pitch 1028).  Build it once per
+    bias (the segmentation modules cache it per table version), not per forward."""
+    H, N, N2 = bias.shape
+    pitch = (N2 + 3) // 4 * 4
+    if pitch % 64 == 0:          # rows a multiple of 256 bytes apart all fall into the same cache sets
+        pitch += 4               # (measured at N = 1024: 233 us with pitch 1024)
+    buf = torch.zeros((H, N, pitch), dtype=torch.float32, device=bias.device)
+    buf[:, :, :N2] = bias
+    return buf[:, :, :N2]
+
+
+def _bias_pitch(bias: torch.Tensor, num_heads: int, N: int):
+    """(tensor to keep alive, row pitch in floats) of an attention bias: an fp32 [heads, N, N] tensor
+    whose rows are dense and evenly pitched is used in place, anything else is made contiguous."""
+    if tuple(bias.shape) != (num_heads, N, N):
+        raise DytError(f"attn_bias: bias must be [heads, N, N] = [{num_heads}, {N}, {N}]")
+    if bias.dtype != torch.float32:
+        bias = bias.to(torch.float32)
+    if not (bias.stride(2) == 1 and bias.stride(1) >= N and bias.stride(0) == N * bias.stride(1)):
+        bias = bias.contiguous()
+    return bias, bias.stride(1)
+
+
 def attn_bias(qkv: torch.Tensor, num_heads: int, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Long-sequence attention with an additive per-head bias.  qkv fp16 [B, N, 3*C]; bias fp32
-    [num_heads, N, N] or None.  Returns fp16 [B, N, C]."""
+    [num_heads, N, N] (dense or a pad_attn_bias view) or None.  Returns fp16 [B, N, C]."""
     _need_cuda(qkv, bias)
     if qkv.dtype != torch.float16 or qkv.dim() != 3:
         raise DytError("attn_bias expects fp16 qkv [B, N, 3C]")
     B, N, C3 = qkv.shape
     Cdim = C3 // 3
     q2 = _rows2d(qkv)
+    ld_bias = 0
     if bias is not None:
-        bias = bias.to(torch.float32).contiguous()
-        if tuple(bias.shape) != (num_heads, N, N):
-            raise DytError(f"attn_bias: bias must be [heads, N, N] = [{num_heads}, {N}, {N}]")
+        bias, ld_bias = _bias_pitch(bias, num_heads, N)
     out = torch.empty((B * N, Cdim), dtype=torch.float16, device=qkv.device)
-    check(_lib.lib().dyt_attn_bias_fwd(q2.data_ptr(), q2.stride(0), _ptr(bias), B, N, num_heads,
+    check(_lib.lib().dyt_attn_bias_fwd(q2.data_ptr(), q2.stride(0), _ptr(bias), ld_bias, B, N, num_heads,
                                        Cdim // num_heads, out.data_ptr(), Cdim, _stream()),
           "dyt_attn_bias_fwd")
     return out.reshape(B, N, Cdim)

@@ -95,11 +95,15 @@ int dyt_attn_varlen_fwd(const void* qkv, int ld_qkv, const int* cu_seqlens, int 
  * Replaces the eager attention path of the segmentation backbone with its relative-position bias
  * (reference dense_tasks/Segmentation/backbone/segmentation_vision_transformer_IN21K.py:181-203;
  * 1025 tokens at 512 x 512).  qkv fp16 [num_seqs * seq_len, 3, num_heads, 64] (row stride ld_qkv),
- * uniform sequences; bias fp32 [num_heads, seq_len, seq_len] contiguous or NULL; out fp16
- * [num_seqs * seq_len, num_heads * 64].  Rounding points of that path under fp16 autocast: q * scale
- * and q k^T fp16, bias add and softmax fp32, probabilities fp16 for the PV product. */
-int dyt_attn_bias_fwd(const void* qkv, int ld_qkv, const float* bias, int num_seqs, int seq_len,
-                      int num_heads, int head_dim, void* out, int ldo, void* stream);
+ * uniform sequences; bias fp32 [num_heads, seq_len, ld_bias] or NULL: element (h, i, j) at
+ * bias[(h * seq_len + i) * ld_bias + j], ld_bias >= seq_len (0 = seq_len, the contiguous
+ * [H, N, N] tensor of the reference).  A pitch that is a multiple of 4 floats on a 16-byte aligned
+ * base is read in 16-byte vectors (1025 tokens: pad the rows to 1028); any other pitch works through
+ * scalar loads.  out fp16 [num_seqs * seq_len, num_heads * 64].  Rounding points of that path under
+ * fp16 autocast: q * scale and q k^T fp16, bias add and softmax fp32, probabilities fp16 for the PV
+ * product. */
+int dyt_attn_bias_fwd(const void* qkv, int ld_qkv, const float* bias, int ld_bias, int num_seqs,
+                      int seq_len, int num_heads, int head_dim, void* out, int ldo, void* stream);
 
 /* LayerNorm(eps) over the last dim of fp32 rows, result rounded once to fp16 (the rounding the
  * consumer Linear applies under autocast).  Output row r reads input row row_idx[r] (or r when
@@ -306,9 +310,10 @@ typedef struct dyt_block_opts {
   int xn_ready;            /* 1: workspace already holds LN1(x) (written by the previous call) */
   const float* next_ln_w;  /* optional: also emit LayerNorm(out) for the next block / final norm */
   const float* next_ln_b;
-  const float* attn_bias;  /* optional [H, N, N] additive attention bias (relative position bias of
-                              the segmentation backbone); sequences > 256 tokens or a bias use
-                              dyt_attn_bias_fwd instead of dyt_attn_varlen_fwd */
+  const float* attn_bias;  /* optional [H, N, attn_bias_ld] additive attention bias (relative position
+                              bias of the segmentation backbone); sequences > 256 tokens or a bias
+                              use dyt_attn_bias_fwd instead of dyt_attn_varlen_fwd */
+  int attn_bias_ld;        /* row pitch of attn_bias in floats (0 = N), see dyt_attn_bias_fwd */
 } dyt_block_opts;
 
 typedef struct dyt_block_buffers { /* where dyt_block_fwd keeps its intermediates (for tests) */

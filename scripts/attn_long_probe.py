@@ -27,7 +27,7 @@ for B, N, H in ((16, 1025, 12), (16, 1024, 12), (64, 577, 12), (2, 300, 2)):
     C = 64 * H
     qkv = (torch.randn(B, N, 3 * C, generator=g) * 1.2).half().to(dev)
     bias = (torch.randn(H, N, N, generator=g) * 1.5).to(dev)
-    for bb in (None, bias):
+    for bb in (None, bias, ops.pad_attn_bias(bias)):
         got = ops.attn_bias(qkv, H, bb)
         q, k, v = qkv.float().reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4).unbind(0)
         s = ((q * 0.125).half().float() @ k.transpose(-1, -2)).half().float()
@@ -37,7 +37,7 @@ for B, N, H in ((16, 1025, 12), (16, 1024, 12), (64, 577, 12), (2, 300, 2)):
         err = (got.float() - ref).abs().max().item()
         t = timed(lambda: ops.attn_bias(qkv, H, bb))
         flops = 4.0 * B * H * N * N * 64
-        print(f"B={B} N={N} H={H} bias={bb is not None}: {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s  max|err|={err:.2e}",
+        print(f"B={B} N={N} H={H} bias={'no' if bb is None else 'pitch %d' % bb.stride(1)}: {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s  max|err|={err:.2e}",
               flush=True)
     qh, kh, vh = qkv.reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4).unbind(0)
     t = timed(lambda: torch.nn.functional.scaled_dot_product_attention(qh, kh, vh))

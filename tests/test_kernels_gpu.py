@@ -398,6 +398,12 @@ def test_attention_with_bias_long_sequences(dev, B, N, H, with_bias):
     got = ops.attn_bias(qkv.to(dev), H, None if bias is None else bias.to(dev))
     assert got.shape == (B, N, C) and got.dtype == torch.float16
     _close(got, ref, atol=2e-3, rtol=4e-3)
+    if with_bias:                        # rows padded to a multiple of 4 floats: the 16-byte load path
+        padded = ops.pad_attn_bias(bias.to(dev))
+        assert padded.stride(1) % 4 == 0 and padded.stride(1) % 64 != 0 and padded.stride(1) >= N
+        assert torch.equal(padded.cpu(), bias)
+        got_p = ops.attn_bias(qkv.to(dev), H, padded)
+        assert torch.equal(got_p, got)
     if not with_bias and N <= 256:      # same answer as the tcgen05 kernel on its own domain
         _close(got, ops.attn_varlen(qkv.to(dev), H), atol=2e-3, rtol=4e-3)
 
