@@ -20,9 +20,9 @@
 //                and sum, own accumulator in TMEM (2 x 64 columns), own PV MMAs, own barriers -- no
 //                exchange between warps inside the key loop, so the two softmax warps of a
 //                sub-partition drift apart and one's exponentials cover the other's TMEM reads.
-//                When a row's max grows the thread rescales its accumulator in TMEM first (skipped
-//                warp-wide when no row of the warp changed, the common case after the first key
-//                tiles).  The bias values of the next tile are requested one tile ahead.  At the end
+//                When a row's max grows by more than 2^8 the thread moves its reference max and
+//                rescales its accumulator in TMEM first (skipped warp-wide otherwise, the common
+//                case after the first key tile).  The bias values of the next tile are requested one tile ahead.  At the end
 //                of the unit the halves are combined exactly (out = (O_0 e^{m_0-m} + O_1 e^{m_1-m}) /
 //                (l_0 e^{m_0-m} + l_1 e^{m_1-m})), rounded once to fp16, staged through shared
 //                memory and stored as full 128-byte rows.
@@ -63,6 +63,7 @@ constexpr int LA_S0 = 0, LA_O = 256;           // two score buffers of 128 colum
 constexpr int LA_XCH = 2 * LA_NP * 128 * 4;    // row max and row sum per part and row (unit end)
 constexpr int LA_SMEM = 1024 + LA_TILE * (1 + 2 * LA_STAGES + 1) + LA_XCH + 256;
 constexpr float LA_LOG2E = 1.4426950408889634f;
+constexpr float LA_RESCALE_LOG2 = 8.0f;        // rescale threshold, log2 units
 
 __device__ __forceinline__ void la_named_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -362,7 +363,12 @@ attn_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const LongAttnPar
             la_load_bias(bv0, brow, (j + 1) * 128, nvalid - 128);
             la_load_bias(bv1, brow, (j + 1) * 128 + 32, nvalid - 160);
           }
-          const float m_new = fmaxf(m_run, mx * m_unit);
+          // The reference max of the part only moves when the tile's max exceeds it by more than
+          // 2^8 (any reference gives the same softmax; p <= 256 is exact enough in fp16 and far from
+          // its range): with a plain running max some row of a warp grows in almost every tile and
+          // every tile pays the accumulator rescale and its wait for the previous PV.
+          const float mx_s = mx * m_unit;
+          const float m_new = (mx_s - m_run) * LA_LOG2E > LA_RESCALE_LOG2 ? mx_s : m_run;
           const float alpha = ex2_approx((m_run - m_new) * LA_LOG2E);   // 0 on the first tile (m_run = -inf)
           // P over the first half of my own (consumed) score columns
           float sum;
