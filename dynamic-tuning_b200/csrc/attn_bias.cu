@@ -16,20 +16,23 @@
 //                consumed scores)
 //   warp 2       TMEM allocator
 //   warps 4-11   softmax: thread = (query row, half of the tile's keys): 64 scores in registers.
-//                The two halves of a row are INDEPENDENT flash-decoding streams: own running max
+//                The two halves of a row are INDEPENDENT flash-decoding streams: own reference max
 //                and sum, own accumulator in TMEM (2 x 64 columns), own PV MMAs, own barriers -- no
-//                exchange between warps inside the key loop, so the two softmax warps of a
-//                sub-partition drift apart and one's exponentials cover the other's TMEM reads.
-//                When a row's max grows by more than 2^8 the thread moves its reference max and
-//                rescales its accumulator in TMEM first (skipped warp-wide otherwise, the common
-//                case after the first key tile).  The bias values of the next tile are requested one tile ahead.  At the end
-//                of the unit the halves are combined exactly (out = (O_0 e^{m_0-m} + O_1 e^{m_1-m}) /
-//                (l_0 e^{m_0-m} + l_1 e^{m_1-m})), rounded once to fp16, staged through shared
-//                memory and stored as full 128-byte rows.
-// Measured on B200 at 16 x 12 x 1025: 159 us without bias (round-1 kernel: HMMA through
-// nvcuda::wmma + cp.async, 343 us), 302 us with an fp32 bias (470 us); design notes and the
-// variants that were slower (16 softmax warps with a per-tile max exchange: 208 us) are in
-// profiles/r2_attention_long.md.  Also serves sequences beyond the 256 tokens of
+//                exchange between warps inside the key loop and no CTA-wide barrier anywhere, so
+//                the two softmax warps of a sub-partition drift apart and one's exponentials cover
+//                the other's TMEM reads.  The reference max of a stream only moves when a tile's
+//                max exceeds it by more than 2^8; then the thread rescales its accumulator in TMEM
+//                first (skipped warp-wide otherwise: the common case after the first key tile; with
+//                a plain running max some row of a warp grows in almost every tile).  The bias
+//                values of the next tile are requested one tile ahead.  At the end of the unit the
+//                halves are combined exactly, out = (O_0 e^{m_0-m} + O_1 e^{m_1-m}) /
+//                (l_0 e^{m_0-m} + l_1 e^{m_1-m}), rounded once to fp16 and stored from registers
+//                (64 contiguous bytes per thread).
+// Measured on B200 at 16 x 12 x 1025: 136 us without bias (round-1 kernel: HMMA through
+// nvcuda::wmma + cp.async, 343 us), 180 us with an fp32 bias whose rows are padded to 16 bytes,
+// 289 us with the dense [H, N, N] bias of an odd N (470 us); the steps that led here and the variants
+// that were slower (16 softmax warps with a per-tile max exchange: 208 us; four key parts: 154 us)
+// are in profiles/r2_attention_long.md.  Also serves sequences beyond the 256 tokens of
 // dyt_attn_varlen_fwd.
 #include <stdarg.h>
 
@@ -52,16 +55,24 @@ struct LongAttnParams {
   int ldo;
 };
 
-constexpr int LA_NP = 2;                       // key parts per row = softmax warps per lane quarter
+#ifndef DYT_LA_NP
+#define DYT_LA_NP 2
+#endif
+constexpr int LA_NP = DYT_LA_NP;               // key parts per row = softmax warps per lane quarter
 constexpr int LA_PK = 128 / LA_NP;             // keys of a tile per thread
-static_assert(LA_NP == 2, "the softmax code loads 2 x 32 scores and owns 32 columns of O per thread");
+constexpr int LA_NH = LA_PK / 32;              // ... in register blocks of 32
+constexpr int LA_CW = 64 / LA_NP;              // output columns per thread at the unit end
+static_assert(LA_NP == 2 || LA_NP == 4, "two or four key parts (TMEM: 2 x 128 score + LA_NP x 64 accumulator columns)");
+// setmaxnreg moves registers inside the launch allocation only: 4 control warps at 56 and
+// 4 LA_NP softmax warps must fit threads x compiled registers (640 x 96 / 384 x 168)
+constexpr int LA_SOFTMAX_REGS = LA_NP == 4 ? 104 : 208;
 constexpr int LA_THREADS = 128 + LA_NP * 128;
 constexpr int LA_STAGES = 3;                   // K / V ring
 constexpr int LA_TILE = 128 * 128;             // bytes of a [128 x 64] fp16 tile
 constexpr int LA_TMEM_COLS = 512;
 constexpr int LA_S0 = 0, LA_O = 256;           // two score buffers of 128 columns, one accumulator of 64 per part
-constexpr int LA_XCH = 2 * LA_NP * 128 * 4;    // row max and row sum per part and row (unit end)
-constexpr int LA_SMEM = 1024 + LA_TILE * (1 + 2 * LA_STAGES + 1) + LA_XCH + 256;
+constexpr int LA_XCH = 2 * 2 * LA_NP * 128 * 4;  // two sets of (row max, row sum) per part and row (unit end)
+constexpr int LA_SMEM = 1024 + LA_TILE * (1 + 2 * LA_STAGES) + LA_XCH + 256;
 constexpr float LA_LOG2E = 1.4426950408889634f;
 constexpr float LA_RESCALE_LOG2 = 8.0f;        // rescale threshold, log2 units
 
@@ -83,9 +94,8 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* ptr) {
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
-}
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
 
 // The 32 bias values of (my row, my keys of the tile at column `col`): 16-byte loads when the
 // address allows (always, with a bias pitch that is a multiple of 4 floats), scalar ones otherwise.
@@ -167,19 +177,18 @@ attn_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const LongAttnPar
                                              ~static_cast<uintptr_t>(1023));
   const uint32_t sQ = smem_u32(smem);
   const uint32_t sKV = sQ + LA_TILE;                        // stage s: K at +2s tiles, V at +2s+1
-  const uint32_t sOut = sKV + 2 * LA_STAGES * LA_TILE;      // output staging tile
-  const uint32_t xch = sOut + LA_TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LA_TILE * (2 + 2 * LA_STAGES) + LA_XCH);
+  const uint32_t xch = sKV + 2 * LA_STAGES * LA_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LA_TILE * (1 + 2 * LA_STAGES) + LA_XCH);
   uint64_t* q_full = bars + 0;
   uint64_t* q_free = bars + 1;     // MMA commit: every S of the unit has read Q
   uint64_t* kv_full = bars + 2;    // [3]
   uint64_t* kv_free = bars + 5;    // [3] MMA commit after PV_j
   uint64_t* s_full = bars + 8;     // [2]
-  uint64_t* p_ready = bars + 10;   // [2 buffers][2 parts] softmax -> MMA (count 4: the part's warps)
-  uint64_t* pv_done = bars + 14;   // [2 parts] MMA commit after the part's PV_j
-  uint64_t* o_read = bars + 16;    // softmax -> MMA: both O of the unit read out (count 8)
-  uint64_t* o_full = bars + 17;    // MMA commit after the unit's last PV
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* o_read = bars + 10;    // softmax -> MMA: the accumulators of the unit read out (count 4 LA_NP)
+  uint64_t* o_full = bars + 11;    // MMA commit after the unit's last PV
+  uint64_t* pv_done = bars + 12;   // [parts] MMA commit after the part's PV_j
+  uint64_t* p_ready = bars + 12 + LA_NP;   // [2 buffers][parts] softmax -> MMA (count 4: the part's warps)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12 + 3 * LA_NP);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -191,10 +200,8 @@ attn_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const LongAttnPar
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_free[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&pv_done[i], 1);
-    }
+    for (int i = 0; i < 2; ++i) mbar_init(&s_full[i], 1);
+    for (int i = 0; i < LA_NP; ++i) mbar_init(&pv_done[i], 1);
     for (int i = 0; i < 2 * LA_NP; ++i) mbar_init(&p_ready[i], 4);
     mbar_init(o_read, 4 * LA_NP);
     mbar_init(o_full, 1);
@@ -302,9 +309,9 @@ attn_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const LongAttnPar
     reg_dealloc<56>();
   } else {
     // ===================== softmax / correction / output =====================
-    reg_alloc<208>();   // 8 x 32 x 208 + 4 x 32 x 56 = 60416 <= 384 x 168
+    reg_alloc<LA_SOFTMAX_REGS>();
     const int q = warp_idx & 3;             // TMEM lane quarter
-    const int pt = (warp_idx - 4) >> 2;     // key part: keys [64 pt, 64 pt + 64) of every tile
+    const int pt = (warp_idx - 4) >> 2;     // key part: keys [LA_PK pt, LA_PK pt + LA_PK) of every tile
     const int rit = q * 32 + lane;          // row inside the query tile = TMEM lane
     const bool has_bias = p.bias != nullptr;
     const float m_unit = has_bias ? 1.0f : 0.125f;   // la_scores leaves raw (unscaled) scores without bias
@@ -326,42 +333,47 @@ attn_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const LongAttnPar
                               ? p.bias + (static_cast<size_t>(h) * p.N + row) * p.ld_bias + pt * LA_PK
                               : nullptr;
       float m_run = -INFINITY, l_run = 0.f;   // of my part of the keys
-      // bias of (my row, my 64 keys) of the coming tile: requested one tile ahead, right after the
+      // bias of (my row, my keys) of the coming tile: requested one tile ahead, right after the
       // previous tile's values have been consumed, so the L2 latency sits behind the exponentials
-      float4 bv0[8], bv1[8];
+      float4 bv[LA_NH][8];
       if (has_bias && rows_live && pt * LA_PK < p.N) {
-        la_load_bias(bv0, brow, 0, p.N - pt * LA_PK);
-        la_load_bias(bv1, brow, 32, p.N - pt * LA_PK - 32);
+#pragma unroll
+        for (int hf = 0; hf < LA_NH; ++hf) la_load_bias(bv[hf], brow, 32 * hf, p.N - pt * LA_PK - 32 * hf);
       }
       for (int j = 0; j < T; ++j, ++g) {
         const int key0 = j * 128 + pt * LA_PK;       // first key of my part
         const bool live = rows_live && key0 < p.N;   // warp-uniform
         const int nvalid = p.N - key0;
-        const uint32_t t_s = t_row + LA_S0 + (g & 1) * 128 + pt * LA_PK;   // my 64 score columns
+        const uint32_t t_s = t_row + LA_S0 + (g & 1) * 128 + pt * LA_PK;   // my score columns
         if (live) {
-          uint32_t r0[32], r1[32];
+          uint32_t r[LA_NH][32];
           mbar_wait(&s_full[g & 1], (g >> 1) & 1);
           tc_fence_after();
-          tmem_ld32(t_s, r0);
-          tmem_ld32(t_s + 32, r1);
+#pragma unroll
+          for (int hf = 0; hf < LA_NH; ++hf) tmem_ld32(t_s + 32 * hf, r[hf]);
           tmem_ld_wait();
-          float mx;
+          float mx = -INFINITY;
           if (has_bias) {
-            if (nvalid >= 64) {
-              mx = fmaxf(la_scores<true, false>(r0, bv0, 32), la_scores<true, false>(r1, bv1, 32));
+            if (nvalid >= LA_PK) {
+#pragma unroll
+              for (int hf = 0; hf < LA_NH; ++hf) mx = fmaxf(mx, la_scores<true, false>(r[hf], bv[hf], 32));
             } else {
-              mx = fmaxf(la_scores<true, true>(r0, bv0, nvalid), la_scores<true, true>(r1, bv1, nvalid - 32));
+#pragma unroll
+              for (int hf = 0; hf < LA_NH; ++hf) mx = fmaxf(mx, la_scores<true, true>(r[hf], bv[hf], nvalid - 32 * hf));
+            }
+            if (nvalid > 128) {   // my keys of the next tile exist
+#pragma unroll
+              for (int hf = 0; hf < LA_NH; ++hf)
+                la_load_bias(bv[hf], brow, (j + 1) * 128 + 32 * hf, nvalid - 128 - 32 * hf);
             }
           } else {
-            if (nvalid >= 64) {
-              mx = fmaxf(la_scores<false, false>(r0, bv0, 32), la_scores<false, false>(r1, bv1, 32));
+            if (nvalid >= LA_PK) {
+#pragma unroll
+              for (int hf = 0; hf < LA_NH; ++hf) mx = fmaxf(mx, la_scores<false, false>(r[hf], bv[hf], 32));
             } else {
-              mx = fmaxf(la_scores<false, true>(r0, bv0, nvalid), la_scores<false, true>(r1, bv1, nvalid - 32));
+#pragma unroll
+              for (int hf = 0; hf < LA_NH; ++hf) mx = fmaxf(mx, la_scores<false, true>(r[hf], bv[hf], nvalid - 32 * hf));
             }
-          }
-          if (has_bias && nvalid > 128) {   // my keys of the next tile exist
-            la_load_bias(bv0, brow, (j + 1) * 128, nvalid - 128);
-            la_load_bias(bv1, brow, (j + 1) * 128 + 32, nvalid - 160);
           }
           // The reference max of the part only moves when the tile's max exceeds it by more than
           // 2^8 (any reference gives the same softmax; p <= 256 is exact enough in fp16 and far from
@@ -371,15 +383,17 @@ attn_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const LongAttnPar
           const float m_new = (mx_s - m_run) * LA_LOG2E > LA_RESCALE_LOG2 ? mx_s : m_run;
           const float alpha = ex2_approx((m_run - m_new) * LA_LOG2E);   // 0 on the first tile (m_run = -inf)
           // P over the first half of my own (consumed) score columns
-          float sum;
+          float sum = 0.f;
           if (has_bias) {
-            sum = la_exps<true>(r0, t_s, m_new) + la_exps<true>(r1, t_s + 16, m_new);
+#pragma unroll
+            for (int hf = 0; hf < LA_NH; ++hf) sum += la_exps<true>(r[hf], t_s + 16 * hf, m_new);
           } else {
-            sum = la_exps<false>(r0, t_s, m_new) + la_exps<false>(r1, t_s + 16, m_new);
+#pragma unroll
+            for (int hf = 0; hf < LA_NH; ++hf) sum += la_exps<false>(r[hf], t_s + 16 * hf, m_new);
           }
           l_run = l_run * alpha + sum;
-          // rescale my accumulator when a row's max grew (not on the first tile: PV_0 overwrites it).
-          // PV_{j-2} is complete (S_j was issued behind it), so the parity wait cannot alias.
+          // rescale my accumulator when a reference max moved (not on the first tile: PV_0 overwrites
+          // it).  PV_{j-2} is complete (S_j was issued behind it), so the parity wait cannot alias.
           if (j > 0 && __any_sync(0xffffffffu, m_new > m_run)) {
             mbar_wait(my_pv_done, (g - 1) & 1);   // PV_{j-1} of my part has accumulated
             tc_fence_after();
@@ -415,56 +429,55 @@ attn_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const LongAttnPar
       // ---- unit end: combine the parts, O / l -> fp16 -> staging tile -> full rows ----
       mbar_wait(o_full, uc & 1);   // the unit's last PV (own barrier: pv_done's parity could alias here)
       tc_fence_after();
-      sts32(row_slot + pt * 512, __float_as_uint(m_run));
-      sts32(row_slot + 1024 + pt * 512, __float_as_uint(l_run));
+      const uint32_t uslot = row_slot + (uc & 1) * (LA_XCH / 2);   // slot sets alternate between units
+      sts32(uslot + pt * 512, __float_as_uint(m_run));
+      sts32(uslot + (LA_NP + pt) * 512, __float_as_uint(l_run));
       la_named_sync(1 + q, LA_NP * 32);
       if (rows_live) {
-        const float m0 = __uint_as_float(lds32(row_slot)), m1 = __uint_as_float(lds32(row_slot + 512));
-        const float l0 = __uint_as_float(lds32(row_slot + 1024)), l1 = __uint_as_float(lds32(row_slot + 1536));
-        const float m = fmaxf(m0, m1);
-        float f0 = ex2_approx((m0 - m) * LA_LOG2E), f1 = ex2_approx((m1 - m) * LA_LOG2E);   // 0 for a part without keys
-        const float inv = 1.0f / (l0 * f0 + l1 * f1);
-        f0 *= inv;
-        f1 *= inv;
-        // my 32 output columns of both accumulators
-        uint32_t o0[32], o1[32];
-        tmem_ld32(t_row + LA_O + pt * 32, o0);
-        tmem_ld32(t_row + LA_O + 64 + pt * 32, o1);
-        tmem_ld_wait();
+        float m = -INFINITY;
+#pragma unroll
+        for (int o = 0; o < LA_NP; ++o) m = fmaxf(m, __uint_as_float(lds32(uslot + o * 512)));
+        float f[LA_NP], den = 0.f;   // e^{m_part - m}: 0 for a part without keys
+#pragma unroll
+        for (int o = 0; o < LA_NP; ++o) {
+          f[o] = ex2_approx((__uint_as_float(lds32(uslot + o * 512)) - m) * LA_LOG2E);
+          den = fmaf(__uint_as_float(lds32(uslot + (LA_NP + o) * 512)), f[o], den);
+        }
+        const float inv = 1.0f / den;
+        // my LA_CW output columns of every accumulator
+        float y[LA_CW];
+#pragma unroll
+        for (int i = 0; i < LA_CW; ++i) y[i] = 0.f;
+#pragma unroll
+        for (int o = 0; o < LA_NP; ++o) {
+          uint32_t a[LA_CW];
+          tmem_ld_cols(t_row + LA_O + o * 64 + pt * LA_CW, a);
+          tmem_ld_wait();
+          const float fo = f[o] * inv;
+#pragma unroll
+          for (int i = 0; i < LA_CW; ++i) y[i] = fmaf(__uint_as_float(a[i]), fo, y[i]);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(o_read);
+        // my LA_CW columns of the row straight from registers: 2 x LA_CW contiguous bytes per
+        // thread in 16-byte stores (whole sectors).  No staging tile and no CTA-wide barrier here:
+        // the softmax warps stay out of phase across units.
+        if (row < p.N) {
+          __half* dst = p.out + (static_cast<size_t>(b) * p.N + row) * p.ldo + h * 64 + pt * LA_CW;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float y[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            y[i] = fmaf(__uint_as_float(o0[8 * c + i]), f0, __uint_as_float(o1[8 * c + i]) * f1);
-          uint4 v;
-          v.x = pack_half2(y[0], y[1]);
-          v.y = pack_half2(y[2], y[3]);
-          v.z = pack_half2(y[4], y[5]);
-          v.w = pack_half2(y[6], y[7]);
-          sts128(sOut + rit * 128 + (((pt * 4 + c) ^ (rit & 7)) << 4), v);
+          for (int c = 0; c < LA_CW / 8; ++c) {
+            uint4 v;
+            v.x = pack_half2(y[8 * c + 0], y[8 * c + 1]);
+            v.y = pack_half2(y[8 * c + 2], y[8 * c + 3]);
+            v.z = pack_half2(y[8 * c + 4], y[8 * c + 5]);
+            v.w = pack_half2(y[8 * c + 6], y[8 * c + 7]);
+            *reinterpret_cast<uint4*>(dst + 8 * c) = v;
+          }
         }
       } else {
         if (lane == 0) mbar_arrive(o_read);
       }
-      la_named_sync(5, LA_NP * 128);
-      {
-        const int mw = warp_idx - 4;
-        __half* dst = p.out + static_cast<size_t>(b * p.N) * p.ldo + h * 64;
-#pragma unroll
-        for (int it = 0; it < 8 / LA_NP; ++it) {
-          const int rr = mw * (32 / LA_NP) + it * 4 + (lane >> 3);
-          const int ch = lane & 7;
-          if (qt * 128 + rr < p.N) {
-            const uint4 v = lds128(sOut + rr * 128 + ((ch ^ (rr & 7)) << 4));
-            *reinterpret_cast<uint4*>(dst + static_cast<size_t>(qt * 128 + rr) * p.ldo + ch * 8) = v;
-          }
-        }
-      }
-      la_named_sync(5, LA_NP * 128);   // the staging tile and the slots are rewritten by the next unit
     }
   }
 
