@@ -153,27 +153,34 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   } while (0)
 #define HP(p) static_cast<const __half*>(p)
 
+  NvtxRange range_block("dyt_block_fwd");
   // 1. LN1 (skipped when the previous block's merge already produced it)
-  if (!opt->xn_ready)
+  if (!opt->xn_ready) {
+    NvtxRange r("dyt.ln1");
     DYT_TRY(layernorm_f16(x, C, nullptr, nullptr, T, C, wt->ln1_w, wt->ln1_b, opt->eps, w.xn, C,
                           stream));
+  }
   // 2. qkv
+  { NvtxRange r("dyt.qkv");
   DYT_TRY(gemm_tn(w.xn, C, HP(wt->qkv_w), C, T, 3 * C, C, nullptr, EPI_BIAS, HP(wt->qkv_b), w.qkv,
-                  3 * C, nullptr, 0, nullptr, 0, 1.0f, stream));
+                  3 * C, nullptr, 0, nullptr, 0, 1.0f, stream)); }
   // 3. attention (uniform sequences of N tokens): the tcgen05 kernel up to 256 tokens; longer
   //    sequences or an additive bias (segmentation backbone, 1025 tokens) take the flash-style kernel
+  { NvtxRange r("dyt.attention");
   if (N > 256 || opt->attn_bias != nullptr)
     DYT_TRY(dyt_attn_bias_fwd(w.qkv, 3 * C, opt->attn_bias, opt->attn_bias_ld, B, N, H, 64, w.attn_o, C,
                               stream_));
   else
     DYT_TRY(attn_varlen_fwd(w.qkv, 3 * C, nullptr, B, N, N, T, H, 64, w.attn_o, C, stream));
+  }
   // 4. proj + residual -> x1 (fp32) and its fp16 copy
   // (the token selector's score Linear rides in the epilogue: per-row partial dot products)
   const int slices = gemm_tn_dot_slices(C);
   const bool fuse_score = C > 128;
+  { NvtxRange r("dyt.proj_residual_score");
   DYT_TRY(gemm_tn(w.attn_o, C, HP(wt->proj_w), C, T, C, C, nullptr, EPI_BIAS_RESID,
                   HP(wt->proj_b), w.x1h, C, w.x1, C, x, C, 1.0f, stream,
-                  fuse_score ? wt->sel_w : nullptr, w.score_part, slices, opt->logit_fp16));
+                  fuse_score ? wt->sel_w : nullptr, w.score_part, slices, opt->logit_fp16)); }
   // adapter on every token (steps 8./9.), forked onto the side stream
   SideStream& ss = side_stream();
   cudaStream_t astream = stream;
@@ -182,28 +189,44 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
     DYT_CUDA(cudaStreamWaitEvent(ss.stream, ss.fork, 0));
     astream = ss.stream;
   }
+  { NvtxRange r("dyt.adapter_down");
   DYT_TRY(gemm_tn(w.x1h, C, HP(wt->down_w), C, T, shape->bottleneck, C, nullptr, EPI_BIAS_RELU,
-                  HP(wt->down_b), w.down, shape->bottleneck, nullptr, 0, nullptr, 0, 1.0f, astream));
-  DYT_TRY(gemm_tn(w.down, shape->bottleneck, HP(wt->up_w), shape->bottleneck, T, C,
-                  shape->bottleneck, nullptr, EPI_BIAS, HP(wt->up_b), w.adapt, C, nullptr, 0,
-                  nullptr, 0, wt->adapter_scale, astream));
+                  HP(wt->down_b), w.down, shape->bottleneck, nullptr, 0, nullptr, 0, 1.0f, astream)); }
+  // the up projection rides in the merge kernel (step 10) unless unsupported / switched off
+  const bool fuse_up = merge_up_supported(C, shape->bottleneck) &&
+                       fuse_up_option().load(std::memory_order_relaxed) != 0;
+  if (!fuse_up) {
+    NvtxRange r("dyt.adapter_up");
+    DYT_TRY(gemm_tn(w.down, shape->bottleneck, HP(wt->up_w), shape->bottleneck, T, C,
+                    shape->bottleneck, nullptr, EPI_BIAS, HP(wt->up_b), w.adapt, C, nullptr, 0,
+                    nullptr, 0, wt->adapter_scale, astream));
+  }
   if (ss.ok) DYT_CUDA(cudaEventRecord(ss.join, ss.stream));
   // 5. dispatcher: score, gate, compaction, LN2 of kept rows
+  { NvtxRange r("dyt.dispatch");
   DYT_TRY(dispatch_fwd(w.x1, C, wt->sel_w, wt->sel_b, opt->logit_fp16, opt->min_kept,
                        opt->noise1, opt->noise2, opt->tau, B, N, C, wt->ln2_w, wt->ln2_b,
                        opt->eps, opt->forced_mask, mask_out, opt->gate_out, logits_out, w.packed_idx,
                        w.token_pos, w.cu_seqlens, w.n_kept, w.packed, C, w.dispatch_ws, stream_,
-                       fuse_score ? w.score_part : nullptr, slices));
+                       fuse_score ? w.score_part : nullptr, slices)); }
   // 6./7. MLP on the kept rows only (row count read from device memory)
+  { NvtxRange r("dyt.mlp_kept_rows");
   DYT_TRY(gemm_tn(w.packed, C, HP(wt->fc1_w), C, T, shape->hidden, C, w.n_kept, EPI_BIAS_GELU,
                   HP(wt->fc1_b), w.hidden, shape->hidden, nullptr, 0, nullptr, 0, 1.0f, stream));
   DYT_TRY(gemm_tn(w.hidden, shape->hidden, HP(wt->fc2_w), shape->hidden, T, C, shape->hidden,
-                  w.n_kept, EPI_BIAS, HP(wt->fc2_b), w.mlp, C, nullptr, 0, nullptr, 0, 1.0f, stream));
+                  w.n_kept, EPI_BIAS, HP(wt->fc2_b), w.mlp, C, nullptr, 0, nullptr, 0, 1.0f, stream)); }
   // join the adapter branch
   if (ss.ok) DYT_CUDA(cudaStreamWaitEvent(stream, ss.join, 0));
   // 10. scatter-merge back to [B, N, C] (in place into x), optionally with the next LayerNorm
-  DYT_TRY(scatter_merge(w.x1, C, w.adapt, C, w.mlp, C, w.token_pos, T, C, x, C, opt->next_ln_w,
-                        opt->next_ln_b, opt->eps, opt->next_ln_w ? w.xn : nullptr, C, stream));
+  NvtxRange range_merge("dyt.merge");
+  if (fuse_up)
+    DYT_TRY(merge_up(w.down, shape->bottleneck, HP(wt->up_w), shape->bottleneck, HP(wt->up_b),
+                     wt->adapter_scale, shape->bottleneck, w.x1, C, w.mlp, C, w.token_pos, T, C, x, C,
+                     opt->next_ln_w, opt->next_ln_b, opt->eps, opt->next_ln_w ? w.xn : nullptr, C,
+                     stream));
+  else
+    DYT_TRY(scatter_merge(w.x1, C, w.adapt, C, w.mlp, C, w.token_pos, T, C, x, C, opt->next_ln_w,
+                          opt->next_ln_b, opt->eps, opt->next_ln_w ? w.xn : nullptr, C, stream));
 #undef DYT_TRY
 #undef HP
   return DYT_OK;

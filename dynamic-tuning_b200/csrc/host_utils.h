@@ -10,6 +10,8 @@
 #include <atomic>
 #include <utility>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: a no-op unless a profiler is attached
+
 namespace dyt {
 
 // Status convention of include/dyt_b200.h: 0 ok, <0 argument error, >0 cudaError_t.
@@ -46,6 +48,15 @@ inline int cuda_status(cudaError_t e, const char* what) {
     int _s = ::dyt::cuda_status((call), #call);             \
     if (_s != 0) return _s;                                 \
   } while (0)
+
+// NVTX range around a host-side launch sequence (shows up as a named span in nsys / ncu --nvtx;
+// costs one pointer check per call when no tool is attached).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -119,6 +130,13 @@ inline std::atomic<int>& pdl_option() {
 // Library option (dyt_configure): cut the tiles of a GEMM's last, partial round into column
 // sub-tiles (gemm_tn.cuh GemmItems).  On by default.
 inline std::atomic<int>& tail_split_option() {
+  static std::atomic<int> v{1};
+  return v;
+}
+
+// Library option (dyt_configure): the block forward computes the adapter's up projection inside the
+// scatter-merge kernel (merge_up.cu).  On by default.
+inline std::atomic<int>& fuse_up_option() {
   static std::atomic<int> v{1};
   return v;
 }

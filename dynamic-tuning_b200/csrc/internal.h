@@ -26,6 +26,13 @@ int scatter_merge(const float* x1, int ldx, const __half* adapt, int lda, const 
                   const float* nln_w, const float* nln_b, float eps, __half* nln_out, int ldn,
                   cudaStream_t stream);
 
+// adapter up-projection + scatter-merge + next LayerNorm in one kernel (merge_up.cu)
+bool merge_up_supported(int C, int K);
+int merge_up(const __half* down, int ld_down, const __half* up_w, int ldw, const __half* up_b,
+             float scale, int K, const float* x1, int ldx, const __half* mlp_packed, int ldm,
+             const int* token_pos, int n_rows, int C, float* out, int ldo, const float* nln_w,
+             const float* nln_b, float eps, __half* nln_out, int ldn, cudaStream_t stream);
+
 int dispatch_fwd(const float* x1, int ldx, const float* sel_w, const float* sel_b, int logit_fp16,
                  float min_kept, const float* noise1, const float* noise2, float tau, int B, int N,
                  int C, const float* ln_w, const float* ln_b, float eps, const float* forced_mask,

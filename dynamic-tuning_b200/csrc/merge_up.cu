@@ -1,0 +1,507 @@
+// Adapter up-projection fused into the scatter-merge (and the next block's LayerNorm):
+//   adapt = f16(f16(down * Wup^T + b_up) * scale)          (never written to HBM)
+//   out   = adapt + (x1 + (kept(t) ? mlp_packed[pos[t]] : 0))
+//   ln    = f16(LayerNorm(out))                            optional
+// Replaces the up Linear of the adapter (reference models/model_speed_test.py:106-111, called at
+// :291), torch.zeros + index_put + the two adds (:302-308) and the next block's norm1.  Before this
+// kernel the [T, C] fp16 adapter output made a round trip through HBM (155 MB per layer at B = 256)
+// and the up GEMM was a launch of its own: measured 79 us per layer of the step (ablation).
+//
+// Persistent CTA per SM, tile = 128 rows x all C columns:
+//   warp 0    TMA: the 128 x 64 `down` tile of a row tile, then Wup in chunks of 128 output columns
+//             (16 KB each, ring of three; Wup is re-streamed from the L2 for every tile so that the
+//             shared memory can hold the epilogue's staging buffers instead)
+//   warp 1    tcgen05.mma issuer: per tile C/128 accumulator chunks of 128 columns (K = 64: four
+//             MMAs each) into a ring of four TMEM buffers
+//   warp 2    TMEM allocator
+//   warps 4.. sixteen epilogue warps, warp = (TMEM lane quarter q, 32-column part of every chunk).
+//             Pass 1 per chunk: accumulator (thread = row) -> bias, fp16 rounding, scale -> fp16
+//             transpose through a per-warp slab -> coalesced layout (8 lanes per row, 128-byte
+//             segments): x1 + mlp + adapt, fp32 store of `out`, running mean / M2 of the row
+//             (Chan's pairwise update: as accurate as the two-pass variance of rowwise.cuh).
+//             Row statistics are merged over the 8 lanes and the 4 part-warps (shared memory,
+//             named barrier per quarter).  Pass 2: every lane re-reads the `out` values it wrote
+//             itself (L2 hits, same-thread read-after-write) and stores f16((v - mean) rstd g + b).
+// The kernel is HBM-bound and its loads are 128-byte pieces of 32 rows per instruction: what
+// matters is bytes in flight.  Every lane therefore owns a private 192-byte staging slot in shared
+// memory that cp.async fills one chunk ahead (x1 / mlp in pass 1, `out` in pass 2): the loads of
+// chunk j+1 are in flight while chunk j is transposed, added and stored, without holding registers.
+// (Register-only versions: 178 us with the loads of a chunk serialised by a scoreboard alias,
+// 112 us with eight row loads in flight per warp; L2 prefetch of whole rows made it slower.)
+#include <stdarg.h>
+
+#include "../../include/dyt_b200.h"
+#include "host_utils.h"
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace dyt {
+
+constexpr int MU_BM = 128;
+constexpr int MU_CH = 128;                     // accumulator chunk (columns)
+constexpr int MU_EW = 16;                      // epilogue warps
+constexpr int MU_THREADS = 128 + MU_EW * 32;   // 640
+constexpr int MU_ABYTES = MU_BM * 128;         // one `down` tile: 128 rows x 64 halves
+constexpr int MU_WBYTES = MU_CH * 128;         // one Wup chunk: 128 output columns x 64 halves
+constexpr int MU_WSTAGES = 3;
+constexpr int MU_SLAB = 32 * 64;               // 32 rows x 32 fp16 per epilogue warp
+constexpr int MU_STAGE = 32 * 128 + 32 * 64;   // per warp: 32 rows x (32 fp32 + 32 fp16)
+constexpr int MU_MAXC = 1024;
+constexpr int MU_EPI_REGS = 104, MU_AUX_REGS = 56;
+
+struct MergeUpParams {
+  int T, C;
+  const __half* bias;   // [C] fp16 or nullptr
+  float scale;
+  const float* x1;
+  int ldx;
+  const __half* mlp;    // packed MLP output
+  int ldm;
+  const int* token_pos; // [T]: row of mlp, or -1
+  float* out;
+  int ldo;
+  const float* ln_w;    // optional next LayerNorm
+  const float* ln_b;
+  float eps;
+  __half* ln_out;
+  int ldn;
+};
+
+static inline int mu_smem_bytes(int C) {
+  return MU_WSTAGES * MU_WBYTES + MU_ABYTES + MU_EW * (MU_SLAB + MU_STAGE) + 3 * C * 4 +
+         2 * 4 * MU_BM * 8 + 256 + 1024;
+}
+
+__device__ __forceinline__ void mu_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+// 16-byte asynchronous copy global -> shared, L2 only; src_bytes = 0 writes zeros
+__device__ __forceinline__ void mu_cp16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mu_cp8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void mu_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void mu_cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(MU_THREADS, 1)
+merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], box 128 x 64
+                const __grid_constant__ CUtensorMap tmap_w,   // Wup  [C, K], box 128 x 64
+                const MergeUpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int C = p.C;
+  const int nch = C / MU_CH;
+  uint8_t* w_smem = smem;                                   // ring of Wup chunks
+  uint8_t* a_smem = w_smem + MU_WSTAGES * MU_WBYTES;        // one `down` tile
+  uint8_t* slabs = a_smem + MU_ABYTES;
+  uint8_t* stages = slabs + MU_EW * MU_SLAB;
+  float* bias_s = reinterpret_cast<float*>(stages + MU_EW * MU_STAGE);   // [C]
+  float* gamma_s = bias_s + C;
+  float* beta_s = gamma_s + C;
+  float2* stats_s = reinterpret_cast<float2*>(beta_s + C);             // [2][4][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stats_s + 2 * 4 * MU_BM);
+  uint64_t* a_full = bars;            // [1]
+  uint64_t* a_empty = bars + 1;       // [1]
+  uint64_t* w_full = bars + 2;        // [3]
+  uint64_t* w_empty = bars + 5;       // [3]
+  uint64_t* t_full = bars + 8;        // [4]
+  uint64_t* t_empty = bars + 12;      // [4]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int s = 0; s < MU_WSTAGES; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(&t_full[b], 1);
+      mbar_init(&t_empty[b], MU_EW);
+    }
+    fence_mbar_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  if (warp_idx >= 4) {
+    // parameters (not produced by the preceding kernels) -> shared memory
+    for (int i = threadIdx.x - 128; i < C; i += MU_EW * 32) {
+      bias_s[i] = p.bias != nullptr ? __half2float(p.bias[i]) : 0.f;
+      gamma_s[i] = p.ln_w != nullptr ? p.ln_w[i] : 1.f;
+      beta_s[i] = p.ln_b != nullptr ? p.ln_b[i] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int num_tiles = (p.T + MU_BM - 1) / MU_BM;
+
+  if (warp_idx < 4) {
+    reg_dealloc<MU_AUX_REGS>();
+    if (warp_idx == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        pdl_wait();   // `down` comes from the preceding kernels
+        int ws = 0;
+        uint32_t wph = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+          mbar_wait(a_empty, (static_cast<uint32_t>(it) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(a_full, MU_ABYTES);
+          tma_load_2d(a_smem, &tmap_a, a_full, 0, tile * MU_BM);
+          for (int j = 0; j < nch; ++j) {
+            mbar_wait(&w_empty[ws], wph ^ 1u);
+            mbar_arrive_expect_tx(&w_full[ws], MU_WBYTES);
+            tma_load_2d(w_smem + ws * MU_WBYTES, &tmap_w, &w_full[ws], 0, j * MU_CH);
+            if (++ws == MU_WSTAGES) {
+              ws = 0;
+              wph ^= 1u;
+            }
+          }
+        }
+      }
+    } else if (warp_idx == 1) {
+      // ===================== MMA issuer (warp-uniform, one elected lane issues) =====================
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t w_u = __shfl_sync(0xffffffffu, smem_u32(w_smem), 0);
+      const uint32_t a_u = __shfl_sync(0xffffffffu, smem_u32(a_smem), 0);
+      constexpr uint32_t idesc = umma_idesc_f16(MU_BM, MU_CH, 0, 0);
+      const uint64_t a_desc = umma_desc_sw128(a_u);
+      int it = 0;
+      int ws = 0;
+      uint32_t wph = 0;
+      uint32_t g = 0;   // chunk counter over the whole kernel: TMEM buffer = g & 3
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(a_full, static_cast<uint32_t>(it) & 1u);
+        tc_fence_after();
+        for (int j = 0; j < nch; ++j, ++g) {
+          const uint32_t buf = g & 3u;
+          mbar_wait(&w_full[ws], wph);
+          mbar_wait(&t_empty[buf], ((g >> 2) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint64_t b_desc = umma_desc_sw128(w_u + ws * MU_WBYTES);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ss_f16(tmem_u + buf * MU_CH, a_desc + 2 * k, b_desc + 2 * k, idesc, k != 0 ? 1u : 0u);
+            umma_commit(&t_full[buf]);
+            umma_commit(&w_empty[ws]);
+            if (j == nch - 1) umma_commit(a_empty);
+          }
+          __syncwarp();
+          if (++ws == MU_WSTAGES) {
+            ws = 0;
+            wph ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    reg_alloc<MU_EPI_REGS>();
+    // ===================== epilogue =====================
+    const int e = warp_idx - 4;
+    const int q = e & 3;       // == warp_idx % 4: the TMEM lane quarter this warp may access
+    const int part = e >> 2;   // 32-column part of every 128-column chunk
+    const uint32_t slab = smem_u32(slabs) + e * MU_SLAB;
+    const uint32_t my_row = slab + lane * 64;
+    const int swz_w = (lane >> 1) & 3;
+    const int p8 = lane & 7;
+    const int r8 = lane >> 3;
+    // this lane's private staging slots: row it*4 + r8, 16 B of x1 / out, 8 B of mlp
+    const uint32_t stage_x = smem_u32(stages) + e * MU_STAGE + r8 * 128 + p8 * 16;
+    const uint32_t stage_m = smem_u32(stages) + e * MU_STAGE + 32 * 128 + r8 * 64 + p8 * 8;
+    const bool plain = p.scale == 1.0f;
+    const bool do_ln = p.ln_out != nullptr;
+    const uint32_t bias_u = smem_u32(bias_s), gamma_u = smem_u32(gamma_s), beta_u = smem_u32(beta_s);
+    const int col_lane = part * 32 + p8 * 4;   // + j * 128
+    pdl_wait();
+
+    // token_pos of a quarter's 32 rows: ONE coalesced load per tile, handed out by shuffles.
+    // (Loaded straight into an array, the registers stay tied to a load scoreboard slot that later
+    // loads reuse: every read of pos[it] then waited for all loads issued before it, which
+    // serialised the eight row loads of a chunk -- 10k clocks per chunk.)
+    auto load_pl = [&](int tile) -> int {
+      const int r = tile * MU_BM + q * 32 + lane;
+      return (tile < num_tiles && r < p.T) ? p.token_pos[r] : -1;
+    };
+    // pass-1 inputs of chunk j -> staging (asynchronous)
+    auto issue_p1 = [&](int tile, int pl, int j) {
+      if (tile < num_tiles) {
+        const int row0 = tile * MU_BM + q * 32;
+        const int col = j * MU_CH + col_lane;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int grow = row0 + it * 4 + r8;
+          const int ps = __shfl_sync(0xffffffffu, pl, it * 4 + r8);
+          const bool in = grow < p.T;
+          mu_cp16(stage_x + it * 512, p.x1 + (in ? static_cast<size_t>(grow) * p.ldx + col : 0), in ? 16u : 0u);
+          if (ps >= 0) mu_cp8(stage_m + it * 256, p.mlp + static_cast<size_t>(ps) * p.ldm + col);
+        }
+      }
+      mu_cp_commit();
+    };
+    // pass-2 input: the `out` values this lane stored in pass 1
+    auto issue_p2 = [&](int tile, int j) {
+      const int row0 = tile * MU_BM + q * 32;
+      const int col = j * MU_CH + col_lane;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int grow = row0 + it * 4 + r8;
+        const bool in = grow < p.T;
+        mu_cp16(stage_x + it * 512, p.out + (in ? static_cast<size_t>(grow) * p.ldo + col : 0), in ? 16u : 0u);
+      }
+      mu_cp_commit();
+    };
+
+    int pl = load_pl(blockIdx.x);
+    issue_p1(blockIdx.x, pl, 0);
+    uint32_t g = 0;
+    int it_tile = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it_tile) {
+      const int row0 = tile * MU_BM + q * 32;
+      const int next_tile = tile + gridDim.x;
+      const int pl_next = load_pl(next_tile);   // in flight for the whole tile
+      unsigned kept = 0;                         // bit it: row it*4 + r8 has an MLP row
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        kept |= (__shfl_sync(0xffffffffu, pl, it * 4 + r8) >= 0 ? 1u : 0u) << it;
+      float mean[8], m2[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) mean[it] = m2[it] = 0.f;
+
+#pragma unroll 1
+      for (int j = 0; j < nch; ++j, ++g) {
+        const uint32_t buf = g & 3u;
+        const int c0 = j * MU_CH + part * 32;   // first column of this warp's 32
+        {
+          uint32_t pk[16];
+          {
+            uint32_t r[32];
+            mbar_wait(&t_full[buf], (g >> 2) & 1u);
+            tc_fence_after();
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * MU_CH + part * 32, r);
+            uint4 bq[8];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) bq[j4] = lds128(bias_u + (c0 + j4 * 4) * 4);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
+            // thread = row: one rounding to fp16 per Linear output, then f16(v * scale)
+#pragma unroll
+            for (int j2 = 0; j2 < 16; ++j2) {
+              const uint4 bv = bq[j2 >> 1];
+              const float b0 = __uint_as_float((j2 & 1) ? bv.z : bv.x);
+              const float b1 = __uint_as_float((j2 & 1) ? bv.w : bv.y);
+              __half2 h = __floats2half2_rn(__uint_as_float(r[2 * j2]) + b0,
+                                            __uint_as_float(r[2 * j2 + 1]) + b1);
+              if (!plain) h = __floats2half2_rn(__low2float(h) * p.scale, __high2float(h) * p.scale);
+              pk[j2] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            sts128(my_row + ((k ^ swz_w) << 4),
+                   make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
+        }
+        __syncwarp();
+        // staged inputs of this chunk -> registers; the slots are refilled at once
+        mu_cp_wait();
+        uint4 xv[8];
+        uint2 mv[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          xv[it] = lds128(stage_x + it * 512);
+          mv[it] = lds64(stage_m + it * 256);
+        }
+        if (j + 1 < nch) issue_p1(tile, pl, j + 1);
+        else if (!do_ln) issue_p1(next_tile, pl_next, 0);
+        // coalesced layout: lane -> (row it*4 + lane/8, columns (lane%8)*4 .. +3)
+        const int col = c0 + p8 * 4;
+        const float w1 = 1.0f / static_cast<float>(j + 1);
+        const float w2 = 4.0f * static_cast<float>(j) * w1;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + r8;
+          const int grow = row0 + rr;
+          const uint2 hv = lds64(slab + rr * 64 + (((p8 >> 1) ^ ((rr >> 1) & 3)) << 4) + (p8 & 1) * 8);
+          float4 v = make_float4(__uint_as_float(xv[it].x), __uint_as_float(xv[it].y),
+                                 __uint_as_float(xv[it].z), __uint_as_float(xv[it].w));
+          if ((kept >> it) & 1u) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&mv[it].x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&mv[it].y));
+            v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
+          }
+          const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&hv.x));
+          const float2 a23 = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
+          v.x += a01.x; v.y += a01.y; v.z += a23.x; v.w += a23.y;
+          if (grow < p.T)
+            *reinterpret_cast<float4*>(p.out + static_cast<size_t>(grow) * p.ldo + col) = v;
+          // running mean / sum of squared deviations of this lane's columns of the row
+          const float m4 = 0.25f * ((v.x + v.y) + (v.z + v.w));
+          const float da = v.x - m4, db = v.y - m4, dc = v.z - m4, dd = v.w - m4;
+          const float q4 = (da * da + db * db) + (dc * dc + dd * dd);
+          const float dl = m4 - mean[it];
+          mean[it] = fmaf(dl, w1, mean[it]);
+          m2[it] += fmaf(dl * dl, w2, q4);
+        }
+        __syncwarp();   // the slab is overwritten by the next chunk
+      }
+      if (!do_ln) {
+        pl = pl_next;
+        continue;
+      }
+      issue_p2(tile, 0);   // in flight during the exchange of the row statistics
+
+      // ---- row statistics: 8 lanes of a row, then the 4 part-warps of the quarter ----
+      float cnt = static_cast<float>(4 * nch);
+#pragma unroll
+      for (int o = 1; o <= 4; o <<= 1) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const float mo = __shfl_xor_sync(0xffffffffu, mean[it], o);
+          const float qo = __shfl_xor_sync(0xffffffffu, m2[it], o);
+          const float d = mean[it] - mo;
+          m2[it] = (m2[it] + qo) + d * d * (0.5f * cnt);
+          mean[it] = 0.5f * (mean[it] + mo);
+        }
+        cnt *= 2.f;
+      }
+      float2* st = stats_s + (it_tile & 1) * 4 * MU_BM;
+      if (p8 == 0) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          st[part * MU_BM + q * 32 + it * 4 + r8] = make_float2(mean[it], m2[it]);
+      }
+      mu_bar_sync(1 + q, 128);
+      float rstd[8];
+      const float inv_c = 1.0f / static_cast<float>(C);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = q * 32 + it * 4 + r8;
+        const float2 s0 = st[0 * MU_BM + rr], s1 = st[1 * MU_BM + rr];
+        const float2 s2 = st[2 * MU_BM + rr], s3 = st[3 * MU_BM + rr];
+        const float d01 = s0.x - s1.x, d23 = s2.x - s3.x;
+        const float m01 = 0.5f * (s0.x + s1.x), m23 = 0.5f * (s2.x + s3.x);
+        const float q01 = (s0.y + s1.y) + d01 * d01 * (0.5f * cnt);
+        const float q23 = (s2.y + s3.y) + d23 * d23 * (0.5f * cnt);
+        const float d = m01 - m23;
+        mean[it] = 0.5f * (m01 + m23);
+        rstd[it] = rsqrtf(((q01 + q23) + d * d * cnt) * inv_c + p.eps);
+      }
+
+      // ---- pass 2: normalise the values this lane wrote ----
+#pragma unroll 1
+      for (int j = 0; j < nch; ++j) {
+        const int col = j * MU_CH + col_lane;
+        mu_cp_wait();
+        uint4 v[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) v[it] = lds128(stage_x + it * 512);
+        if (j + 1 < nch) issue_p2(tile, j + 1);
+        else issue_p1(next_tile, pl_next, 0);
+        const uint4 gq = lds128(gamma_u + col * 4);
+        const uint4 bq = lds128(beta_u + col * 4);
+        const float g0 = __uint_as_float(gq.x), g1 = __uint_as_float(gq.y), g2 = __uint_as_float(gq.z),
+                    g3 = __uint_as_float(gq.w);
+        const float b0 = __uint_as_float(bq.x), b1 = __uint_as_float(bq.y), b2 = __uint_as_float(bq.z),
+                    b3 = __uint_as_float(bq.w);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int grow = row0 + it * 4 + r8;
+          const float y0 = (__uint_as_float(v[it].x) - mean[it]) * rstd[it] * g0 + b0;
+          const float y1 = (__uint_as_float(v[it].y) - mean[it]) * rstd[it] * g1 + b1;
+          const float y2 = (__uint_as_float(v[it].z) - mean[it]) * rstd[it] * g2 + b2;
+          const float y3 = (__uint_as_float(v[it].w) - mean[it]) * rstd[it] * g3 + b3;
+          if (grow < p.T)
+            *reinterpret_cast<uint2*>(p.ln_out + static_cast<size_t>(grow) * p.ldn + col) =
+                make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
+        }
+      }
+      pl = pl_next;
+    }
+    mu_cp_wait();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+bool merge_up_supported(int C, int K) {
+  return C % MU_CH == 0 && C >= MU_CH && C <= MU_MAXC && K >= 8 && K <= 64 && K % 8 == 0;
+}
+
+int merge_up(const __half* down, int ld_down, const __half* up_w, int ldw, const __half* up_b,
+             float scale, int K, const float* x1, int ldx, const __half* mlp_packed, int ldm,
+             const int* token_pos, int n_rows, int C, float* out, int ldo, const float* nln_w,
+             const float* nln_b, float eps, __half* nln_out, int ldn, cudaStream_t stream) {
+  DYT_CHECK_ARG(down && up_w && x1 && mlp_packed && token_pos && out, "merge_up: null buffer");
+  if (!merge_up_supported(C, K))
+    return fail(DYT_EUNSUPPORTED, "merge_up: needs C %% 128 == 0, C <= %d, K <= 64 (C=%d K=%d)", MU_MAXC, C, K);
+  DYT_CHECK_ARG(ldx % 4 == 0 && ldm % 4 == 0 && ldo % 4 == 0 && ld_down >= K && ldw >= K,
+                "merge_up: strides");
+  DYT_CHECK_ARG(nln_out == nullptr || (nln_w && nln_b && ldn % 4 == 0), "merge_up: next-LN args");
+  DYT_CHECK_ARG(out != x1, "merge_up: out must not alias x1");
+  if (n_rows == 0) return DYT_OK;
+  CUtensorMap ta, tw;
+  int s = make_tmap_f16_sw128(&ta, down, static_cast<uint64_t>(n_rows), static_cast<uint64_t>(K),
+                              static_cast<uint64_t>(ld_down), MU_BM);
+  if (s != DYT_OK) return s;
+  s = make_tmap_f16_sw128(&tw, up_w, static_cast<uint64_t>(C), static_cast<uint64_t>(K),
+                          static_cast<uint64_t>(ldw), MU_CH);
+  if (s != DYT_OK) return s;
+  static SmemAttrCache smem_cache;
+  s = ensure_dyn_smem(merge_up_kernel, mu_smem_bytes(MU_MAXC), smem_cache);
+  if (s != DYT_OK) return s;
+  MergeUpParams p;
+  p.T = n_rows; p.C = C;
+  p.bias = up_b; p.scale = scale;
+  p.x1 = x1; p.ldx = ldx;
+  p.mlp = mlp_packed; p.ldm = ldm;
+  p.token_pos = token_pos;
+  p.out = out; p.ldo = ldo;
+  p.ln_w = nln_w; p.ln_b = nln_b; p.eps = eps;
+  p.ln_out = nln_out; p.ldn = ldn;
+  const int tiles = (n_rows + MU_BM - 1) / MU_BM;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  // at least 120 KB of shared memory per CTA: one CTA per SM, which owns all 512 TMEM columns
+  int smem = mu_smem_bytes(C);
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  return cuda_status(launch_pdl(merge_up_kernel, dim3(grid), dim3(MU_THREADS), smem, stream, ta, tw, p),
+                     "merge_up_kernel launch");
+}
+
+}  // namespace dyt
+
+extern "C" int dyt_merge_up_fwd(const void* down_f16, int ld_down, const void* up_w_f16, int ldw,
+                                const void* up_b_f16, float scale, int K, const float* x1, int ldx,
+                                const void* mlp_packed_f16, int ldm, const int* token_pos, int n_rows,
+                                int C, float* out, int ldo, const float* next_ln_w,
+                                const float* next_ln_b, float eps, void* next_ln_out_f16, int ldn,
+                                void* stream) {
+  return dyt::merge_up(static_cast<const __half*>(down_f16), ld_down,
+                       static_cast<const __half*>(up_w_f16), ldw,
+                       static_cast<const __half*>(up_b_f16), scale, K, x1, ldx,
+                       static_cast<const __half*>(mlp_packed_f16), ldm, token_pos, n_rows, C, out, ldo,
+                       next_ln_w, next_ln_b, eps, static_cast<__half*>(next_ln_out_f16), ldn,
+                       static_cast<cudaStream_t>(stream));
+}

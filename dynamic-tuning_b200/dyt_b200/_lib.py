@@ -18,6 +18,7 @@ EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_BIAS_RESID = 0, 1, 2, 3
 EPI_BIAS_GELU_KEEP, EPI_DGELU = 4, 5
 OPT_PDL = 1
 OPT_GEMM_TAIL_SPLIT = 2
+OPT_FUSE_ADAPTER_UP = 3
 EW_GELU_FWD, EW_GELU_BWD, EW_RELU_DROP_BWD, EW_MUL = 0, 1, 2, 3
 
 
@@ -72,6 +73,8 @@ SIGNATURES = {
                                   _vp]),
     "dyt_scatter_merge_fwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _f,
                                    _vp, _i, _vp]),
+    "dyt_merge_up_fwd": (_i, [_vp, _i, _vp, _i, _vp, _f, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _i,
+                              _vp, _vp, _f, _vp, _i, _vp]),
     "dyt_patch_embed_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "dyt_patch_embed_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "dyt_pool_layernorm_f16": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp]),

@@ -296,6 +296,35 @@ def scatter_merge(x1: torch.Tensor, adapt: torch.Tensor, mlp_packed: torch.Tenso
     return (out, None if nln_out is None else nln_out.reshape(x1.shape))
 
 
+def merge_up(down: torch.Tensor, up_w: torch.Tensor, up_b: Optional[torch.Tensor], scale: float,
+             x1: torch.Tensor, mlp_packed: torch.Tensor, token_pos: torch.Tensor,
+             next_ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, eps: float = 1e-6):
+    """out = f16(f16(down up_w^T + up_b) * scale) + (x1 + scatter(mlp_packed)) in one kernel (the
+    adapter output never reaches HBM); optionally also LayerNorm(out) in fp16.  Same results as
+    linear_f16(down, up_w, up_b, scale=scale) followed by scatter_merge."""
+    _need_cuda(down, up_w, x1, mlp_packed, token_pos)
+    x2 = _rows2d(x1)
+    d2 = _rows2d(down)
+    m2 = _rows2d(mlp_packed)
+    T, Cdim = x2.shape
+    K = d2.shape[1]
+    assert d2.dtype == torch.float16 and up_w.dtype == torch.float16 and up_w.shape == (Cdim, K)
+    up_w = up_w.contiguous()
+    out = torch.empty((T, Cdim), dtype=torch.float32, device=x1.device)
+    nln_out = None
+    nw = nb = None
+    if next_ln is not None:
+        nw, nb = next_ln
+        nln_out = torch.empty((T, Cdim), dtype=torch.float16, device=x1.device)
+    check(_lib.lib().dyt_merge_up_fwd(
+        d2.data_ptr(), d2.stride(0), up_w.data_ptr(), up_w.stride(0), _ptr(up_b), float(scale), K,
+        x2.data_ptr(), x2.stride(0), m2.data_ptr(), m2.stride(0), token_pos.data_ptr(), T, Cdim,
+        out.data_ptr(), Cdim, _ptr(nw), _ptr(nb), float(eps), _ptr(nln_out), Cdim, _stream()),
+        "dyt_merge_up_fwd")
+    out = out.reshape(x1.shape)
+    return (out, None if nln_out is None else nln_out.reshape(x1.shape))
+
+
 _stem_ws = {}
 # fp16 / fp32 working copies of the stem parameters, keyed by the identity of the PARAMETER OBJECT
 # (held weakly: the entry is dropped when the parameter dies), so a new model whose tensors land on

@@ -49,9 +49,13 @@ const char* dyt_last_error(void);
  *   capturable.  0 = plain stream order (the default: no gain was measured on B200).
  *   DYT_OPT_GEMM_TAIL_SPLIT (default 1): the persistent GEMM cuts the tiles of its last, partial
  *   round into 2 or 4 column sub-tiles when the leftover tiles number at most half / a quarter of
- *   the CTA pairs (wave quantisation: 297 tile pairs on 74 pairs = 4 rounds + 1 tile). */
+ *   the CTA pairs (wave quantisation: 297 tile pairs on 74 pairs = 4 rounds + 1 tile).
+ *   DYT_OPT_FUSE_ADAPTER_UP (default 1): dyt_block_fwd computes the adapter's up projection inside
+ *   the scatter-merge kernel (dyt_merge_up_fwd) instead of a GEMM launch whose [T, C] output makes a
+ *   round trip through HBM; 0 = the separate dyt_linear_f16 + dyt_scatter_merge_fwd launches. */
 #define DYT_OPT_PDL 1
 #define DYT_OPT_GEMM_TAIL_SPLIT 2
+#define DYT_OPT_FUSE_ADAPTER_UP 3
 int dyt_configure(int option, int value);
 
 /* y = epilogue(x[M,K] * w[N,K]^T): the nn.Linear forward under fp16 autocast.
@@ -159,6 +163,20 @@ int dyt_scatter_merge_fwd(const float* x1, int ldx, const void* adapt_f16, int l
                           int C, float* out, int ldo, const float* next_ln_w,
                           const float* next_ln_b, float eps, void* next_ln_out_f16, int ldn,
                           void* stream);
+
+/* Adapter up-projection fused into the scatter-merge:
+ *   adapt = f16(f16(down[T,K] * up_w[C,K]^T + up_b) * scale)        (stays on chip)
+ *   out[t] = adapt[t] + (x1[t] + (token_pos[t] >= 0 ? mlp[token_pos[t]] : 0))
+ *   next_ln_out = f16(LayerNorm(out))                                 (optional)
+ * Replaces Adapter.up_proj * scale (reference models/model_speed_test.py:106-111, :291) together
+ * with torch.zeros + index_put + the two adds (:302-308) and the next block's norm1.  Same results
+ * as dyt_linear_f16(EPI_BIAS, scale) followed by dyt_scatter_merge_fwd.  Needs C % 128 == 0,
+ * C <= 1024, K <= 64, K % 8 == 0 (DYT_EUNSUPPORTED otherwise); out must not alias x1. */
+int dyt_merge_up_fwd(const void* down_f16, int ld_down, const void* up_w_f16, int ldw,
+                     const void* up_b_f16, float scale, int K, const float* x1, int ldx,
+                     const void* mlp_packed_f16, int ldm, const int* token_pos, int n_rows, int C,
+                     float* out, int ldo, const float* next_ln_w, const float* next_ln_b, float eps,
+                     void* next_ln_out_f16, int ldn, void* stream);
 
 /* ViT stem: x[b,0] = cls + pos[0]; x[b,1+p] = f16(patch_p . W^T + bias) + pos[1+p]  (fp32 out).
  * Replaces PatchEmbed.proj (Conv2d k = s = P) + cls concat + pos_embed add (reference

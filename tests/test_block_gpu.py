@@ -174,9 +174,43 @@ def test_fused_next_layernorm_is_equivalent(dev, vitb_sd):
     m = _speed_model(sd, dev)
     from dyt_b200 import engine
     x = torch.randn(2, 197, 768, generator=torch.Generator().manual_seed(5)).to(dev)
-    a = engine.run_blocks(x, list(m.blocks[:4]), fuse_next_ln=True)
-    b = engine.run_blocks(x, list(m.blocks[:4]), fuse_next_ln=False)
-    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    from dyt_b200 import _lib
+    lib = _lib.lib()
+    try:
+        # separate up GEMM + scatter-merge: the merge's LayerNorm is the stand-alone kernel's code
+        assert lib.dyt_configure(_lib.OPT_FUSE_ADAPTER_UP, 0) == 0
+        a = engine.run_blocks(x, list(m.blocks[:4]), fuse_next_ln=True)
+        b = engine.run_blocks(x, list(m.blocks[:4]), fuse_next_ln=False)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    finally:
+        assert lib.dyt_configure(_lib.OPT_FUSE_ADAPTER_UP, 1) == 0
+    # adapter-up fused into the merge (default): same fp32 stream after one block bit for bit; its
+    # LayerNorm sums in another order (one fp16 ulp on a few elements), so deeper outputs agree to
+    # rounding noise
+    c1 = engine.run_blocks(x, list(m.blocks[:1]), fuse_next_ln=True)
+    b1 = engine.run_blocks(x, list(m.blocks[:1]), fuse_next_ln=False)
+    assert torch.equal(c1[0], b1[0]) and torch.equal(c1[1], b1[1])
+    c = engine.run_blocks(x, list(m.blocks[:4]), fuse_next_ln=True)
+    assert torch.equal(c[1], b[1])
+    assert _rel(c[0], b[0]) <= 2e-4
+
+
+def test_block_fused_adapter_up_equals_separate_launches(dev, vitb_sd):
+    """dyt_block_fwd with DYT_OPT_FUSE_ADAPTER_UP on / off: one block's output, mask and logits are
+    bit-equal (the fused kernel performs the same roundings and fp32 additions)."""
+    g, sd, img = vitb_sd
+    m = _speed_model(sd, dev)
+    from dyt_b200 import engine, _lib
+    lib = _lib.lib()
+    x = torch.randn(3, 197, 768, generator=torch.Generator().manual_seed(6)).to(dev)
+    on = engine.run_blocks(x, list(m.blocks[2:3]), fuse_next_ln=False)
+    try:
+        assert lib.dyt_configure(_lib.OPT_FUSE_ADAPTER_UP, 0) == 0
+        off = engine.run_blocks(x, list(m.blocks[2:3]), fuse_next_ln=False)
+    finally:
+        assert lib.dyt_configure(_lib.OPT_FUSE_ADAPTER_UP, 1) == 0
+    for u, v in zip(on[:3], off[:3]):
+        assert torch.equal(u, v)
 
 
 # ---------------------------------------------------------------------------------------------

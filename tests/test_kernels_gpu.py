@@ -357,6 +357,56 @@ def test_scatter_merge(dev):
     _close(ln, O._r16(O.layer_norm(ref, lw, lb)), atol=1e-3, rtol=1e-3)
 
 
+@pytest.mark.parametrize("B,N,C,K,scale", [(3, 197, 768, 64, 0.1), (2, 50, 128, 8, 1.0),
+                                           (5, 197, 1024, 64, 0.5), (1, 17, 384, 32, 0.1),
+                                           (300, 197, 768, 64, 0.1)])
+def test_merge_up_fused_matches_linear_plus_scatter_merge(dev, B, N, C, K, scale):
+    """dyt_merge_up_fwd (adapter up-projection inside the merge kernel) against the two separate
+    launches it replaces and against the oracle's arithmetic (model_speed_test.py:106-111, :302-308):
+    the fp32 stream bit-equal, the fused LayerNorm within one fp16 ulp of the two-pass kernel."""
+    from dyt_b200 import ops, _lib
+    g = _gen(11 + B)
+    x1 = torch.randn(B, N, C, generator=g) * 3 + 0.5
+    down = torch.relu(torch.randn(B, N, K, generator=g)).half()
+    up_w = (torch.randn(C, K, generator=g) * 0.05).half()
+    up_b = (torch.randn(C, generator=g) * 0.1).half()
+    mask = (torch.rand(B, N, 1, generator=g) > 0.5).float()
+    idx, _ = O.compact(mask)
+    mlp = torch.randn(idx.numel(), C, generator=g).half()
+    pos = torch.full((B * N,), -1, dtype=torch.int32)
+    pos[idx] = torch.arange(idx.numel(), dtype=torch.int32)
+    lw, lb = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    d = lambda t: t.to(dev)
+    adapt, _ = ops.linear_f16(d(down).reshape(B * N, K), d(up_w), d(up_b), scale=scale)
+    out0, ln0 = ops.scatter_merge(d(x1), adapt.reshape(B, N, C), d(mlp), d(pos), next_ln=(d(lw), d(lb)))
+    out1, ln1 = ops.merge_up(d(down), d(up_w), d(up_b), scale, d(x1), d(mlp), d(pos),
+                             next_ln=(d(lw), d(lb)))
+    out2, none = ops.merge_up(d(down), d(up_w), d(up_b), scale, d(x1), d(mlp), d(pos))
+    assert none is None
+    assert torch.equal(out1, out0) and torch.equal(out2, out0)
+    # LayerNorm: same mean / variance up to fp32 rounding of a different summation order
+    diff = (ln1.float() - ln0.float()).abs()
+    ulp = torch.maximum(ln0.float().abs(), torch.tensor(2.0 ** -14, device=dev)) * 2.0 ** -10
+    assert bool((diff <= ulp).all())
+    assert float((diff > 0).float().mean()) < 0.01
+    if B <= 5:   # oracle arithmetic on the CPU
+        a_ref = O._r16(O._r16(down.float().reshape(-1, K) @ up_w.float().t() + up_b.float()) * scale)
+        full = torch.zeros(B * N, C)
+        full[idx] = mlp.float()
+        ref = a_ref.reshape(B, N, C) + (x1 + full.reshape(B, N, C))
+        _close(out1, ref, atol=2e-3, rtol=1e-3)
+        _close(ln1, O._r16(O.layer_norm(ref, lw, lb)), atol=2e-3, rtol=2e-3)
+
+
+def test_merge_up_refuses_unsupported_shapes(dev):
+    from dyt_b200 import ops, _lib
+    x1 = torch.zeros(1, 4, 192, device=dev)
+    with pytest.raises(_lib.DytError):
+        ops.merge_up(torch.zeros(1, 4, 64, device=dev).half(), torch.zeros(192, 64, device=dev).half(),
+                     None, 1.0, x1, torch.zeros(4, 192, device=dev).half(),
+                     torch.zeros(4, dtype=torch.int32, device=dev))
+
+
 def test_keep_stats_kernel_matches_reference_accounting():
     """dyt_keep_stats / dyt_b200.flops.batch_select_flops against the reference's
     block_flops_dict.batch_select_flops (golden, bit-equal: same fp32 additions in the same order) and
