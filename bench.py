@@ -344,12 +344,12 @@ def kernel_table(model, x_blocks, kept_total, peaks, device):
         2.0 * K * HIDDEN * C_DIM, K * (C_DIM + HIDDEN) * 2, "tensor")
     add("gemm adapter down + ReLU", lambda: ops.linear_f16(xn, dn_w, dn_b, epilogue=_lib.EPI_BIAS_RELU, out=out_d),
         2.0 * T * BOTTLENECK * C_DIM, T * (C_DIM + BOTTLENECK) * 2, "hbm")
-    add("gemm adapter up * scale", lambda: ops.linear_f16(dn, up_w, up_b, scale=0.1, out=out_c),
-        2.0 * T * BOTTLENECK * C_DIM, T * (C_DIM + BOTTLENECK) * 2, "hbm")
-    add("scatter-merge (+ next LN1)",
-        lambda: ops.scatter_merge(x_blocks, out_c.reshape(x_blocks.shape), out_c, d["token_pos"],
-                                  next_ln=(ln_w, ln_b)),
-        0.0, T * C_DIM * (4 + 2 + 4 + 2) + K * C_DIM * 2, "hbm")
+    # adapter up-projection + scatter-merge + next LN1 in one kernel (the default block path)
+    dn_relu = torch.relu(dn)
+    add("adapter up + scatter-merge + next LN1 (fused)",
+        lambda: ops.merge_up(dn_relu.reshape(x_blocks.shape[0], N_TOK, BOTTLENECK), up_w, up_b, 0.1,
+                             x_blocks, out_c, d["token_pos"], next_ln=(ln_w, ln_b)),
+        2.0 * T * BOTTLENECK * C_DIM, T * C_DIM * (4 + 4 + 2) + K * C_DIM * 2 + T * BOTTLENECK * 2, "hbm")
     return rows
 
 
@@ -495,7 +495,9 @@ def run_ours(args, world, rank, local):
                 "h2d_bytes_per_step": host_images.numel() * 4,
                 "d2h_bytes_per_step": host_logits.numel() * 2},
         # 9 per block + first LN1 + 3 stem kernels + final LN + head GEMM
-        "gpu_launches": args.steps * (DEPTH * 9 + 1 + 3 + 2),
+        # per layer: qkv, attention, proj, adapter down, dispatcher, fc1, fc2, fused up + merge;
+        # + first LN1, 3 stem kernels, final LN + head
+        "gpu_launches": args.steps * (DEPTH * 8 + 1 + 3 + 2),
         "speed_py_style_images_per_s_per_gpu": wall_value,
         "model_flops_per_image": fl_img,
         "model_tflops": value / world * fl_img / 1e12,

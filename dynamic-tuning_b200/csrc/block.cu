@@ -193,7 +193,7 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   DYT_TRY(gemm_tn(w.x1h, C, HP(wt->down_w), C, T, shape->bottleneck, C, nullptr, EPI_BIAS_RELU,
                   HP(wt->down_b), w.down, shape->bottleneck, nullptr, 0, nullptr, 0, 1.0f, astream)); }
   // the up projection rides in the merge kernel (step 10) unless unsupported / switched off
-  const bool fuse_up = merge_up_supported(C, shape->bottleneck) &&
+  const bool fuse_up = merge_up_supported(C, shape->bottleneck, T) &&
                        fuse_up_option().load(std::memory_order_relaxed) != 0;
   if (!fuse_up) {
     NvtxRange r("dyt.adapter_up");

@@ -27,7 +27,7 @@ int scatter_merge(const float* x1, int ldx, const __half* adapt, int lda, const 
                   cudaStream_t stream);
 
 // adapter up-projection + scatter-merge + next LayerNorm in one kernel (merge_up.cu)
-bool merge_up_supported(int C, int K);
+bool merge_up_supported(int C, int K, long long rows);
 int merge_up(const __half* down, int ld_down, const __half* up_w, int ldw, const __half* up_b,
              float scale, int K, const float* x1, int ldx, const __half* mlp_packed, int ldm,
              const int* token_pos, int n_rows, int C, float* out, int ldo, const float* nln_w,

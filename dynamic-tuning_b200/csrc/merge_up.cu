@@ -75,16 +75,18 @@ static inline int mu_smem_bytes(int C) {
 __device__ __forceinline__ void mu_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
-// 16-byte asynchronous copy global -> shared, L2 only; src_bytes = 0 writes zeros
-__device__ __forceinline__ void mu_cp16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
-               : "memory");
+// 16-byte asynchronous copy global -> shared, L2 only
+__device__ __forceinline__ void mu_cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void mu_cp8(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+// 8-byte copy; src_bytes = 0 writes zeros instead
+__device__ __forceinline__ void mu_cp8z(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
 }
 __device__ __forceinline__ void mu_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void mu_cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mu_cp_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 __global__ void __launch_bounds__(MU_THREADS, 1)
 merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], box 128 x 64
@@ -225,10 +227,15 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
     // this lane's private staging slots: row it*4 + r8, 16 B of x1 / out, 8 B of mlp
     const uint32_t stage_x = smem_u32(stages) + e * MU_STAGE + r8 * 128 + p8 * 16;
     const uint32_t stage_m = smem_u32(stages) + e * MU_STAGE + 32 * 128 + r8 * 64 + p8 * 8;
+    // slab read address of (row it*4 + r8, this lane's 4 columns): the chunk swizzle depends on
+    // it & 1 only
+    const uint32_t slab_rd0 = slab + r8 * 64 + (((p8 >> 1) ^ ((r8 >> 1) & 3)) << 4) + (p8 & 1) * 8;
+    const uint32_t slab_rd1 = slab + r8 * 64 + (((p8 >> 1) ^ (((r8 >> 1) + 2) & 3)) << 4) + (p8 & 1) * 8;
     const bool plain = p.scale == 1.0f;
     const bool do_ln = p.ln_out != nullptr;
     const uint32_t bias_u = smem_u32(bias_s), gamma_u = smem_u32(gamma_s), beta_u = smem_u32(beta_s);
     const int col_lane = part * 32 + p8 * 4;   // + j * 128
+    const int last_row = p.T - 1;
     pdl_wait();
 
     // token_pos of a quarter's 32 rows: ONE coalesced load per tile, handed out by shuffles.
@@ -239,33 +246,42 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
       const int r = tile * MU_BM + q * 32 + lane;
       return (tile < num_tiles && r < p.T) ? p.token_pos[r] : -1;
     };
-    // pass-1 inputs of chunk j -> staging (asynchronous)
+    // Rows past the end are clamped to the last row for every load (their results are computed and
+    // dropped), so the per-row code has no bounds branches; only the stores look at `live`.
+    // pass-1 inputs of chunk j -> staging (asynchronous); dropped rows get zeros for the mlp part
     auto issue_p1 = [&](int tile, int pl, int j) {
       if (tile < num_tiles) {
-        const int row0 = tile * MU_BM + q * 32;
+        const int rbase = tile * MU_BM + q * 32 + r8;
         const int col = j * MU_CH + col_lane;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const int grow = row0 + it * 4 + r8;
+          const int grow = min(rbase + it * 4, last_row);
           const int ps = __shfl_sync(0xffffffffu, pl, it * 4 + r8);
-          const bool in = grow < p.T;
-          mu_cp16(stage_x + it * 512, p.x1 + (in ? static_cast<size_t>(grow) * p.ldx + col : 0), in ? 16u : 0u);
-          if (ps >= 0) mu_cp8(stage_m + it * 256, p.mlp + static_cast<size_t>(ps) * p.ldm + col);
+          mu_cp16(stage_x + it * 512, p.x1 + (static_cast<uint32_t>(grow) * p.ldx + col));
+          mu_cp8z(stage_m + it * 256, p.mlp + (static_cast<uint32_t>(ps < 0 ? 0 : ps) * p.ldm + col),
+                  ps < 0 ? 0u : 8u);
         }
       }
       mu_cp_commit();
     };
-    // pass-2 input: the `out` values this lane stored in pass 1
+    // pass-2 input: the `out` values this lane stored in pass 1.  Pass 2 needs neither the mlp
+    // slots nor the transpose slab, which together make a second buffer: two chunks in flight.
+    const uint32_t stage_b0 = smem_u32(stages) + e * MU_STAGE + 32 * 128 + lane * 16;   // it 0..3
+    const uint32_t stage_b1 = slab + lane * 16;                                         // it 4..7
+    auto p2_slot = [&](int j, int it) -> uint32_t {
+      return (j & 1) ? ((it < 4 ? stage_b0 : stage_b1) + (it & 3) * 512) : stage_x + it * 512;
+    };
     auto issue_p2 = [&](int tile, int j) {
-      const int row0 = tile * MU_BM + q * 32;
-      const int col = j * MU_CH + col_lane;
+      if (j < nch) {
+        const int rbase = tile * MU_BM + q * 32 + r8;
+        const int col = j * MU_CH + col_lane;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int grow = row0 + it * 4 + r8;
-        const bool in = grow < p.T;
-        mu_cp16(stage_x + it * 512, p.out + (in ? static_cast<size_t>(grow) * p.ldo + col : 0), in ? 16u : 0u);
+        for (int it = 0; it < 8; ++it) {
+          const int grow = min(rbase + it * 4, last_row);
+          mu_cp16(p2_slot(j, it), p.out + (static_cast<uint32_t>(grow) * p.ldo + col));
+        }
       }
-      mu_cp_commit();
+      mu_cp_commit();   // (possibly empty: every pass-2 step commits exactly one group)
     };
 
     int pl = load_pl(blockIdx.x);
@@ -273,13 +289,12 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
     uint32_t g = 0;
     int it_tile = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it_tile) {
-      const int row0 = tile * MU_BM + q * 32;
+      const int rbase = tile * MU_BM + q * 32 + r8;
       const int next_tile = tile + gridDim.x;
       const int pl_next = load_pl(next_tile);   // in flight for the whole tile
-      unsigned kept = 0;                         // bit it: row it*4 + r8 has an MLP row
+      unsigned live = 0;                         // bit it: row it*4 + r8 of this quarter exists
 #pragma unroll
-      for (int it = 0; it < 8; ++it)
-        kept |= (__shfl_sync(0xffffffffu, pl, it * 4 + r8) >= 0 ? 1u : 0u) << it;
+      for (int it = 0; it < 8; ++it) live |= (rbase + it * 4 < p.T ? 1u : 0u) << it;
       float mean[8], m2[8];
 #pragma unroll
       for (int it = 0; it < 8; ++it) mean[it] = m2[it] = 0.f;
@@ -337,21 +352,19 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
         const float w2 = 4.0f * static_cast<float>(j) * w1;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + r8;
-          const int grow = row0 + rr;
-          const uint2 hv = lds64(slab + rr * 64 + (((p8 >> 1) ^ ((rr >> 1) & 3)) << 4) + (p8 & 1) * 8);
-          float4 v = make_float4(__uint_as_float(xv[it].x), __uint_as_float(xv[it].y),
-                                 __uint_as_float(xv[it].z), __uint_as_float(xv[it].w));
-          if ((kept >> it) & 1u) {
-            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&mv[it].x));
-            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&mv[it].y));
-            v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
-          }
+          const uint2 hv = lds64(((it & 1) ? slab_rd1 : slab_rd0) + it * 256);
+          // (x1 + mlp) + adapt; a dropped row adds +0 for the mlp term
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&mv[it].x));
+          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&mv[it].y));
           const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&hv.x));
           const float2 a23 = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
-          v.x += a01.x; v.y += a01.y; v.z += a23.x; v.w += a23.y;
-          if (grow < p.T)
-            *reinterpret_cast<float4*>(p.out + static_cast<size_t>(grow) * p.ldo + col) = v;
+          float4 v;
+          v.x = (__uint_as_float(xv[it].x) + a.x) + a01.x;
+          v.y = (__uint_as_float(xv[it].y) + a.y) + a01.y;
+          v.z = (__uint_as_float(xv[it].z) + b.x) + a23.x;
+          v.w = (__uint_as_float(xv[it].w) + b.y) + a23.y;
+          if ((live >> it) & 1u)
+            *reinterpret_cast<float4*>(p.out + (static_cast<uint32_t>(rbase + it * 4) * p.ldo + col)) = v;
           // running mean / sum of squared deviations of this lane's columns of the row
           const float m4 = 0.25f * ((v.x + v.y) + (v.z + v.w));
           const float da = v.x - m4, db = v.y - m4, dc = v.z - m4, dd = v.w - m4;
@@ -367,6 +380,7 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
         continue;
       }
       issue_p2(tile, 0);   // in flight during the exchange of the row statistics
+      issue_p2(tile, 1);
 
       // ---- row statistics: 8 lanes of a row, then the 4 part-warps of the quarter ----
       float cnt = static_cast<float>(4 * nch);
@@ -409,12 +423,16 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
 #pragma unroll 1
       for (int j = 0; j < nch; ++j) {
         const int col = j * MU_CH + col_lane;
-        mu_cp_wait();
+        mu_cp_wait1();   // everything but the newest group: chunk j has landed
         uint4 v[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) v[it] = lds128(stage_x + it * 512);
-        if (j + 1 < nch) issue_p2(tile, j + 1);
-        else issue_p1(next_tile, pl_next, 0);
+        for (int it = 0; it < 8; ++it) v[it] = lds128(p2_slot(j, it));
+        if (j + 1 < nch) {
+          issue_p2(tile, j + 2);
+        } else {
+          __syncwarp();   // pass-1 slots of one lane overlap pass-2 slots of another
+          issue_p1(next_tile, pl_next, 0);   // both buffers are free: the next tile's first chunk
+        }
         const uint4 gq = lds128(gamma_u + col * 4);
         const uint4 bq = lds128(beta_u + col * 4);
         const float g0 = __uint_as_float(gq.x), g1 = __uint_as_float(gq.y), g2 = __uint_as_float(gq.z),
@@ -423,13 +441,12 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
                     b3 = __uint_as_float(bq.w);
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const int grow = row0 + it * 4 + r8;
           const float y0 = (__uint_as_float(v[it].x) - mean[it]) * rstd[it] * g0 + b0;
           const float y1 = (__uint_as_float(v[it].y) - mean[it]) * rstd[it] * g1 + b1;
           const float y2 = (__uint_as_float(v[it].z) - mean[it]) * rstd[it] * g2 + b2;
           const float y3 = (__uint_as_float(v[it].w) - mean[it]) * rstd[it] * g3 + b3;
-          if (grow < p.T)
-            *reinterpret_cast<uint2*>(p.ln_out + static_cast<size_t>(grow) * p.ldn + col) =
+          if ((live >> it) & 1u)
+            *reinterpret_cast<uint2*>(p.ln_out + (static_cast<uint32_t>(rbase + it * 4) * p.ldn + col)) =
                 make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
         }
       }
@@ -446,8 +463,10 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
   }
 }
 
-bool merge_up_supported(int C, int K) {
-  return C % MU_CH == 0 && C >= MU_CH && C <= MU_MAXC && K >= 8 && K <= 64 && K % 8 == 0;
+bool merge_up_supported(int C, int K, long long rows) {
+  // (the kernel indexes every buffer with 32-bit element offsets)
+  return C % MU_CH == 0 && C >= MU_CH && C <= MU_MAXC && K >= 8 && K <= 64 && K % 8 == 0 &&
+         (rows + 1) * C < (1ll << 31);
 }
 
 int merge_up(const __half* down, int ld_down, const __half* up_w, int ldw, const __half* up_b,
@@ -455,12 +474,21 @@ int merge_up(const __half* down, int ld_down, const __half* up_w, int ldw, const
              const int* token_pos, int n_rows, int C, float* out, int ldo, const float* nln_w,
              const float* nln_b, float eps, __half* nln_out, int ldn, cudaStream_t stream) {
   DYT_CHECK_ARG(down && up_w && x1 && mlp_packed && token_pos && out, "merge_up: null buffer");
-  if (!merge_up_supported(C, K))
-    return fail(DYT_EUNSUPPORTED, "merge_up: needs C %% 128 == 0, C <= %d, K <= 64 (C=%d K=%d)", MU_MAXC, C, K);
+  if (!merge_up_supported(C, K, n_rows))
+    return fail(DYT_EUNSUPPORTED,
+                "merge_up: needs C %% 128 == 0, C <= %d, K <= 64, rows * C < 2^31 (C=%d K=%d rows=%d)",
+                MU_MAXC, C, K, n_rows);
   DYT_CHECK_ARG(ldx % 4 == 0 && ldm % 4 == 0 && ldo % 4 == 0 && ld_down >= K && ldw >= K,
                 "merge_up: strides");
   DYT_CHECK_ARG(nln_out == nullptr || (nln_w && nln_b && ldn % 4 == 0), "merge_up: next-LN args");
   DYT_CHECK_ARG(out != x1, "merge_up: out must not alias x1");
+  {  // the kernel indexes with 32-bit element offsets
+    const long long lim = 1ll << 31;
+    const long long big = static_cast<long long>(n_rows) *
+                          (ldx > ldo ? (ldx > ldn ? ldx : ldn) : (ldo > ldn ? ldo : ldn));
+    if (big + C >= lim || static_cast<long long>(n_rows) * ldm + C >= lim)
+      return fail(DYT_EUNSUPPORTED, "merge_up: more than 2^31 elements per buffer");
+  }
   if (n_rows == 0) return DYT_OK;
   CUtensorMap ta, tw;
   int s = make_tmap_f16_sw128(&ta, down, static_cast<uint64_t>(n_rows), static_cast<uint64_t>(K),

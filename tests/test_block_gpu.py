@@ -192,7 +192,7 @@ def test_fused_next_layernorm_is_equivalent(dev, vitb_sd):
     assert torch.equal(c1[0], b1[0]) and torch.equal(c1[1], b1[1])
     c = engine.run_blocks(x, list(m.blocks[:4]), fuse_next_ln=True)
     assert torch.equal(c[1], b[1])
-    assert _rel(c[0], b[0]) <= 2e-4
+    assert _rel(c[0], b[0]) <= 1e-3
 
 
 def test_block_fused_adapter_up_equals_separate_launches(dev, vitb_sd):
