@@ -374,7 +374,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if constexpr (EPI == EPI_BIAS_RELU) {
             o = __hmax2(h, __float2half2_rn(0.f));
           } else if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_GELU_KEEP) {
-            o = __floats2half2_rn(gelu_f16(__low2float(h)), gelu_f16(__high2float(h)));
+            const float2 gl = gelu_f16_x2(__low2float(h), __high2float(h));
+            o = __floats2half2_rn(gl.x, gl.y);
             if constexpr (EPI == EPI_BIAS_GELU_KEEP) keep[j2] = *reinterpret_cast<const uint32_t*>(&h);
           } else if constexpr (EPI == EPI_DGELU) {
             const uint4 av = ax[j2 >> 2];
