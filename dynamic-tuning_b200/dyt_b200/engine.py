@@ -12,6 +12,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
+from ._wscache import StreamWorkspaces
 from ._lib import BlockBuffers, BlockOpts, BlockShape, BlockWeights, DytError, check
 from .gate import min_kept_logit
 
@@ -75,7 +76,7 @@ class PreparedBlock:
         return self.struct
 
 
-_workspaces: Dict[Tuple, torch.Tensor] = {}
+_workspaces = StreamWorkspaces(zero_filled=True)    # zero-filled once (ABI contract)
 
 
 def block_shape_of(block: torch.nn.Module, B: int, N: int) -> BlockShape:
@@ -91,14 +92,17 @@ def _workspace(shape: BlockShape, device: torch.device) -> torch.Tensor:
     if need == 0:
         raise DytError("dyt_block_workspace_bytes rejected the shape: " +
                        _lib.lib().dyt_last_error().decode())
-    key = (device.index, torch.cuda.current_stream().cuda_stream)
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() < need:
-        ws = None
-        _workspaces.pop(key, None)
-        ws = torch.zeros(need, dtype=torch.uint8, device=device)   # zero-filled once (ABI contract)
-        _workspaces[key] = ws
-    return ws
+    return _workspaces.get(device, need)
+
+
+def release_stream_workspaces(device: torch.device, stream: torch.cuda.Stream) -> None:
+    """Free the scratch buffers that calls on `stream` allocated (block workspace, dispatcher words,
+    stem buffer), unless a CUDA-graph capture used them.  For wrappers that warm up on a throw-away
+    stream before capturing."""
+    from . import ops
+    _workspaces.release_stream(device, stream)
+    ops._dispatch_ws.release_stream(device, stream)
+    ops._stem_ws.release_stream(device, stream)
 
 
 def workspace_buffers(shape: BlockShape, ws: torch.Tensor) -> BlockBuffers:

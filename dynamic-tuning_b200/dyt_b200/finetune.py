@@ -76,6 +76,9 @@ class FinetuneStep:
             for _ in range(2):                       # warm-up off the capture: caches, workspaces
                 self._forward_backward(self._img, self._tgt)
         torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from . import engine
+        engine.release_stream_workspaces(self._img.device, side)   # the warm-up stream's scratch buffers
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._loss = self._forward_backward(self._img, self._tgt)

@@ -22,12 +22,15 @@ class GraphedForward:
     `images` may be any CUDA tensor of a shape seen before (one graph per shape and per static
     input slot); the result tensor is owned by the graph and overwritten by the next call on the
     same slot.  `slot` selects one of several static input buffers so that a caller can fill the
-    next input (e.g. an H2D copy on another stream, via `input_buffer`) while a replay runs."""
+    next input (e.g. an H2D copy on another stream, via `input_buffer`) while a replay runs.
+    All graphs of one GraphedForward share the library's scratch buffers (one block workspace per
+    device): replay them on one stream at a time."""
 
     def __init__(self, model: torch.nn.Module, autocast_dtype=torch.float16):
         self.model = model
         self.dtype = autocast_dtype
         self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, torch.Tensor, object]] = {}
+        self._capture_streams: Dict[torch.device, torch.cuda.Stream] = {}
 
     def _eager(self, x):
         with torch.no_grad(), torch.autocast("cuda", dtype=self.dtype):
@@ -40,14 +43,22 @@ class GraphedForward:
             if self.model.training:
                 raise DytError("GraphedForward is for inference: call model.eval() first")
             static_in = torch.zeros(shape, dtype=dtype, device=device)
-            side = torch.cuda.Stream(device=device)
+            # Warm-up and capture run on ONE stream owned by this object: the scratch buffers are
+            # keyed by stream, so the warm-up allocates (and zero-fills, once) the workspace the
+            # capture then reuses.  Captured on a fresh stream instead, the allocation happened
+            # inside the capture and its zero-fill (1.1 GB at 256 images) was replayed every step.
+            side = self._capture_streams.get(device)
+            if side is None:
+                side = torch.cuda.Stream(device=device)
+                self._capture_streams[device] = side
             side.wait_stream(torch.cuda.current_stream(device))
             with torch.cuda.stream(side):
                 for _ in range(2):                 # warm-up: weight casts, workspaces, lazy init
                     self._eager(static_in)
             torch.cuda.current_stream(device).wait_stream(side)
+            torch.cuda.synchronize(device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=side):
                 static_out = self._eager(static_in)
             ent = (graph, static_in, static_out)
             self._graphs[key] = ent

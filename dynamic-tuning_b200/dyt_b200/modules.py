@@ -397,12 +397,16 @@ class VisionTransformer(nn.Module):
             cache = (key, w16, b16, nc)
             self.__dict__["_dyt_head"] = cache
         _, w16, b16, nc = cache
+        # row indices of the cls tokens, one small tensor per (B, N, device), never freed: a CUDA
+        # graph captured for one batch size keeps reading its tensor after another size was seen
+        # (a single-entry cache here was a use-after-free: replaying the 256-image graph after a
+        # 128-image call faulted)
+        icache = self.__dict__.setdefault("_dyt_cls_idx", {})
         ikey = (B, N, tokens.device)
-        icache = self.__dict__.get("_dyt_cls_idx")
-        if icache is None or icache[0] != ikey:
-            icache = (ikey, torch.arange(B, device=tokens.device, dtype=torch.int32) * N)
-            self.__dict__["_dyt_cls_idx"] = icache
-        idx = icache[1]
+        idx = icache.get(ikey)
+        if idx is None:
+            idx = torch.arange(B, device=tokens.device, dtype=torch.int32) * N
+            icache[ikey] = idx
         cls_n = ops.layernorm_f16(tokens.float(), self.norm.weight.detach().float(),
                                   self.norm.bias.detach().float(), float(self.norm.eps), row_idx=idx)
         logits, _ = ops.linear_f16(cls_n, w16, b16)

@@ -8,6 +8,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
+from ._wscache import StreamWorkspaces
 from ._lib import DytError, check
 from .gate import min_kept_logit
 
@@ -183,17 +184,12 @@ def layernorm_f16(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps
     return out if row_idx is not None else out.reshape(*x.shape[:-1], Cdim)
 
 
-_dispatch_ws = {}
+_dispatch_ws = StreamWorkspaces(zero_filled=True, min_bytes=4096)
 
 
 def _dispatch_workspace(device: torch.device, B: int) -> torch.Tensor:
     need = int(_lib.lib().dyt_dispatch_workspace_bytes(B))
-    key = (device.index, torch.cuda.current_stream().cuda_stream)
-    ws = _dispatch_ws.get(key)
-    if ws is None or ws.numel() < need:
-        ws = torch.zeros(max(need, 4096), dtype=torch.uint8, device=device)
-        _dispatch_ws[key] = ws
-    return ws
+    return _dispatch_ws.get(device, need)
 
 
 def dispatch(x1: torch.Tensor, sel_w: torch.Tensor, sel_b: torch.Tensor, *,
@@ -325,7 +321,7 @@ def merge_up(down: torch.Tensor, up_w: torch.Tensor, up_b: Optional[torch.Tensor
     return (out, None if nln_out is None else nln_out.reshape(x1.shape))
 
 
-_stem_ws = {}
+_stem_ws = StreamWorkspaces(zero_filled=False)
 # fp16 / fp32 working copies of the stem parameters, keyed by the identity of the PARAMETER OBJECT
 # (held weakly: the entry is dropped when the parameter dies), so a new model whose tensors land on
 # recycled device addresses can never pick up another model's copies (a cache keyed by data_ptr
@@ -367,11 +363,7 @@ def patch_embed(img: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torch.
     need = int(_lib.lib().dyt_patch_embed_workspace_bytes(B, H, W, patch, Cin, Cdim))
     if need == 0:
         raise DytError(f"patch_embed: unsupported geometry H={H} W={W} P={patch}")
-    key = (img.device.index, torch.cuda.current_stream().cuda_stream)
-    ws = _stem_ws.get(key)
-    if ws is None or ws.numel() < need:
-        ws = torch.empty(need, dtype=torch.uint8, device=img.device)
-        _stem_ws[key] = ws
+    ws = _stem_ws.get(img.device, need)
     x = torch.empty((B, L + 1, Cdim), dtype=torch.float32, device=img.device)
     check(_lib.lib().dyt_patch_embed_fwd(
         img.data_ptr(), B, Cin, H, W, patch, w16.data_ptr(), _ptr(b16), cls.data_ptr(),

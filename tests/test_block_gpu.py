@@ -505,6 +505,29 @@ def test_forward_is_cuda_graph_capturable_and_replay_safe(dev, vitb_sd):
         assert torch.equal(static_out, ref)
 
 
+def test_graphed_forward_several_batch_sizes_interleaved(dev, vitb_sd):
+    """Graphs of different batch sizes captured one after the other (larger first) and replayed
+    interleaved, with allocator churn in between: no captured graph may read a cache entry or a
+    workspace that a later call replaced (regression: the cls-row index tensor of the head was a
+    single-entry cache -- replaying the larger graph after a smaller call faulted)."""
+    from dyt_b200 import GraphedForward
+    g, sd, img = vitb_sd
+    m = _speed_model(sd, dev)
+    gm = GraphedForward(m)
+    xs = {b: torch.randn(b, 3, 224, 224, generator=torch.Generator().manual_seed(40 + b)).to(dev)
+          for b in (6, 3, 8)}
+    refs = {}
+    for b, x in xs.items():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            refs[b] = m(x).clone()
+    for b in (6, 3, 6, 8, 3, 6, 8):
+        out = gm(xs[b])
+        junk = [torch.full((1 << 18,), float(b), device=dev) for _ in range(8)]   # reuse freed blocks
+        torch.cuda.synchronize()
+        assert torch.equal(out, refs[b]), f"batch {b}"
+        del junk
+
+
 def test_graphed_forward_public_wrapper(dev, vitb_sd):
     """dyt_b200.GraphedForward: same logits as the eager call for new input contents, per shape and
     per static-input slot; writing straight into a slot's input buffer + replay works (bench e2e)."""
