@@ -135,19 +135,25 @@ def invalidate_caches(module: torch.nn.Module) -> None:
 def run_blocks(x: torch.Tensor, blocks: Sequence[torch.nn.Module], *, eps: float = 1e-6,
                logit_dtype: torch.dtype = torch.float16, forced_masks=None,
                noises=None, final_ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-               fuse_next_ln: bool = True, report_gate: bool = False, attn_biases=None):
+               fuse_next_ln: bool = True, report_gate: bool = False, attn_biases=None,
+               consume_input: bool = False):
     """x [B, N, C] fp32 CUDA -> (x_out fp32 [B,N,C], masks [L,B,N] f32, logits [L,B,N-1] f32,
     final_ln_out f16 [B,N,C] or None).  report_gate=True returns the selectors' own decisions as
     `masks` even where a mask is forced (teacher pass, complete_model=True).  forced_masks[i] ([B,N] or [B,N,1]) imposes layer i's mask;
     noises[i] = (g1, g2) switches layer i's gate to the train-mode Gumbel form.  attn_biases[i]
     (fp32 [H, N, N] or None) adds a per-head bias to layer i's attention scores (segmentation
-    backbone); sequences longer than 256 tokens or a bias run the flash-style attention kernel."""
+    backbone); sequences longer than 256 tokens or a bias run the flash-style attention kernel.
+    consume_input=True lets the call overwrite `x` (the returned stream may alias it)."""
     if not x.is_cuda:
         raise DytError("dyt_b200.run_blocks needs a CUDA tensor: the sm_100a kernels are the only "
                        "implementation (no CPU fallback)")
     if x.dim() != 3:
         raise DytError("run_blocks expects x [B, N, C]")
-    x = x.to(torch.float32).contiguous().clone()
+    # the blocks update the stream in place: work on a copy unless the caller hands over a temporary
+    # (consume_input=True: the model path passes the stem's fresh output -- saves a 155 MB copy per
+    # forward at 256 images)
+    x32 = x.to(torch.float32).contiguous()
+    x = x32 if (consume_input or x32.data_ptr() != x.data_ptr()) else x32.clone()
     B, N, _ = x.shape
     L = len(blocks)
     dev = x.device

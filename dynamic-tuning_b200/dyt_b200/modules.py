@@ -412,7 +412,8 @@ class VisionTransformer(nn.Module):
         logits, _ = ops.linear_f16(cls_n, w16, b16)
         return logits[:, :nc]
 
-    def _blocks(self, x, complete_model=False):
+    def _blocks(self, x, complete_model=False, consume_input=True):
+        """x: the stem's output (a temporary of this forward: the blocks may overwrite it)."""
         _no_backward("VisionTransformer (inference path)", x, *self.blocks.parameters())
         for blk in self.blocks:
             if not hasattr(blk, "mlp_token_select"):
@@ -425,7 +426,8 @@ class VisionTransformer(nn.Module):
         # complete_model: the reported masks are the selectors' decisions on the teacher's activations
         x, masks, logits, _ = engine.run_blocks(x.float(), list(self.blocks),
                                                 eps=float(self.blocks[0].norm1.eps),
-                                                forced_masks=forced, report_gate=complete_model)
+                                                forced_masks=forced, report_gate=complete_model,
+                                                consume_input=consume_input)
         return x, masks, logits
 
     def forward_head(self, x, pre_logits: bool = False):
