@@ -41,17 +41,6 @@ __device__ __forceinline__ float gelu_f16(float x) {
 // takes 7 issue slots instead of 14.  Same arithmetic as gelu_f16 element by element (the
 // polynomial is evaluated in b = -a with the odd coefficients negated, which is exact: only signs
 // change), so the results are bit-identical.
-__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b,
-                                                        unsigned long long c) {
-  unsigned long long r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
 __device__ __forceinline__ float2 gelu_f16_x2(float x0, float x1) {
   // b = -min(|x|, 5.75)
   const float b0 = fmaxf(-fabsf(x0), -5.75f), b1 = fmaxf(-fabsf(x1), -5.75f);

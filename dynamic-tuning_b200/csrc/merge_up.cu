@@ -353,22 +353,29 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const uint2 hv = lds64(((it & 1) ? slab_rd1 : slab_rd0) + it * 256);
-          // (x1 + mlp) + adapt; a dropped row adds +0 for the mlp term
+          // (x1 + mlp) + adapt on packed fp32 pairs; a dropped row adds +0 for the mlp term
           const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&mv[it].x));
           const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&mv[it].y));
           const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&hv.x));
           const float2 a23 = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
-          float4 v;
-          v.x = (__uint_as_float(xv[it].x) + a.x) + a01.x;
-          v.y = (__uint_as_float(xv[it].y) + a.y) + a01.y;
-          v.z = (__uint_as_float(xv[it].z) + b.x) + a23.x;
-          v.w = (__uint_as_float(xv[it].w) + b.y) + a23.y;
-          if ((live >> it) & 1u)
-            *reinterpret_cast<float4*>(p.out + (static_cast<uint32_t>(rbase + it * 4) * p.ldo + col)) = v;
+          const unsigned long long v01 =
+              f32x2_add(f32x2_add(f32x2_pack(__uint_as_float(xv[it].x), __uint_as_float(xv[it].y)),
+                                  f32x2_pack(a.x, a.y)), f32x2_pack(a01.x, a01.y));
+          const unsigned long long v23 =
+              f32x2_add(f32x2_add(f32x2_pack(__uint_as_float(xv[it].z), __uint_as_float(xv[it].w)),
+                                  f32x2_pack(b.x, b.y)), f32x2_pack(a23.x, a23.y));
+          if ((live >> it) & 1u) {
+            const float2 lo = f32x2_unpack(v01), hi = f32x2_unpack(v23);
+            *reinterpret_cast<float4*>(p.out + (static_cast<uint32_t>(rbase + it * 4) * p.ldo + col)) =
+                make_float4(lo.x, lo.y, hi.x, hi.y);
+          }
           // running mean / sum of squared deviations of this lane's columns of the row
-          const float m4 = 0.25f * ((v.x + v.y) + (v.z + v.w));
-          const float da = v.x - m4, db = v.y - m4, dc = v.z - m4, dd = v.w - m4;
-          const float q4 = (da * da + db * db) + (dc * dc + dd * dd);
+          const float2 s2 = f32x2_unpack(f32x2_add(v01, v23));
+          const float m4 = 0.25f * (s2.x + s2.y);
+          const unsigned long long nm = f32x2_pack(-m4, -m4);
+          const unsigned long long d01 = f32x2_add(v01, nm), d23 = f32x2_add(v23, nm);
+          const float2 q2 = f32x2_unpack(f32x2_fma(d01, d01, f32x2_mul(d23, d23)));
+          const float q4 = q2.x + q2.y;
           const float dl = m4 - mean[it];
           mean[it] = fmaf(dl, w1, mean[it]);
           m2[it] += fmaf(dl * dl, w2, q4);
@@ -435,19 +442,24 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
         }
         const uint4 gq = lds128(gamma_u + col * 4);
         const uint4 bq = lds128(beta_u + col * 4);
-        const float g0 = __uint_as_float(gq.x), g1 = __uint_as_float(gq.y), g2 = __uint_as_float(gq.z),
-                    g3 = __uint_as_float(gq.w);
-        const float b0 = __uint_as_float(bq.x), b1 = __uint_as_float(bq.y), b2 = __uint_as_float(bq.z),
-                    b3 = __uint_as_float(bq.w);
+        const unsigned long long g01 = f32x2_pack(__uint_as_float(gq.x), __uint_as_float(gq.y));
+        const unsigned long long g23 = f32x2_pack(__uint_as_float(gq.z), __uint_as_float(gq.w));
+        const unsigned long long b01 = f32x2_pack(__uint_as_float(bq.x), __uint_as_float(bq.y));
+        const unsigned long long b23 = f32x2_pack(__uint_as_float(bq.z), __uint_as_float(bq.w));
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const float y0 = (__uint_as_float(v[it].x) - mean[it]) * rstd[it] * g0 + b0;
-          const float y1 = (__uint_as_float(v[it].y) - mean[it]) * rstd[it] * g1 + b1;
-          const float y2 = (__uint_as_float(v[it].z) - mean[it]) * rstd[it] * g2 + b2;
-          const float y3 = (__uint_as_float(v[it].w) - mean[it]) * rstd[it] * g3 + b3;
+          // ((v - mean) * rstd) * g + b, two columns per instruction (same roundings as rowwise.cuh)
+          const unsigned long long nm = f32x2_pack(-mean[it], -mean[it]);
+          const unsigned long long rs = f32x2_pack(rstd[it], rstd[it]);
+          const float2 y01 = f32x2_unpack(f32x2_fma(
+              f32x2_mul(f32x2_add(f32x2_pack(__uint_as_float(v[it].x), __uint_as_float(v[it].y)), nm), rs),
+              g01, b01));
+          const float2 y23 = f32x2_unpack(f32x2_fma(
+              f32x2_mul(f32x2_add(f32x2_pack(__uint_as_float(v[it].z), __uint_as_float(v[it].w)), nm), rs),
+              g23, b23));
           if ((live >> it) & 1u)
             *reinterpret_cast<uint2*>(p.ln_out + (static_cast<uint32_t>(rbase + it * 4) * p.ldn + col)) =
-                make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
+                make_uint2(pack_half2(y01.x, y01.y), pack_half2(y23.x, y23.y));
         }
       }
       pl = pl_next;

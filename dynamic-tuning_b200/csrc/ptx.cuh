@@ -425,6 +425,36 @@ __device__ __forceinline__ void tmem_st_wait() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2, one issue slot for two IEEE fp32 operations)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 f32x2_unpack(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b,
+                                                        unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
 // fp16 helpers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
