@@ -481,8 +481,12 @@ class TrainVisionTransformer(VisionTransformer):
         noises = mults = [None] * len(self.blocks)
         if self.training and not (train._fixed["noises"] or train._fixed["drop_mults"]):
             noises, mults = train.draw_pass_randomness(list(self.blocks), B, N, x.device)
-        for i, blk in enumerate(self.blocks):
-            x, sel, lg = train.block_train(blk, x, complete_model, noises[i], mults[i])
+        xn = None          # f16(norm1(x)) of the next block, emitted by the merge kernel of this one
+        blocks = list(self.blocks)
+        for i, blk in enumerate(blocks):
+            nxt = blocks[i + 1] if i + 1 < len(blocks) else None
+            x, sel, lg, xn = train.block_train(blk, x, complete_model, noises[i], mults[i], xn=xn,
+                                               next_block=nxt, return_xn=True)
             sels.append(sel[:, 1:])
             lgs.append(lg)
         dt = _act_dtype()

@@ -125,7 +125,7 @@ class DytBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, down_w, down_b, up_w, up_b, sel_w, sel_b, block, complete_model, noise,
-                drop_mult, eps, training_gate):
+                drop_mult, eps, training_gate, xn_in=None, next_ln=None):
         ctx.set_materialize_grads(False)
         fz = _frozen(block)
         h16 = torch.float16
@@ -140,7 +140,8 @@ class DytBlockFn(torch.autograd.Function):
         ad = _adapter_f16(block, down_w, down_b, up_w, up_b)
         dw16, db16, uw16, ub16 = ad["dw"], ad["db"], ad["uw"], ad["ub"]
 
-        xn = ops.layernorm_f16(x, fz["ln1_w"], fz["ln1_b"], eps)
+        # norm1: handed over by the previous block's merge kernel when the caller chains the blocks
+        xn = xn_in if xn_in is not None else ops.layernorm_f16(x, fz["ln1_w"], fz["ln1_b"], eps)
         qkv, _ = ops.linear_f16(xn, fz["qkv_w"], fz["qkv_b"])
         o = ops.attn_varlen(qkv.reshape(B, N, -1), H)
         x1, x1h = ops.linear_f16(o, fz["proj_w"], fz["proj_b"], epilogue=_lib.EPI_BIAS_RESID,
@@ -169,7 +170,6 @@ class DytBlockFn(torch.autograd.Function):
         hd, _ = ops.linear_f16(x1h, dw16, db16, epilogue=_lib.EPI_BIAS_RELU)
         if drop_mult is not None:
             hd = ops.eltwise_f16(_lib.EW_MUL, hd, drop_mult.reshape(hd.shape))
-        up, _ = ops.linear_f16(hd, uw16, ub16, epilogue=_lib.EPI_BIAS, scale=scale)
         if complete_model:
             token_pos = _arange_i32(T, x.device)
         elif sparse_bwd:
@@ -177,8 +177,15 @@ class DytBlockFn(torch.autograd.Function):
             token_pos = torch.where(mask.reshape(-1) > 0, ar, torch.full_like(ar, -1))
         else:
             token_pos = row_of          # written by the selector kernel: t if kept else -1
-        out, _ = ops.scatter_merge(x1.reshape(B, N, Cd), up.reshape(B, N, Cd), mlp_x.reshape(T, Cd),
-                                   token_pos)
+        bott_f = hd.shape[-1]
+        if Cd % 128 == 0 and Cd <= 1024 and bott_f <= 64 and bott_f % 8 == 0 and T * Cd < (1 << 31) - Cd:
+            # adapter up-projection inside the merge kernel (+ the next block's norm1)
+            out, xn_next = ops.merge_up(hd.reshape(B, N, bott_f), uw16, ub16, scale, x1.reshape(B, N, Cd),
+                                        mlp_x.reshape(T, Cd), token_pos, next_ln=next_ln, eps=eps)
+        else:
+            up, _ = ops.linear_f16(hd, uw16, ub16, epilogue=_lib.EPI_BIAS, scale=scale)
+            out, xn_next = ops.scatter_merge(x1.reshape(B, N, Cd), up.reshape(B, N, Cd),
+                                             mlp_x.reshape(T, Cd), token_pos, next_ln=next_ln, eps=eps)
         ctx.block = block
         ctx.meta = (B, N, Cd, H, scale, tau, eps, bool(complete_model), bool(training_gate))
         ctx.noise = noise if training_gate else None
@@ -187,10 +194,13 @@ class DytBlockFn(torch.autograd.Function):
                               sel_w.detach(), *compaction)
         if debug_keep is not None:   # tests: look at the forward intermediates
             debug_keep.update(x1=x1, x1h=x1h, pre=pre, mlp_x=mlp_x, hd=hd, qkv=qkv, o=o)
-        return out, mask, logits
+        if xn_next is None:
+            xn_next = torch.empty(0, dtype=torch.float16, device=x.device)
+        ctx.mark_non_differentiable(xn_next)
+        return out, mask, logits, xn_next
 
     @staticmethod
-    def backward(ctx, g_out, g_sel, g_logits):
+    def backward(ctx, g_out, g_sel, g_logits, _g_xn=None):
         (x, qkv, o, x1, x1h, mask, logits, pre, mlp_x, hd, dwT, uwT, sel_w, token_pos, packed_idx,
          n_kept) = ctx.saved_tensors
         B, N, Cd, H, scale, tau, eps, complete_model, training_gate = ctx.meta
@@ -266,7 +276,7 @@ class DytBlockFn(torch.autograd.Function):
                                        resid=g_x1.reshape(T, Cd))
             g_x = g_x.reshape(B, N, Cd)
         return (g_x, d_down_w, d_down_b, d_up_w, d_up_b, d_sel_w, d_sel_b,
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None)
 
 
 _fixed = {"noises": None, "drop_mults": None}
@@ -320,10 +330,14 @@ def draw_pass_randomness(blocks, B: int, N: int, device):
 
 def block_train(block, x: torch.Tensor, complete_model: bool = False,
                 noise: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-                drop_mult: Optional[torch.Tensor] = None):
+                drop_mult: Optional[torch.Tensor] = None, *, xn: Optional[torch.Tensor] = None,
+                next_block=None, return_xn: bool = False):
     """Train-mode block with autograd.  `noise` = the two Gumbel draws [B, N-1, 1] (drawn here in the
     reference's order when None and the block is in train mode); `drop_mult` = the adapter dropout
-    multiplier keep / (1 - p), fp16 [B, N, bottleneck] (drawn here when None and p > 0)."""
+    multiplier keep / (1 - p), fp16 [B, N, bottleneck] (drawn here when None and p > 0).
+    Chaining (the model's block loop): `xn` = f16(norm1(x)) of THIS block as produced by the previous
+    block's merge kernel, `next_block` = the block whose norm1 this block's merge should emit;
+    with return_xn=True the call returns (out, mask, logits, xn_of_next_block or None)."""
     if not x.is_cuda:
         raise DytError("dyt_b200 needs CUDA tensors (no CPU fallback)")
     if not hasattr(block, "mlp_token_select"):
@@ -345,9 +359,17 @@ def block_train(block, x: torch.Tensor, complete_model: bool = False,
         drop_mult = drop_mult.to(device=x.device, dtype=torch.float16).contiguous()
     a, s = block.adaptmlp, block.mlp_token_select.mlp_head
     sel_b = s.bias if s.bias is not None else torch.zeros(1, device=x.device)
-    return DytBlockFn.apply(x, a.down_proj.weight, a.down_proj.bias, a.up_proj.weight,
-                            a.up_proj.bias, s.weight, sel_b, block, bool(complete_model), noise,
-                            drop_mult, float(block.norm1.eps), training_gate)
+    next_ln = None
+    if next_block is not None:
+        fzn = _frozen(next_block)
+        next_ln = (fzn["ln1_w"], fzn["ln1_b"])
+    out, mask, logits, xn_next = DytBlockFn.apply(
+        x, a.down_proj.weight, a.down_proj.bias, a.up_proj.weight, a.up_proj.bias, s.weight, sel_b,
+        block, bool(complete_model), noise, drop_mult, float(block.norm1.eps), training_gate, xn,
+        next_ln)
+    if return_xn:
+        return out, mask, logits, (xn_next if xn_next.numel() else None)
+    return out, mask, logits
 
 
 class DytHeadFn(torch.autograd.Function):
