@@ -69,6 +69,9 @@ class TokenSelect(nn.Module):
         self.is_hard = is_hard
         self.tau = tau
         self.threshold = threshold
+        # train-mode Gumbel noise as in models/dynamic_adapter.py:25-54; the speed model's gate
+        # (models/model_speed_test.py:27-38) never draws noise, whatever the module mode
+        self.noise_in_training = True
 
     def set_tau(self, tau):
         self.tau = tau
@@ -79,7 +82,7 @@ class TokenSelect(nn.Module):
         if not self.is_hard:
             raise NotImplementedError("TokenSelect(is_hard=False) is never used by the reference")
         dt = _act_dtype()
-        if self.training and noise is None:
+        if self.training and self.noise_in_training and noise is None:
             noise = draw_gumbel_pair((x.shape[0], x.shape[1] - 1, 1),
                                      dt if dt != torch.float32 else torch.float32, x.device)
         bias = self.mlp_head.bias if self.mlp_head.bias is not None else x.new_zeros(1)
@@ -217,6 +220,7 @@ class SpeedBlock(_BlockBase):
         super().__init__(*args, select=select, **kwargs)
         if select:
             self.mlp_token_select = TokenSelect(self.attn.qkv.in_features, num_sub_layer=1)
+            self.mlp_token_select.noise_in_training = False   # model_speed_test.py:27-38
         else:
             # reference quirk (model_speed_test.py:229-232): without a selector the block cannot run
             self.token_select = None
@@ -250,9 +254,11 @@ class TrainBlock(_BlockBase):
         if self.count_flops:
             return self.forward_count_flops(x)
         B, N, _ = x.shape
-        if _wants_grad(self, x):
+        if _wants_grad(self, x) or self.training:
             # fine-tuning: dense masked block with autograd (Gumbel gate + adapter dropout in
-            # train() mode), forward and backward on the sm_100a kernels (dyt_b200.train)
+            # train() mode), forward and backward on the sm_100a kernels (dyt_b200.train).  A
+            # train()-mode call without autograd (no_grad, everything frozen) takes the same path:
+            # the reference draws the Gumbel noise and the adapter dropout whenever self.training
             out, sel, logit = train.block_train(self, x, complete_model)
             dt = _act_dtype()
             return out, dict(sub_token_select=sel.to(dt), token_logits=logit.to(dt))
@@ -495,7 +501,7 @@ class TrainVisionTransformer(VisionTransformer):
         return x, token_select
 
     def forward(self, x, complete_model=False):
-        if _wants_grad(self, x):
+        if _wants_grad(self, x) or self.training:   # train() mode keeps its semantics without autograd
             if not (self.global_pool == "token" and isinstance(self.fc_norm, nn.Identity) and
                     isinstance(self.head, nn.Linear) and self.head_drop.p == 0):
                 raise NotImplementedError("dyt_b200 fine-tuning implements the reference head: token "

@@ -48,11 +48,6 @@ class FrozenWeights:
         params = [_get(blk, d).weight for d in _FROZEN.values()] + [blk.norm1.weight, blk.norm2.weight]
         key = tuple((p.data_ptr(), p._version) for p in params)
         if key != self.key:
-            for name, p in blk.named_parameters():
-                if p.requires_grad and not name.startswith(_TRAINABLE_PREFIXES):
-                    raise NotImplementedError(
-                        f"dyt_b200 fine-tuning implements the reference's PEFT setting (frozen "
-                        f"backbone, main_image.py:242-256); '{name}' requires grad")
             with torch.no_grad():
                 h16 = torch.float16
                 for short, dotted in _FROZEN.items():
@@ -68,6 +63,16 @@ class FrozenWeights:
                     self.t[short + "_b"] = ln.bias.detach().float().contiguous()
             self.key = key
         return self.t
+
+
+def _check_peft(block) -> None:
+    """The backward has data gradients through the frozen backbone and weight gradients only for
+    adaptmlp.* / mlp_token_select.* (+ head): anything else that wants a gradient is refused."""
+    for name, p in block.named_parameters():
+        if p.requires_grad and not name.startswith(_TRAINABLE_PREFIXES):
+            raise NotImplementedError(
+                f"dyt_b200 fine-tuning implements the reference's PEFT setting (frozen "
+                f"backbone, main_image.py:242-256); '{name}' requires grad")
 
 
 def _frozen(block) -> Dict[str, torch.Tensor]:
@@ -342,6 +347,8 @@ def block_train(block, x: torch.Tensor, complete_model: bool = False,
         raise DytError("dyt_b200 needs CUDA tensors (no CPU fallback)")
     if not hasattr(block, "mlp_token_select"):
         raise AttributeError("'Block' object has no attribute 'mlp_token_select'")
+    if torch.is_grad_enabled():      # (a no_grad train()-mode forward needs no such guarantee)
+        _check_peft(block)
     B, N, _ = x.shape
     training_gate = bool(block.training)
     if noise is None and _fixed["noises"]:
