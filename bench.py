@@ -545,6 +545,10 @@ def gather_extras_after(args, world, rank, local):
         ex["finetune_b16"].update(allreduce_bytes_per_step=ft["config"]["allreduce_bytes_per_step"],
                                   allreduce_us=ft["config"]["allreduce_us"], loss=ft["config"]["loss"],
                                   images_per_gpu=64, workload=ft["config"]["workload"])
+    if world > 1:
+        st = measure_strong_scaling(world, rank, local)
+        if st is not None:
+            ex["strong_scaling_b256_global"] = st
     if world == 1:
         for wl in ("vit_l16", "video_b16"):
             r = measure_extra(wl, 8, 4, world, rank, local)
@@ -552,6 +556,43 @@ def gather_extras_after(args, world, rank, local):
                 ex[wl] = {"value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"],
                           "workload": r["config"]["workload"]}
     return ex
+
+
+def measure_strong_scaling(world, rank, local, steps=15, warmup=6):
+    """The headline workload with the GLOBAL batch fixed at 256 images (256 / N per GPU): strong
+    scaling.  At 32 images per GPU the 50 row tiles no longer fill the 74 CTA pairs of a GEMM, so
+    this is the unfavourable reading of the metric; the headline line keeps 256 images per GPU."""
+    device = torch.device("cuda", local)
+    from dyt_b200 import GraphedForward, synthetic
+    per = BATCH // world
+    if per < 1:
+        return None
+    model = synthetic.build_vit_b16(device, num_classes=NUM_CLASSES, seed=0)
+    cal = torch.randn(64, 3, 224, 224, generator=torch.Generator().manual_seed(0)).to(device)
+    synthetic.calibrate_keep_rate(model, cal, RATE)
+    images = torch.randn(per, 3, 224, 224, generator=torch.Generator().manual_seed(rank)).to(device)
+    fwd = GraphedForward(model)
+    buf = fwd.input_buffer(images.shape, images.dtype, device)
+    buf.copy_(images)
+    for _ in range(warmup):
+        fwd.replay(images.shape, images.dtype, device)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        fwd.replay(images.shape, images.dtype, device)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    sec = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, world, device)
+    del fwd, model
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {"value": per * world * steps / sec, "unit": "images/s", "ms_per_step": sec / steps * 1e3,
+            "images_per_gpu": per, "n_gpus": world, "scaling": "strong",
+            "workload": f"ViT-B/16 DyT inference, 256 images global = {per} per GPU, r~0.5"}
 
 
 def measure_extra(workload, steps, warmup, world, rank, local):
