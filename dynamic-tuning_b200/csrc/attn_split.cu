@@ -1,0 +1,426 @@
+// Multi-head attention for uniform sequences of 129..256 tokens, four independent streams per SM.
+//
+// attn_varlen.cu runs two streams per SM (one per 128-query tile), each a serial chain
+// S = QK^T -> row max -> exponentials -> PV with ONE score buffer (TMEM holds 2 x 208 + O columns),
+// so the MUFU pipe idles whenever a stream is outside its exponentials and a lone softmax warp
+// per sub-partition sustains only 14 clk per exponential against the pipe's 8.  Here every
+// (query tile, key half) pair is a stream of its own -- flash-decoding partials: own S = Q K_h^T
+// (N = 112 / 96 at 197 tokens), own row max / sum, own P and PV_h accumulator -- so the TMEM splits
+// into four 128-column regions (S at +0, fp16 P over its first half, O at +64: it lands on score
+// columns that are dead once P is complete), sixteen softmax warps put four warps on every
+// sub-partition's MUFU, and the chains of the four streams drift out of phase.  The output warps
+// combine the two key halves of a tile exactly: O = (w0 O_0 + w1 O_1) / (w0 l_0 + w1 l_1),
+// w_h = 2^(m_h - max(m_0, m_1)).
+//   warp 0        TMA producer (Q both tiles, K, V of the next unit; 2-stage ring)
+//   warps 1-4     tcgen05.mma issuers, one per stream (warp-uniform, one elected lane issues)
+//   warp 5        TMEM allocator
+//   warps 8-23    softmax: stream = (warp - 8) / 4, TMEM lane quarter = warp % 4, thread = query row
+//   warps 24-27   output: per tile both partial O (two 32-column pieces), combine, normalise, fp16,
+//                 transpose through smem, 128-byte row stores
+//
+// Replaces F.scaled_dot_product_attention in Attention.forward of the reference
+// (models/model_speed_test.py:145-166): non-causal, scale = head_dim^-0.5, head_dim 64.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "../../include/dyt_b200.h"
+#include "host_utils.h"
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace dyt {
+
+struct AttnSplitParams {
+  int seq_len;    // tokens per sequence (129..256)
+  int nk;         // round_up(seq_len, 16): rows of the K / V box
+  int nk0;        // keys of half 0 (multiple of 16); half 1 covers [nk0, nk)
+  int C, H;
+  int num_units;  // sequences * heads
+  __half* out;
+  int ldo;
+  float scale_log2e;
+};
+
+constexpr int AS_BM = 128;
+constexpr int AS_D = 64;
+constexpr int AS_WARPS = 28;
+constexpr int AS_THREADS = AS_WARPS * 32;        // 896
+constexpr int AS_Q_BYTES = 2 * AS_BM * 128;      // both query tiles of a unit
+constexpr int AS_OSTAGE_BYTES = 4 * 32 * 128;    // per-output-warp transpose slabs
+constexpr int AS_STAT_BYTES = 2 * 4 * AS_BM * 8; // {max * scale, sum}: [unit parity][stream][row]
+constexpr int AS_REGION = 128;                   // TMEM columns per stream
+constexpr int AS_OCOL = 64;                      // O inside the stream's region
+
+__device__ __forceinline__ void as_max32(const uint32_t (&r)[32], float (&mx)[4]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(r[j]));
+}
+__device__ __forceinline__ void as_mask16(uint32_t (&r)[16], int k0, int seq_len) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (k0 + j >= seq_len) r[j] = 0xff800000u;  // -inf
+}
+__device__ __forceinline__ void as_exp32(uint32_t (&r)[32], float sl2, float mb, float (&sum)[4],
+                                         uint32_t p_addr) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    r[j] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(r[j]), sl2, -mb)));
+  uint32_t pk[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float e0 = __uint_as_float(r[2 * j]), e1 = __uint_as_float(r[2 * j + 1]);
+    sum[j & 3] += e0 + e1;
+    pk[j] = pack_half2(e0, e1);
+  }
+  tmem_st16(p_addr, pk);
+}
+__device__ __forceinline__ void as_exp16(uint32_t (&r)[16], float sl2, float mb, float (&sum)[4],
+                                         uint32_t p_addr) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    r[j] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(r[j]), sl2, -mb)));
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float e0 = __uint_as_float(r[2 * j]), e1 = __uint_as_float(r[2 * j + 1]);
+    sum[j & 3] += e0 + e1;
+    pk[j] = pack_half2(e0, e1);
+  }
+  tmem_st8(p_addr, pk);
+}
+
+__global__ void __launch_bounds__(AS_THREADS, 1)
+attn_split_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                  const __grid_constant__ CUtensorMap tmap_kv, const AttnSplitParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const uint32_t kv_bytes = static_cast<uint32_t>(p.nk) * 128u;
+  const uint32_t stage_bytes = AS_Q_BYTES + 2 * kv_bytes;  // multiple of 2 KB
+  uint8_t* o_stage = smem + 2 * stage_bytes;
+  const uint32_t stat_addr = smem_u32(o_stage + AS_OSTAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(o_stage + AS_OSTAGE_BYTES + AS_STAT_BYTES);
+  uint64_t* full_qk = bars + 0;     // [2] TMA -> MMA
+  uint64_t* full_v = bars + 2;      // [2] TMA -> MMA
+  uint64_t* qk_empty = bars + 4;    // [2] MMA -> TMA: all four streams' S MMAs have read Q / K
+  uint64_t* v_empty = bars + 6;     // [2] MMA -> TMA: all four streams' PV MMAs have read V
+  uint64_t* s_full = bars + 8;      // [4: stream] MMA -> softmax
+  uint64_t* p_full = bars + 12;     // [4] softmax -> MMA
+  uint64_t* o_full = bars + 16;     // [4] MMA -> output warps
+  uint64_t* o_free = bars + 20;     // [4] output warps -> MMA (O read out: the region may take the next S)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full_qk[i], 1);
+      mbar_init(&full_v[i], 1);
+      mbar_init(&qk_empty[i], 4);  // one arrival per stream
+      mbar_init(&v_empty[i], 4);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv);
+  }
+  if (warp_idx == 5) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  const int seq_len = p.seq_len;
+  // register budget (896 threads start at 72 each = 64512): control 2 x 128 x 40, softmax 512 x 80,
+  // output 128 x 96 -> 10240 + 40960 + 12288 = 63488
+
+  if (warp_idx < 8) {
+    reg_dealloc<40>();
+    if (warp_idx == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        int it = 0;
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
+          const int b = unit / p.H, h = unit - b * p.H;
+          const int seq_start = b * seq_len;
+          const int s = it & 1;
+          mbar_wait(&qk_empty[s], ((it >> 1) & 1) ^ 1);
+          uint8_t* sQ = smem + s * stage_bytes;
+          uint8_t* sK = sQ + AS_Q_BYTES;
+          uint8_t* sV = sK + kv_bytes;
+          mbar_arrive_expect_tx(&full_qk[s], 2u * AS_BM * 128u + kv_bytes);
+          tma_load_2d(sQ, &tmap_q, &full_qk[s], h * AS_D, seq_start);
+          tma_load_2d(sK, &tmap_kv, &full_qk[s], p.C + h * AS_D, seq_start);
+          tma_load_2d(sQ + AS_BM * 128, &tmap_q, &full_qk[s], h * AS_D, seq_start + AS_BM);
+          mbar_wait(&v_empty[s], ((it >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_v[s], kv_bytes);
+          tma_load_2d(sV, &tmap_kv, &full_v[s], 2 * p.C + h * AS_D, seq_start);
+        }
+      }
+    } else if (warp_idx <= 4) {
+      // ===================== MMA issuer of stream (tile, half) =====================
+      const int stream = warp_idx - 1;
+      const int tile = stream >> 1, half = stream & 1;
+      const int k_lo = half ? p.nk0 : 0;
+      const int nkh = half ? p.nk - p.nk0 : p.nk0;   // keys of this half (multiple of 16)
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t region = tmem_u + stream * AS_REGION;
+      const uint32_t d_tmem = region + AS_OCOL;
+      const uint32_t idesc_s = umma_idesc_f16(AS_BM, nkh, 0, 0);
+      const uint32_t idesc_o = umma_idesc_f16(AS_BM, AS_D, 0, 1);  // B = V is MN-major
+      const uint32_t smem_base_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const int steps = nkh / 16;
+      uint32_t k = 0;
+      int it = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it, ++k) {
+        const int s = it & 1;
+        const uint32_t ring_par = (it >> 1) & 1;
+        const uint32_t stage_addr = smem_base_u + s * stage_bytes;
+        mbar_wait(&full_qk[s], ring_par);
+        mbar_wait(&o_free[stream], (k & 1) ^ 1);   // O(k-1) sits on this region's score columns
+        tc_fence_after();
+        {
+          const uint64_t q_desc = umma_desc_sw128(stage_addr + tile * AS_BM * 128);
+          const uint64_t k_desc = umma_desc_sw128(stage_addr + AS_Q_BYTES + k_lo * 128);
+          if (elect_one()) {
+#pragma unroll
+            for (int k16 = 0; k16 < AS_D / 16; ++k16)
+              umma_ss_f16(region, q_desc + 2 * k16, k_desc + 2 * k16, idesc_s, k16 != 0 ? 1u : 0u);
+            umma_commit(&s_full[stream]);
+            umma_commit(&qk_empty[s]);
+          }
+          __syncwarp();
+        }
+        // O_h = P_h V_h: 16 keys per MMA = 8 TMEM columns of packed fp16 P, 16 V rows = 2048 B
+        const uint64_t v_desc = umma_desc_sw128(stage_addr + AS_Q_BYTES + kv_bytes) + (k_lo / 16) * 128;
+        mbar_wait(&p_full[stream], k & 1);
+        mbar_wait(&full_v[s], ring_par);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int kk = 0; kk < steps; ++kk)
+            umma_ts_f16(d_tmem, region + kk * 8, v_desc + kk * 128, idesc_o, kk != 0 ? 1u : 0u);
+          umma_commit(&o_full[stream]);
+          umma_commit(&v_empty[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp_idx < 24) {
+    // ===================== softmax of stream (tile, half) =====================
+    reg_alloc<80>();
+    const int stream = (warp_idx - 8) >> 2;
+    const int tile = stream >> 1, half = stream & 1;
+    const int q = warp_idx & 3;
+    const int k_lo = half ? p.nk0 : 0;
+    const int k_hi = half ? seq_len : min(p.nk0, seq_len);   // valid keys are [k_lo, k_hi)
+    const int len = k_hi - k_lo;
+    const int nkh = half ? p.nk - p.nk0 : p.nk0;
+    const int nfull = len >> 5;                               // full 32-key chunks
+    const int ntail = (((len + 15) & ~15) - nfull * 32) >> 4;  // 16-key tail pieces (0..2), within nkh
+    const uint32_t s_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + stream * AS_REGION;
+    const float sl2 = p.scale_log2e;
+    const bool active = tile * AS_BM + q * 32 < seq_len;   // warp-uniform
+    (void)nkh;
+    uint32_t cnt = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++cnt) {
+      mbar_wait(&s_full[stream], cnt & 1);
+      tc_fence_after();
+      if (active) {
+        float mx;
+        {
+          // ---- pass 1: row max over this half's keys, two chunk loads in flight ----
+          uint32_t ra[32];
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+          for (int c = 0; c < nfull; ++c) {
+            tmem_ld32(s_addr + c * 32, ra);
+            tmem_ld_wait();
+            as_max32(ra, mx4);
+          }
+#pragma unroll 1
+          for (int t = 0; t < ntail; ++t) {
+            uint32_t rt[16];
+            const int k0 = nfull * 32 + t * 16;
+            tmem_ld16(s_addr + k0, rt);
+            tmem_ld_wait();
+            as_mask16(rt, k_lo + k0, seq_len);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(rt[j]));
+          }
+          mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        }
+        // ---- pass 2: exponentials, row sum, P -> TMEM over the consumed scores ----
+        const float mb = mx * sl2;
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+          uint32_t ra[32];
+#pragma unroll 1
+          for (int c = 0; c < nfull; ++c) {
+            tmem_ld32(s_addr + c * 32, ra);
+            tmem_ld_wait();
+            as_exp32(ra, sl2, mb, sum4, s_addr + c * 16);
+          }
+#pragma unroll 1
+          for (int t = 0; t < ntail; ++t) {
+            uint32_t rt[16];
+            const int k0 = nfull * 32 + t * 16;
+            tmem_ld16(s_addr + k0, rt);
+            tmem_ld_wait();
+            as_mask16(rt, k_lo + k0, seq_len);
+            as_exp16(rt, sl2, mb, sum4, s_addr + (k0 >> 1));
+          }
+        }
+        tmem_st_wait();
+        sts64(stat_addr + (((cnt & 1) * 4 + stream) * AS_BM + q * 32 + lane) * 8, __float_as_uint(mb),
+              __float_as_uint((sum4[0] + sum4[1]) + (sum4[2] + sum4[3])));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[stream]);
+    }
+  } else {
+    // ===================== output: combine the two key halves of a tile =====================
+    reg_alloc<96>();
+    const int q = warp_idx & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t stg = smem_u32(o_stage) + q * (32 * 128);
+    uint32_t cnt = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++cnt) {
+      const int b = unit / p.H, h = unit - b * p.H;
+      const int seq_start = b * seq_len;
+#pragma unroll 1
+      for (int tile = 0; tile < 2; ++tile) {
+        const bool active = tile * AS_BM + q * 32 < seq_len;  // warp-uniform
+        const int s0 = tile * 2, s1 = tile * 2 + 1;
+        mbar_wait(&o_full[s0], cnt & 1);
+        mbar_wait(&o_full[s1], cnt & 1);
+        tc_fence_after();
+        float w0 = 0.f, w1 = 0.f;
+        if (active) {
+          const uint2 st0 = lds64(stat_addr + (((cnt & 1) * 4 + s0) * AS_BM + q * 32 + lane) * 8);
+          const uint2 st1 = lds64(stat_addr + (((cnt & 1) * 4 + s1) * AS_BM + q * 32 + lane) * 8);
+          const float m0 = __uint_as_float(st0.x), m1 = __uint_as_float(st1.x);
+          const float m = fmaxf(m0, m1);
+          const float e0 = ex2_approx(m0 - m), e1 = ex2_approx(m1 - m);
+          const float inv = 1.0f / (e0 * __uint_as_float(st0.y) + e1 * __uint_as_float(st1.y));
+          w0 = e0 * inv;
+          w1 = e1 * inv;
+        }
+        const uint32_t o_a = tmem_base + lane_off + s0 * AS_REGION + AS_OCOL;
+        const uint32_t o_b = tmem_base + lane_off + s1 * AS_REGION + AS_OCOL;
+        const uint32_t my = stg + lane * 128;
+#pragma unroll 1
+        for (int piece = 0; piece < 2; ++piece) {
+          uint32_t a[32], c[32];
+          if (active) {
+            tmem_ld32(o_a + piece * 32, a);
+            tmem_ld32(o_b + piece * 32, c);
+            tmem_ld_wait();
+          }
+          if (piece == 1) {   // both regions are read out: they may take their next S
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&o_free[s0]);
+              mbar_arrive(&o_free[s1]);
+            }
+          }
+          if (active) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 v;
+              v.x = pack_half2(fmaf(__uint_as_float(a[8 * j + 0]), w0, __uint_as_float(c[8 * j + 0]) * w1),
+                               fmaf(__uint_as_float(a[8 * j + 1]), w0, __uint_as_float(c[8 * j + 1]) * w1));
+              v.y = pack_half2(fmaf(__uint_as_float(a[8 * j + 2]), w0, __uint_as_float(c[8 * j + 2]) * w1),
+                               fmaf(__uint_as_float(a[8 * j + 3]), w0, __uint_as_float(c[8 * j + 3]) * w1));
+              v.z = pack_half2(fmaf(__uint_as_float(a[8 * j + 4]), w0, __uint_as_float(c[8 * j + 4]) * w1),
+                               fmaf(__uint_as_float(a[8 * j + 5]), w0, __uint_as_float(c[8 * j + 5]) * w1));
+              v.w = pack_half2(fmaf(__uint_as_float(a[8 * j + 6]), w0, __uint_as_float(c[8 * j + 6]) * w1),
+                               fmaf(__uint_as_float(a[8 * j + 7]), w0, __uint_as_float(c[8 * j + 7]) * w1));
+              sts128(my + (((piece * 4 + j) ^ (lane & 7)) << 4), v);
+            }
+          }
+        }
+        if (active) {
+          __syncwarp();
+          const int ch = lane & 7;
+          const int rs = lane >> 3;
+          const int row0 = tile * AS_BM + q * 32;
+          __half* gbase = p.out + static_cast<size_t>(seq_start) * p.ldo + h * AS_D + ch * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rs;
+            const uint4 v = lds128(stg + r * 128 + ((ch ^ (r & 7)) << 4));
+            if (row0 + r < seq_len)
+              *reinterpret_cast<uint4*>(gbase + static_cast<size_t>(row0 + r) * p.ldo) = v;
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+bool attn_split_supported(const int* cu_seqlens, int uniform_len, int head_dim) {
+  return cu_seqlens == nullptr && head_dim == 64 && uniform_len > 160 && uniform_len <= 256;
+}
+
+int attn_split_fwd(const __half* qkv, int ld_qkv, int num_seqs, int seq_len, int total_tokens,
+                   int num_heads, __half* out, int ldo, cudaStream_t stream) {
+  DYT_CHECK_ARG(qkv != nullptr && out != nullptr, "attn: null buffer");
+  DYT_CHECK_ARG(attn_split_supported(nullptr, seq_len, 64), "attn_split: 161..256 tokens per sequence");
+  const int C = num_heads * AS_D;
+  DYT_CHECK_ARG(ld_qkv >= 3 * C && ldo >= C && ldo % 8 == 0, "attn: bad leading dimensions");
+  if (num_seqs == 0 || total_tokens == 0) return DYT_OK;
+  const int nk = (seq_len + 15) & ~15;
+  CUtensorMap tq, tkv;
+  int s = make_tmap_f16_sw128(&tq, qkv, static_cast<uint64_t>(total_tokens),
+                              static_cast<uint64_t>(3 * C), static_cast<uint64_t>(ld_qkv), AS_BM);
+  if (s != DYT_OK) return s;
+  s = make_tmap_f16_sw128(&tkv, qkv, static_cast<uint64_t>(total_tokens),
+                          static_cast<uint64_t>(3 * C), static_cast<uint64_t>(ld_qkv),
+                          static_cast<uint32_t>(nk));
+  if (s != DYT_OK) return s;
+  AttnSplitParams p;
+  p.seq_len = seq_len;
+  p.nk = nk;
+  p.nk0 = ((nk / 2) + 15) & ~15;     // 197 tokens: 208 -> 112 + 96
+  p.C = C;
+  p.H = num_heads;
+  p.num_units = num_seqs * num_heads;
+  p.out = out;
+  p.ldo = ldo;
+  p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(AS_D));
+  const int smem_bytes = 1024 + 2 * (AS_Q_BYTES + 2 * nk * 128) + AS_OSTAGE_BYTES + AS_STAT_BYTES + 256;
+  static SmemAttrCache smem_cache;
+  {
+    const int st = ensure_dyn_smem(attn_split_kernel, 232448, smem_cache);
+    if (st != DYT_OK) return st;
+  }
+  const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
+  return cuda_status(launch_pdl(attn_split_kernel, dim3(grid), dim3(AS_THREADS), smem_bytes, stream,
+                                tq, tkv, p),
+                     "attn_split_kernel launch");
+}
+
+}  // namespace dyt

@@ -32,6 +32,7 @@
 
 #include "../../include/dyt_b200.h"
 #include "host_utils.h"
+#include "internal.h"
 #include "ptx.cuh"
 
 namespace dyt {
@@ -488,6 +489,10 @@ int attn_varlen_fwd(const __half* qkv, int ld_qkv, const int* cu_seqlens, int nu
   const int C = num_heads * head_dim;
   DYT_CHECK_ARG(ld_qkv >= 3 * C && ldo >= C && ldo % 8 == 0, "attn: bad leading dimensions");
   if (num_seqs == 0 || total_tokens == 0) return DYT_OK;
+
+  if (attn_split_option().load(std::memory_order_relaxed) != 0 &&
+      attn_split_supported(cu_seqlens, uniform_len, head_dim))
+    return attn_split_fwd(qkv, ld_qkv, num_seqs, uniform_len, total_tokens, num_heads, out, ldo, stream);
 
   const int nk_box = (max_seqlen + 15) & ~15;
   CUtensorMap tq, tkv;

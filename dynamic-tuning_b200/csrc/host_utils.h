@@ -141,6 +141,13 @@ inline std::atomic<int>& fuse_up_option() {
   return v;
 }
 
+// Library option (dyt_configure): uniform sequences of 161..256 tokens run the four-stream
+// attention kernel (attn_split.cu) instead of the two-stream one (attn_varlen.cu).
+inline std::atomic<int>& attn_split_option() {
+  static std::atomic<int> v{1};
+  return v;
+}
+
 // <<<grid, block, smem, stream>>> with the PDL attribute (the kernel must call pdl_wait() before
 // its first dependent global access)
 template <typename... KArgs, typename... Args>

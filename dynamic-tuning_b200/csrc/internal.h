@@ -17,6 +17,11 @@ int attn_varlen_fwd(const __half* qkv, int ld_qkv, const int* cu_seqlens, int nu
                     int uniform_len, int max_seqlen, int total_tokens, int num_heads, int head_dim,
                     __half* out, int ldo, cudaStream_t stream);
 
+// four-stream attention for uniform sequences of 161..256 tokens (attn_split.cu)
+bool attn_split_supported(const int* cu_seqlens, int uniform_len, int head_dim);
+int attn_split_fwd(const __half* qkv, int ld_qkv, int num_seqs, int seq_len, int total_tokens,
+                   int num_heads, __half* out, int ldo, cudaStream_t stream);
+
 int layernorm_f16(const float* x, int ldx, const int* row_idx, const int* n_rows_dev, int n_rows,
                   int C, const float* gamma, const float* beta, float eps, __half* out, int ldo,
                   cudaStream_t stream);

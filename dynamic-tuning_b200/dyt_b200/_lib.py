@@ -19,6 +19,7 @@ EPI_BIAS_GELU_KEEP, EPI_DGELU = 4, 5
 OPT_PDL = 1
 OPT_GEMM_TAIL_SPLIT = 2
 OPT_FUSE_ADAPTER_UP = 3
+OPT_ATTN_SPLIT = 4
 EW_GELU_FWD, EW_GELU_BWD, EW_RELU_DROP_BWD, EW_MUL = 0, 1, 2, 3
 
 

@@ -52,10 +52,14 @@ const char* dyt_last_error(void);
  *   the CTA pairs (wave quantisation: 297 tile pairs on 74 pairs = 4 rounds + 1 tile).
  *   DYT_OPT_FUSE_ADAPTER_UP (default 1): dyt_block_fwd computes the adapter's up projection inside
  *   the scatter-merge kernel (dyt_merge_up_fwd) instead of a GEMM launch whose [T, C] output makes a
- *   round trip through HBM; 0 = the separate dyt_linear_f16 + dyt_scatter_merge_fwd launches. */
+ *   round trip through HBM; 0 = the separate dyt_linear_f16 + dyt_scatter_merge_fwd launches.
+ *   DYT_OPT_ATTN_SPLIT (default 1): dyt_attn_varlen_fwd runs uniform sequences of 161..256 tokens
+ *   on the four-stream kernel (query tile x key half, exact combine of the halves); 0 = the
+ *   two-stream kernel for every length. */
 #define DYT_OPT_PDL 1
 #define DYT_OPT_GEMM_TAIL_SPLIT 2
 #define DYT_OPT_FUSE_ADAPTER_UP 3
+#define DYT_OPT_ATTN_SPLIT 4
 int dyt_configure(int option, int value);
 
 /* y = epilogue(x[M,K] * w[N,K]^T): the nn.Linear forward under fp16 autocast.
