@@ -177,31 +177,36 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   // (the token selector's score Linear rides in the epilogue: per-row partial dot products)
   const int slices = gemm_tn_dot_slices(C);
   const bool fuse_score = C > 128;
+  // the adapter's up projection rides in the merge kernel (step 10) unless unsupported / switched
+  // off; with the down projection fused too, the whole adapter branch does: no fp16 copy of x1, no
+  // `down` buffer, no side stream
+  const bool fuse_up = merge_up_supported(C, shape->bottleneck, T) &&
+                       fuse_up_option().load(std::memory_order_relaxed) != 0;
+  const bool fuse_down = fuse_up && C % 64 == 0 &&
+                         fuse_down_option().load(std::memory_order_relaxed) != 0;
   { NvtxRange r("dyt.proj_residual_score");
   DYT_TRY(gemm_tn(w.attn_o, C, HP(wt->proj_w), C, T, C, C, nullptr, EPI_BIAS_RESID,
-                  HP(wt->proj_b), w.x1h, C, w.x1, C, x, C, 1.0f, stream,
+                  HP(wt->proj_b), fuse_down ? nullptr : w.x1h, C, w.x1, C, x, C, 1.0f, stream,
                   fuse_score ? wt->sel_w : nullptr, w.score_part, slices, opt->logit_fp16)); }
   // adapter on every token (steps 8./9.), forked onto the side stream
   SideStream& ss = side_stream();
   cudaStream_t astream = stream;
-  if (ss.ok) {
+  const bool fork = ss.ok && !fuse_down;
+  if (fork) {
     DYT_CUDA(cudaEventRecord(ss.fork, stream));
     DYT_CUDA(cudaStreamWaitEvent(ss.stream, ss.fork, 0));
     astream = ss.stream;
   }
-  { NvtxRange r("dyt.adapter_down");
+  if (!fuse_down) { NvtxRange r("dyt.adapter_down");
   DYT_TRY(gemm_tn(w.x1h, C, HP(wt->down_w), C, T, shape->bottleneck, C, nullptr, EPI_BIAS_RELU,
                   HP(wt->down_b), w.down, shape->bottleneck, nullptr, 0, nullptr, 0, 1.0f, astream)); }
-  // the up projection rides in the merge kernel (step 10) unless unsupported / switched off
-  const bool fuse_up = merge_up_supported(C, shape->bottleneck, T) &&
-                       fuse_up_option().load(std::memory_order_relaxed) != 0;
   if (!fuse_up) {
     NvtxRange r("dyt.adapter_up");
     DYT_TRY(gemm_tn(w.down, shape->bottleneck, HP(wt->up_w), shape->bottleneck, T, C,
                     shape->bottleneck, nullptr, EPI_BIAS, HP(wt->up_b), w.adapt, C, nullptr, 0,
                     nullptr, 0, wt->adapter_scale, astream));
   }
-  if (ss.ok) DYT_CUDA(cudaEventRecord(ss.join, ss.stream));
+  if (fork) DYT_CUDA(cudaEventRecord(ss.join, ss.stream));
   // 5. dispatcher: score, gate, compaction, LN2 of kept rows
   { NvtxRange r("dyt.dispatch");
   DYT_TRY(dispatch_fwd(w.x1, C, wt->sel_w, wt->sel_b, opt->logit_fp16, opt->min_kept,
@@ -216,14 +221,14 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   DYT_TRY(gemm_tn(w.hidden, shape->hidden, HP(wt->fc2_w), shape->hidden, T, C, shape->hidden,
                   w.n_kept, EPI_BIAS, HP(wt->fc2_b), w.mlp, C, nullptr, 0, nullptr, 0, 1.0f, stream)); }
   // join the adapter branch
-  if (ss.ok) DYT_CUDA(cudaStreamWaitEvent(stream, ss.join, 0));
+  if (fork) DYT_CUDA(cudaStreamWaitEvent(stream, ss.join, 0));
   // 10. scatter-merge back to [B, N, C] (in place into x), optionally with the next LayerNorm
   NvtxRange range_merge("dyt.merge");
   if (fuse_up)
     DYT_TRY(merge_up(w.down, shape->bottleneck, HP(wt->up_w), shape->bottleneck, HP(wt->up_b),
                      wt->adapter_scale, shape->bottleneck, w.x1, C, w.mlp, C, w.token_pos, T, C, x, C,
                      opt->next_ln_w, opt->next_ln_b, opt->eps, opt->next_ln_w ? w.xn : nullptr, C,
-                     stream));
+                     stream, fuse_down ? HP(wt->down_w) : nullptr, C, HP(wt->down_b)));
   else
     DYT_TRY(scatter_merge(w.x1, C, w.adapt, C, w.mlp, C, w.token_pos, T, C, x, C, opt->next_ln_w,
                           opt->next_ln_b, opt->eps, opt->next_ln_w ? w.xn : nullptr, C, stream));

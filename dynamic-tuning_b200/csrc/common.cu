@@ -15,6 +15,9 @@ extern "C" int dyt_configure(int option, int value) {
     case DYT_OPT_GEMM_TAIL_SPLIT:
       dyt::tail_split_option().store(value != 0 ? 1 : 0);
       return dyt::DYT_OK;
+    case DYT_OPT_FUSE_ADAPTER_DOWN:
+      dyt::fuse_down_option().store(value != 0 ? 1 : 0);
+      return dyt::DYT_OK;
     case DYT_OPT_ATTN_SPLIT:
       dyt::attn_split_option().store(value != 0 ? 1 : 0);
       return dyt::DYT_OK;

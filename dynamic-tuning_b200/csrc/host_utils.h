@@ -141,6 +141,15 @@ inline std::atomic<int>& fuse_up_option() {
   return v;
 }
 
+// Library option (dyt_configure): the block forward also computes the adapter's down projection
+// inside the merge kernel (no fp16 copy of x1, no `down` buffer, no side stream).  Off by default:
+// 167 MB less HBM traffic per layer, but the pre-pass over the tile's x1 rows costs the merge kernel
+// 36 us against 18 us for the separate down GEMM, and the step does not move (9.16 vs 9.31 ms).
+inline std::atomic<int>& fuse_down_option() {
+  static std::atomic<int> v{0};
+  return v;
+}
+
 // Library option (dyt_configure): uniform sequences of 161..256 tokens run the four-stream
 // attention kernel (attn_split.cu) instead of the two-stream one (attn_varlen.cu).
 inline std::atomic<int>& attn_split_option() {

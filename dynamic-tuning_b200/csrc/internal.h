@@ -36,7 +36,8 @@ bool merge_up_supported(int C, int K, long long rows);
 int merge_up(const __half* down, int ld_down, const __half* up_w, int ldw, const __half* up_b,
              float scale, int K, const float* x1, int ldx, const __half* mlp_packed, int ldm,
              const int* token_pos, int n_rows, int C, float* out, int ldo, const float* nln_w,
-             const float* nln_b, float eps, __half* nln_out, int ldn, cudaStream_t stream);
+             const float* nln_b, float eps, __half* nln_out, int ldn, cudaStream_t stream,
+             const __half* down_w = nullptr, int ld_dw = 0, const __half* down_b = nullptr);
 
 int dispatch_fwd(const float* x1, int ldx, const float* sel_w, const float* sel_b, int logit_fp16,
                  float min_kept, const float* noise1, const float* noise2, float tau, int B, int N,

@@ -48,6 +48,10 @@ constexpr int MU_SLAB = 32 * 64;               // 32 rows x 32 fp16 per epilogue
 constexpr int MU_STAGE = 32 * 128 + 32 * 64;   // per warp: 32 rows x (32 fp32 + 32 fp16)
 constexpr int MU_MAXC = 1024;
 constexpr int MU_EPI_REGS = 104, MU_AUX_REGS = 56;
+constexpr int MU_TBUF = 3;                      // TMEM accumulator buffers of the up projection (3 x 128 columns)
+constexpr int MU_DCOL = MU_TBUF * MU_CH;        // TMEM column of the down projection's 128 x 64 accumulator
+constexpr int MU_KBUF = 3;                      // fp16 x1 chunks (128 x 64) in flight to the down MMAs
+constexpr int MU_WDBYTES = 64 * 128;            // one Wdown chunk: 64 outputs x 64 halves of K
 
 struct MergeUpParams {
   int T, C;
@@ -65,11 +69,16 @@ struct MergeUpParams {
   float eps;
   __half* ln_out;
   int ldn;
+  // fused adapter down-projection (tmap_wd valid): down = relu(f16(f16(x1) Wd^T + bd)) is computed
+  // from the tile's x1 rows in a pre-pass instead of being read from HBM
+  int fuse_down;
+  const __half* down_bias;   // [Kd] fp16 or nullptr
+  int Kd;                    // adapter bottleneck (<= 64)
 };
 
 static inline int mu_smem_bytes(int C) {
-  return MU_WSTAGES * MU_WBYTES + MU_ABYTES + MU_EW * (MU_SLAB + MU_STAGE) + 3 * C * 4 +
-         2 * 4 * MU_BM * 8 + 256 + 1024;
+  return MU_WSTAGES * MU_WBYTES + MU_ABYTES + MU_EW * (MU_SLAB + MU_STAGE) + 3 * C * 4 + 64 * 4 +
+         2 * 4 * MU_BM * 8 + 512 + 1024;
 }
 
 __device__ __forceinline__ void mu_bar_sync(int id, int threads) {
@@ -91,6 +100,7 @@ __device__ __forceinline__ void mu_cp_wait1() { asm volatile("cp.async.wait_grou
 __global__ void __launch_bounds__(MU_THREADS, 1)
 merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], box 128 x 64
                 const __grid_constant__ CUtensorMap tmap_w,   // Wup  [C, K], box 128 x 64
+                const __grid_constant__ CUtensorMap tmap_wd,  // Wdown [K, C], box 64 x 64 (fuse_down)
                 const MergeUpParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -104,15 +114,21 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
   float* bias_s = reinterpret_cast<float*>(stages + MU_EW * MU_STAGE);   // [C]
   float* gamma_s = bias_s + C;
   float* beta_s = gamma_s + C;
-  float2* stats_s = reinterpret_cast<float2*>(beta_s + C);             // [2][4][128]
+  float* dbias_s = beta_s + C;                                          // [64]
+  float2* stats_s = reinterpret_cast<float2*>(dbias_s + 64);           // [2][4][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(stats_s + 2 * 4 * MU_BM);
   uint64_t* a_full = bars;            // [1]
   uint64_t* a_empty = bars + 1;       // [1]
   uint64_t* w_full = bars + 2;        // [3]
   uint64_t* w_empty = bars + 5;       // [3]
-  uint64_t* t_full = bars + 8;        // [4]
-  uint64_t* t_empty = bars + 12;      // [4]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* t_full = bars + 8;        // [3]
+  uint64_t* t_empty = bars + 12;      // [3]
+  uint64_t* ak_ready = bars + 16;     // [3] epilogue warps -> MMA: fp16 x1 chunk written
+  uint64_t* ak_free = bars + 19;      // [3] MMA -> epilogue warps
+  uint64_t* down_done = bars + 22;    // [1] MMA -> epilogue warps: the down accumulator is complete
+  uint64_t* down_ready = bars + 23;   // [1] epilogue warps -> MMA: the `down` tile is in shared memory
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 24);
+  uint8_t* ak_smem = stages;          // the x1 chunks live in the staging area (idle during the pre-pass)
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,6 +137,7 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
+    if (p.fuse_down) tma_prefetch_desc(&tmap_wd);
   }
   if (warp_idx == 1 && lane == 0) {
     mbar_init(a_full, 1);
@@ -129,10 +146,16 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
     }
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < MU_TBUF; ++b) {
       mbar_init(&t_full[b], 1);
       mbar_init(&t_empty[b], MU_EW);
     }
+    for (int b = 0; b < MU_KBUF; ++b) {
+      mbar_init(&ak_ready[b], MU_EW);
+      mbar_init(&ak_free[b], 1);
+    }
+    mbar_init(down_done, 1);
+    mbar_init(down_ready, MU_EW);
     fence_mbar_init();
   }
   if (warp_idx == 2) {
@@ -145,6 +168,10 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
       bias_s[i] = p.bias != nullptr ? __half2float(p.bias[i]) : 0.f;
       gamma_s[i] = p.ln_w != nullptr ? p.ln_w[i] : 1.f;
       beta_s[i] = p.ln_b != nullptr ? p.ln_b[i] : 0.f;
+    }
+    if (threadIdx.x - 128 < 64) {
+      const int i = threadIdx.x - 128;
+      dbias_s[i] = (p.fuse_down && p.down_bias != nullptr && i < p.Kd) ? __half2float(p.down_bias[i]) : 0.f;
     }
   }
   tc_fence_before();
@@ -163,9 +190,22 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
         uint32_t wph = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-          mbar_wait(a_empty, (static_cast<uint32_t>(it) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(a_full, MU_ABYTES);
-          tma_load_2d(a_smem, &tmap_a, a_full, 0, tile * MU_BM);
+          if (!p.fuse_down) {
+            mbar_wait(a_empty, (static_cast<uint32_t>(it) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(a_full, MU_ABYTES);
+            tma_load_2d(a_smem, &tmap_a, a_full, 0, tile * MU_BM);
+          } else {
+            // the weight ring first carries Wdown in K chunks of 64 columns (8 KB each)
+            for (int kc = 0; kc < C / 64; ++kc) {
+              mbar_wait(&w_empty[ws], wph ^ 1u);
+              mbar_arrive_expect_tx(&w_full[ws], MU_WDBYTES);
+              tma_load_2d(w_smem + ws * MU_WBYTES, &tmap_wd, &w_full[ws], kc * 64, 0);
+              if (++ws == MU_WSTAGES) {
+                ws = 0;
+                wph ^= 1u;
+              }
+            }
+          }
           for (int j = 0; j < nch; ++j) {
             mbar_wait(&w_empty[ws], wph ^ 1u);
             mbar_arrive_expect_tx(&w_full[ws], MU_WBYTES);
@@ -187,14 +227,46 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
       int it = 0;
       int ws = 0;
       uint32_t wph = 0;
-      uint32_t g = 0;   // chunk counter over the whole kernel: TMEM buffer = g & 3
+      uint32_t buf = 0, bph = 0;   // TMEM accumulator ring of the up projection
+      uint32_t ab = 0, aph = 0;    // x1 chunk ring of the down projection
+      constexpr uint32_t idesc_d = umma_idesc_f16(MU_BM, 64, 0, 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        mbar_wait(a_full, static_cast<uint32_t>(it) & 1u);
+        if (p.fuse_down) {
+          // down[128, 64] = f16(x1)[128, C] Wdown[64, C]^T, K in chunks of 64 written by the epilogue warps
+          const uint32_t ak_u = __shfl_sync(0xffffffffu, smem_u32(ak_smem), 0);
+          const int nkc = C / 64;
+          for (int kc = 0; kc < nkc; ++kc) {
+            mbar_wait(&w_full[ws], wph);
+            mbar_wait(&ak_ready[ab], aph);
+            tc_fence_after();
+            const uint64_t xa_desc = umma_desc_sw128(ak_u + ab * MU_ABYTES);
+            const uint64_t wd_desc = umma_desc_sw128(w_u + ws * MU_WBYTES);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_ss_f16(tmem_u + MU_DCOL, xa_desc + 2 * k, wd_desc + 2 * k, idesc_d, (kc | k) != 0 ? 1u : 0u);
+              umma_commit(&w_empty[ws]);
+              umma_commit(&ak_free[ab]);
+              if (kc == nkc - 1) umma_commit(down_done);
+            }
+            __syncwarp();
+            if (++ws == MU_WSTAGES) {
+              ws = 0;
+              wph ^= 1u;
+            }
+            if (++ab == MU_KBUF) {
+              ab = 0;
+              aph ^= 1u;
+            }
+          }
+          mbar_wait(down_ready, static_cast<uint32_t>(it) & 1u);   // the `down` tile is in a_smem
+        } else {
+          mbar_wait(a_full, static_cast<uint32_t>(it) & 1u);
+        }
         tc_fence_after();
-        for (int j = 0; j < nch; ++j, ++g) {
-          const uint32_t buf = g & 3u;
+        for (int j = 0; j < nch; ++j) {
           mbar_wait(&w_full[ws], wph);
-          mbar_wait(&t_empty[buf], ((g >> 2) & 1u) ^ 1u);
+          mbar_wait(&t_empty[buf], bph ^ 1u);
           tc_fence_after();
           const uint64_t b_desc = umma_desc_sw128(w_u + ws * MU_WBYTES);
           if (elect_one()) {
@@ -203,12 +275,16 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
               umma_ss_f16(tmem_u + buf * MU_CH, a_desc + 2 * k, b_desc + 2 * k, idesc, k != 0 ? 1u : 0u);
             umma_commit(&t_full[buf]);
             umma_commit(&w_empty[ws]);
-            if (j == nch - 1) umma_commit(a_empty);
+            if (j == nch - 1 && !p.fuse_down) umma_commit(a_empty);
           }
           __syncwarp();
           if (++ws == MU_WSTAGES) {
             ws = 0;
             wph ^= 1u;
+          }
+          if (++buf == MU_TBUF) {
+            buf = 0;
+            bph ^= 1u;
           }
         }
       }
@@ -284,14 +360,101 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
       mu_cp_commit();   // (possibly empty: every pass-2 step commits exactly one group)
     };
 
+    const bool fuse_down = p.fuse_down != 0;
+    // ---- pre-pass (fuse_down): this warp turns rows e*8 .. e*8+7 of the tile's x1 into the fp16
+    // A operand of the down projection, one 64-column K chunk at a time: lane -> (row 2i + lane/16,
+    // 4 columns), 16 lanes cover the 256 bytes of a row; the chunk is written in the canonical
+    // K-major 128B-swizzled layout (16-byte unit index XOR row % 8) the MMA descriptors expect.
+    const int pr = lane >> 4, pc4 = (lane & 15) * 4;
+    uint32_t ka = 0, kph = 0;   // x1 chunk ring position / phase (runs over the whole kernel)
+    auto load_x1_chunk = [&](int tile, int kc, float4 (&v)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int grow = min(tile * MU_BM + e * 8 + 2 * i + pr, last_row);
+        v[i] = *reinterpret_cast<const float4*>(p.x1 + (static_cast<uint32_t>(grow) * p.ldx + kc * 64 + pc4));
+      }
+    };
+    auto store_x1_chunk = [&](const float4 (&v)[4]) {
+      const uint32_t base = smem_u32(ak_smem) + ka * MU_ABYTES;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = e * 8 + 2 * i + pr;   // row of the tile; r / 8 == e, r % 8 == 2i + pr
+        const uint32_t addr = base + e * 1024 + (2 * i + pr) * 128 +
+                              ((((pc4 >> 3) ^ (2 * i + pr)) & 7) << 4) + (pc4 & 7) * 2;
+        (void)r;
+        sts64(addr, pack_half2(v[i].x, v[i].y), pack_half2(v[i].z, v[i].w));
+      }
+    };
+
     int pl = load_pl(blockIdx.x);
-    issue_p1(blockIdx.x, pl, 0);
-    uint32_t g = 0;
+    if (!fuse_down) issue_p1(blockIdx.x, pl, 0);
+    uint32_t buf = 0, bph = 0;   // TMEM accumulator ring of the up projection
     int it_tile = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it_tile) {
       const int rbase = tile * MU_BM + q * 32 + r8;
       const int next_tile = tile + gridDim.x;
       const int pl_next = load_pl(next_tile);   // in flight for the whole tile
+      if (fuse_down) {
+        // every warp is done with the previous tile's staged data: the staging area becomes the
+        // x1 chunk ring of the pre-pass
+        mu_cp_wait();
+        mu_bar_sync(5, MU_EW * 32);
+        const int nkc = C / 64;
+        // four chunks of this warp's x1 rows in flight (registers), MU_KBUF converted chunks in
+        // flight to the MMAs (shared memory)
+        float4 va[4], vb[4], vc[4], vd[4];
+        load_x1_chunk(tile, 0, va);
+        load_x1_chunk(tile, 1, vb);
+        load_x1_chunk(tile, 2, vc);
+        load_x1_chunk(tile, 3, vd);
+#pragma unroll 1
+        for (int kc = 0; kc < nkc; kc += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (kc + u < nkc) {
+              mbar_wait(&ak_free[ka], kph ^ 1u);
+              float4 (&v)[4] = u == 0 ? va : (u == 1 ? vb : (u == 2 ? vc : vd));
+              store_x1_chunk(v);
+              fence_proxy_async_smem();   // generic-proxy stores -> visible to the MMA's async-proxy reads
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&ak_ready[ka]);
+              if (kc + u + 4 < nkc) load_x1_chunk(tile, kc + u + 4, v);
+              if (++ka == MU_KBUF) {
+                ka = 0;
+                kph ^= 1u;
+              }
+            }
+          }
+        }
+        // the down accumulator is complete (and the MMAs have read the last chunk: the staging area
+        // is free again): first chunk of pass 1 on its way, then bias + ReLU -> the `down` tile
+        mbar_wait(down_done, static_cast<uint32_t>(it_tile) & 1u);
+        tc_fence_after();
+        issue_p1(tile, pl, 0);
+        {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + MU_DCOL + part * 16, r);
+          tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int j2 = 0; j2 < 8; ++j2) {
+            const float b0 = dbias_s[part * 16 + 2 * j2], b1 = dbias_s[part * 16 + 2 * j2 + 1];
+            const __half2 h = __floats2half2_rn(__uint_as_float(r[2 * j2]) + b0,
+                                                __uint_as_float(r[2 * j2 + 1]) + b1);
+            const __half2 o = __hmax2(h, __float2half2_rn(0.f));
+            pk[j2] = *reinterpret_cast<const uint32_t*>(&o);
+          }
+          // row q*32 + lane of the 128 x 64 fp16 tile, 16-byte units 2*part and 2*part + 1
+          const int row = q * 32 + lane;
+          const uint32_t rowaddr = smem_u32(a_smem) + (row >> 3) * 1024 + (row & 7) * 128;
+          sts128(rowaddr + ((((2 * part) ^ row) & 7) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+          sts128(rowaddr + ((((2 * part + 1) ^ row) & 7) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(down_ready);
+        }
+      }
       unsigned live = 0;                         // bit it: row it*4 + r8 of this quarter exists
 #pragma unroll
       for (int it = 0; it < 8; ++it) live |= (rbase + it * 4 < p.T ? 1u : 0u) << it;
@@ -300,14 +463,13 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
       for (int it = 0; it < 8; ++it) mean[it] = m2[it] = 0.f;
 
 #pragma unroll 1
-      for (int j = 0; j < nch; ++j, ++g) {
-        const uint32_t buf = g & 3u;
+      for (int j = 0; j < nch; ++j) {
         const int c0 = j * MU_CH + part * 32;   // first column of this warp's 32
         {
           uint32_t pk[16];
           {
             uint32_t r[32];
-            mbar_wait(&t_full[buf], (g >> 2) & 1u);
+            mbar_wait(&t_full[buf], bph);
             tc_fence_after();
             tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * MU_CH + part * 32, r);
             uint4 bq[8];
@@ -317,6 +479,10 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[buf]);
+            if (++buf == MU_TBUF) {
+              buf = 0;
+              bph ^= 1u;
+            }
             // thread = row: one rounding to fp16 per Linear output, then f16(v * scale)
 #pragma unroll
             for (int j2 = 0; j2 < 16; ++j2) {
@@ -345,7 +511,7 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
           mv[it] = lds64(stage_m + it * 256);
         }
         if (j + 1 < nch) issue_p1(tile, pl, j + 1);
-        else if (!do_ln) issue_p1(next_tile, pl_next, 0);
+        else if (!do_ln && !fuse_down) issue_p1(next_tile, pl_next, 0);
         // coalesced layout: lane -> (row it*4 + lane/8, columns (lane%8)*4 .. +3)
         const int col = c0 + p8 * 4;
         const float w1 = 1.0f / static_cast<float>(j + 1);
@@ -438,7 +604,9 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
           issue_p2(tile, j + 2);
         } else {
           __syncwarp();   // pass-1 slots of one lane overlap pass-2 slots of another
-          issue_p1(next_tile, pl_next, 0);   // both buffers are free: the next tile's first chunk
+          // both buffers are free: the next tile's first chunk (with the fused down projection the
+          // staging area first serves the pre-pass of that tile)
+          if (!fuse_down) issue_p1(next_tile, pl_next, 0);
         }
         const uint4 gq = lds128(gamma_u + col * 4);
         const uint4 bq = lds128(beta_u + col * 4);
@@ -484,14 +652,19 @@ bool merge_up_supported(int C, int K, long long rows) {
 int merge_up(const __half* down, int ld_down, const __half* up_w, int ldw, const __half* up_b,
              float scale, int K, const float* x1, int ldx, const __half* mlp_packed, int ldm,
              const int* token_pos, int n_rows, int C, float* out, int ldo, const float* nln_w,
-             const float* nln_b, float eps, __half* nln_out, int ldn, cudaStream_t stream) {
-  DYT_CHECK_ARG(down && up_w && x1 && mlp_packed && token_pos && out, "merge_up: null buffer");
+             const float* nln_b, float eps, __half* nln_out, int ldn, cudaStream_t stream,
+             const __half* down_w, int ld_dw, const __half* down_b) {
+  // down_w != nullptr: the adapter's down projection (down_w [K, C], down_b [K]) is computed inside
+  // the kernel from x1 and `down` is not read
+  const bool fuse_down = down_w != nullptr;
+  DYT_CHECK_ARG((down || fuse_down) && up_w && x1 && mlp_packed && token_pos && out, "merge_up: null buffer");
   if (!merge_up_supported(C, K, n_rows))
     return fail(DYT_EUNSUPPORTED,
                 "merge_up: needs C %% 128 == 0, C <= %d, K <= 64, rows * C < 2^31 (C=%d K=%d rows=%d)",
                 MU_MAXC, C, K, n_rows);
-  DYT_CHECK_ARG(ldx % 4 == 0 && ldm % 4 == 0 && ldo % 4 == 0 && ld_down >= K && ldw >= K,
+  DYT_CHECK_ARG(ldx % 4 == 0 && ldm % 4 == 0 && ldo % 4 == 0 && (fuse_down || ld_down >= K) && ldw >= K,
                 "merge_up: strides");
+  DYT_CHECK_ARG(!fuse_down || (ld_dw >= C && C % 64 == 0), "merge_up: down_w stride");
   DYT_CHECK_ARG(nln_out == nullptr || (nln_w && nln_b && ldn % 4 == 0), "merge_up: next-LN args");
   DYT_CHECK_ARG(out != x1, "merge_up: out must not alias x1");
   {  // the kernel indexes with 32-bit element offsets
@@ -502,10 +675,18 @@ int merge_up(const __half* down, int ld_down, const __half* up_w, int ldw, const
       return fail(DYT_EUNSUPPORTED, "merge_up: more than 2^31 elements per buffer");
   }
   if (n_rows == 0) return DYT_OK;
-  CUtensorMap ta, tw;
-  int s = make_tmap_f16_sw128(&ta, down, static_cast<uint64_t>(n_rows), static_cast<uint64_t>(K),
-                              static_cast<uint64_t>(ld_down), MU_BM);
-  if (s != DYT_OK) return s;
+  CUtensorMap ta, tw, twd;
+  int s = DYT_OK;
+  if (fuse_down) {
+    s = make_tmap_f16_sw128(&twd, down_w, static_cast<uint64_t>(K), static_cast<uint64_t>(C),
+                            static_cast<uint64_t>(ld_dw), 64);
+    if (s != DYT_OK) return s;
+    ta = twd;   // (unused by the kernel in this mode)
+  } else {
+    s = make_tmap_f16_sw128(&ta, down, static_cast<uint64_t>(n_rows), static_cast<uint64_t>(K),
+                            static_cast<uint64_t>(ld_down), MU_BM);
+    if (s != DYT_OK) return s;
+  }
   s = make_tmap_f16_sw128(&tw, up_w, static_cast<uint64_t>(C), static_cast<uint64_t>(K),
                           static_cast<uint64_t>(ldw), MU_CH);
   if (s != DYT_OK) return s;
@@ -521,12 +702,16 @@ int merge_up(const __half* down, int ld_down, const __half* up_w, int ldw, const
   p.out = out; p.ldo = ldo;
   p.ln_w = nln_w; p.ln_b = nln_b; p.eps = eps;
   p.ln_out = nln_out; p.ldn = ldn;
+  p.fuse_down = fuse_down ? 1 : 0;
+  p.down_bias = down_b;
+  p.Kd = K;
+  if (!fuse_down) twd = tw;
   const int tiles = (n_rows + MU_BM - 1) / MU_BM;
   int grid = tiles < sm_count() ? tiles : sm_count();
   // at least 120 KB of shared memory per CTA: one CTA per SM, which owns all 512 TMEM columns
   int smem = mu_smem_bytes(C);
   if (smem < 120 * 1024) smem = 120 * 1024;
-  return cuda_status(launch_pdl(merge_up_kernel, dim3(grid), dim3(MU_THREADS), smem, stream, ta, tw, p),
+  return cuda_status(launch_pdl(merge_up_kernel, dim3(grid), dim3(MU_THREADS), smem, stream, ta, tw, twd, p),
                      "merge_up_kernel launch");
 }
 
@@ -543,5 +728,20 @@ extern "C" int dyt_merge_up_fwd(const void* down_f16, int ld_down, const void* u
                        static_cast<const __half*>(up_b_f16), scale, K, x1, ldx,
                        static_cast<const __half*>(mlp_packed_f16), ldm, token_pos, n_rows, C, out, ldo,
                        next_ln_w, next_ln_b, eps, static_cast<__half*>(next_ln_out_f16), ldn,
-                       static_cast<cudaStream_t>(stream));
+                       static_cast<cudaStream_t>(stream), nullptr, 0, nullptr);
+}
+
+extern "C" int dyt_adapter_merge_fwd(const void* down_w_f16, int ld_dw, const void* down_b_f16,
+                                     const void* up_w_f16, int ldw, const void* up_b_f16, float scale,
+                                     int K, const float* x1, int ldx, const void* mlp_packed_f16,
+                                     int ldm, const int* token_pos, int n_rows, int C, float* out,
+                                     int ldo, const float* next_ln_w, const float* next_ln_b,
+                                     float eps, void* next_ln_out_f16, int ldn, void* stream) {
+  if (down_w_f16 == nullptr) return dyt::fail(dyt::DYT_EINVAL, "adapter_merge: null down_w");
+  return dyt::merge_up(nullptr, 0, static_cast<const __half*>(up_w_f16), ldw,
+                       static_cast<const __half*>(up_b_f16), scale, K, x1, ldx,
+                       static_cast<const __half*>(mlp_packed_f16), ldm, token_pos, n_rows, C, out, ldo,
+                       next_ln_w, next_ln_b, eps, static_cast<__half*>(next_ln_out_f16), ldn,
+                       static_cast<cudaStream_t>(stream), static_cast<const __half*>(down_w_f16), ld_dw,
+                       static_cast<const __half*>(down_b_f16));
 }

@@ -20,6 +20,7 @@ OPT_PDL = 1
 OPT_GEMM_TAIL_SPLIT = 2
 OPT_FUSE_ADAPTER_UP = 3
 OPT_ATTN_SPLIT = 4
+OPT_FUSE_ADAPTER_DOWN = 5
 EW_GELU_FWD, EW_GELU_BWD, EW_RELU_DROP_BWD, EW_MUL = 0, 1, 2, 3
 
 
@@ -76,6 +77,8 @@ SIGNATURES = {
                                    _vp, _i, _vp]),
     "dyt_merge_up_fwd": (_i, [_vp, _i, _vp, _i, _vp, _f, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _i,
                               _vp, _vp, _f, _vp, _i, _vp]),
+    "dyt_adapter_merge_fwd": (_i, [_vp, _i, _vp, _vp, _i, _vp, _f, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp,
+                                   _i, _vp, _vp, _f, _vp, _i, _vp]),
     "dyt_patch_embed_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "dyt_patch_embed_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "dyt_pool_layernorm_f16": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp]),

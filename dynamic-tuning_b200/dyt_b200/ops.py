@@ -321,6 +321,36 @@ def merge_up(down: torch.Tensor, up_w: torch.Tensor, up_b: Optional[torch.Tensor
     return (out, None if nln_out is None else nln_out.reshape(x1.shape))
 
 
+def adapter_merge(down_w: torch.Tensor, down_b: Optional[torch.Tensor], up_w: torch.Tensor,
+                  up_b: Optional[torch.Tensor], scale: float, x1: torch.Tensor,
+                  mlp_packed: torch.Tensor, token_pos: torch.Tensor,
+                  next_ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, eps: float = 1e-6):
+    """The whole adapter branch inside the merge kernel:
+    out = f16(f16(relu(f16(f16(x1) down_w^T + down_b)) up_w^T + up_b) * scale) + (x1 + scatter(mlp_packed)),
+    optionally also LayerNorm(out) in fp16.  down_w [K, C], up_w [C, K] fp16."""
+    _need_cuda(down_w, up_w, x1, mlp_packed, token_pos)
+    x2 = _rows2d(x1)
+    m2 = _rows2d(mlp_packed)
+    T, Cdim = x2.shape
+    K = down_w.shape[0]
+    assert down_w.dtype == torch.float16 and up_w.dtype == torch.float16
+    assert down_w.shape == (K, Cdim) and up_w.shape == (Cdim, K)
+    down_w, up_w = down_w.contiguous(), up_w.contiguous()
+    out = torch.empty((T, Cdim), dtype=torch.float32, device=x1.device)
+    nln_out = None
+    nw = nb = None
+    if next_ln is not None:
+        nw, nb = next_ln
+        nln_out = torch.empty((T, Cdim), dtype=torch.float16, device=x1.device)
+    check(_lib.lib().dyt_adapter_merge_fwd(
+        down_w.data_ptr(), down_w.stride(0), _ptr(down_b), up_w.data_ptr(), up_w.stride(0), _ptr(up_b),
+        float(scale), K, x2.data_ptr(), x2.stride(0), m2.data_ptr(), m2.stride(0),
+        token_pos.data_ptr(), T, Cdim, out.data_ptr(), Cdim, _ptr(nw), _ptr(nb), float(eps),
+        _ptr(nln_out), Cdim, _stream()), "dyt_adapter_merge_fwd")
+    out = out.reshape(x1.shape)
+    return (out, None if nln_out is None else nln_out.reshape(x1.shape))
+
+
 _stem_ws = StreamWorkspaces(zero_filled=False)
 # fp16 / fp32 working copies of the stem parameters, keyed by the identity of the PARAMETER OBJECT
 # (held weakly: the entry is dropped when the parameter dies), so a new model whose tensors land on

@@ -53,6 +53,10 @@ const char* dyt_last_error(void);
  *   DYT_OPT_FUSE_ADAPTER_UP (default 1): dyt_block_fwd computes the adapter's up projection inside
  *   the scatter-merge kernel (dyt_merge_up_fwd) instead of a GEMM launch whose [T, C] output makes a
  *   round trip through HBM; 0 = the separate dyt_linear_f16 + dyt_scatter_merge_fwd launches.
+ *   DYT_OPT_FUSE_ADAPTER_DOWN (default 0, needs DYT_OPT_FUSE_ADAPTER_UP): 1 = dyt_block_fwd computes
+ *   the adapter's down projection inside the merge kernel as well (dyt_adapter_merge_fwd): the proj
+ *   GEMM no longer writes an fp16 copy of x1 and the down GEMM launch disappears (167 MB less HBM
+ *   traffic per layer at 256 images; measured neutral on the step); 0 = down GEMM on a side stream.
  *   DYT_OPT_ATTN_SPLIT (default 0): 1 = dyt_attn_varlen_fwd runs uniform sequences of 161..256
  *   tokens on the four-stream kernel (query tile x key half, exact combine of the halves: 96 -> 89 us
  *   at 256 x 12 x 197 alone, no change of the whole step); 0 = the two-stream kernel for every length. */
@@ -60,6 +64,7 @@ const char* dyt_last_error(void);
 #define DYT_OPT_GEMM_TAIL_SPLIT 2
 #define DYT_OPT_FUSE_ADAPTER_UP 3
 #define DYT_OPT_ATTN_SPLIT 4
+#define DYT_OPT_FUSE_ADAPTER_DOWN 5
 int dyt_configure(int option, int value);
 
 /* y = epilogue(x[M,K] * w[N,K]^T): the nn.Linear forward under fp16 autocast.
@@ -181,6 +186,19 @@ int dyt_merge_up_fwd(const void* down_f16, int ld_down, const void* up_w_f16, in
                      const void* mlp_packed_f16, int ldm, const int* token_pos, int n_rows, int C,
                      float* out, int ldo, const float* next_ln_w, const float* next_ln_b, float eps,
                      void* next_ln_out_f16, int ldn, void* stream);
+
+/* The whole adapter branch fused into the scatter-merge: like dyt_merge_up_fwd, and `down` itself is
+ * computed inside the kernel from the tile's x1 rows,
+ *   down = relu(f16(f16(x1) down_w[K,C]^T + down_b)),
+ * so neither the fp16 copy of x1 nor `down` touches HBM and Adapter.down_proj + ReLU (reference
+ * models/model_speed_test.py:106-108) needs no launch of its own.  Same restrictions as
+ * dyt_merge_up_fwd plus C % 64 == 0. */
+int dyt_adapter_merge_fwd(const void* down_w_f16, int ld_dw, const void* down_b_f16,
+                          const void* up_w_f16, int ldw, const void* up_b_f16, float scale, int K,
+                          const float* x1, int ldx, const void* mlp_packed_f16, int ldm,
+                          const int* token_pos, int n_rows, int C, float* out, int ldo,
+                          const float* next_ln_w, const float* next_ln_b, float eps,
+                          void* next_ln_out_f16, int ldn, void* stream);
 
 /* ViT stem: x[b,0] = cls + pos[0]; x[b,1+p] = f16(patch_p . W^T + bias) + pos[1+p]  (fp32 out).
  * Replaces PatchEmbed.proj (Conv2d k = s = P) + cls concat + pos_embed add (reference

@@ -44,6 +44,15 @@ def fused():
     return ops.merge_up(down, up_w, up_b, 0.1, x1, mlp, pos, next_ln=(lw, lb))
 
 
+down_w = (torch.randn(K, C, generator=g) * 0.03).half().to(dev)
+down_b = (torch.randn(K, generator=g) * 0.1).half().to(dev)
+x1h = x1.half()
+from dyt_b200 import _lib
+def down_then_fused():
+    dn, _ = ops.linear_f16(x1h.reshape(B * N, C), down_w, down_b, epilogue=_lib.EPI_BIAS_RELU)
+    return ops.merge_up(dn.reshape(B, N, K), up_w, up_b, 0.1, x1, mlp, pos, next_ln=(lw, lb))
+print("down GEMM + fused merge_up us:", round(timed(down_then_fused), 1))
+print("whole adapter branch fused (adapter_merge) us:", round(timed(lambda: ops.adapter_merge(down_w, down_b, up_w, up_b, 0.1, x1, mlp, pos, next_ln=(lw, lb))), 1))
 print("unfused (up GEMM + scatter_merge) us:", round(timed(unfused), 1))
 print("fused merge_up us:", round(timed(fused), 1))
 print("fused, no LayerNorm us:", round(timed(lambda: ops.merge_up(down, up_w, up_b, 0.1, x1, mlp, pos)), 1))

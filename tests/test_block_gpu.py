@@ -169,6 +169,26 @@ def test_block_imposed_mask_config1(dev, vitb_sd):
     assert not torch.equal(out_all.cpu()[~kept], out.cpu()[~kept])
 
 
+def test_block_fused_adapter_down_option(dev, vitb_sd):
+    """DYT_OPT_FUSE_ADAPTER_DOWN: the whole adapter branch inside the merge kernel (no fp16 copy of x1,
+    no down GEMM) against the default path on one ViT-B block: same gate decisions, outputs to
+    rounding noise (the down accumulation runs in another tile shape)."""
+    g, sd, img = vitb_sd
+    m = _speed_model(sd, dev)
+    from dyt_b200 import engine, _lib
+    lib = _lib.lib()
+    x = torch.randn(3, 197, 768, generator=torch.Generator().manual_seed(7)).to(dev)
+    base = engine.run_blocks(x, list(m.blocks[1:3]), fuse_next_ln=True)
+    try:
+        assert lib.dyt_configure(_lib.OPT_FUSE_ADAPTER_DOWN, 1) == 0
+        fused = engine.run_blocks(x, list(m.blocks[1:3]), fuse_next_ln=True)
+    finally:
+        assert lib.dyt_configure(_lib.OPT_FUSE_ADAPTER_DOWN, 0) == 0
+    assert torch.equal(fused[1], base[1])
+    assert _rel(fused[0], base[0]) <= 5e-4
+    assert _rel(fused[2], base[2]) <= 2e-3
+
+
 def test_fused_next_layernorm_is_equivalent(dev, vitb_sd):
     g, sd, img = vitb_sd
     m = _speed_model(sd, dev)

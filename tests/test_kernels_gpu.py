@@ -398,6 +398,49 @@ def test_merge_up_fused_matches_linear_plus_scatter_merge(dev, B, N, C, K, scale
         _close(ln1, O._r16(O.layer_norm(ref, lw, lb)), atol=2e-3, rtol=2e-3)
 
 
+@pytest.mark.parametrize("B,N,C,K,scale", [(3, 197, 768, 64, 0.1), (2, 50, 128, 8, 1.0),
+                                           (5, 197, 1024, 64, 0.5), (1, 17, 384, 32, 0.1),
+                                           (300, 197, 768, 64, 0.1), (7, 197, 768, 16, 1.0)])
+def test_adapter_merge_fused_down_and_up(dev, B, N, C, K, scale):
+    """dyt_adapter_merge_fwd (down projection + ReLU + up projection + merge + LayerNorm in one kernel,
+    x1 read as fp32) against the separate launches: down GEMM on the fp16 copy of x1, then
+    dyt_merge_up_fwd.  The down accumulation runs in another tile shape, so `down` may differ in a
+    last fp16 bit on a few elements: outputs are compared to rounding noise, and against the oracle's
+    arithmetic (model_speed_test.py:106-111, :302-308)."""
+    from dyt_b200 import ops, _lib
+    g = _gen(31 + B)
+    x1 = torch.randn(B, N, C, generator=g) * 2 + 0.3
+    down_w = (torch.randn(K, C, generator=g) * 0.03).half()
+    down_b = (torch.randn(K, generator=g) * 0.1).half()
+    up_w = (torch.randn(C, K, generator=g) * 0.05).half()
+    up_b = (torch.randn(C, generator=g) * 0.1).half()
+    mask = (torch.rand(B, N, 1, generator=g) > 0.5).float()
+    idx, _ = O.compact(mask)
+    mlp = torch.randn(idx.numel(), C, generator=g).half()
+    pos = torch.full((B * N,), -1, dtype=torch.int32)
+    pos[idx] = torch.arange(idx.numel(), dtype=torch.int32)
+    lw, lb = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    d = lambda t: t.to(dev)
+    x1h = d(x1).half()
+    down, _ = ops.linear_f16(x1h.reshape(B * N, C), d(down_w), d(down_b), epilogue=_lib.EPI_BIAS_RELU)
+    out0, ln0 = ops.merge_up(down.reshape(B, N, K), d(up_w), d(up_b), scale, d(x1), d(mlp), d(pos),
+                             next_ln=(d(lw), d(lb)))
+    out1, ln1 = ops.adapter_merge(d(down_w), d(down_b), d(up_w), d(up_b), scale, d(x1), d(mlp), d(pos),
+                                  next_ln=(d(lw), d(lb)))
+    out2, none = ops.adapter_merge(d(down_w), d(down_b), d(up_w), d(up_b), scale, d(x1), d(mlp), d(pos))
+    assert none is None and torch.equal(out2, out1)
+    _close(out1, out0.cpu(), atol=2e-3, rtol=1e-3)
+    assert float((out1 != out0).float().mean()) < 0.02       # the same up to rare last-bit flips of `down`
+    _close(ln1, ln0.float().cpu(), atol=4e-3, rtol=2e-3)
+    if B <= 7:
+        dn = torch.relu(O._r16(O._r16(x1).reshape(-1, C) @ down_w.float().t() + down_b.float()))
+        a_ref = O._r16(O._r16(dn @ up_w.float().t() + up_b.float()) * scale)
+        full = torch.zeros(B * N, C)
+        full[idx] = mlp.float()
+        ref = a_ref.reshape(B, N, C) + (x1 + full.reshape(B, N, C))
+        _close(out1, ref, atol=3e-3, rtol=1e-3)
+
+
 def test_merge_up_refuses_unsupported_shapes(dev):
     from dyt_b200 import ops, _lib
     x1 = torch.zeros(1, 4, 192, device=dev)
