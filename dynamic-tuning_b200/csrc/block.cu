@@ -180,7 +180,12 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   // the adapter's up projection rides in the merge kernel (step 10) unless unsupported / switched
   // off; with the down projection fused too, the whole adapter branch does: no fp16 copy of x1, no
   // `down` buffer, no side stream
-  const bool fuse_up = merge_up_supported(C, shape->bottleneck, T) &&
+  const bool moe = opt->moe_experts > 1;
+  if (moe) {
+    DYT_CHECK_ARG(opt->moe_router_w != nullptr && opt->moe_workspace != nullptr,
+                  "block: MoE-adapter needs the router weights and a workspace");
+  }
+  const bool fuse_up = !moe && merge_up_supported(C, shape->bottleneck, T) &&
                        fuse_up_option().load(std::memory_order_relaxed) != 0;
   const bool fuse_down = fuse_up && C % 64 == 0 &&
                          fuse_down_option().load(std::memory_order_relaxed) != 0;
@@ -197,10 +202,17 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
     DYT_CUDA(cudaStreamWaitEvent(ss.stream, ss.fork, 0));
     astream = ss.stream;
   }
-  if (!fuse_down) { NvtxRange r("dyt.adapter_down");
+  if (moe) {
+    NvtxRange r("dyt.moe_adapter");
+    DYT_TRY(moe_adapter_fwd(w.x1, C, w.x1h, C, B, N, C, opt->moe_experts, shape->bottleneck,
+                            opt->moe_router_w, opt->moe_router_b, HP(wt->down_w), HP(wt->down_b),
+                            HP(wt->up_w), wt->adapter_scale, w.adapt, C, opt->moe_workspace,
+                            opt->moe_workspace_bytes, astream));
+  }
+  if (!fuse_down && !moe) { NvtxRange r("dyt.adapter_down");
   DYT_TRY(gemm_tn(w.x1h, C, HP(wt->down_w), C, T, shape->bottleneck, C, nullptr, EPI_BIAS_RELU,
                   HP(wt->down_b), w.down, shape->bottleneck, nullptr, 0, nullptr, 0, 1.0f, astream)); }
-  if (!fuse_up) {
+  if (!fuse_up && !moe) {
     NvtxRange r("dyt.adapter_up");
     DYT_TRY(gemm_tn(w.down, shape->bottleneck, HP(wt->up_w), shape->bottleneck, T, C,
                     shape->bottleneck, nullptr, EPI_BIAS, HP(wt->up_b), w.adapt, C, nullptr, 0,

@@ -39,6 +39,13 @@ int merge_up(const __half* down, int ld_down, const __half* up_w, int ldw, const
              const float* nln_b, float eps, __half* nln_out, int ldn, cudaStream_t stream,
              const __half* down_w = nullptr, int ld_dw = 0, const __half* down_b = nullptr);
 
+// MoE-adapter branch (moe.cu; not in the reference: own oracle, no reference parity)
+size_t moe_workspace_bytes(int B, int N, int E, int K);
+int moe_adapter_fwd(const float* x1, int ldx, const __half* x1h, int ldxh, int B, int N, int C, int E,
+                    int K, const float* router_w, const float* router_b, const __half* down_cat,
+                    const __half* down_b, const __half* up_cat, float scale, __half* adapt, int ld_adapt,
+                    void* ws, size_t ws_bytes, cudaStream_t stream);
+
 int dispatch_fwd(const float* x1, int ldx, const float* sel_w, const float* sel_b, int logit_fp16,
                  float min_kept, const float* noise1, const float* noise2, float tau, int B, int N,
                  int C, const float* ln_w, const float* ln_b, float eps, const float* forced_mask,

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdyt_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_BIAS_RESID = 0, 1, 2, 3
 EPI_BIAS_GELU_KEEP, EPI_DGELU = 4, 5
@@ -46,7 +46,9 @@ class BlockOpts(C.Structure):
                 ("noise1", C.c_void_p), ("noise2", C.c_void_p), ("tau", C.c_float),
                 ("forced_mask", C.c_void_p), ("gate_out", C.c_void_p), ("xn_ready", C.c_int),
                 ("next_ln_w", C.c_void_p), ("next_ln_b", C.c_void_p), ("attn_bias", C.c_void_p),
-                ("attn_bias_ld", C.c_int)]
+                ("attn_bias_ld", C.c_int), ("moe_experts", C.c_int), ("moe_router_w", C.c_void_p),
+                ("moe_router_b", C.c_void_p), ("moe_workspace", C.c_void_p),
+                ("moe_workspace_bytes", C.c_size_t)]
 
 
 class BlockBuffers(C.Structure):
@@ -79,6 +81,9 @@ SIGNATURES = {
                               _vp, _vp, _f, _vp, _i, _vp]),
     "dyt_adapter_merge_fwd": (_i, [_vp, _i, _vp, _vp, _i, _vp, _f, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp,
                                    _i, _vp, _vp, _f, _vp, _i, _vp]),
+    "dyt_moe_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "dyt_moe_adapter_fwd": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i,
+                                 _vp, _sz, _vp]),
     "dyt_patch_embed_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "dyt_patch_embed_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "dyt_pool_layernorm_f16": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp]),

@@ -47,18 +47,52 @@ class PreparedBlock:
         self.tensors: Dict[str, torch.Tensor] = {}
         self.struct = BlockWeights()
 
+    def _is_moe(self) -> bool:
+        return getattr(self.block.adaptmlp, "num_experts", 0) > 1
+
     def _signature(self):
         sig = []
+        moe = self._is_moe()
         for dotted in list(_WEIGHT_FIELDS_F16.values()) + list(_WEIGHT_FIELDS_F32.values()):
+            if moe and dotted.startswith("adaptmlp."):
+                continue
             p = _get(self.block, dotted)
             sig.append((p.data_ptr(), p._version, p.device))
+        if moe:
+            for p in self.block.adaptmlp.parameters():
+                sig.append((p.data_ptr(), p._version, p.device))
         return tuple(sig)
+
+    def _prepare_moe(self):
+        """MoE-adapter: the experts' weights in the layout dyt_moe_adapter_fwd takes (see the header):
+        down_cat [E*K, C], down_b [E, K], up_cat [C, round8(E*K + E)] with the biases as columns."""
+        a = self.block.adaptmlp
+        E, K, Cd = a.num_experts, a.down_size, a.n_embd
+        h16 = torch.float16
+        dev = a.router.weight.device
+        down_cat = torch.cat([l.weight.detach() for l in a.down_proj], dim=0).to(h16).contiguous()
+        down_b = torch.stack([l.bias.detach() for l in a.down_proj], dim=0).to(h16).contiguous()
+        kup = (E * K + E + 7) // 8 * 8
+        up_cat = torch.zeros((Cd, kup), dtype=h16, device=dev)
+        for i, l in enumerate(a.up_proj):
+            up_cat[:, i * K:(i + 1) * K] = l.weight.detach().to(h16)
+            up_cat[:, E * K + i] = l.bias.detach().to(h16)
+        self.tensors.update(down_w=down_cat, down_b=down_b, up_w=up_cat, up_b=down_b,
+                            moe_router_w=a.router.weight.detach().float().contiguous(),
+                            moe_router_b=a.router.bias.detach().float().contiguous())
+        for field in ("down_w", "down_b", "up_w", "up_b"):
+            setattr(self.struct, field, self.tensors[field].data_ptr())
 
     def get(self) -> BlockWeights:
         sig = self._signature()
         if sig != self.key:
             with torch.no_grad():
+                moe = self._is_moe()
+                if moe:
+                    self._prepare_moe()
                 for field, dotted in _WEIGHT_FIELDS_F16.items():
+                    if moe and dotted.startswith("adaptmlp."):
+                        continue
                     p = _get(self.block, dotted)
                     if not p.is_cuda:
                         raise DytError("dyt_b200: block parameters must live on a CUDA device")
@@ -77,6 +111,7 @@ class PreparedBlock:
 
 
 _workspaces = StreamWorkspaces(zero_filled=True)    # zero-filled once (ABI contract)
+_moe_workspaces = StreamWorkspaces(zero_filled=False)
 
 
 def block_shape_of(block: torch.nn.Module, B: int, N: int) -> BlockShape:
@@ -84,7 +119,9 @@ def block_shape_of(block: torch.nn.Module, B: int, N: int) -> BlockShape:
     H = block.attn.num_heads
     if C_ != 64 * H:
         raise DytError(f"dyt_b200 attention kernel needs head_dim 64 (C={C_}, heads={H})")
-    return BlockShape(B, N, C_, H, block.mlp.fc1.out_features, block.adaptmlp.down_proj.out_features)
+    bott = (block.adaptmlp.down_size if getattr(block.adaptmlp, "num_experts", 0) > 1
+            else block.adaptmlp.down_proj.out_features)
+    return BlockShape(B, N, C_, H, block.mlp.fc1.out_features, bott)
 
 
 def _workspace(shape: BlockShape, device: torch.device) -> torch.Tensor:
@@ -101,6 +138,7 @@ def release_stream_workspaces(device: torch.device, stream: torch.cuda.Stream) -
     stream before capturing."""
     from . import ops
     _workspaces.release_stream(device, stream)
+    _moe_workspaces.release_stream(device, stream)
     ops._dispatch_ws.release_stream(device, stream)
     ops._stem_ws.release_stream(device, stream)
 
@@ -193,6 +231,16 @@ def run_blocks(x: torch.Tensor, blocks: Sequence[torch.nn.Module], *, eps: float
             keep_alive.append(ab)
             opts.attn_bias = ab.data_ptr()
             opts.attn_bias_ld = ab_ld
+        if getattr(blk.adaptmlp, "num_experts", 0) > 1:      # MoE-adapter (not in the reference)
+            prep = _prepared(blk)
+            E_, K_ = blk.adaptmlp.num_experts, blk.adaptmlp.down_size
+            need = int(lib.dyt_moe_workspace_bytes(B, N, E_, K_))
+            mws = _moe_workspaces.get(dev, need)
+            opts.moe_experts = E_
+            opts.moe_router_w = prep.tensors["moe_router_w"].data_ptr()
+            opts.moe_router_b = prep.tensors["moe_router_b"].data_ptr()
+            opts.moe_workspace = mws.data_ptr()
+            opts.moe_workspace_bytes = mws.numel()
         opts.xn_ready = xn_ready
         nxt = None
         if fuse_next_ln:

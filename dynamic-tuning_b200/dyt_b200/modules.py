@@ -139,6 +139,37 @@ class Adapter(nn.Module):
         return up
 
 
+class MoEAdapter(nn.Module):
+    """MoE-adapter of the DyT paper (arXiv 2403.11808; BASELINE configs[3]).  NOT part of the reference
+    repository: the arithmetic is this repository's own restatement
+    (oracle/dyt_oracle.py `moe_adapter`), there is no reference parity.
+      alpha = softmax(router(mean over the tokens of x));  W_mix = sum_i alpha_i W^i (down, up, biases)
+      out = scale * (relu(x W_down_mix^T + b_down_mix) W_up_mix^T + b_up_mix)
+    Enabled by `tuning_config.moe_experts > 1`; inference only (the block forward computes it through
+    dyt_moe_adapter_fwd)."""
+
+    def __init__(self, config=None, d_model=None, bottleneck=None, num_experts=4, dropout=0.0,
+                 adapter_scalar="1.0"):
+        super().__init__()
+        self.n_embd = config.d_model if d_model is None else d_model
+        self.down_size = config.attn_bn if bottleneck is None else bottleneck
+        self.num_experts = int(num_experts)
+        if not 2 <= self.num_experts <= 8:
+            raise NotImplementedError("MoEAdapter: 2..8 experts")
+        if adapter_scalar == "learnable_scalar":
+            raise NotImplementedError("MoEAdapter: learnable_scalar is not built")
+        self.scale = float(adapter_scalar)
+        self.router = nn.Linear(self.n_embd, self.num_experts)
+        self.down_proj = nn.ModuleList(nn.Linear(self.n_embd, self.down_size) for _ in range(self.num_experts))
+        self.non_linear_func = nn.ReLU()
+        self.up_proj = nn.ModuleList(nn.Linear(self.down_size, self.n_embd) for _ in range(self.num_experts))
+        self.dropout = dropout
+
+    def forward(self, x, add_residual=True, residual=None):
+        raise NotImplementedError("MoEAdapter runs inside the block forward (dyt_block_fwd); it has no "
+                                  "stand-alone forward")
+
+
 class Attention(nn.Module):
     def __init__(self, dim, num_heads=8, qkv_bias=False, qk_norm=False, attn_drop=0.0,
                  proj_drop=0.0, norm_layer=nn.LayerNorm):
@@ -198,10 +229,17 @@ class _BlockBase(nn.Module):
                              act_layer=act_layer, drop=proj_drop)
         self.ls2 = nn.Identity()
         self.drop_path2 = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
-        self.adaptmlp = Adapter(self.tuning_config, dropout=0.1, bottleneck=tuning_config.ffn_num,
-                                init_option=tuning_config.ffn_adapter_init_option,
-                                adapter_scalar=tuning_config.ffn_adapter_scalar,
-                                adapter_layernorm_option=tuning_config.ffn_adapter_layernorm_option)
+        n_exp = int(tuning_config.get("moe_experts", 0) if hasattr(tuning_config, "get")
+                    else getattr(tuning_config, "moe_experts", 0))
+        if n_exp > 1:   # MoE-adapter (BASELINE configs[3]; not in the reference, see MoEAdapter)
+            self.adaptmlp = MoEAdapter(self.tuning_config, bottleneck=tuning_config.ffn_num,
+                                       num_experts=n_exp, dropout=0.1,
+                                       adapter_scalar=tuning_config.ffn_adapter_scalar)
+        else:
+            self.adaptmlp = Adapter(self.tuning_config, dropout=0.1, bottleneck=tuning_config.ffn_num,
+                                    init_option=tuning_config.ffn_adapter_init_option,
+                                    adapter_scalar=tuning_config.ffn_adapter_scalar,
+                                    adapter_layernorm_option=tuning_config.ffn_adapter_layernorm_option)
 
     def _eps(self) -> float:
         return float(self.norm1.eps)

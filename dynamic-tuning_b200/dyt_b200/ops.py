@@ -351,6 +351,38 @@ def adapter_merge(down_w: torch.Tensor, down_b: Optional[torch.Tensor], up_w: to
     return (out, None if nln_out is None else nln_out.reshape(x1.shape))
 
 
+def moe_adapter(x1: torch.Tensor, router_w: torch.Tensor, router_b: Optional[torch.Tensor],
+                down_ws, down_bs, up_ws, up_bs, scale: float) -> torch.Tensor:
+    """MoE-adapter branch on the kernels (dyt_moe_adapter_fwd; not in the reference, see the header):
+    x1 [B, N, C] fp32; lists of E expert weights (down [K, C], up [C, K]) and biases.  Returns
+    adapt [B, N, C] fp16."""
+    _need_cuda(x1, router_w)
+    B, N, Cd = x1.shape
+    E, K = len(down_ws), down_ws[0].shape[0]
+    h16 = torch.float16
+    x32 = x1.to(torch.float32).contiguous()
+    x16 = x32.to(h16)
+    down_cat = torch.cat([w.detach() for w in down_ws], 0).to(h16).contiguous()
+    down_b = torch.stack([b.detach() for b in down_bs], 0).to(h16).contiguous()
+    kup = (E * K + E + 7) // 8 * 8
+    up_cat = torch.zeros((Cd, kup), dtype=h16, device=x1.device)
+    for i in range(E):
+        up_cat[:, i * K:(i + 1) * K] = up_ws[i].detach().to(h16)
+        up_cat[:, E * K + i] = up_bs[i].detach().to(h16)
+    rw = router_w.detach().float().contiguous()
+    rb = None if router_b is None else router_b.detach().float().contiguous()
+    need = int(_lib.lib().dyt_moe_workspace_bytes(B, N, E, K))
+    if need == 0:
+        raise DytError("moe_adapter: unsupported shape")
+    ws = torch.empty(need, dtype=torch.uint8, device=x1.device)
+    out = torch.empty((B * N, Cd), dtype=h16, device=x1.device)
+    check(_lib.lib().dyt_moe_adapter_fwd(
+        x32.data_ptr(), Cd, x16.data_ptr(), Cd, B, N, Cd, E, K, rw.data_ptr(), _ptr(rb),
+        down_cat.data_ptr(), down_b.data_ptr(), up_cat.data_ptr(), float(scale), out.data_ptr(), Cd,
+        ws.data_ptr(), ws.numel(), _stream()), "dyt_moe_adapter_fwd")
+    return out.reshape(B, N, Cd)
+
+
 _stem_ws = StreamWorkspaces(zero_filled=False)
 # fp16 / fp32 working copies of the stem parameters, keyed by the identity of the PARAMETER OBJECT
 # (held weakly: the entry is dropped when the parameter dies), so a new model whose tensors land on

@@ -67,6 +67,34 @@ def build_vit_l16(device, num_classes: int = 100, seed: int = 0, ffn_num: int = 
     return model.eval().to(device)
 
 
+def _randomise_moe_parts(model, seed: int):
+    g = torch.Generator().manual_seed(seed + 3)
+    with torch.no_grad():
+        for blk in model.blocks:
+            a = blk.adaptmlp
+            a.router.weight.copy_(0.3 * torch.randn(a.router.weight.shape, generator=g))
+            for lin in a.up_proj:
+                lin.weight.copy_(0.02 * torch.randn(lin.weight.shape, generator=g))
+                lin.bias.copy_(0.02 * torch.randn(lin.bias.shape, generator=g))
+            blk.mlp_token_select.mlp_head.weight.copy_(
+                0.5 * torch.randn(blk.mlp_token_select.mlp_head.weight.shape, generator=g))
+
+
+def build_vit_l16_moe(device, num_classes: int = 100, seed: int = 0, ffn_num: int = 64,
+                      scalar: str = "0.1", experts: int = 4):
+    """BASELINE configs[3]: ViT-L/16 DyT with the MoE-adapter (`tuning_config.moe_experts`; the
+    MoE-adapter is not in the reference: own restatement, no reference parity)."""
+    from models.model_speed_test import VisionTransformer
+    tuning, select = reference_configs(ffn_num=ffn_num, scalar=scalar, d_model=1024, ratio=0.7)
+    tuning["moe_experts"] = experts
+    torch.manual_seed(seed)
+    model = VisionTransformer(patch_size=16, embed_dim=1024, depth=24, num_heads=16, mlp_ratio=4.0,
+                              qkv_bias=True, num_classes=num_classes, drop_path_rate=0.0,
+                              tuning_config=tuning, select_config=select)
+    _randomise_moe_parts(model, seed)
+    return model.eval().to(device)
+
+
 def build_video_b16(device, num_classes: int = 174, seed: int = 0, ffn_num: int = 64,
                     scalar: str = "0.1"):
     """BASELINE configs[4] model: per-frame ViT-B/16 DyT + attentive pooling head."""

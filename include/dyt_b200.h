@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DYT_ABI_VERSION 2
+#define DYT_ABI_VERSION 3
 
 /* epilogues of dyt_linear_f16 */
 #define DYT_EPI_BIAS 0       /* y = f16(x W^T + b)                                            */
@@ -200,6 +200,22 @@ int dyt_adapter_merge_fwd(const void* down_w_f16, int ld_dw, const void* down_b_
                           const float* next_ln_w, const float* next_ln_b, float eps,
                           void* next_ln_out_f16, int ldn, void* stream);
 
+/* MoE-adapter branch (BASELINE configs[3]; DyT paper arXiv 2403.11808).  NOT in the reference
+ * repository: no reference interface is replaced and there is no reference parity -- pinned to this
+ * repository's own restatement (oracle/dyt_oracle.py moe_adapter).
+ *   alpha[b] = softmax(router(mean_tokens(x1[b])));  W_mix = sum_i alpha_i W^i (down and up, biases too)
+ *   adapt = f16(f16(relu(f16(x1 W_down_mix^T + b_down_mix)) W_up_mix^T + b_up_mix) * scale)
+ * computed through the linearity in the weights: one GEMM over the concatenated experts, a per-image
+ * mixture of the expert outputs, one GEMM with K' = round8(E * K + E).  x1 [B*N, C] fp32, x1_f16 its
+ * fp16 copy, down_cat [E*K, C], down_b [E, K], up_cat [C, K'] (= [W_up^1 | .. | W_up^E | b_up^1 ..
+ * b_up^E | 0]), router_w [E, C] fp32, router_b [E] fp32 or NULL; adapt [B*N, C] fp16. */
+size_t dyt_moe_workspace_bytes(int B, int N, int E, int K);
+int dyt_moe_adapter_fwd(const float* x1, int ldx, const void* x1_f16, int ldxh, int B, int N, int C,
+                        int E, int K, const float* router_w, const float* router_b,
+                        const void* down_cat_f16, const void* down_b_f16, const void* up_cat_f16,
+                        float scale, void* adapt_f16, int ld_adapt, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* ViT stem: x[b,0] = cls + pos[0]; x[b,1+p] = f16(patch_p . W^T + bias) + pos[1+p]  (fp32 out).
  * Replaces PatchEmbed.proj (Conv2d k = s = P) + cls concat + pos_embed add (reference
  * models/model_speed_test.py:467-472).  img [B, Cin, H, W] fp32; w_f16 [C, Cin*P*P] (the conv
@@ -354,6 +370,15 @@ typedef struct dyt_block_opts {
                               bias of the segmentation backbone); sequences > 256 tokens or a bias
                               use dyt_attn_bias_fwd instead of dyt_attn_varlen_fwd */
   int attn_bias_ld;        /* row pitch of attn_bias in floats (0 = N), see dyt_attn_bias_fwd */
+  /* MoE-adapter (moe_experts > 1; not in the reference repository, see dyt_moe_adapter_fwd): the
+   * weights struct then holds down_w = the experts' down projections concatenated [E * K, C],
+   * down_b = [E, K], up_w = [C, round8(E * K + E)] = [W_up^1 | .. | W_up^E | b_up^1 .. b_up^E | 0],
+   * up_b unused, K = shape.bottleneck. */
+  int moe_experts;
+  const float* moe_router_w;   /* [E, C] fp32 */
+  const float* moe_router_b;   /* [E] fp32 or NULL */
+  void* moe_workspace;         /* dyt_moe_workspace_bytes(B, N, E, K) bytes, 256-byte aligned */
+  size_t moe_workspace_bytes;
 } dyt_block_opts;
 
 typedef struct dyt_block_buffers { /* where dyt_block_fwd keeps its intermediates (for tests) */

@@ -153,6 +153,65 @@ def adapter(x: Tensor, p: Dict[str, Tensor], prefix: str, scale: float,
 
 
 # ----------------------------------------------------------------------------------------------
+# MoE-adapter (BASELINE configs[3]).  NOT in the reference repository: this is
+# a restatement of the published description (DyT paper, arXiv 2403.11808: routing weights from the
+# token mean, experts mixed in WEIGHT space, so the cost stays that of one adapter).  PARITY UNPINNED:
+# there is no reference implementation, golden vector or test to check it against; the `fp32` policy
+# below is the definition, the `amp16` policy states the rounding points the kernels implement.
+#   alpha = softmax(router(mean_tokens(x)));  W_mix = sum_i alpha_i W^i (down, up and their biases)
+#   out = scale * (relu(x W_down_mix^T + b_down_mix) W_up_mix^T + b_up_mix)
+# ----------------------------------------------------------------------------------------------
+def moe_adapter(x: Tensor, p: Dict[str, Tensor], prefix: str, scale: float, num_experts: int,
+                policy: str = "fp32") -> Tensor:
+    E = num_experts
+    wd = torch.stack([p[f"{prefix}down_proj.{i}.weight"] for i in range(E)])   # [E, K, C]
+    bd = torch.stack([p[f"{prefix}down_proj.{i}.bias"] for i in range(E)])     # [E, K]
+    wu = torch.stack([p[f"{prefix}up_proj.{i}.weight"] for i in range(E)])     # [E, C, K]
+    bu = torch.stack([p[f"{prefix}up_proj.{i}.bias"] for i in range(E)])       # [E, C]
+    mean = x.float().mean(dim=1)                                               # [B, C]
+    alpha = torch.softmax(linear(mean, p[prefix + "router.weight"], p[prefix + "router.bias"], policy).float(), -1)
+    if policy == "fp32":
+        wd_mix = torch.einsum("be,ekc->bkc", alpha, wd)
+        wu_mix = torch.einsum("be,eck->bck", alpha, wu)
+        down = F.relu(torch.einsum("bnc,bkc->bnk", x, wd_mix) + (alpha @ bd)[:, None, :])
+        up = torch.einsum("bnk,bck->bnc", down, wu_mix) + (alpha @ bu)[:, None, :]
+        return up * scale
+    # amp16: the same mixture applied to the experts' OUTPUTS (both projections are linear in their
+    # weights); rounding points of dyt_moe_adapter_fwd: every expert's down output rounded to fp16,
+    # mixture + mixed bias in fp32 -> fp16 -> ReLU, operand alpha_i * d rounded to fp16, fp32
+    # accumulation of the up projection incl. the bias terms f16(alpha_i) * f16(b_up^i), fp16, * scale
+    hid = torch.stack([linear(x, wd[i], None, policy) for i in range(E)])                 # [E, B, N, K]
+    a = alpha.t()[:, :, None, None]                                                       # [E, B, 1, 1]
+    down = F.relu(_r16((a * hid).sum(0) + (alpha @ _r16(bd))[:, None, :]))
+    aup = _r16(a * down[None])                                                            # [E, B, N, K]
+    acc = sum(F.linear(aup[i], _r16(wu[i])) for i in range(E))
+    acc = acc + (_r16(alpha) @ _r16(bu))[:, None, :]
+    return _r16(_r16(acc) * scale)
+
+
+def block_sparse_moe(x: Tensor, p: Dict[str, Tensor], prefix: str, num_heads: int, scale: float,
+                     num_experts: int, policy: str = "fp32",
+                     forced_mask: Optional[Tensor] = None) -> Dict[str, Tensor]:
+    """block_sparse with the MoE-adapter in place of the plain Adapter (no reference parity)."""
+    bsz, n, c = x.shape
+    x1 = x + attention(layer_norm(x, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"]), p,
+                       prefix + "attn.", num_heads, policy)
+    mask, logits = token_select(x1, p[prefix + "mlp_token_select.mlp_head.weight"],
+                                p[prefix + "mlp_token_select.mlp_head.bias"], policy)
+    if forced_mask is not None:
+        mask = forced_mask.float()
+    adapt_x = moe_adapter(x1, p, prefix + "adaptmlp.", scale, num_experts, policy)
+    packed_idx, cu = compact(mask)
+    flat = x1.reshape(bsz * n, c)
+    kept = mlp(layer_norm(flat[packed_idx, :], p[prefix + "norm2.weight"], p[prefix + "norm2.bias"]), p,
+               prefix + "mlp.", policy)
+    mlp_x = torch.zeros(flat.shape, dtype=kept.dtype, device=flat.device)
+    mlp_x[packed_idx, :] = kept
+    out = adapt_x + (x1 + mlp_x.reshape(bsz, n, c))
+    return dict(out=out, x1=x1, mask=mask, logits=logits, adapt=adapt_x)
+
+
+# ----------------------------------------------------------------------------------------------
 # a6: Attention.forward (reference models/vision_transformer_IN21K.py:54-75 ==
 #     models/model_speed_test.py:145-166); q_norm/k_norm Identity, dropout 0
 # ----------------------------------------------------------------------------------------------

@@ -88,7 +88,7 @@ def test_block_opts_struct_size_is_enforced():
     st = lib.dyt_block_fwd(ctypes.byref(shape), ctypes.byref(wt), ctypes.byref(opts), 256, 256, 256,
                            256, 1 << 40, None)
     assert st < 0 and b"struct_size" in lib.dyt_last_error()
-    assert ctypes.sizeof(_lib.BlockOpts) == 104                   # 64-bit layout of the header struct
+    assert ctypes.sizeof(_lib.BlockOpts) == 136                   # 64-bit layout of the header struct
 
 
 def test_argument_errors_are_reported_not_raised_across_the_abi():

@@ -189,6 +189,62 @@ def test_block_fused_adapter_down_option(dev, vitb_sd):
     assert _rel(fused[2], base[2]) <= 2e-3
 
 
+def _moe_params(C, K, E, seed):
+    g = torch.Generator().manual_seed(seed)
+    p = {"adaptmlp.router.weight": torch.randn(E, C, generator=g) * 0.3,
+         "adaptmlp.router.bias": torch.randn(E, generator=g) * 0.2}
+    for i in range(E):
+        p[f"adaptmlp.down_proj.{i}.weight"] = torch.randn(K, C, generator=g) * 0.03
+        p[f"adaptmlp.down_proj.{i}.bias"] = torch.randn(K, generator=g) * 0.1
+        p[f"adaptmlp.up_proj.{i}.weight"] = torch.randn(C, K, generator=g) * 0.05
+        p[f"adaptmlp.up_proj.{i}.bias"] = torch.randn(C, generator=g) * 0.1
+    return p
+
+
+@pytest.mark.parametrize("B,N,C,K,E", [(3, 197, 768, 64, 4), (2, 50, 128, 16, 2), (5, 197, 1024, 64, 8)])
+def test_moe_adapter_kernels_vs_own_oracle(dev, B, N, C, K, E):
+    """dyt_moe_adapter_fwd against this repository's own restatement (oracle.moe_adapter): the
+    MoE-adapter is NOT in the reference, so there is no reference parity to claim.  amp16 rounding
+    points to 2e-3, and the weight-space fp32 definition to fp16 noise."""
+    from dyt_b200 import ops
+    p = _moe_params(C, K, E, 50 + E)
+    x1 = torch.randn(B, N, C, generator=torch.Generator().manual_seed(3)) * 2 + 0.2
+    got = ops.moe_adapter(x1.to(dev), p["adaptmlp.router.weight"].to(dev), p["adaptmlp.router.bias"].to(dev),
+                          [p[f"adaptmlp.down_proj.{i}.weight"].to(dev) for i in range(E)],
+                          [p[f"adaptmlp.down_proj.{i}.bias"].to(dev) for i in range(E)],
+                          [p[f"adaptmlp.up_proj.{i}.weight"].to(dev) for i in range(E)],
+                          [p[f"adaptmlp.up_proj.{i}.bias"].to(dev) for i in range(E)], 0.5).float().cpu()
+    amp = O.moe_adapter(x1, p, "adaptmlp.", 0.5, E, "amp16")
+    ref = O.moe_adapter(x1, p, "adaptmlp.", 0.5, E, "fp32")
+    assert float((got - amp).abs().max()) <= 2e-3 * float(amp.abs().max()) + 1e-3
+    assert float((got - ref).abs().max()) <= 6e-3 * float(ref.abs().max()) + 2e-3
+
+
+def test_block_with_moe_adapter_vs_own_oracle(dev, vitb_sd):
+    """A ViT-B block whose adapter is the MoE-adapter (tuning_config.moe_experts = 4) through
+    dyt_block_fwd against oracle.block_sparse_moe (own restatement: no reference parity)."""
+    from models.model_speed_test import Block
+    from dyt_b200 import engine
+    g, sd, img = vitb_sd
+    tuning, _ = configs()
+    tuning["moe_experts"] = 4
+    blk = Block(dim=768, num_heads=12, mlp_ratio=4.0, qkv_bias=True, tuning_config=tuning, select=True)
+    own = {k[len("blocks.2."):]: v for k, v in sd.items()
+           if k.startswith("blocks.2.") and "adaptmlp" not in k}
+    own.update(_moe_params(768, 64, 4, 77))
+    blk.load_state_dict(own, strict=True)
+    blk = blk.eval().to(dev)
+    x = torch.randn(3, 197, 768, generator=torch.Generator().manual_seed(8))
+    out, masks, logits, _ = engine.run_blocks(x.to(dev), [blk], fuse_next_ln=False)
+    p = {"blocks.2." + k: v for k, v in own.items()}
+    ref = O.block_sparse_moe(x, p, "blocks.2.", 12, g["scale"], 4, "amp16",
+                             forced_mask=masks[0].cpu().unsqueeze(-1))
+    assert _rel(out, ref["out"]) <= 1e-3
+    own_gate = O.block_sparse_moe(x, p, "blocks.2.", 12, g["scale"], 4, "amp16")
+    flips = int((own_gate["mask"][..., 0] != masks[0].cpu()).sum())
+    assert flips <= 2
+
+
 def test_fused_next_layernorm_is_equivalent(dev, vitb_sd):
     g, sd, img = vitb_sd
     m = _speed_model(sd, dev)
