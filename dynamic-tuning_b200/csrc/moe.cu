@@ -12,8 +12,9 @@
 // ordinary GEMM over the concatenated experts [E * K, C] -- and  d W_up_mix^T = [alpha_1 d | ... |
 // alpha_E d | alpha] [W_up^1 | ... | W_up^E | b_up^1 .. b_up^E]^T  -- one ordinary GEMM with
 // K' = E * K + E (the mixed bias rides along as E extra columns).  Two small kernels sit in between:
-//   moe_route_kernel    mean over the tokens of an image (fp32), router logits with fp16 operands /
-//                       fp32 accumulation / one fp16 rounding, softmax in fp32
+//   moe_mean_kernel     mean over the tokens of an image (fp32)
+//   moe_route_kernel    router logits with fp16 operands / fp32 accumulation / one fp16 rounding,
+//                       softmax in fp32
 //   moe_combine_kernel  d = relu(f16(sum_i alpha_i h_i + sum_i alpha_i b_down^i)); writes the
 //                       expanded operand [alpha_i * d | alpha] of the up GEMM (fp16)
 #include <stdarg.h>
@@ -27,32 +28,60 @@ namespace dyt {
 
 constexpr int MOE_MAX_E = 8;
 
+// mean over the tokens of an image, fp32: CTA = (image, slab of 256 columns), thread = (row group
+// tid / 64, four columns): every row group reads 1 KB contiguous per row, four rows in flight per
+// thread; the four row groups are summed through shared memory.  (One CTA per image walking its
+// columns thread by thread took 192 us per layer at 128 x 197 x 1024.)
 __global__ void __launch_bounds__(256)
-moe_route_kernel(const float* __restrict__ x1, int ldx, int N, int C, const float* __restrict__ rw,
-                 const float* __restrict__ rb, int E, float* __restrict__ alpha) {
-  extern __shared__ float mr_smem[];   // [C] token mean (fp16-rounded), [E] logits
-  float* mean_s = mr_smem;
-  float* logit_s = mr_smem + C;
+moe_mean_kernel(const float* __restrict__ x1, int ldx, int N, int C, float* __restrict__ mean) {
+  __shared__ float4 part[4][64];
   const int b = blockIdx.x;
-  const float* xb = x1 + static_cast<size_t>(b) * N * ldx;
-  const float inv_n = 1.0f / static_cast<float>(N);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int n = 0;
-    for (; n + 3 < N; n += 4) {
-      s0 += xb[static_cast<size_t>(n) * ldx + c];
-      s1 += xb[static_cast<size_t>(n + 1) * ldx + c];
-      s2 += xb[static_cast<size_t>(n + 2) * ldx + c];
-      s3 += xb[static_cast<size_t>(n + 3) * ldx + c];
+  const int rg = threadIdx.x >> 6, c4 = threadIdx.x & 63;
+  const int col = blockIdx.y * 256 + c4 * 4;
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+  if (col < C) {
+    const float* xb = x1 + static_cast<size_t>(b) * N * ldx + col;
+    int n = rg;
+    for (; n + 12 < N; n += 16) {
+      const float4 a = *reinterpret_cast<const float4*>(xb + static_cast<size_t>(n) * ldx);
+      const float4 bb = *reinterpret_cast<const float4*>(xb + static_cast<size_t>(n + 4) * ldx);
+      const float4 c = *reinterpret_cast<const float4*>(xb + static_cast<size_t>(n + 8) * ldx);
+      const float4 d = *reinterpret_cast<const float4*>(xb + static_cast<size_t>(n + 12) * ldx);
+      s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+      s1.x += bb.x; s1.y += bb.y; s1.z += bb.z; s1.w += bb.w;
+      s2.x += c.x; s2.y += c.y; s2.z += c.z; s2.w += c.w;
+      s3.x += d.x; s3.y += d.y; s3.z += d.z; s3.w += d.w;
     }
-    for (; n < N; ++n) s0 += xb[static_cast<size_t>(n) * ldx + c];
-    mean_s[c] = round_f16(((s0 + s1) + (s2 + s3)) * inv_n);   // the router Linear sees fp16 (autocast)
+    for (; n < N; n += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(xb + static_cast<size_t>(n) * ldx);
+      s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+    }
   }
+  part[rg][c4] = make_float4((s0.x + s1.x) + (s2.x + s3.x), (s0.y + s1.y) + (s2.y + s3.y),
+                             (s0.z + s1.z) + (s2.z + s3.z), (s0.w + s1.w) + (s2.w + s3.w));
   __syncthreads();
+  if (rg == 0 && col < C) {
+    const float inv_n = 1.0f / static_cast<float>(N);
+    const float4 p0 = part[0][c4], p1 = part[1][c4], p2 = part[2][c4], p3 = part[3][c4];
+    *reinterpret_cast<float4*>(mean + static_cast<size_t>(b) * C + col) =
+        make_float4(((p0.x + p1.x) + (p2.x + p3.x)) * inv_n, ((p0.y + p1.y) + (p2.y + p3.y)) * inv_n,
+                    ((p0.z + p1.z) + (p2.z + p3.z)) * inv_n, ((p0.w + p1.w) + (p2.w + p3.w)) * inv_n);
+  }
+}
+
+// router logits (fp16 operands, fp32 accumulation, one fp16 rounding: the autocast Linear) and the
+// softmax (fp32) of one image: a warp per expert
+__global__ void __launch_bounds__(256)
+moe_route_kernel(const float* __restrict__ mean, int C, const float* __restrict__ rw,
+                 const float* __restrict__ rb, int E, float* __restrict__ alpha) {
+  __shared__ float logit_s[MOE_MAX_E];
+  const int b = blockIdx.x;
+  const float* mb = mean + static_cast<size_t>(b) * C;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int e = warp; e < E; e += blockDim.x >> 5) {
     float acc = 0.f;
-    for (int c = lane; c < C; c += 32) acc = fmaf(mean_s[c], round_f16(rw[static_cast<size_t>(e) * C + c]), acc);
+    for (int c = lane; c < C; c += 32)
+      acc = fmaf(round_f16(mb[c]), round_f16(rw[static_cast<size_t>(e) * C + c]), acc);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) logit_s[e] = round_f16(acc + round_f16(rb != nullptr ? rb[e] : 0.f));
@@ -109,7 +138,8 @@ size_t moe_workspace_bytes(int B, int N, int E, int K) {
   const size_t T = static_cast<size_t>(B) * N;
   const size_t kup = (static_cast<size_t>(E) * K + E + 7) & ~static_cast<size_t>(7);
   auto a256 = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
-  return a256(static_cast<size_t>(B) * E * 4) + a256(T * E * K * 2) + a256(T * kup * 2);
+  return a256(static_cast<size_t>(B) * E * 4) + a256(T * E * K * 2) + a256(T * kup * 2) +
+         a256(static_cast<size_t>(B) * 1024 * 4);   // + the token means [B, C <= 1024]
 }
 
 // adapt[T, C] = scale * MoE-adapter(x1): x1 fp32 [B*N, C], x1h its fp16 copy; weights:
@@ -120,8 +150,8 @@ int moe_adapter_fwd(const float* x1, int ldx, const __half* x1h, int ldxh, int B
                     const __half* down_b, const __half* up_cat, float scale, __half* adapt, int ld_adapt,
                     void* ws, size_t ws_bytes, cudaStream_t stream) {
   DYT_CHECK_ARG(x1 && x1h && router_w && down_cat && up_cat && adapt && ws, "moe_adapter: null buffer");
-  DYT_CHECK_ARG(E >= 1 && E <= MOE_MAX_E && K >= 8 && K % 8 == 0 && C % 8 == 0,
-                "moe_adapter: 1..8 experts, bottleneck multiple of 8 (E=%d K=%d)", E, K);
+  DYT_CHECK_ARG(E >= 1 && E <= MOE_MAX_E && K >= 8 && K % 8 == 0 && C % 8 == 0 && C <= 1024 && ldx % 4 == 0,
+                "moe_adapter: 1..8 experts, bottleneck multiple of 8, C <= 1024 (E=%d K=%d C=%d)", E, K, C);
   DYT_CHECK_ARG(ws_bytes >= moe_workspace_bytes(B, N, E, K), "moe_adapter: workspace too small");
   const int T = B * N;
   const int kup = (E * K + E + 7) & ~7;
@@ -131,7 +161,12 @@ int moe_adapter_fwd(const float* x1, int ldx, const __half* x1h, int ldxh, int B
   __half* hid = reinterpret_cast<__half*>(base + a256(static_cast<size_t>(B) * E * 4));
   __half* aup = reinterpret_cast<__half*>(base + a256(static_cast<size_t>(B) * E * 4) +
                                           a256(static_cast<size_t>(T) * E * K * 2));
-  moe_route_kernel<<<B, 256, (C + MOE_MAX_E) * sizeof(float), stream>>>(x1, ldx, N, C, router_w, router_b, E, alpha);
+  float* mean = reinterpret_cast<float*>(base + a256(static_cast<size_t>(B) * E * 4) +
+                                         a256(static_cast<size_t>(T) * E * K * 2) +
+                                         a256(static_cast<size_t>(T) * kup * 2));
+  moe_mean_kernel<<<dim3(B, (C + 255) / 256), 256, 0, stream>>>(x1, ldx, N, C, mean);
+  DYT_CUDA(cudaGetLastError());
+  moe_route_kernel<<<B, 256, 0, stream>>>(mean, C, router_w, router_b, E, alpha);
   DYT_CUDA(cudaGetLastError());
   // every expert's down projection in one GEMM (no bias, no activation: both are applied after the mixture)
   int st = gemm_tn(x1h, ldxh, down_cat, C, T, E * K, C, nullptr, 0 /* EPI_BIAS */, nullptr, hid, E * K,
