@@ -21,7 +21,7 @@ for name, pdl in (("opt_off", 0), ("opt_on", 1)):
     buf = g.input_buffer(images.shape, images.dtype, dev)
     buf.copy_(images)
     arms[name] = (g, buf)
-lib.dyt_configure(OPT, 0 if OPT == _lib.OPT_PDL else 1)   # back to the default
+lib.dyt_configure(OPT, 0 if OPT in (_lib.OPT_PDL, _lib.OPT_FUSE_ADAPTER_DOWN) else 1)   # back to the default
 
 ref = None
 for name, (g, buf) in arms.items():

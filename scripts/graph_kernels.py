@@ -6,6 +6,9 @@ import torch
 from torch.profiler import profile, ProfilerActivity
 from dyt_b200 import synthetic, GraphedForward
 dev = torch.device("cuda:0")
+from dyt_b200 import _lib
+if os.environ.get("ATTN_SPLIT"):
+    _lib.lib().dyt_configure(_lib.OPT_ATTN_SPLIT, 1)
 model = synthetic.build_vit_b16(dev, num_classes=100, seed=0)
 cal = torch.randn(64, 3, 224, 224, generator=torch.Generator().manual_seed(0)).to(dev)
 synthetic.calibrate_keep_rate(model, cal, 0.5)
