@@ -8,9 +8,10 @@
 // (N = 112 / 96 at 197 tokens), own row max / sum, own P and PV_h accumulator -- so the TMEM splits
 // into four 128-column regions (S at +0, fp16 P over its first half, O at +64: it lands on score
 // columns that are dead once P is complete), sixteen softmax warps put four warps on every
-// sub-partition's MUFU, and the chains of the four streams drift out of phase.  The output warps
-// combine the two key halves of a tile exactly: O = (w0 O_0 + w1 O_1) / (w0 l_0 + w1 l_1),
-// w_h = 2^(m_h - max(m_0, m_1)).
+// sub-partition's MUFU.  The two halves of a row exchange their maxima once per unit (shared memory,
+// 64-thread named barrier), so the probabilities are rounded to fp16 relative to the ROW maximum
+// exactly as in the two-stream kernel (and in the oracle); the output warps add the halves:
+// O = (O_0 + O_1) / (l_0 + l_1).
 //   warp 0        TMA producer (Q both tiles, K, V of the next unit; 2-stage ring)
 //   warps 1-4     tcgen05.mma issuers, one per stream (warp-uniform, one elected lane issues)
 //   warp 5        TMEM allocator
@@ -48,6 +49,7 @@ constexpr int AS_THREADS = AS_WARPS * 32;        // 896
 constexpr int AS_Q_BYTES = 2 * AS_BM * 128;      // both query tiles of a unit
 constexpr int AS_OSTAGE_BYTES = 4 * 32 * 128;    // per-output-warp transpose slabs
 constexpr int AS_STAT_BYTES = 2 * 4 * AS_BM * 8; // {max * scale, sum}: [unit parity][stream][row]
+constexpr int AS_MX_BYTES = 2 * 2 * AS_BM * 4;   // row maxima exchanged between the key halves
 constexpr int AS_REGION = 128;                   // TMEM columns per stream
 constexpr int AS_OCOL = 64;                      // O inside the stream's region
 
@@ -99,7 +101,8 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t stage_bytes = AS_Q_BYTES + 2 * kv_bytes;  // multiple of 2 KB
   uint8_t* o_stage = smem + 2 * stage_bytes;
   const uint32_t stat_addr = smem_u32(o_stage + AS_OSTAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(o_stage + AS_OSTAGE_BYTES + AS_STAT_BYTES);
+  const uint32_t mx_addr = stat_addr + AS_STAT_BYTES;           // row maxima of the halves: float [2][2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(o_stage + AS_OSTAGE_BYTES + AS_STAT_BYTES + AS_MX_BYTES);
   uint64_t* full_qk = bars + 0;     // [2] TMA -> MMA
   uint64_t* full_v = bars + 2;      // [2] TMA -> MMA
   uint64_t* qk_empty = bars + 4;    // [2] MMA -> TMA: all four streams' S MMAs have read Q / K
@@ -262,6 +265,19 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmap_q,
           }
           mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         }
+        // ---- the two key halves of a row agree on ONE maximum (shared memory + a 64-thread named
+        // barrier per (tile, quarter) pair): P = f16(2^(s - m_row)) is then rounded exactly like the
+        // two-stream kernel and the oracle round it, and the halves' partial sums / accumulators
+        // simply add up.  (With a maximum per half the results are equally accurate but differ by
+        // fp16 rounding noise, which is enough to flip gate decisions 1e-4 from the threshold.) ----
+        {
+          const uint32_t slot = mx_addr + ((half * 2 + tile) * AS_BM + q * 32 + lane) * 4;
+          sts32(slot, __float_as_uint(mx));
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + tile * 4 + q) : "memory");
+          const float other = __uint_as_float(lds32(mx_addr + (((half ^ 1) * 2 + tile) * AS_BM + q * 32 + lane) * 4));
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + tile * 4 + q) : "memory");   // read before the next unit's write
+          mx = fmaxf(mx, other);
+        }
         // ---- pass 2: exponentials, row sum, P -> TMEM over the consumed scores ----
         const float mb = mx * sl2;
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -312,12 +328,11 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (active) {
           const uint2 st0 = lds64(stat_addr + (((cnt & 1) * 4 + s0) * AS_BM + q * 32 + lane) * 8);
           const uint2 st1 = lds64(stat_addr + (((cnt & 1) * 4 + s1) * AS_BM + q * 32 + lane) * 8);
-          const float m0 = __uint_as_float(st0.x), m1 = __uint_as_float(st1.x);
-          const float m = fmaxf(m0, m1);
-          const float e0 = ex2_approx(m0 - m), e1 = ex2_approx(m1 - m);
-          const float inv = 1.0f / (e0 * __uint_as_float(st0.y) + e1 * __uint_as_float(st1.y));
-          w0 = e0 * inv;
-          w1 = e1 * inv;
+          // both halves used the row maximum: the partial sums and accumulators add up
+          const float inv = 1.0f / (__uint_as_float(st0.y) + __uint_as_float(st1.y));
+          w0 = inv;
+          w1 = inv;
+          (void)w1;
         }
         const uint32_t o_a = tmem_base + lane_off + s0 * AS_REGION + AS_OCOL;
         const uint32_t o_b = tmem_base + lane_off + s1 * AS_REGION + AS_OCOL;
@@ -342,14 +357,14 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 v;
-              v.x = pack_half2(fmaf(__uint_as_float(a[8 * j + 0]), w0, __uint_as_float(c[8 * j + 0]) * w1),
-                               fmaf(__uint_as_float(a[8 * j + 1]), w0, __uint_as_float(c[8 * j + 1]) * w1));
-              v.y = pack_half2(fmaf(__uint_as_float(a[8 * j + 2]), w0, __uint_as_float(c[8 * j + 2]) * w1),
-                               fmaf(__uint_as_float(a[8 * j + 3]), w0, __uint_as_float(c[8 * j + 3]) * w1));
-              v.z = pack_half2(fmaf(__uint_as_float(a[8 * j + 4]), w0, __uint_as_float(c[8 * j + 4]) * w1),
-                               fmaf(__uint_as_float(a[8 * j + 5]), w0, __uint_as_float(c[8 * j + 5]) * w1));
-              v.w = pack_half2(fmaf(__uint_as_float(a[8 * j + 6]), w0, __uint_as_float(c[8 * j + 6]) * w1),
-                               fmaf(__uint_as_float(a[8 * j + 7]), w0, __uint_as_float(c[8 * j + 7]) * w1));
+              v.x = pack_half2((__uint_as_float(a[8 * j + 0]) + __uint_as_float(c[8 * j + 0])) * w0,
+                               (__uint_as_float(a[8 * j + 1]) + __uint_as_float(c[8 * j + 1])) * w0);
+              v.y = pack_half2((__uint_as_float(a[8 * j + 2]) + __uint_as_float(c[8 * j + 2])) * w0,
+                               (__uint_as_float(a[8 * j + 3]) + __uint_as_float(c[8 * j + 3])) * w0);
+              v.z = pack_half2((__uint_as_float(a[8 * j + 4]) + __uint_as_float(c[8 * j + 4])) * w0,
+                               (__uint_as_float(a[8 * j + 5]) + __uint_as_float(c[8 * j + 5])) * w0);
+              v.w = pack_half2((__uint_as_float(a[8 * j + 6]) + __uint_as_float(c[8 * j + 6])) * w0,
+                               (__uint_as_float(a[8 * j + 7]) + __uint_as_float(c[8 * j + 7])) * w0);
               sts128(my + (((piece * 4 + j) ^ (lane & 7)) << 4), v);
             }
           }
@@ -411,7 +426,8 @@ int attn_split_fwd(const __half* qkv, int ld_qkv, int num_seqs, int seq_len, int
   p.out = out;
   p.ldo = ldo;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(AS_D));
-  const int smem_bytes = 1024 + 2 * (AS_Q_BYTES + 2 * nk * 128) + AS_OSTAGE_BYTES + AS_STAT_BYTES + 256;
+  const int smem_bytes = 1024 + 2 * (AS_Q_BYTES + 2 * nk * 128) + AS_OSTAGE_BYTES + AS_STAT_BYTES +
+                         AS_MX_BYTES + 256;
   static SmemAttrCache smem_cache;
   {
     const int st = ensure_dyn_smem(attn_split_kernel, 232448, smem_cache);

@@ -153,11 +153,9 @@ inline std::atomic<int>& fuse_down_option() {
 // Library option (dyt_configure): uniform sequences of 161..256 tokens run the four-stream
 // attention kernel (attn_split.cu) instead of the two-stream one (attn_varlen.cu).
 inline std::atomic<int>& attn_split_option() {
-  // Off by default: 96 -> 89 us alone, 112.6 -> 103.8 us per launch inside the step (-0.1 ms), but its
-  // probabilities are rounded to fp16 relative to the maximum of their key HALF, not of the row, so
-  // x1 differs from the oracle's rounding points by fp16 noise and gate decisions of tokens within
-  // ~1e-4 of the threshold flip (the two-stream kernel reproduces them to ~1e-6).
-  static std::atomic<int> v{0};
+  // On by default: 96 -> 88 us alone, 112.6 -> 103.8 us per launch inside the step (-0.1 ms).  The key
+  // halves of a row share one maximum, so the fp16 rounding points are those of the two-stream kernel.
+  static std::atomic<int> v{1};
   return v;
 }
 

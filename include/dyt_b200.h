@@ -57,12 +57,11 @@ const char* dyt_last_error(void);
  *   the adapter's down projection inside the merge kernel as well (dyt_adapter_merge_fwd): the proj
  *   GEMM no longer writes an fp16 copy of x1 and the down GEMM launch disappears (167 MB less HBM
  *   traffic per layer at 256 images; measured neutral on the step); 0 = down GEMM on a side stream.
- *   DYT_OPT_ATTN_SPLIT (default 0): 1 = dyt_attn_varlen_fwd runs uniform sequences of 161..256
+ *   DYT_OPT_ATTN_SPLIT (default 1): dyt_attn_varlen_fwd runs uniform sequences of 161..256
  *   tokens on the four-stream kernel (query tile x key half, exact combine of the halves: 96 -> 89 us
- *   at 256 x 12 x 197 alone, -0.1 ms on the step).  Its fp16 roundings of the probabilities are taken
- *   relative to the maximum of a key half instead of the row: outputs agree with the two-stream
- *   kernel to fp16 noise, but gate decisions of tokens within ~1e-4 of the threshold can flip, so the
- *   default stays the two-stream kernel (mask parity first).  0 = two-stream kernel for every length. */
+ *   at 256 x 12 x 197 alone, -0.1 ms on the step).  The two key halves of a row share one maximum, so
+ *   the probabilities are rounded to fp16 exactly as in the two-stream kernel (results differ only by
+ *   the fp32 summation order of the PV product).  0 = two-stream kernel for every length. */
 #define DYT_OPT_PDL 1
 #define DYT_OPT_GEMM_TAIL_SPLIT 2
 #define DYT_OPT_FUSE_ADAPTER_UP 3

@@ -452,7 +452,7 @@ def test_merge_up_refuses_unsupported_shapes(dev):
 
 @pytest.mark.parametrize("B,H,N", [(3, 12, 197), (2, 4, 161), (1, 2, 256), (40, 12, 197), (2, 3, 224)])   # 256: falls back to the two-stream kernel
 def test_attention_four_stream_kernel(dev, B, H, N):
-    """DYT_OPT_ATTN_SPLIT: the four-stream kernel (query tile x key half, partial softmax per half,
+    """DYT_OPT_ATTN_SPLIT (default on): the four-stream kernel (query tile x key half, partial softmax per half,
     exact combine) against the oracle's attention and against the two-stream kernel."""
     from dyt_b200 import ops, _lib
     lib = _lib.lib()
@@ -460,15 +460,18 @@ def test_attention_four_stream_kernel(dev, B, H, N):
     qkv = (torch.randn(B, N, 3 * H * 64, generator=g) * 1.5).half()
     # one head with peaked scores late in the sequence: the halves' maxima differ widely
     qkv[:, N - 7, H * 64:H * 64 + 64] *= 6.0
-    base = ops.attn_varlen(qkv.to(dev), H)
+    out = ops.attn_varlen(qkv.to(dev), H)            # the default for these lengths
     try:
-        assert lib.dyt_configure(_lib.OPT_ATTN_SPLIT, 1) == 0
-        out = ops.attn_varlen(qkv.to(dev), H)
-    finally:
         assert lib.dyt_configure(_lib.OPT_ATTN_SPLIT, 0) == 0
+        base = ops.attn_varlen(qkv.to(dev), H)       # the two-stream kernel
+    finally:
+        assert lib.dyt_configure(_lib.OPT_ATTN_SPLIT, 1) == 0
     ref = O.attention_core(qkv.float(), H, "amp16")
     _close(out, ref, atol=2e-3, rtol=3e-3)
-    _close(out, base.float().cpu(), atol=2e-3, rtol=3e-3)
+    # same rounding points as the two-stream kernel (row maximum shared by the key halves): only the
+    # fp32 summation order of the PV product differs
+    d = (out.float() - base.float()).abs()
+    assert float((d > 0).float().mean()) < 0.05 and float(d.max()) <= 2e-3
 
 
 def test_keep_stats_kernel_matches_reference_accounting():
