@@ -117,7 +117,8 @@ struct GemmCfg {
   static constexpr int PART_COLS = BN / PARTS;  // columns owned by one epilogue warp
   static constexpr int THREADS = 128 + EPI_WARPS * 32;
   static constexpr int SLAB_BYTES = 32 * 64;   // 32 rows x 32 fp16 (one 32-column chunk), per warp
-  static constexpr int BIAS_BYTES = PART_COLS * 4;  // fp32 bias of the warp's columns
+  static constexpr int BIAS_BYTES = 2 * PART_COLS * 4;  // fp32 bias of the warp's columns + the fused
+                                                        // row-dot's weights of the same columns
   static constexpr int EPI_BYTES = EPI_WARPS * (SLAB_BYTES + BIAS_BYTES);
   static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);  // power of two
   static constexpr int BAR_BYTES = 256;
@@ -304,6 +305,24 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         sts128(bias_s + i * 16, make_uint4(__float_as_uint(bv.x), __float_as_uint(bv.y),
                                            __float_as_uint(bv.z), __float_as_uint(bv.w)));
       }
+      if constexpr (EPI == EPI_BIAS_RESID) {
+        // the fused row-dot's weights of this warp's columns (rounded as the selector Linear sees
+        // them) next to the bias: read per chunk straight from global memory they cost an exposed
+        // L2 round trip per chunk (13 % of the proj GEMM's stall samples)
+        if (p.dot_w != nullptr) {
+          for (int i = lane; i < my_n * 8; i += 32) {
+            const int col = n0 + i * 4;
+            float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col < p.N) {
+              dv = *reinterpret_cast<const float4*>(p.dot_w + col);
+              if (p.dot_f16)
+                dv = make_float4(round_f16(dv.x), round_f16(dv.y), round_f16(dv.z), round_f16(dv.w));
+            }
+            sts128(bias_s + HALF * 4 + i * 16, make_uint4(__float_as_uint(dv.x), __float_as_uint(dv.y),
+                                                          __float_as_uint(dv.z), __float_as_uint(dv.w)));
+          }
+        }
+      }
       __syncwarp();
 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -422,10 +441,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const int col = n0 + c * 32 + (lane & 7) * 4;
           const int p8 = lane & 7;
           float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.dot_w != nullptr && col < p.N) {
-            dw = *reinterpret_cast<const float4*>(p.dot_w + col);
-            if (p.dot_f16)
-              dw = make_float4(round_f16(dw.x), round_f16(dw.y), round_f16(dw.z), round_f16(dw.w));
+          if (p.dot_w != nullptr) {
+            const uint4 dq = lds128(bias_s + HALF * 4 + (c * 32 + p8 * 4) * 4);
+            dw = make_float4(__uint_as_float(dq.x), __uint_as_float(dq.y), __uint_as_float(dq.z),
+                             __uint_as_float(dq.w));
           }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
