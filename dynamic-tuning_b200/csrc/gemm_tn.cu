@@ -8,11 +8,11 @@
 
 namespace dyt {
 
-template <int BN, int EPI, int EW>
+template <int BN, int EPI, int EW, bool RS = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap (&tb)[3], const GemmParams& p,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, EW>;
-  auto kern = gemm_tn_kernel<BN, EPI, EW>;
+  using Cfg = GemmCfg<BN, EW, RS>;
+  auto kern = gemm_tn_kernel<BN, EPI, EW, RS>;
   static SmemAttrCache smem_cache;   // one per kernel instantiation, per device inside
   {
     const int st = ensure_dyn_smem(kern, Cfg::SMEM_BYTES, smem_cache);
@@ -60,6 +60,12 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap (&tb)[
   }
   if (epi == EPI_BIAS_GELU_KEEP || epi == EPI_DGELU)
     return fail(DYT_EUNSUPPORTED, "gemm: the fused GELU training epilogues need N > 64");
+  if constexpr (BN == 256) {
+    // residual staged one chunk ahead by cp.async: full tiles only (no tail split: the fused row-dot
+    // case, i.e. the proj GEMM of the block) and a residual whose rows can take 16-byte copies
+    if (epi == EPI_BIAS_RESID && p.tail_split == 0 && p.N % 256 == 0)
+      return launch_gemm<BN, EPI_BIAS_RESID, 8, true>(ta, tb, p, s);
+  }
   switch (epi) {
     case EPI_BIAS: return launch_gemm<BN, EPI_BIAS, 8>(ta, tb, p, s);
     case EPI_BIAS_GELU: return launch_gemm<BN, EPI_BIAS_GELU, 8>(ta, tb, p, s);

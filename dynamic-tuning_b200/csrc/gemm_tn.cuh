@@ -100,15 +100,20 @@ struct GemmItems {
 
 // EW = epilogue warps: 8 (two per TMEM lane quarter) or 16 (four per quarter, for epilogue-bound
 // shapes: GELU, K <= 128 -- the arithmetic epilogue is latency-bound and wants more warps in flight)
-template <int BN, int EW = 8>
+// RS (residual staging, EPI_BIAS_RESID on full 256-wide tiles only): every epilogue lane owns a
+// 128-byte slot in shared memory that cp.async fills with its piece of the residual one chunk
+// ahead (one pipeline stage is given up for the 32 KB); without it the residual loads of a chunk
+// are issued at the top of that chunk and their latency is only partly covered.
+template <int BN, int EW = 8, bool RS = false>
 struct GemmCfg {
   static_assert(BN == 64 || BN == 128 || BN == 192 || BN == 256, "tile widths: 64 / 128 / 192 / 256");
   static_assert(EW == 8 || (EW == 16 && (BN == 128 || BN == 256)),
                 "epilogue warps: 8, or 16 for BN = 128 / 256 (column slices of 32-column chunks)");
   static constexpr int BM = 128;
   static constexpr int BK = 64;  // 64 halves = 128 B = one swizzle row
+  static_assert(!RS || (BN == 256 && EW == 8), "residual staging: the 256-wide tile with 8 epilogue warps");
   static constexpr int STAGES =
-      (BN == 256) ? (EW == 16 ? 5 : 6) : (BN == 192 ? 7 : (BN == 128 && EW == 16 ? 7 : 8));
+      (BN == 256) ? ((EW == 16 || RS) ? 5 : 6) : (BN == 192 ? 7 : (BN == 128 && EW == 16 ? 7 : 8));
   static constexpr int A_BYTES = BM * BK * 2;         // this CTA's 128 rows of A
   static constexpr int B_BYTES = (BN / 2) * BK * 2;   // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -119,20 +124,21 @@ struct GemmCfg {
   static constexpr int SLAB_BYTES = 32 * 64;   // 32 rows x 32 fp16 (one 32-column chunk), per warp
   static constexpr int BIAS_BYTES = 2 * PART_COLS * 4;  // fp32 bias of the warp's columns + the fused
                                                         // row-dot's weights of the same columns
-  static constexpr int EPI_BYTES = EPI_WARPS * (SLAB_BYTES + BIAS_BYTES);
+  static constexpr int RSTAGE_BYTES = RS ? 32 * 128 : 0;   // per warp: 32 rows x 32 fp32 of the residual
+  static constexpr int EPI_BYTES = EPI_WARPS * (SLAB_BYTES + BIAS_BYTES + RSTAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);  // power of two
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
 };
 
-template <int BN, int EPI, int EW>
-__global__ void __launch_bounds__(GemmCfg<BN, EW>::THREADS, 1)
+template <int BN, int EPI, int EW, bool RS = false>
+__global__ void __launch_bounds__(GemmCfg<BN, EW, RS>::THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                const __grid_constant__ CUtensorMap tmap_b,    // box = BN / 2 rows of W per CTA
                const __grid_constant__ CUtensorMap tmap_b2,   // box = BN / 4 rows (half-width sub-tiles)
                const __grid_constant__ CUtensorMap tmap_b4,   // box = BN / 8 rows (quarter-width)
                const GemmParams p) {
-  using Cfg = GemmCfg<BN, EW>;
+  using Cfg = GemmCfg<BN, EW, RS>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -273,12 +279,38 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int e = warp_idx - 4;
     const int q = e & 3;              // == warp_idx % 4: TMEM lane quarter this warp may access
     const int half = e >> 2;          // which column slice of the tile
-    const uint32_t slab = smem_u32(epi_smem) + e * (Cfg::SLAB_BYTES + Cfg::BIAS_BYTES);
+    const uint32_t slab = smem_u32(epi_smem) + e * (Cfg::SLAB_BYTES + Cfg::BIAS_BYTES + Cfg::RSTAGE_BYTES);
     const uint32_t bias_s = slab + Cfg::SLAB_BYTES;
     const uint32_t my_row = slab + lane * 64;
     const int swz_w = (lane >> 1) & 3;  // chunk swizzle of the row this lane writes
     int acc = 0;
     uint32_t acc_phase = 0;
+    // RS: this lane's staging slots (row it*4 + lane/8, 16 bytes) and the asynchronous fetch of the
+    // residual piece of (tile rows m0.., 32 columns from column cfirst)
+    const uint32_t rstage = slab + Cfg::SLAB_BYTES + Cfg::BIAS_BYTES + (lane >> 3) * 128 + (lane & 7) * 16;
+    auto rs_issue = [&](int m0_, int cfirst) {
+      if constexpr (RS) {
+        const int col = cfirst + (lane & 7) * 4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          int grow = m0_ + q * 32 + it * 4 + (lane >> 3);
+          const bool in = grow < m_eff && col < p.N;
+          grow = in ? grow : 0;
+          const float* src = p.resid + static_cast<size_t>(grow) * p.ld_res + (in ? col : 0);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(rstage + it * 512), "l"(src),
+                       "r"(in ? 16u : 0u)
+                       : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+    };
+    if constexpr (RS) {
+      if (cluster_id < items.total) {
+        int mp, nt, b0;
+        items.decode(cluster_id, BN, mp, nt, b0);
+        rs_issue((mp * 2 + cta_rank) * BM, nt + half * (b0 >> 5) / Cfg::PARTS * 32);
+      }
+    }
     for (int item = cluster_id; item < items.total; item += num_clusters) {
       int m_pair, n_tile0, bn;
       items.decode(item, BN, m_pair, n_tile0, bn);
@@ -341,7 +373,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tmem_ld32(t_row + c * 32, r);
         // residual rows of this chunk (coalesced layout, see below): in flight during the math
         float4 res[8];
-        if constexpr (EPI == EPI_BIAS_RESID) {
+        if constexpr (EPI == EPI_BIAS_RESID && !RS) {
           const int col = n0 + c * 32 + (lane & 7) * 4;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
@@ -436,6 +468,24 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         };
         slab_write(pk);
+        if constexpr (RS) {
+          // the staged residual of this chunk -> registers; the slots are refilled at once with the
+          // next chunk's piece (of this tile, or the first chunk of this warp's next tile)
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const uint4 rv = lds128(rstage + it * 512);
+            res[it] = make_float4(__uint_as_float(rv.x), __uint_as_float(rv.y), __uint_as_float(rv.z),
+                                  __uint_as_float(rv.w));
+          }
+          if (c + 1 < my_n) {
+            rs_issue(m0, n0 + (c + 1) * 32);
+          } else if (item + num_clusters < items.total) {
+            int mp, nt, b1;
+            items.decode(item + num_clusters, BN, mp, nt, b1);
+            rs_issue((mp * 2 + cta_rank) * BM, nt + c_first * 32);
+          }
+        }
         if constexpr (EPI == EPI_BIAS_RESID) {
           // lane -> (row it*4 + lane/8, columns (lane%8)*4 .. +3): 128-byte fp32 row segments
           const int col = n0 + c * 32 + (lane & 7) * 4;
