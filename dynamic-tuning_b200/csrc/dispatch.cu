@@ -193,6 +193,26 @@ dispatch_kernel(const DispatchParams p) {
       if (k) s_list[cnt + __popc(ballot & ((1u << lane) - 1u))] = static_cast<short>(n);
       cnt += __popc(ballot);
     }
+    if (lane == 0) s_cnt = cnt;
+  }
+  __syncthreads();   // the image's list of kept tokens is complete
+  // While warp 0 walks the look-back (it waits for the images before this one), the other warps load
+  // and normalise their first two kept rows: only the DESTINATION of a packed row needs the base.
+  const bool do_pack = p.packed != nullptr;
+  float4 v0[NV], v1[NV];
+  bool preloaded = false;
+  if (warp != 0 && do_pack) {
+    const int c0 = s_cnt;
+    if (warp < c0) {
+      load_row_f32<NV>(x_img + static_cast<size_t>(s_list[warp]) * p.ldx, lane, v0);
+      if (warp + 8 < c0) load_row_f32<NV>(x_img + static_cast<size_t>(s_list[warp + 8]) * p.ldx, lane, v1);
+      row_layernorm<NV>(v0, p.ln_w, p.ln_b, p.eps, lane);
+      if (warp + 8 < c0) row_layernorm<NV>(v1, p.ln_w, p.ln_b, p.eps, lane);
+      preloaded = true;
+    }
+  }
+  if (warp == 0) {
+    const int cnt = s_cnt;
     // ------------------------------- prefix over the images: decoupled look-back ----------------
     int excl = 0;
     if (b > 0) {
@@ -224,7 +244,6 @@ dispatch_kernel(const DispatchParams p) {
     }
     if (lane == 0) {
       st_status(&p.status[b], tag | ST_PREFIX | static_cast<unsigned int>(excl + cnt));
-      s_cnt = cnt;
       s_base = excl;
       p.cu_seqlens[b] = excl;
       if (b == p.B - 1) {
@@ -247,18 +266,18 @@ dispatch_kernel(const DispatchParams p) {
 
   // ------------------------------- pack -------------------------------
   // LayerNorm2 of the kept rows into the packed fp16 buffer, two rows in flight per warp
-  if (p.packed != nullptr) {
+  if (do_pack) {
     for (int r = warp; r < cnt; r += 16) {
       const int r1 = r + 8;
-      float4 v0[NV], v1[NV];
-      load_row_f32<NV>(x_img + static_cast<size_t>(s_list[r]) * p.ldx, lane, v0);
-      if (r1 < cnt) load_row_f32<NV>(x_img + static_cast<size_t>(s_list[r1]) * p.ldx, lane, v1);
-      row_layernorm<NV>(v0, p.ln_w, p.ln_b, p.eps, lane);
-      store_row_f16<NV>(p.packed + static_cast<size_t>(base + r) * p.ldp, lane, v0);
-      if (r1 < cnt) {
-        row_layernorm<NV>(v1, p.ln_w, p.ln_b, p.eps, lane);
-        store_row_f16<NV>(p.packed + static_cast<size_t>(base + r1) * p.ldp, lane, v1);
+      if (!preloaded) {
+        load_row_f32<NV>(x_img + static_cast<size_t>(s_list[r]) * p.ldx, lane, v0);
+        if (r1 < cnt) load_row_f32<NV>(x_img + static_cast<size_t>(s_list[r1]) * p.ldx, lane, v1);
+        row_layernorm<NV>(v0, p.ln_w, p.ln_b, p.eps, lane);
+        if (r1 < cnt) row_layernorm<NV>(v1, p.ln_w, p.ln_b, p.eps, lane);
       }
+      preloaded = false;
+      store_row_f16<NV>(p.packed + static_cast<size_t>(base + r) * p.ldp, lane, v0);
+      if (r1 < cnt) store_row_f16<NV>(p.packed + static_cast<size_t>(base + r1) * p.ldp, lane, v1);
     }
   }
 
