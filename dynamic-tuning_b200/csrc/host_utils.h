@@ -119,11 +119,12 @@ inline int sm_count() {
 }
 
 // Library option (dyt_configure): launch the forward-path kernels with programmatic stream
-// serialization so that each kernel's prologue overlaps its predecessor's tail.  Off by default:
-// measured neutral on the headline step (same box, interleaved: 9.43-9.62 ms without, 9.50-10.01 ms
-// with) -- the step runs at the board's power cap in every phase, not on launch gaps.
+// serialization so that each kernel's prologue overlaps its predecessor's tail.  On by default
+// since the end of round 2: with the shorter kernels of that round the interleaved same-box A/B
+// (scripts/ab_step.py, six rounds of 20 replays) gives 9.16-9.22 ms without, 9.09-9.17 ms with
+// (-0.08 ms, bit-identical logits); the first measurement (9.43-9.62 vs 9.50-10.01 ms) was noise.
 inline std::atomic<int>& pdl_option() {
-  static std::atomic<int> v{0};
+  static std::atomic<int> v{1};
   return v;
 }
 

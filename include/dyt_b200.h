@@ -42,11 +42,11 @@ int dyt_version(void);
 const char* dyt_last_error(void);
 
 /* Process-wide library options (thread-safe; take effect for subsequent launches).
- *   DYT_OPT_PDL (default 0): launch the forward-path kernels with programmatic stream serialization
+ *   DYT_OPT_PDL (default 1): launch the forward-path kernels with programmatic stream serialization
  *   (cudaLaunchAttributeProgrammaticStreamSerialization): every kernel signals launch_dependents at
  *   its start and executes griddepcontrol.wait after its prologue (barrier init, TMEM allocation,
  *   tensor-map prefetch), so that prologue overlaps the previous kernel's tail.  CUDA-graph
- *   capturable.  0 = plain stream order (the default: no gain was measured on B200).
+ *   capturable.  0 = plain stream order.  Measured -0.08 ms per 9.1 ms step on B200.
  *   DYT_OPT_GEMM_TAIL_SPLIT (default 1): the persistent GEMM cuts the tiles of its last, partial
  *   round into 2 or 4 column sub-tiles when the leftover tiles number at most half / a quarter of
  *   the CTA pairs (wave quantisation: 297 tile pairs on 74 pairs = 4 rounds + 1 tile).

@@ -31,7 +31,7 @@ for name, (g, buf) in arms.items():
     print(name, "logits equal to first arm:", bool(torch.equal(out, ref)))
 
 
-def run(g, buf, n=20):
+def run(g, buf, n=int(os.environ.get("AB_N", 20))):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); a.record()
     for _ in range(n):
@@ -41,5 +41,5 @@ def run(g, buf, n=20):
 
 for name, (g, buf) in arms.items():
     run(g, buf, 10)
-for rnd in range(4):
+for rnd in range(int(os.environ.get("AB_ROUNDS", 4))):
     print("round", rnd, "  ".join(f"{name} {run(g, buf):.3f} ms" for name, (g, buf) in arms.items()), flush=True)

@@ -604,6 +604,33 @@ def test_graphed_forward_several_batch_sizes_interleaved(dev, vitb_sd):
         del junk
 
 
+def test_programmatic_dependent_launch_is_bit_identical(dev, vitb_sd):
+    """DYT_OPT_PDL (default on): every forward-path kernel is launched with programmatic stream
+    serialization and waits (griddepcontrol.wait) before its first dependent global access.  The
+    whole model, eager and as a CUDA graph, must give bit-identical logits with and without it,
+    repeatedly (a missing wait would show up as a race)."""
+    from dyt_b200 import GraphedForward, _lib
+    lib = _lib.lib()
+    g, sd, img = vitb_sd
+    m = _speed_model(sd, dev)
+    xs = [torch.randn(b, 3, 224, 224, generator=torch.Generator().manual_seed(60 + b)).to(dev) for b in (2, 24)]
+
+    def fwd(x):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            return m(x).clone()
+
+    try:
+        assert lib.dyt_configure(_lib.OPT_PDL, 0) == 0
+        ref = [fwd(x) for x in xs]
+    finally:
+        assert lib.dyt_configure(_lib.OPT_PDL, 1) == 0
+    gm = GraphedForward(m)            # captured with PDL edges
+    for rep in range(6):
+        for x, r in zip(xs, ref):
+            assert torch.equal(fwd(x), r), f"eager, repetition {rep}"
+            assert torch.equal(gm(x), r), f"graph replay, repetition {rep}"
+
+
 def test_graphed_forward_public_wrapper(dev, vitb_sd):
     """dyt_b200.GraphedForward: same logits as the eager call for new input contents, per shape and
     per static-input slot; writing straight into a slot's input buffer + replay works (bench e2e)."""
