@@ -161,9 +161,11 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
                           stream));
   }
   // 2. qkv
+  const int tile_order = tile_order_option().load(std::memory_order_relaxed);
   { NvtxRange r("dyt.qkv");
   DYT_TRY(gemm_tn(w.xn, C, HP(wt->qkv_w), C, T, 3 * C, C, nullptr, EPI_BIAS, HP(wt->qkv_b), w.qkv,
-                  3 * C, nullptr, 0, nullptr, 0, 1.0f, stream)); }
+                  3 * C, nullptr, 0, nullptr, 0, 1.0f, stream, nullptr, nullptr, 0, 0, nullptr, 0,
+                  tile_order & 1)); }
   // 3. attention (uniform sequences of N tokens): the tcgen05 kernel up to 256 tokens; longer
   //    sequences or an additive bias (segmentation backbone, 1025 tokens) take the flash-style kernel
   { NvtxRange r("dyt.attention");
@@ -192,7 +194,8 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   { NvtxRange r("dyt.proj_residual_score");
   DYT_TRY(gemm_tn(w.attn_o, C, HP(wt->proj_w), C, T, C, C, nullptr, EPI_BIAS_RESID,
                   HP(wt->proj_b), fuse_down ? nullptr : w.x1h, C, w.x1, C, x, C, 1.0f, stream,
-                  fuse_score ? wt->sel_w : nullptr, w.score_part, slices, opt->logit_fp16)); }
+                  fuse_score ? wt->sel_w : nullptr, w.score_part, slices, opt->logit_fp16, nullptr, 0,
+                  tile_order & 2)); }
   // adapter on every token (steps 8./9.), forked onto the side stream
   SideStream& ss = side_stream();
   cudaStream_t astream = stream;
@@ -229,9 +232,11 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   // 6./7. MLP on the kept rows only (row count read from device memory)
   { NvtxRange r("dyt.mlp_kept_rows");
   DYT_TRY(gemm_tn(w.packed, C, HP(wt->fc1_w), C, T, shape->hidden, C, w.n_kept, EPI_BIAS_GELU,
-                  HP(wt->fc1_b), w.hidden, shape->hidden, nullptr, 0, nullptr, 0, 1.0f, stream));
+                  HP(wt->fc1_b), w.hidden, shape->hidden, nullptr, 0, nullptr, 0, 1.0f, stream, nullptr,
+                  nullptr, 0, 0, nullptr, 0, tile_order & 8));
   DYT_TRY(gemm_tn(w.hidden, shape->hidden, HP(wt->fc2_w), shape->hidden, T, C, shape->hidden,
-                  w.n_kept, EPI_BIAS, HP(wt->fc2_b), w.mlp, C, nullptr, 0, nullptr, 0, 1.0f, stream)); }
+                  w.n_kept, EPI_BIAS, HP(wt->fc2_b), w.mlp, C, nullptr, 0, nullptr, 0, 1.0f, stream,
+                  nullptr, nullptr, 0, 0, nullptr, 0, tile_order & 4)); }
   // join the adapter branch
   if (fork) DYT_CUDA(cudaStreamWaitEvent(stream, ss.join, 0));
   // 10. scatter-merge back to [B, N, C] (in place into x), optionally with the next LayerNorm

@@ -84,7 +84,8 @@ int gemm_tn_dot_slices(int N) {
 int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, int K,
             const int* m_dev, int epi, const __half* bias, __half* out_h, int ldo_h, float* out_f,
             int ldo_f, const float* resid, int ld_res, float scale, cudaStream_t stream,
-            const float* dot_w, float* dot_out, int dot_ld, int dot_f16, __half* aux, int ld_aux) {
+            const float* dot_w, float* dot_out, int dot_ld, int dot_f16, __half* aux, int ld_aux,
+            int reverse_m) {
   DYT_CHECK_ARG(a != nullptr && w != nullptr, "gemm: null operand");
   DYT_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   DYT_CHECK_ARG(N % 8 == 0 && K % 8 == 0, "gemm: N and K must be multiples of 8 (N=%d K=%d)", N, K);
@@ -141,6 +142,7 @@ int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, in
   p.dot_w = dot_w; p.dot_out = dot_out; p.dot_ld = dot_ld; p.dot_f16 = dot_f16;
   p.aux = aux; p.ld_aux = ld_aux;
   p.tail_split = tail_split ? 1 : 0;
+  p.reverse_m = reverse_m ? 1 : 0;
   if (epi == EPI_BIAS_GELU_KEEP || epi == EPI_DGELU) {
     DYT_CHECK_ARG(aux != nullptr && ld_aux >= N && ld_aux % 8 == 0 && N % 8 == 0 &&
                       (reinterpret_cast<uintptr_t>(aux) & 15) == 0 && ldo_h % 8 == 0 &&
@@ -171,7 +173,7 @@ extern "C" int dyt_linear_f16(const void* x, int ldx, const void* w, int ldw, in
   return dyt::gemm_tn(static_cast<const __half*>(x), ldx, static_cast<const __half*>(w), ldw, M, N,
                       K, m_dev, epilogue, static_cast<const __half*>(bias),
                       static_cast<__half*>(out_f16), ldo_f16, out_f32, ldo_f32, resid, ld_resid,
-                      scale, static_cast<cudaStream_t>(stream), nullptr, nullptr, 0, 0, nullptr, 0);
+                      scale, static_cast<cudaStream_t>(stream), nullptr, nullptr, 0, 0, nullptr, 0, 0);
 }
 
 extern "C" int dyt_linear_f16_aux(const void* x, int ldx, const void* w, int ldw, int M, int N, int K,
@@ -183,5 +185,5 @@ extern "C" int dyt_linear_f16_aux(const void* x, int ldx, const void* w, int ldw
                       K, m_dev, epilogue, static_cast<const __half*>(bias),
                       static_cast<__half*>(out_f16), ldo_f16, nullptr, 0, nullptr, 0, 1.0f,
                       static_cast<cudaStream_t>(stream), nullptr, nullptr, 0, 0,
-                      static_cast<__half*>(aux_f16), ld_aux);
+                      static_cast<__half*>(aux_f16), ld_aux, 0);
 }

@@ -64,6 +64,8 @@ struct GemmParams {
   int ld_aux;
   int tail_split;  // 1 (BN = 256 only): tiles of the last, partial round are cut into 2 or 4 column
                    // sub-tiles when that lets every cluster take one (wave quantisation)
+  int reverse_m;   // 1: row pairs are taken from the last to the first (the rows the producing kernel
+                   // wrote last are still in the L2 when this kernel starts; the results are the same)
 };
 
 // One work item of the persistent tile loop: a full BM x BN tile pair, or -- in the last round,
@@ -72,9 +74,11 @@ struct GemmParams {
 // tile pairs on 74 clusters the fifth round held ONE tile and cost a whole round; cut in four it
 // costs the A-bound time of a 64-wide tile.
 struct GemmItems {
-  int n_tiles, full, split, total;
-  __device__ __forceinline__ void init(int total_tiles, int n_tiles_, int clusters, int allow) {
+  int n_tiles, full, split, total, last_pair;   // last_pair >= 0: row pairs in descending order
+  __device__ __forceinline__ void init(int total_tiles, int n_tiles_, int clusters, int allow,
+                                       int reverse = 0) {
     n_tiles = n_tiles_;
+    last_pair = reverse ? total_tiles / n_tiles_ - 1 : -1;
     full = (total_tiles / clusters) * clusters;
     const int rem = total_tiles - full;
     split = 1;
@@ -95,6 +99,7 @@ struct GemmItems {
     }
     m_pair = tile / n_tiles;
     n0 = (tile % n_tiles) * bn_full + sub * bn;
+    if (last_pair >= 0) m_pair = last_pair - m_pair;
   }
 };
 
@@ -199,7 +204,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
   GemmItems items;
-  items.init(total_tiles, n_tiles, num_clusters, BN == 256 ? p.tail_split : 0);
+  items.init(total_tiles, n_tiles, num_clusters, BN == 256 ? p.tail_split : 0, p.reverse_m);
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================

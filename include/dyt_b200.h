@@ -61,12 +61,17 @@ const char* dyt_last_error(void);
  *   tokens on the four-stream kernel (query tile x key half, exact combine of the halves: 96 -> 89 us
  *   at 256 x 12 x 197 alone, -0.1 ms on the step).  The two key halves of a row share one maximum, so
  *   the probabilities are rounded to fp16 exactly as in the two-stream kernel (results differ only by
- *   the fp32 summation order of the PV product).  0 = two-stream kernel for every length. */
+ *   the fp32 summation order of the PV product).  0 = two-stream kernel for every length.
+ *   DYT_OPT_TILE_ORDER (bit mask, default 7): GEMMs of dyt_block_fwd that take their row tiles from
+ *   the last to the first (1 = qkv, 2 = proj, 4 = fc2, 8 = fc1), so that each starts on the rows its
+ *   producer wrote last (still in the L2) and ends on the rows the ascending kernel behind it reads
+ *   first.  Bit-identical results; -0.08 ms on the 8.9 ms step. */
 #define DYT_OPT_PDL 1
 #define DYT_OPT_GEMM_TAIL_SPLIT 2
 #define DYT_OPT_FUSE_ADAPTER_UP 3
 #define DYT_OPT_ATTN_SPLIT 4
 #define DYT_OPT_FUSE_ADAPTER_DOWN 5
+#define DYT_OPT_TILE_ORDER 6
 int dyt_configure(int option, int value);
 
 /* y = epilogue(x[M,K] * w[N,K]^T): the nn.Linear forward under fp16 autocast.

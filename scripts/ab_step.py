@@ -15,13 +15,15 @@ images = torch.randn(256, 3, 224, 224, generator=torch.Generator().manual_seed(0
 
 arms = {}
 OPT = getattr(_lib, os.environ.get("AB_OPT", "OPT_GEMM_TAIL_SPLIT"))
-for name, pdl in (("opt_off", 0), ("opt_on", 1)):
+# AB_VALUES="0,7,3": one arm per option value (default: off / on)
+VALUES = [int(v) for v in os.environ.get("AB_VALUES", "0,1").split(",")]
+for name, pdl in [((f"opt_{v}" if VALUES != [0, 1] else ("opt_off", "opt_on")[v]), v) for v in VALUES]:
     assert lib.dyt_configure(OPT, pdl) == 0
     g = GraphedForward(model)
     buf = g.input_buffer(images.shape, images.dtype, dev)
     buf.copy_(images)
     arms[name] = (g, buf)
-lib.dyt_configure(OPT, 0 if OPT in (_lib.OPT_PDL, _lib.OPT_FUSE_ADAPTER_DOWN) else 1)   # back to the default
+lib.dyt_configure(OPT, {_lib.OPT_FUSE_ADAPTER_DOWN: 0, _lib.OPT_TILE_ORDER: 7}.get(OPT, 1))   # back to the default
 
 ref = None
 for name, (g, buf) in arms.items():

@@ -631,6 +631,32 @@ def test_programmatic_dependent_launch_is_bit_identical(dev, vitb_sd):
             assert torch.equal(gm(x), r), f"graph replay, repetition {rep}"
 
 
+def test_gemm_tile_order_is_bit_identical(dev, vitb_sd):
+    """DYT_OPT_TILE_ORDER (default 7: the qkv, proj and fc2 GEMMs walk their row tiles from the last to
+    the first so that each starts on the rows its producer left in the L2): only the order of the
+    tiles changes, so the whole model must give bit-identical logits for every mask, including
+    shapes with a partial last row pair and a split tail round."""
+    from dyt_b200 import _lib
+    lib = _lib.lib()
+    g, sd, img = vitb_sd
+    m = _speed_model(sd, dev)
+    xs = [torch.randn(b, 3, 224, 224, generator=torch.Generator().manual_seed(70 + b)).to(dev) for b in (3, 40)]
+
+    def fwd(x):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            return m(x).clone()
+
+    try:
+        assert lib.dyt_configure(_lib.OPT_TILE_ORDER, 0) == 0
+        ref = [fwd(x) for x in xs]
+        for mask in (1, 2, 4, 8, 7, 15):
+            assert lib.dyt_configure(_lib.OPT_TILE_ORDER, mask) == 0
+            for x, r in zip(xs, ref):
+                assert torch.equal(fwd(x), r), f"tile order mask {mask}, batch {x.shape[0]}"
+    finally:
+        assert lib.dyt_configure(_lib.OPT_TILE_ORDER, 7) == 0
+
+
 def test_graphed_forward_public_wrapper(dev, vitb_sd):
     """dyt_b200.GraphedForward: same logits as the eager call for new input contents, per shape and
     per static-input slot; writing straight into a slot's input buffer + replay works (bench e2e)."""
