@@ -64,6 +64,7 @@ struct GemmParams {
   int ld_aux;
   int tail_split;  // 1 (BN = 256 only): tiles of the last, partial round are cut into 2 or 4 column
                    // sub-tiles when that lets every cluster take one (wave quantisation)
+  int resid_evict_first;  // 1: the residual is read exactly once: L2 evict_first policy on its loads
   int reverse_m;   // 1: row pairs are taken from the last to the first (the rows the producing kernel
                    // wrote last are still in the L2 when this kernel starts; the results are the same)
 };
@@ -293,6 +294,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // RS: this lane's staging slots (row it*4 + lane/8, 16 bytes) and the asynchronous fetch of the
     // residual piece of (tile rows m0.., 32 columns from column cfirst)
     const uint32_t rstage = slab + Cfg::SLAB_BYTES + Cfg::BIAS_BYTES + (lane >> 3) * 128 + (lane & 7) * 16;
+    const uint64_t rs_pol = l2_policy(RS && p.resid_evict_first != 0);
     auto rs_issue = [&](int m0_, int cfirst) {
       if constexpr (RS) {
         const int col = cfirst + (lane & 7) * 4;
@@ -302,8 +304,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const bool in = grow < m_eff && col < p.N;
           grow = in ? grow : 0;
           const float* src = p.resid + static_cast<size_t>(grow) * p.ld_res + (in ? col : 0);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(rstage + it * 512), "l"(src),
-                       "r"(in ? 16u : 0u)
+          asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(rstage + it * 512),
+                       "l"(src), "r"(in ? 16u : 0u), "l"(rs_pol)
                        : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
