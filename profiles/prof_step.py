@@ -17,8 +17,12 @@ from dyt_b200 import engine, synthetic  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--layers", type=int, default=12)
+ap.add_argument("--tile-order", type=int, default=None, help="dyt_configure(DYT_OPT_TILE_ORDER, v)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
+if args.tile_order is not None:
+    from dyt_b200 import _lib
+    assert _lib.lib().dyt_configure(_lib.OPT_TILE_ORDER, args.tile_order) == 0
 model = synthetic.build_vit_b16(dev, seed=0)
 cal = torch.randn(32, 3, 224, 224, generator=torch.Generator().manual_seed(0)).to(dev)
 print("calibrated keep rate", synthetic.calibrate_keep_rate(model, cal, 0.5))
