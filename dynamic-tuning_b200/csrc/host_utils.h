@@ -169,6 +169,8 @@ inline std::atomic<int>& tile_order_option() {
 // attention, 2 = residual loads of the proj GEMM, 4 = x1 row loads of the dispatcher, 8 = x1 / mlp loads
 // of the fused up + merge kernel).  Hints only: results are bit-identical.  Off: same-box interleaved A/B
 // (five rounds of 20 replays) 8.84 ms with 0; 8.90 / 8.92 / 8.91 / 8.84 / 8.87 ms with 1 / 2 / 4 / 8 / 15.
+// Bits 16 / 32 / 64 / 128: the same policy on the A operand (TMA) loads of fc2 / qkv / fc1 / proj, whose
+// input is dead afterwards: 9.09 ms with 0; 9.14 / 9.11 / 9.10 / 9.14 ms -- no gain either.
 inline std::atomic<int>& cache_hints_option() {
   static std::atomic<int> v{0};
   return v;

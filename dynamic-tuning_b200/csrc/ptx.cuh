@@ -223,6 +223,19 @@ __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMa
       : "memory");
 }
 
+// tma_load_2d_cg2 with an L2 cache policy
+__device__ __forceinline__ void tma_load_2d_cg2_hint(void* smem_dst, const CUtensorMap* m,
+                                                     uint32_t bar_cluster_addr, int32_t c0, int32_t c1,
+                                                     uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0),
+        "r"(c1), "l"(policy)
+      : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // thread-block clusters
 // ---------------------------------------------------------------------------------------------

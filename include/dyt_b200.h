@@ -68,8 +68,9 @@ const char* dyt_last_error(void);
  *   first.  Bit-identical results; -0.08 ms on the 8.9 ms step.
  *   DYT_OPT_CACHE_HINTS (bit mask, default 0; experiment record): L2 evict_first policy on loads of data
  *   that is read exactly once (1 = Q / K / V of the four-stream attention, 2 = residual of the proj
- *   GEMM, 4 = x1 rows of the dispatcher, 8 = x1 / mlp of the fused up + merge kernel).  Hints only
- *   (bit-identical); measured neutral (4, 8) or slower (1, 2: +0.05 ms) on the step, so all off. */
+ *   GEMM, 4 = x1 rows of the dispatcher, 8 = x1 / mlp of the fused up + merge kernel) and on the A
+ *   operand loads of the GEMMs whose input is dead afterwards (16 = fc2, 32 = qkv, 64 = fc1, 128 = proj).
+ *   Hints only (bit-identical); every bit measured neutral or slower (up to +0.05 ms) on the step: all off. */
 #define DYT_OPT_PDL 1
 #define DYT_OPT_GEMM_TAIL_SPLIT 2
 #define DYT_OPT_FUSE_ADAPTER_UP 3
