@@ -129,6 +129,42 @@ def dist_setup(n_gpus: int):
     return world, rank, local
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Multi-rank runs: keep this rank (and the pinned host buffers it is about to allocate) on the
+    NUMA node its GPU hangs off, so that the H2D copies of the end-to-end loop do not cross the
+    socket interconnect.  Best effort: returns the node, or None when the topology is not exposed."""
+    try:
+        bdf = torch.cuda.get_device_properties(local).pci_bus_id  # torch >= 2.5
+    except Exception:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+            if isinstance(bdf, bytes):
+                bdf = bdf.decode()
+        except Exception:
+            return None
+    try:
+        bdf = str(bdf).lower()
+        if len(bdf.split(":")[0]) == 8:      # 00000000:1B:00.0 -> 0000:1b:00.0
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def shard_images(total: int, world: int, rank: int):
     """Contiguous image shard of rank `rank`: images are independent (no cross-image state), the
     reference shards the same way (strided Subset, speed.py:188).  Returns (start, count)."""
@@ -359,6 +395,8 @@ def run_ours(args, world, rank, local):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    # several ranks on one host: each stays on its GPU's NUMA node (pinned buffers, launch thread)
+    numa_node = bind_to_gpu_numa_node(local) if (world > 1 and not os.environ.get("DYT_NO_NUMA_BIND")) else None
     from dyt_b200 import engine, lib, synthetic
     lib()
     peaks = load_peaks()
@@ -493,7 +531,8 @@ def run_ours(args, world, rank, local):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s",
                 "h2d_bytes_per_step": host_images.numel() * 4,
-                "d2h_bytes_per_step": host_logits.numel() * 2},
+                "d2h_bytes_per_step": host_logits.numel() * 2,
+                "host_numa_node_rank0": numa_node},
         # 9 per block + first LN1 + 3 stem kernels + final LN + head GEMM
         # per layer: qkv, attention, proj, adapter down, dispatcher, fc1, fc2, fused up + merge;
         # + first LN1, 3 stem kernels, final LN + head
