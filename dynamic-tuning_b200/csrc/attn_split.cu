@@ -40,7 +40,6 @@ struct AttnSplitParams {
   __half* out;
   int ldo;
   float scale_log2e;
-  int evict_first;  // Q / K / V are read exactly once: L2 evict_first policy on their TMA loads
 };
 
 constexpr int AS_BM = 128;
@@ -157,7 +156,6 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmap_q,
       // ===================== TMA producer =====================
       if (lane == 0) {
         int it = 0;
-        const uint64_t pol = l2_policy(p.evict_first != 0);
         for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
           const int b = unit / p.H, h = unit - b * p.H;
           const int seq_start = b * seq_len;
@@ -167,12 +165,12 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmap_q,
           uint8_t* sK = sQ + AS_Q_BYTES;
           uint8_t* sV = sK + kv_bytes;
           mbar_arrive_expect_tx(&full_qk[s], 2u * AS_BM * 128u + kv_bytes);
-          tma_load_2d_hint(sQ, &tmap_q, &full_qk[s], h * AS_D, seq_start, pol);
-          tma_load_2d_hint(sK, &tmap_kv, &full_qk[s], p.C + h * AS_D, seq_start, pol);
-          tma_load_2d_hint(sQ + AS_BM * 128, &tmap_q, &full_qk[s], h * AS_D, seq_start + AS_BM, pol);
+          tma_load_2d(sQ, &tmap_q, &full_qk[s], h * AS_D, seq_start);
+          tma_load_2d(sK, &tmap_kv, &full_qk[s], p.C + h * AS_D, seq_start);
+          tma_load_2d(sQ + AS_BM * 128, &tmap_q, &full_qk[s], h * AS_D, seq_start + AS_BM);
           mbar_wait(&v_empty[s], ((it >> 1) & 1) ^ 1);
           mbar_arrive_expect_tx(&full_v[s], kv_bytes);
-          tma_load_2d_hint(sV, &tmap_kv, &full_v[s], 2 * p.C + h * AS_D, seq_start, pol);
+          tma_load_2d(sV, &tmap_kv, &full_v[s], 2 * p.C + h * AS_D, seq_start);
         }
       }
     } else if (warp_idx <= 4) {
@@ -428,7 +426,6 @@ int attn_split_fwd(const __half* qkv, int ld_qkv, int num_seqs, int seq_len, int
   p.out = out;
   p.ldo = ldo;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(AS_D));
-  p.evict_first = cache_hints_option().load(std::memory_order_relaxed) & 1;
   const int smem_bytes = 1024 + 2 * (AS_Q_BYTES + 2 * nk * 128) + AS_OSTAGE_BYTES + AS_STAT_BYTES +
                          AS_MX_BYTES + 256;
   static SmemAttrCache smem_cache;

@@ -162,11 +162,10 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   }
   // 2. qkv
   const int tile_order = tile_order_option().load(std::memory_order_relaxed);
-  const int hints = cache_hints_option().load(std::memory_order_relaxed);   // 16 / 32 / 64 / 128: A loads of fc2 / qkv / fc1 / proj
   { NvtxRange r("dyt.qkv");
   DYT_TRY(gemm_tn(w.xn, C, HP(wt->qkv_w), C, T, 3 * C, C, nullptr, EPI_BIAS, HP(wt->qkv_b), w.qkv,
                   3 * C, nullptr, 0, nullptr, 0, 1.0f, stream, nullptr, nullptr, 0, 0, nullptr, 0,
-                  ((tile_order & 1) ? 1 : 0) | ((hints & 32) ? 2 : 0))); }
+                  tile_order & 1)); }
   // 3. attention (uniform sequences of N tokens): the tcgen05 kernel up to 256 tokens; longer
   //    sequences or an additive bias (segmentation backbone, 1025 tokens) take the flash-style kernel
   { NvtxRange r("dyt.attention");
@@ -196,7 +195,7 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   DYT_TRY(gemm_tn(w.attn_o, C, HP(wt->proj_w), C, T, C, C, nullptr, EPI_BIAS_RESID,
                   HP(wt->proj_b), fuse_down ? nullptr : w.x1h, C, w.x1, C, x, C, 1.0f, stream,
                   fuse_score ? wt->sel_w : nullptr, w.score_part, slices, opt->logit_fp16, nullptr, 0,
-                  ((tile_order & 2) ? 1 : 0) | ((hints & 128) ? 2 : 0))); }
+                  tile_order & 2)); }
   // adapter on every token (steps 8./9.), forked onto the side stream
   SideStream& ss = side_stream();
   cudaStream_t astream = stream;
@@ -234,10 +233,10 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   { NvtxRange r("dyt.mlp_kept_rows");
   DYT_TRY(gemm_tn(w.packed, C, HP(wt->fc1_w), C, T, shape->hidden, C, w.n_kept, EPI_BIAS_GELU,
                   HP(wt->fc1_b), w.hidden, shape->hidden, nullptr, 0, nullptr, 0, 1.0f, stream, nullptr,
-                  nullptr, 0, 0, nullptr, 0, ((tile_order & 8) ? 1 : 0) | ((hints & 64) ? 2 : 0)));
+                  nullptr, 0, 0, nullptr, 0, tile_order & 8));
   DYT_TRY(gemm_tn(w.hidden, shape->hidden, HP(wt->fc2_w), shape->hidden, T, C, shape->hidden,
                   w.n_kept, EPI_BIAS, HP(wt->fc2_b), w.mlp, C, nullptr, 0, nullptr, 0, 1.0f, stream,
-                  nullptr, nullptr, 0, 0, nullptr, 0, ((tile_order & 4) ? 1 : 0) | ((hints & 16) ? 2 : 0))); }
+                  nullptr, nullptr, 0, 0, nullptr, 0, tile_order & 4)); }
   // join the adapter branch
   if (fork) DYT_CUDA(cudaStreamWaitEvent(stream, ss.join, 0));
   // 10. scatter-merge back to [B, N, C] (in place into x), optionally with the next LayerNorm

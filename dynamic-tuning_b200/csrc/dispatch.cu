@@ -56,7 +56,6 @@ struct DispatchParams {
   int n_partials;         // column slices by the producer of x1 (proj GEMM epilogue); summed in order
   unsigned int* ctl;            // workspace: [0] ticket, [1] finished CTAs, [2] launch epoch
   unsigned long long* status;   // workspace: [B] per-image (epoch tag << 32 | flag << 30 | count)
-  int evict_first;  // 1: the kept x1 rows are read exactly once here (scores came as partials)
 };
 
 constexpr int DISPATCH_MAX_N = 2048;
@@ -200,15 +199,13 @@ dispatch_kernel(const DispatchParams p) {
   // While warp 0 walks the look-back (it waits for the images before this one), the other warps load
   // and normalise their first two kept rows: only the DESTINATION of a packed row needs the base.
   const bool do_pack = p.packed != nullptr;
-  const uint64_t pol = l2_policy(p.evict_first != 0);
   float4 v0[NV], v1[NV];
   bool preloaded = false;
   if (warp != 0 && do_pack) {
     const int c0 = s_cnt;
     if (warp < c0) {
-      load_row_f32_hint<NV>(x_img + static_cast<size_t>(s_list[warp]) * p.ldx, lane, v0, pol);
-      if (warp + 8 < c0)
-        load_row_f32_hint<NV>(x_img + static_cast<size_t>(s_list[warp + 8]) * p.ldx, lane, v1, pol);
+      load_row_f32<NV>(x_img + static_cast<size_t>(s_list[warp]) * p.ldx, lane, v0);
+      if (warp + 8 < c0) load_row_f32<NV>(x_img + static_cast<size_t>(s_list[warp + 8]) * p.ldx, lane, v1);
       row_layernorm<NV>(v0, p.ln_w, p.ln_b, p.eps, lane);
       if (warp + 8 < c0) row_layernorm<NV>(v1, p.ln_w, p.ln_b, p.eps, lane);
       preloaded = true;
@@ -273,8 +270,8 @@ dispatch_kernel(const DispatchParams p) {
     for (int r = warp; r < cnt; r += 16) {
       const int r1 = r + 8;
       if (!preloaded) {
-        load_row_f32_hint<NV>(x_img + static_cast<size_t>(s_list[r]) * p.ldx, lane, v0, pol);
-        if (r1 < cnt) load_row_f32_hint<NV>(x_img + static_cast<size_t>(s_list[r1]) * p.ldx, lane, v1, pol);
+        load_row_f32<NV>(x_img + static_cast<size_t>(s_list[r]) * p.ldx, lane, v0);
+        if (r1 < cnt) load_row_f32<NV>(x_img + static_cast<size_t>(s_list[r1]) * p.ldx, lane, v1);
         row_layernorm<NV>(v0, p.ln_w, p.ln_b, p.eps, lane);
         if (r1 < cnt) row_layernorm<NV>(v1, p.ln_w, p.ln_b, p.eps, lane);
       }
@@ -463,7 +460,6 @@ int dyt::dispatch_fwd(const float* x1, int ldx, const float* sel_w, const float*
                 "dispatch: packed output needs norm2 parameters");
   DYT_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "dispatch: workspace alignment");
   DispatchParams p;
-  p.evict_first = (partials != nullptr && (cache_hints_option().load(std::memory_order_relaxed) & 4)) ? 1 : 0;
   p.x1 = x1; p.ldx = ldx; p.sel_w = sel_w; p.sel_b = sel_b;
   p.logit_fp16 = logit_fp16; p.min_kept = min_kept;
   p.noise1 = noise1; p.noise2 = noise2; p.tau = tau;

@@ -64,9 +64,6 @@ struct GemmParams {
   int ld_aux;
   int tail_split;  // 1 (BN = 256 only): tiles of the last, partial round are cut into 2 or 4 column
                    // sub-tiles when that lets every cluster take one (wave quantisation)
-  int a_evict_first;      // 1: L2 evict_first policy on the A operand loads (activations that are dead
-                          // after this GEMM: they then leave the L2 before the rows this GEMM writes)
-  int resid_evict_first;  // 1: the residual is read exactly once: L2 evict_first policy on its loads
   int reverse_m;   // 1: row pairs are taken from the last to the first (the rows the producing kernel
                    // wrote last are still in the L2 when this kernel starts; the results are the same)
 };
@@ -214,7 +211,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint64_t a_pol = l2_policy(p.a_evict_first != 0);
       for (int item = cluster_id; item < items.total; item += num_clusters) {
         int m_pair, n0, bn;
         items.decode(item, BN, m_pair, n0, bn);
@@ -228,7 +224,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           // all four boxes of the pair (2 x A, 2 x B half) complete on the leader's barrier
           if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-          tma_load_2d_cg2_hint(sa, &tmap_a, lead_bar, kb * BK, m0, a_pol);
+          tma_load_2d_cg2(sa, &tmap_a, lead_bar, kb * BK, m0);
           tma_load_2d_cg2(sb, tb, lead_bar, kb * BK, n0 + cta_rank * (bn / 2));
           if (++stage == STAGES) {
             stage = 0;
@@ -297,7 +293,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // RS: this lane's staging slots (row it*4 + lane/8, 16 bytes) and the asynchronous fetch of the
     // residual piece of (tile rows m0.., 32 columns from column cfirst)
     const uint32_t rstage = slab + Cfg::SLAB_BYTES + Cfg::BIAS_BYTES + (lane >> 3) * 128 + (lane & 7) * 16;
-    const uint64_t rs_pol = l2_policy(RS && p.resid_evict_first != 0);
     auto rs_issue = [&](int m0_, int cfirst) {
       if constexpr (RS) {
         const int col = cfirst + (lane & 7) * 4;
@@ -307,8 +302,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const bool in = grow < m_eff && col < p.N;
           grow = in ? grow : 0;
           const float* src = p.resid + static_cast<size_t>(grow) * p.ld_res + (in ? col : 0);
-          asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(rstage + it * 512),
-                       "l"(src), "r"(in ? 16u : 0u), "l"(rs_pol)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(rstage + it * 512), "l"(src),
+                       "r"(in ? 16u : 0u)
                        : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");

@@ -164,18 +164,6 @@ inline std::atomic<int>& tile_order_option() {
   return v;
 }
 
-// Library option (dyt_configure), bit mask: L2 evict_first policy on loads of data that is read exactly
-// once, so that it does not push out what the next kernel reads (1 = Q / K / V loads of the four-stream
-// attention, 2 = residual loads of the proj GEMM, 4 = x1 row loads of the dispatcher, 8 = x1 / mlp loads
-// of the fused up + merge kernel).  Hints only: results are bit-identical.  Off: same-box interleaved A/B
-// (five rounds of 20 replays) 8.84 ms with 0; 8.90 / 8.92 / 8.91 / 8.84 / 8.87 ms with 1 / 2 / 4 / 8 / 15.
-// Bits 16 / 32 / 64 / 128: the same policy on the A operand (TMA) loads of fc2 / qkv / fc1 / proj, whose
-// input is dead afterwards: 9.09 ms with 0; 9.14 / 9.11 / 9.10 / 9.14 ms -- no gain either.
-inline std::atomic<int>& cache_hints_option() {
-  static std::atomic<int> v{0};
-  return v;
-}
-
 // Library option (dyt_configure): uniform sequences of 161..256 tokens run the four-stream
 // attention kernel (attn_split.cu) instead of the two-stream one (attn_varlen.cu).
 inline std::atomic<int>& attn_split_option() {

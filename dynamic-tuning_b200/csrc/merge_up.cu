@@ -74,7 +74,6 @@ struct MergeUpParams {
   int fuse_down;
   const __half* down_bias;   // [Kd] fp16 or nullptr
   int Kd;                    // adapter bottleneck (<= 64)
-  int evict_first;           // 1: L2 evict_first policy on the x1 / mlp loads (each read exactly once)
 };
 
 static inline int mu_smem_bytes(int C) {
@@ -88,15 +87,6 @@ __device__ __forceinline__ void mu_bar_sync(int id, int threads) {
 // 16-byte asynchronous copy global -> shared, L2 only
 __device__ __forceinline__ void mu_cp16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void mu_cp16_hint(uint32_t dst, const void* src, uint64_t pol) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol)
-               : "memory");
-}
-__device__ __forceinline__ void mu_cp8z_hint(uint32_t dst, const void* src, uint32_t src_bytes, uint64_t pol) {
-  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2, %3;" ::"r"(dst), "l"(src),
-               "r"(src_bytes), "l"(pol)
-               : "memory");
 }
 // 8-byte copy; src_bytes = 0 writes zeros instead
 __device__ __forceinline__ void mu_cp8z(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -335,7 +325,6 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
     // Rows past the end are clamped to the last row for every load (their results are computed and
     // dropped), so the per-row code has no bounds branches; only the stores look at `live`.
     // pass-1 inputs of chunk j -> staging (asynchronous); dropped rows get zeros for the mlp part
-    const uint64_t pol_in = l2_policy(p.evict_first != 0);
     auto issue_p1 = [&](int tile, int pl, int j) {
       if (tile < num_tiles) {
         const int rbase = tile * MU_BM + q * 32 + r8;
@@ -344,9 +333,9 @@ merge_up_kernel(const __grid_constant__ CUtensorMap tmap_a,   // down [T, K], bo
         for (int it = 0; it < 8; ++it) {
           const int grow = min(rbase + it * 4, last_row);
           const int ps = __shfl_sync(0xffffffffu, pl, it * 4 + r8);
-          mu_cp16_hint(stage_x + it * 512, p.x1 + (static_cast<uint32_t>(grow) * p.ldx + col), pol_in);
-          mu_cp8z_hint(stage_m + it * 256, p.mlp + (static_cast<uint32_t>(ps < 0 ? 0 : ps) * p.ldm + col),
-                       ps < 0 ? 0u : 8u, pol_in);
+          mu_cp16(stage_x + it * 512, p.x1 + (static_cast<uint32_t>(grow) * p.ldx + col));
+          mu_cp8z(stage_m + it * 256, p.mlp + (static_cast<uint32_t>(ps < 0 ? 0 : ps) * p.ldm + col),
+                  ps < 0 ? 0u : 8u);
         }
       }
       mu_cp_commit();
@@ -705,7 +694,6 @@ int merge_up(const __half* down, int ld_down, const __half* up_w, int ldw, const
   s = ensure_dyn_smem(merge_up_kernel, mu_smem_bytes(MU_MAXC), smem_cache);
   if (s != DYT_OK) return s;
   MergeUpParams p;
-  p.evict_first = (down_w == nullptr && (cache_hints_option().load(std::memory_order_relaxed) & 8)) ? 1 : 0;
   p.T = n_rows; p.C = C;
   p.bias = up_b; p.scale = scale;
   p.x1 = x1; p.ldx = ldx;

@@ -174,27 +174,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
-// L2 cache policy operand for .L2::cache_hint accesses: evict_first for data that is read exactly once
-// (it then leaves the L2 before the lines the next kernel wants), evict_normal = no preference.
-__device__ __forceinline__ uint64_t l2_policy(bool evict_first) {
-  uint64_t pol;
-  if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-
-// tma_load_2d with an L2 cache policy
-__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
-                                                 int32_t c0, int32_t c1, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      :
-      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0),
-        "r"(c1), "l"(policy)
-      : "memory");
-}
-
 // 2-D tiled load multicast to the CTAs of the cluster selected by cta_mask: the box lands at the
 // same shared-memory offset in every destination CTA and signals complete_tx on the mbarrier at
 // the same offset there.
@@ -220,19 +199,6 @@ __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMa
       :
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0),
         "r"(c1)
-      : "memory");
-}
-
-// tma_load_2d_cg2 with an L2 cache policy
-__device__ __forceinline__ void tma_load_2d_cg2_hint(void* smem_dst, const CUtensorMap* m,
-                                                     uint32_t bar_cluster_addr, int32_t c0, int32_t c1,
-                                                     uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-      :
-      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0),
-        "r"(c1), "l"(policy)
       : "memory");
 }
 

@@ -23,18 +23,6 @@ __device__ __forceinline__ void load_row_f32(const float* __restrict__ row, int 
   for (int i = 0; i < NV; ++i) v[i] = p[i * 32 + lane];
 }
 
-// load_row_f32 with an L2 cache policy (ptx.cuh l2_policy)
-template <int NV>
-__device__ __forceinline__ void load_row_f32_hint(const float* __restrict__ row, int lane,
-                                                  float4 (&v)[NV], uint64_t policy) {
-  const float4* p = reinterpret_cast<const float4*>(row);
-#pragma unroll
-  for (int i = 0; i < NV; ++i)
-    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-                 : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
-                 : "l"(p + i * 32 + lane), "l"(policy));
-}
-
 // LayerNorm of a register-resident row; biased variance, two-pass (mean, then squared deviations)
 template <int NV>
 __device__ __forceinline__ void row_layernorm(float4 (&v)[NV], const float* __restrict__ gamma,

@@ -65,19 +65,13 @@ const char* dyt_last_error(void);
  *   DYT_OPT_TILE_ORDER (bit mask, default 7): GEMMs of dyt_block_fwd that take their row tiles from
  *   the last to the first (1 = qkv, 2 = proj, 4 = fc2, 8 = fc1), so that each starts on the rows its
  *   producer wrote last (still in the L2) and ends on the rows the ascending kernel behind it reads
- *   first.  Bit-identical results; -0.08 ms on the 8.9 ms step.
- *   DYT_OPT_CACHE_HINTS (bit mask, default 0; experiment record): L2 evict_first policy on loads of data
- *   that is read exactly once (1 = Q / K / V of the four-stream attention, 2 = residual of the proj
- *   GEMM, 4 = x1 rows of the dispatcher, 8 = x1 / mlp of the fused up + merge kernel) and on the A
- *   operand loads of the GEMMs whose input is dead afterwards (16 = fc2, 32 = qkv, 64 = fc1, 128 = proj).
- *   Hints only (bit-identical); every bit measured neutral or slower (up to +0.05 ms) on the step: all off. */
+ *   first.  Bit-identical results; -0.08 ms on the 8.9 ms step. */
 #define DYT_OPT_PDL 1
 #define DYT_OPT_GEMM_TAIL_SPLIT 2
 #define DYT_OPT_FUSE_ADAPTER_UP 3
 #define DYT_OPT_ATTN_SPLIT 4
 #define DYT_OPT_FUSE_ADAPTER_DOWN 5
 #define DYT_OPT_TILE_ORDER 6
-#define DYT_OPT_CACHE_HINTS 7
 int dyt_configure(int option, int value);
 
 /* y = epilogue(x[M,K] * w[N,K]^T): the nn.Linear forward under fp16 autocast.
