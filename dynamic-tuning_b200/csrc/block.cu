@@ -199,12 +199,14 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   // adapter on every token (steps 8./9.), forked onto the side stream
   SideStream& ss = side_stream();
   cudaStream_t astream = stream;
-  const bool fork = ss.ok && !fuse_down;
-  if (fork) {
+  const int side_plan = side_plan_option().load(std::memory_order_relaxed);
+  const bool fork = ss.ok && !fuse_down && !(side_plan & 2);
+  if (fork) {   // the branch depends on proj only, wherever its kernels are launched below
     DYT_CUDA(cudaEventRecord(ss.fork, stream));
     DYT_CUDA(cudaStreamWaitEvent(ss.stream, ss.fork, 0));
     astream = ss.stream;
   }
+  auto adapter_branch = [&]() -> int {
   if (moe) {
     NvtxRange r("dyt.moe_adapter");
     DYT_TRY(moe_adapter_fwd(w.x1, C, w.x1h, C, B, N, C, opt->moe_experts, shape->bottleneck,
@@ -214,7 +216,8 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   }
   if (!fuse_down && !moe) { NvtxRange r("dyt.adapter_down");
   DYT_TRY(gemm_tn(w.x1h, C, HP(wt->down_w), C, T, shape->bottleneck, C, nullptr, EPI_BIAS_RELU,
-                  HP(wt->down_b), w.down, shape->bottleneck, nullptr, 0, nullptr, 0, 1.0f, astream)); }
+                  HP(wt->down_b), w.down, shape->bottleneck, nullptr, 0, nullptr, 0, 1.0f, astream, nullptr,
+                  nullptr, 0, 0, nullptr, 0, (fork && (side_plan & 1)) ? 4 : 0)); }
   if (!fuse_up && !moe) {
     NvtxRange r("dyt.adapter_up");
     DYT_TRY(gemm_tn(w.down, shape->bottleneck, HP(wt->up_w), shape->bottleneck, T, C,
@@ -222,6 +225,9 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
                     nullptr, 0, wt->adapter_scale, astream));
   }
   if (fork) DYT_CUDA(cudaEventRecord(ss.join, ss.stream));
+  return DYT_OK;
+  };
+  if (!(side_plan & 4)) DYT_TRY(adapter_branch());
   // 5. dispatcher: score, gate, compaction, LN2 of kept rows
   { NvtxRange r("dyt.dispatch");
   DYT_TRY(dispatch_fwd(w.x1, C, wt->sel_w, wt->sel_b, opt->logit_fp16, opt->min_kept,
@@ -229,6 +235,7 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
                        opt->eps, opt->forced_mask, mask_out, opt->gate_out, logits_out, w.packed_idx,
                        w.token_pos, w.cu_seqlens, w.n_kept, w.packed, C, w.dispatch_ws, stream_,
                        fuse_score ? w.score_part : nullptr, slices)); }
+  if (side_plan & 4) DYT_TRY(adapter_branch());   // experiment: the adapter branch is launched after the dispatcher
   // 6./7. MLP on the kept rows only (row count read from device memory)
   { NvtxRange r("dyt.mlp_kept_rows");
   DYT_TRY(gemm_tn(w.packed, C, HP(wt->fc1_w), C, T, shape->hidden, C, w.n_kept, EPI_BIAS_GELU,

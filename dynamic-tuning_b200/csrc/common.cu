@@ -24,6 +24,9 @@ extern "C" int dyt_configure(int option, int value) {
     case DYT_OPT_FUSE_ADAPTER_UP:
       dyt::fuse_up_option().store(value != 0 ? 1 : 0);
       return dyt::DYT_OK;
+    case DYT_OPT_SIDE_PLAN:
+      dyt::side_plan_option().store(value & 7);
+      return dyt::DYT_OK;
     case DYT_OPT_TILE_ORDER:
       dyt::tile_order_option().store(value & 15);
       return dyt::DYT_OK;

@@ -85,8 +85,7 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
 // be zero before the first launch; the last CTA of a launch resets ticket / finished and bumps the
 // epoch, so stale status words of earlier launches never match (graph-replay safe: no host state).
 template <int NV>
-__global__ void __launch_bounds__(256)
-dispatch_kernel(const DispatchParams p) {
+__device__ __forceinline__ void dispatch_body(const DispatchParams& p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int N = p.N;
@@ -295,6 +294,11 @@ dispatch_kernel(const DispatchParams p) {
   }
 }
 
+template <int NV>
+__global__ void __launch_bounds__(256)
+dispatch_kernel(const DispatchParams p) {
+  dispatch_body<NV>(p);
+}
 template <int NV>
 static int launch_dispatch(const DispatchParams& p, cudaStream_t stream) {
   // one CTA per image, taken in ticket order

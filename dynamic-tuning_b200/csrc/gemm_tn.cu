@@ -21,7 +21,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap (&tb)[3], const 
   const int m_tiles = (p.M + Cfg::BM - 1) / Cfg::BM;
   const int n_tiles = (p.N + BN - 1) / BN;
   int clusters = ((m_tiles + 1) / 2) * n_tiles;  // one pair of tiles per cluster of two CTAs
-  const int max_clusters = sm_count() / 2;
+  const int max_clusters = p.half_grid ? sm_count() / 4 : sm_count() / 2;
   if (clusters > max_clusters) clusters = max_clusters;
   if (clusters < 1) clusters = 1;
   cudaLaunchConfig_t cfg = {};
@@ -142,7 +142,8 @@ int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, in
   p.dot_w = dot_w; p.dot_out = dot_out; p.dot_ld = dot_ld; p.dot_f16 = dot_f16;
   p.aux = aux; p.ld_aux = ld_aux;
   p.tail_split = tail_split ? 1 : 0;
-  p.reverse_m = reverse_m ? 1 : 0;
+  p.reverse_m = (reverse_m & 1) ? 1 : 0;
+  p.half_grid = (reverse_m & 4) ? 1 : 0;
   if (epi == EPI_BIAS_GELU_KEEP || epi == EPI_DGELU) {
     DYT_CHECK_ARG(aux != nullptr && ld_aux >= N && ld_aux % 8 == 0 && N % 8 == 0 &&
                       (reinterpret_cast<uintptr_t>(aux) & 15) == 0 && ldo_h % 8 == 0 &&

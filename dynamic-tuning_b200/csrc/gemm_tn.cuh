@@ -64,6 +64,7 @@ struct GemmParams {
   int ld_aux;
   int tail_split;  // 1 (BN = 256 only): tiles of the last, partial round are cut into 2 or 4 column
                    // sub-tiles when that lets every cluster take one (wave quantisation)
+  int half_grid;   // launcher only: 1 = at most half of the clusters (a GEMM that shares the machine)
   int reverse_m;   // 1: row pairs are taken from the last to the first (the rows the producing kernel
                    // wrote last are still in the L2 when this kernel starts; the results are the same)
 };

@@ -22,6 +22,7 @@ OPT_FUSE_ADAPTER_UP = 3
 OPT_ATTN_SPLIT = 4
 OPT_FUSE_ADAPTER_DOWN = 5
 OPT_TILE_ORDER = 6
+OPT_SIDE_PLAN = 7
 EW_GELU_FWD, EW_GELU_BWD, EW_RELU_DROP_BWD, EW_MUL = 0, 1, 2, 3
 
 

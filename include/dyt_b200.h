@@ -65,13 +65,18 @@ const char* dyt_last_error(void);
  *   DYT_OPT_TILE_ORDER (bit mask, default 7): GEMMs of dyt_block_fwd that take their row tiles from
  *   the last to the first (1 = qkv, 2 = proj, 4 = fc2, 8 = fc1), so that each starts on the rows its
  *   producer wrote last (still in the L2) and ends on the rows the ascending kernel behind it reads
- *   first.  Bit-identical results; -0.08 ms on the 8.9 ms step. */
+ *   first.  Bit-identical results; -0.08 ms on the 8.9 ms step.
+ *   DYT_OPT_SIDE_PLAN (bit mask, default 1): how the adapter's down GEMM on the library's side stream
+ *   shares the GPU with the dispatcher.  1 = the GEMM takes at most half of the SMs, so that the
+ *   dispatcher's CTAs (which do not fit beside a persistent GEMM CTA) start at once on the others
+ *   (-0.07 ms on the step); 2 = no side stream; 4 = branch launched after the dispatcher.  Bit-identical. */
 #define DYT_OPT_PDL 1
 #define DYT_OPT_GEMM_TAIL_SPLIT 2
 #define DYT_OPT_FUSE_ADAPTER_UP 3
 #define DYT_OPT_ATTN_SPLIT 4
 #define DYT_OPT_FUSE_ADAPTER_DOWN 5
 #define DYT_OPT_TILE_ORDER 6
+#define DYT_OPT_SIDE_PLAN 7
 int dyt_configure(int option, int value);
 
 /* y = epilogue(x[M,K] * w[N,K]^T): the nn.Linear forward under fp16 autocast.

@@ -631,7 +631,7 @@ def test_programmatic_dependent_launch_is_bit_identical(dev, vitb_sd):
             assert torch.equal(gm(x), r), f"graph replay, repetition {rep}"
 
 
-def test_gemm_tile_order_is_bit_identical(dev, vitb_sd):
+def test_gemm_tile_order_and_side_plan_are_bit_identical(dev, vitb_sd):
     """DYT_OPT_TILE_ORDER (default 7: the qkv, proj and fc2 GEMMs walk their row tiles from the last to
     the first so that each starts on the rows its producer left in the L2): only the order of the
     tiles changes, so the whole model must give bit-identical logits for every mask, including
@@ -653,8 +653,16 @@ def test_gemm_tile_order_is_bit_identical(dev, vitb_sd):
             assert lib.dyt_configure(_lib.OPT_TILE_ORDER, mask) == 0
             for x, r in zip(xs, ref):
                 assert torch.equal(fwd(x), r), f"tile order mask {mask}, batch {x.shape[0]}"
+        assert lib.dyt_configure(_lib.OPT_TILE_ORDER, 7) == 0
+        # DYT_OPT_SIDE_PLAN (default 1: the adapter's down GEMM on half of the SMs beside the
+        # dispatcher): scheduling only
+        for plan in (0, 2, 4, 5, 1):
+            assert lib.dyt_configure(_lib.OPT_SIDE_PLAN, plan) == 0
+            for x, r in zip(xs, ref):
+                assert torch.equal(fwd(x), r), f"side plan {plan}, batch {x.shape[0]}"
     finally:
         assert lib.dyt_configure(_lib.OPT_TILE_ORDER, 7) == 0
+        assert lib.dyt_configure(_lib.OPT_SIDE_PLAN, 1) == 0
 
 
 def test_graphed_forward_public_wrapper(dev, vitb_sd):
