@@ -24,6 +24,9 @@ extern "C" int dyt_configure(int option, int value) {
     case DYT_OPT_FUSE_ADAPTER_UP:
       dyt::fuse_up_option().store(value != 0 ? 1 : 0);
       return dyt::DYT_OK;
+    case DYT_OPT_SM_LIMIT:
+      dyt::sm_limit_option().store(value < 0 ? 0 : value);
+      return dyt::DYT_OK;
     case DYT_OPT_SIDE_PLAN:
       dyt::side_plan_option().store(value & 7);
       return dyt::DYT_OK;

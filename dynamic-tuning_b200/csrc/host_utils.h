@@ -106,6 +106,14 @@ inline int current_device() {
   return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
 
+// Library option (dyt_configure): size every persistent grid for at most this many SMs (0 = all).  Two
+// forwards on two streams, each limited to half of the SMs, then really run side by side (a full-size
+// persistent kernel leaves no room for another one's CTAs).  For experiments with concurrent streams.
+inline std::atomic<int>& sm_limit_option() {
+  static std::atomic<int> v{0};
+  return v;
+}
+
 inline int sm_count() {
   static std::atomic<int> n[kMaxDevices];
   const int dev = current_device();
@@ -115,6 +123,8 @@ inline int sm_count() {
     if (v <= 0) v = 148;
     n[dev].store(v, std::memory_order_relaxed);
   }
+  const int lim = sm_limit_option().load(std::memory_order_relaxed);
+  if (lim >= 2 && lim < v) v = lim & ~1;
   return v;
 }
 

@@ -23,6 +23,7 @@ OPT_ATTN_SPLIT = 4
 OPT_FUSE_ADAPTER_DOWN = 5
 OPT_TILE_ORDER = 6
 OPT_SIDE_PLAN = 7
+OPT_SM_LIMIT = 8
 EW_GELU_FWD, EW_GELU_BWD, EW_RELU_DROP_BWD, EW_MUL = 0, 1, 2, 3
 
 

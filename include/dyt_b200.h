@@ -69,7 +69,10 @@ const char* dyt_last_error(void);
  *   DYT_OPT_SIDE_PLAN (bit mask, default 1): how the adapter's down GEMM on the library's side stream
  *   shares the GPU with the dispatcher.  1 = the GEMM takes at most half of the SMs, so that the
  *   dispatcher's CTAs (which do not fit beside a persistent GEMM CTA) start at once on the others
- *   (-0.07 ms on the step); 2 = no side stream; 4 = branch launched after the dispatcher.  Bit-identical. */
+ *   (-0.07 ms on the step); 2 = no side stream; 4 = branch launched after the dispatcher.  Bit-identical.
+ *   DYT_OPT_SM_LIMIT (default 0 = all): every persistent grid is sized for at most this many SMs, so that
+ *   two forwards on two streams can share the GPU side by side (experiments: two half batches on 74 SMs
+ *   each are slower than one batch on 148). */
 #define DYT_OPT_PDL 1
 #define DYT_OPT_GEMM_TAIL_SPLIT 2
 #define DYT_OPT_FUSE_ADAPTER_UP 3
@@ -77,6 +80,7 @@ const char* dyt_last_error(void);
 #define DYT_OPT_FUSE_ADAPTER_DOWN 5
 #define DYT_OPT_TILE_ORDER 6
 #define DYT_OPT_SIDE_PLAN 7
+#define DYT_OPT_SM_LIMIT 8
 int dyt_configure(int option, int value);
 
 /* y = epilogue(x[M,K] * w[N,K]^T): the nn.Linear forward under fp16 autocast.
