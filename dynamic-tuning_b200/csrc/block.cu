@@ -165,7 +165,7 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   { NvtxRange r("dyt.qkv");
   DYT_TRY(gemm_tn(w.xn, C, HP(wt->qkv_w), C, T, 3 * C, C, nullptr, EPI_BIAS, HP(wt->qkv_b), w.qkv,
                   3 * C, nullptr, 0, nullptr, 0, 1.0f, stream, nullptr, nullptr, 0, 0, nullptr, 0,
-                  tile_order & 1)); }
+                  (tile_order & 1) ? GEMM_FLAG_REVERSE : 0)); }
   // 3. attention (uniform sequences of N tokens): the tcgen05 kernel up to 256 tokens; longer
   //    sequences or an additive bias (segmentation backbone, 1025 tokens) take the flash-style kernel
   { NvtxRange r("dyt.attention");
@@ -195,7 +195,7 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   DYT_TRY(gemm_tn(w.attn_o, C, HP(wt->proj_w), C, T, C, C, nullptr, EPI_BIAS_RESID,
                   HP(wt->proj_b), fuse_down ? nullptr : w.x1h, C, w.x1, C, x, C, 1.0f, stream,
                   fuse_score ? wt->sel_w : nullptr, w.score_part, slices, opt->logit_fp16, nullptr, 0,
-                  tile_order & 2)); }
+                  (tile_order & 2) ? GEMM_FLAG_REVERSE : 0)); }
   // adapter on every token (steps 8./9.), forked onto the side stream
   SideStream& ss = side_stream();
   cudaStream_t astream = stream;
@@ -217,7 +217,7 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   if (!fuse_down && !moe) { NvtxRange r("dyt.adapter_down");
   DYT_TRY(gemm_tn(w.x1h, C, HP(wt->down_w), C, T, shape->bottleneck, C, nullptr, EPI_BIAS_RELU,
                   HP(wt->down_b), w.down, shape->bottleneck, nullptr, 0, nullptr, 0, 1.0f, astream, nullptr,
-                  nullptr, 0, 0, nullptr, 0, (fork && (side_plan & 1)) ? 4 : 0)); }
+                  nullptr, 0, 0, nullptr, 0, (fork && (side_plan & 1)) ? GEMM_FLAG_HALF_GRID : 0)); }
   if (!fuse_up && !moe) {
     NvtxRange r("dyt.adapter_up");
     DYT_TRY(gemm_tn(w.down, shape->bottleneck, HP(wt->up_w), shape->bottleneck, T, C,
@@ -240,10 +240,10 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
   { NvtxRange r("dyt.mlp_kept_rows");
   DYT_TRY(gemm_tn(w.packed, C, HP(wt->fc1_w), C, T, shape->hidden, C, w.n_kept, EPI_BIAS_GELU,
                   HP(wt->fc1_b), w.hidden, shape->hidden, nullptr, 0, nullptr, 0, 1.0f, stream, nullptr,
-                  nullptr, 0, 0, nullptr, 0, tile_order & 8));
+                  nullptr, 0, 0, nullptr, 0, (tile_order & 8) ? GEMM_FLAG_REVERSE : 0));
   DYT_TRY(gemm_tn(w.hidden, shape->hidden, HP(wt->fc2_w), shape->hidden, T, C, shape->hidden,
                   w.n_kept, EPI_BIAS, HP(wt->fc2_b), w.mlp, C, nullptr, 0, nullptr, 0, 1.0f, stream,
-                  nullptr, nullptr, 0, 0, nullptr, 0, tile_order & 4)); }
+                  nullptr, nullptr, 0, 0, nullptr, 0, (tile_order & 4) ? GEMM_FLAG_REVERSE : 0)); }
   // join the adapter branch
   if (fork) DYT_CUDA(cudaStreamWaitEvent(stream, ss.join, 0));
   // 10. scatter-merge back to [B, N, C] (in place into x), optionally with the next LayerNorm

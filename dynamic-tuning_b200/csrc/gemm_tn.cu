@@ -142,8 +142,8 @@ int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, in
   p.dot_w = dot_w; p.dot_out = dot_out; p.dot_ld = dot_ld; p.dot_f16 = dot_f16;
   p.aux = aux; p.ld_aux = ld_aux;
   p.tail_split = tail_split ? 1 : 0;
-  p.reverse_m = (reverse_m & 1) ? 1 : 0;
-  p.half_grid = (reverse_m & 4) ? 1 : 0;
+  p.reverse_m = (reverse_m & GEMM_FLAG_REVERSE) ? 1 : 0;
+  p.half_grid = (reverse_m & GEMM_FLAG_HALF_GRID) ? 1 : 0;
   if (epi == EPI_BIAS_GELU_KEEP || epi == EPI_DGELU) {
     DYT_CHECK_ARG(aux != nullptr && ld_aux >= N && ld_aux % 8 == 0 && N % 8 == 0 &&
                       (reinterpret_cast<uintptr_t>(aux) & 15) == 0 && ldo_h % 8 == 0 &&

@@ -174,19 +174,24 @@ inline std::atomic<int>& tile_order_option() {
   return v;
 }
 
+// launch flags of the internal gemm_tn() entry (internal.h)
+constexpr int GEMM_FLAG_REVERSE = 1;     // row tiles descending (L2-aware order)
+constexpr int GEMM_FLAG_HALF_GRID = 4;   // at most half of the clusters (a GEMM that shares the machine
+                                         // with a kernel on another stream)
+
 // Library option (dyt_configure), bit mask: how the adapter's down GEMM (side stream) shares the machine
-// with the dispatcher (caller's stream); both become runnable when the proj GEMM ends.
-// bit 0 (default on): the down GEMM takes at most half of the clusters (37 on a B200).  A persistent
-// GEMM CTA (384 threads x 96 registers, 185 KB of shared memory) leaves no room for a dispatcher CTA
-// (256 x 128 registers) on its SM, so with a CTA on every SM the two kernels ran one after the other;
-// on half of the SMs the GEMM takes twice as long but the dispatcher starts at once on the other half.
-// Same-box interleaved A/B (ten rounds of 30 replays): 9.41 ms with 0, 9.34 ms with 1 (24 / 32 / 48 / 56
-// clusters: 8.97 / 8.94 / 9.04 / 9.04 ms against 9.05 / 8.95 ms for 74 / 37 on another box).
-// bit 1: no side stream (the GEMM stays on the caller's stream, before the dispatcher): 9.55 ms against 9.46.
-// bit 2: the side-stream branch is launched after the dispatcher instead of before it: no gain.
-// (A dispatcher held to 112 registers, which fits beside a GEMM CTA, spills and was slower: removed.)
+// with the dispatcher (caller's stream); both become runnable when the proj GEMM ends.  A persistent GEMM
+// CTA (384 threads x 96 registers, 185 KB of shared memory) leaves no room for a dispatcher CTA (256 x 128
+// registers) on its SM, so the two kernels mostly run one after the other whatever the streams say.
+// bit 0: the down GEMM takes at most half of the clusters (37 on a B200), leaving the other SMs to the
+// dispatcher; bit 1: no side stream (the GEMM stays on the caller's stream, before the dispatcher);
+// bit 2: the side-stream branch is launched after the dispatcher instead of before it.
+// Measured (same box, twelve interleaved rounds of 30 replays): 9.023 / 9.013 / 9.007 ms for 0 / 1 / 2 --
+// no difference, so the default stays 0.  (A first measurement that showed -0.07 ms for bit 0 was taken with
+// a flag mix-up that also put the fc2 GEMM on half of the SMs in every arm; a dispatcher held to 112
+// registers so that it fits beside a GEMM CTA spills and was slower: removed.)
 inline std::atomic<int>& side_plan_option() {
-  static std::atomic<int> v{1};
+  static std::atomic<int> v{0};
   return v;
 }
 

@@ -10,8 +10,7 @@ int gemm_tn(const __half* a, int lda, const __half* w, int ldw, int M, int N, in
             int ldo_f, const float* resid, int ld_res, float scale, cudaStream_t stream,
             const float* dot_w = nullptr, float* dot_out = nullptr, int dot_ld = 0, int dot_f16 = 0,
             __half* aux = nullptr, int ld_aux = 0, int reverse_m = 0);
-// reverse_m: launch flags -- bit 0 = row tiles descending (L2-aware order), bit 2 = at most half of the
-// clusters (a GEMM that shares the machine with a kernel on another stream)
+// reverse_m: launch flags GEMM_FLAG_REVERSE / GEMM_FLAG_HALF_GRID (host_utils.h)
 // number of per-row partial sums the fused row-dot of a residual-epilogue GEMM writes (N columns)
 int gemm_tn_dot_slices(int N);
 

@@ -66,10 +66,9 @@ const char* dyt_last_error(void);
  *   the last to the first (1 = qkv, 2 = proj, 4 = fc2, 8 = fc1), so that each starts on the rows its
  *   producer wrote last (still in the L2) and ends on the rows the ascending kernel behind it reads
  *   first.  Bit-identical results; -0.08 ms on the 8.9 ms step.
- *   DYT_OPT_SIDE_PLAN (bit mask, default 1): how the adapter's down GEMM on the library's side stream
- *   shares the GPU with the dispatcher.  1 = the GEMM takes at most half of the SMs, so that the
- *   dispatcher's CTAs (which do not fit beside a persistent GEMM CTA) start at once on the others
- *   (-0.07 ms on the step); 2 = no side stream; 4 = branch launched after the dispatcher.  Bit-identical.
+ *   DYT_OPT_SIDE_PLAN (bit mask, default 0): how the adapter's down GEMM on the library's side stream
+ *   shares the GPU with the dispatcher.  1 = the GEMM takes at most half of the SMs, 2 = no side stream,
+ *   4 = branch launched after the dispatcher.  Bit-identical; measured equal on the step.
  *   DYT_OPT_SM_LIMIT (default 0 = all): every persistent grid is sized for at most this many SMs, so that
  *   two forwards on two streams can share the GPU side by side (experiments: two half batches on 74 SMs
  *   each are slower than one batch on 148). */

@@ -23,7 +23,7 @@ for name, pdl in [((f"opt_{v}" if VALUES != [0, 1] else ("opt_off", "opt_on")[v]
     buf = g.input_buffer(images.shape, images.dtype, dev)
     buf.copy_(images)
     arms[name] = (g, buf)
-lib.dyt_configure(OPT, {_lib.OPT_FUSE_ADAPTER_DOWN: 0, _lib.OPT_TILE_ORDER: 7, _lib.OPT_SIDE_PLAN: 1}.get(OPT, 1))   # back to the default
+lib.dyt_configure(OPT, {_lib.OPT_FUSE_ADAPTER_DOWN: 0, _lib.OPT_TILE_ORDER: 7, _lib.OPT_SIDE_PLAN: 0}.get(OPT, 1))   # back to the default
 
 ref = None
 for name, (g, buf) in arms.items():

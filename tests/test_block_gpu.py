@@ -654,15 +654,15 @@ def test_gemm_tile_order_and_side_plan_are_bit_identical(dev, vitb_sd):
             for x, r in zip(xs, ref):
                 assert torch.equal(fwd(x), r), f"tile order mask {mask}, batch {x.shape[0]}"
         assert lib.dyt_configure(_lib.OPT_TILE_ORDER, 7) == 0
-        # DYT_OPT_SIDE_PLAN (default 1: the adapter's down GEMM on half of the SMs beside the
-        # dispatcher): scheduling only
-        for plan in (0, 2, 4, 5, 1):
+        # DYT_OPT_SIDE_PLAN (where and how wide the adapter's down GEMM runs beside the dispatcher):
+        # scheduling only
+        for plan in (1, 2, 4, 5, 0):
             assert lib.dyt_configure(_lib.OPT_SIDE_PLAN, plan) == 0
             for x, r in zip(xs, ref):
                 assert torch.equal(fwd(x), r), f"side plan {plan}, batch {x.shape[0]}"
     finally:
         assert lib.dyt_configure(_lib.OPT_TILE_ORDER, 7) == 0
-        assert lib.dyt_configure(_lib.OPT_SIDE_PLAN, 1) == 0
+        assert lib.dyt_configure(_lib.OPT_SIDE_PLAN, 0) == 0
 
 
 def test_graphed_forward_public_wrapper(dev, vitb_sd):
