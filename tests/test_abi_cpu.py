@@ -35,6 +35,23 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().dyt_version() == _lib.ABI_VERSION
 
 
+def test_option_ids_match_the_header_and_configure_accepts_them():
+    """Every DYT_OPT_* id of the header has the same value in the binding, dyt_configure accepts each
+    of them (host-side switches: no GPU needed) and rejects an unknown id with a status + text."""
+    from dyt_b200 import _lib
+    ids = dict(re.findall(r"#define\s+DYT_OPT_([A-Z_]+)\s+(\d+)", open(HEADER).read()))
+    assert len(ids) >= 8 and len(set(ids.values())) == len(ids), "duplicate option ids"
+    defaults = {"PDL": 1, "GEMM_TAIL_SPLIT": 1, "FUSE_ADAPTER_UP": 1, "ATTN_SPLIT": 1,
+                "FUSE_ADAPTER_DOWN": 0, "TILE_ORDER": 7, "SIDE_PLAN": 0, "SM_LIMIT": 0}
+    assert set(defaults) == set(ids), "an option without a documented default (or the reverse)"
+    lib = _lib.lib()
+    for name, value in ids.items():
+        assert getattr(_lib, "OPT_" + name) == int(value), name
+        assert lib.dyt_configure(int(value), defaults[name]) == 0, name    # the default again
+    assert lib.dyt_configure(999, 1) != 0
+    assert b"unknown option" in lib.dyt_last_error()
+
+
 def test_struct_layouts_match_header_field_order():
     from dyt_b200 import _lib
     src = open(HEADER).read()
