@@ -665,6 +665,40 @@ def test_gemm_tile_order_and_side_plan_are_bit_identical(dev, vitb_sd):
         assert lib.dyt_configure(_lib.OPT_SIDE_PLAN, 0) == 0
 
 
+def test_full_batch_kernels_run_on_full_grids(dev, vitb_sd, tmp_path):
+    """At the BASELINE batch (256 images x 2 layers) every persistent kernel of the block is launched on
+    one CTA per SM and every launch is one of the library's kernels (a scheduling flag that leaked into
+    the wrong GEMM once halved fc2's grid without changing any result: results cannot catch that)."""
+    import json
+    from torch.profiler import profile, ProfilerActivity
+    from dyt_b200 import engine
+    g, sd, img = vitb_sd
+    m = _speed_model(sd, dev)
+    x = torch.randn(256, 197, 768, generator=torch.Generator().manual_seed(3)).to(dev) * 0.7
+    blocks = list(m.blocks[:2])
+    engine.run_blocks(x.clone(), blocks)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        engine.run_blocks(x.clone(), blocks)
+        torch.cuda.synchronize()
+    path = str(tmp_path / "trace.json")
+    prof.export_chrome_trace(path)
+    events = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    seen = {}
+    for e in events:
+        name, grid = e["name"], e["args"]["grid"]
+        if "dyt::" not in name:
+            assert "elementwise" in name or "copy" in name.lower() or "fill" in name.lower(), name   # the clone
+            continue
+        for key in ("gemm_tn_kernel", "attn_split_kernel", "merge_up_kernel", "dispatch_kernel"):
+            if key in name:
+                seen.setdefault(key, []).append(grid[0])
+    assert len(seen["gemm_tn_kernel"]) == 2 * 5 and set(seen["gemm_tn_kernel"]) == {sms}, seen
+    assert set(seen["attn_split_kernel"]) == {sms} and set(seen["merge_up_kernel"]) == {sms}, seen
+    assert set(seen["dispatch_kernel"]) == {256}, seen
+
+
 def test_graphed_forward_public_wrapper(dev, vitb_sd):
     """dyt_b200.GraphedForward: same logits as the eager call for new input contents, per shape and
     per static-input slot; writing straight into a slot's input buffer + replay works (bench e2e)."""
