@@ -207,25 +207,25 @@ extern "C" int dyt_block_fwd(const dyt_block_shape* shape, const dyt_block_weigh
     astream = ss.stream;
   }
   auto adapter_branch = [&]() -> int {
-  if (moe) {
-    NvtxRange r("dyt.moe_adapter");
-    DYT_TRY(moe_adapter_fwd(w.x1, C, w.x1h, C, B, N, C, opt->moe_experts, shape->bottleneck,
-                            opt->moe_router_w, opt->moe_router_b, HP(wt->down_w), HP(wt->down_b),
-                            HP(wt->up_w), wt->adapter_scale, w.adapt, C, opt->moe_workspace,
-                            opt->moe_workspace_bytes, astream));
-  }
-  if (!fuse_down && !moe) { NvtxRange r("dyt.adapter_down");
-  DYT_TRY(gemm_tn(w.x1h, C, HP(wt->down_w), C, T, shape->bottleneck, C, nullptr, EPI_BIAS_RELU,
-                  HP(wt->down_b), w.down, shape->bottleneck, nullptr, 0, nullptr, 0, 1.0f, astream, nullptr,
-                  nullptr, 0, 0, nullptr, 0, (fork && (side_plan & 1)) ? GEMM_FLAG_HALF_GRID : 0)); }
-  if (!fuse_up && !moe) {
-    NvtxRange r("dyt.adapter_up");
-    DYT_TRY(gemm_tn(w.down, shape->bottleneck, HP(wt->up_w), shape->bottleneck, T, C,
-                    shape->bottleneck, nullptr, EPI_BIAS, HP(wt->up_b), w.adapt, C, nullptr, 0,
-                    nullptr, 0, wt->adapter_scale, astream));
-  }
-  if (fork) DYT_CUDA(cudaEventRecord(ss.join, ss.stream));
-  return DYT_OK;
+    if (moe) {
+      NvtxRange r("dyt.moe_adapter");
+      DYT_TRY(moe_adapter_fwd(w.x1, C, w.x1h, C, B, N, C, opt->moe_experts, shape->bottleneck,
+                              opt->moe_router_w, opt->moe_router_b, HP(wt->down_w), HP(wt->down_b),
+                              HP(wt->up_w), wt->adapter_scale, w.adapt, C, opt->moe_workspace,
+                              opt->moe_workspace_bytes, astream));
+    }
+    if (!fuse_down && !moe) { NvtxRange r("dyt.adapter_down");
+    DYT_TRY(gemm_tn(w.x1h, C, HP(wt->down_w), C, T, shape->bottleneck, C, nullptr, EPI_BIAS_RELU,
+                    HP(wt->down_b), w.down, shape->bottleneck, nullptr, 0, nullptr, 0, 1.0f, astream, nullptr,
+                    nullptr, 0, 0, nullptr, 0, (fork && (side_plan & 1)) ? GEMM_FLAG_HALF_GRID : 0)); }
+    if (!fuse_up && !moe) {
+      NvtxRange r("dyt.adapter_up");
+      DYT_TRY(gemm_tn(w.down, shape->bottleneck, HP(wt->up_w), shape->bottleneck, T, C,
+                      shape->bottleneck, nullptr, EPI_BIAS, HP(wt->up_b), w.adapt, C, nullptr, 0,
+                      nullptr, 0, wt->adapter_scale, astream));
+    }
+    if (fork) DYT_CUDA(cudaEventRecord(ss.join, ss.stream));
+    return DYT_OK;
   };
   if (!(side_plan & 4)) DYT_TRY(adapter_branch());
   // 5. dispatcher: score, gate, compaction, LN2 of kept rows
