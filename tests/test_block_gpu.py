@@ -678,12 +678,17 @@ def test_full_batch_kernels_run_on_full_grids(dev, vitb_sd, tmp_path):
     blocks = list(m.blocks[:2])
     engine.run_blocks(x.clone(), blocks)
     torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-        engine.run_blocks(x.clone(), blocks)
-        torch.cuda.synchronize()
     path = str(tmp_path / "trace.json")
-    prof.export_chrome_trace(path)
+    try:
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            engine.run_blocks(x.clone(), blocks)
+            torch.cuda.synchronize()
+        prof.export_chrome_trace(path)
+    except RuntimeError as e:   # CUPTI taken by another tool
+        pytest.skip(f"torch profiler unavailable: {e}")
     events = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
+    if not events:   # no CUPTI activity records (e.g. the tests themselves run under ncu / nsys)
+        pytest.skip("the torch profiler recorded no kernels here")
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     seen = {}
     for e in events:
